@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Builds libopencl_render_b200.so in-tree (opencl_render_b200/): nvcc for the CUDA runtime + kernels (sm_100a only,
+-fmad=false so fp32 results equal the reference's non-FMA x86 build), g++/gcc -ffp-contract=off for the C-ABI, the
+scene packer and the host builders.  No CPU compute path is compiled into the library.
+
+    python -m opencl_render_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OBJ = PKG / "csrc" / "build"
+LIB = PKG / "libopencl_render_b200.so"
+CUDA = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-prec-div=true",
+              "-prec-sqrt=true", "-ftz=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v"]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-unused-function", f"-I{CUDA / 'include'}", "-pthread"]
+C_FLAGS = ["-O2", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-Wall"]
+
+SOURCES = [("runtime.cu", "nvcc"), ("abi.cpp", "g++"), ("scene_pack.cpp", "g++"), ("builders.cpp", "g++"), ("abi_helpers.c", "gcc")]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.c*")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "oclr_abi.h", Path(__file__)]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    stamp = OBJ / "stamp.txt"
+    dig = _digest()
+    if LIB.is_file() and not force and stamp.is_file() and stamp.read_text() == dig:
+        return LIB
+    if not (CUDA / "bin" / "nvcc").is_file():
+        if LIB.is_file():
+            return LIB  # prebuilt library travelled with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt libopencl_render_b200.so")
+    OBJ.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for name, tool in SOURCES:
+        src = CSRC / name
+        obj = OBJ / (name + ".o")
+        if tool == "nvcc":
+            cmd = [str(CUDA / "bin" / "nvcc"), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        elif tool == "g++":
+            cmd = ["g++", *CXX_FLAGS, "-c", str(src), "-o", str(obj)]
+        else:
+            cmd = ["gcc", *C_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            print("[build]", " ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if tool == "nvcc":
+            (OBJ / (name + ".ptxas.txt")).write_text(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        if verbose and r.stderr:
+            print(r.stderr, file=sys.stderr)
+        objs.append(str(obj))
+    cmd = [str(CUDA / "bin" / "nvcc"), "-shared", "-o", str(LIB), *objs, "-cudart", "static", "-Xlinker", "-Bsymbolic", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    stamp.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

@@ -1,0 +1,455 @@
+// abi.cpp -- the exported C-ABI (include/oclr_abi.h).  Part 1 mirrors source/opencl/raytrace.h:46-106 symbol for
+// symbol; Part 2 is the resident scene/frame extension.  Compiled by g++ (the by-value OpenCL vector unions carry
+// GCC vector members, see the header), calls into the CUDA runtime layer through runtime.h.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/oclr_abi.h"
+#include "runtime.h"
+
+namespace oclr {
+void set_camera(oclr_camera* out, const float position[3], const float object[3], const float up3[3], float fov, uint32_t w,
+                uint32_t h);
+bool build_camera_lists(const oclr_camera* cam, uint32_t vertexCount, const float4* vertex, uint32_t triangleCount,
+                        const int32_t* triIdx, oclr_camera_lists* out);
+bool build_scene_grid(int32_t n, uint32_t vertexCount, const float4* vertex, uint32_t triangleCount, const int32_t* triIdx,
+                      oclr_scene_grid* out);
+}  // namespace oclr
+
+using namespace oclr;
+
+static_assert(sizeof(cl_float3) == 16 && sizeof(cl_int3) == 16 && sizeof(cl_uint2) == 8 && sizeof(cl_float2) == 8 &&
+                  sizeof(cl_uchar3) == 4,
+              "OpenCL host type layout (cl_platform.h)");
+static_assert(sizeof(oclr_counters) == sizeof(Counters), "counter layout");
+static_assert(sizeof(oclr_camera) == sizeof(Camera), "camera layout");
+
+static thread_local std::string g_err;
+static void fail(const std::string& m) {
+    g_err = m;
+    fprintf(stderr, "[opencl_render_b200] %s\n", m.c_str());
+}
+
+struct oclr_scene {
+    Scene* impl;
+};
+struct oclr_frame {
+    Frame* impl;
+    oclr_scene* scene;
+};
+
+// ---- device list: raytrace.c:73-153 ------------------------------------------------------------------------------------
+static std::mutex g_devMutex;
+static std::atomic<cl_uint> g_devUpdated(CL_FALSE);
+static int g_devCount = 0;
+static char g_devName[256][256];
+
+void InitOpenCL(void) {
+    std::lock_guard<std::mutex> lock(g_devMutex);
+    int n = device_count();
+    if (n > 254) n = 254;
+    for (int i = 0; i < n; ++i)
+        if (!device_name(i, g_devName[i], sizeof(g_devName[i]))) snprintf(g_devName[i], sizeof(g_devName[i]), "CUDA device #%d", i);
+    g_devCount = n;
+    if (n > 1) snprintf(g_devName[n], sizeof(g_devName[n]), "CUDA all %d devices (row bands of 128)", n);
+    g_devUpdated = CL_TRUE;
+}
+void ResetComputationType(void) {
+    std::lock_guard<std::mutex> lock(g_devMutex);
+    if (g_devUpdated) {
+        g_devUpdated = CL_FALSE;
+        g_devCount = 0;
+    }
+}
+cl_bool GetIsComputationTypeUpdated(void) { return g_devUpdated; }
+size_t GetComputationTypeCount(void) {
+    std::lock_guard<std::mutex> lock(g_devMutex);
+    return 1 + (size_t)g_devCount + (g_devCount > 1 ? 1 : 0);
+}
+cl_bool GetComputationTypeName(size_t id, size_t strLen, cl_char* str) {
+    std::lock_guard<std::mutex> lock(g_devMutex);
+    const char* name = nullptr;
+    if (id == 0)
+        name = "Local CPU single thread";  // label kept for list-index compatibility; RaytraceAll(0) is refused
+    else if (id - 1 < (size_t)g_devCount + (g_devCount > 1 ? 1 : 0))
+        name = g_devName[id - 1];
+    if (!name || !str) return CL_FALSE;
+    if (strlen(name) <= strLen) {  // the reference's (off-by-one tolerant) length rule, raytrace.c:139,146
+        memcpy(str, name, strlen(name) + (strlen(name) < strLen ? 1 : 0));
+        return CL_TRUE;
+    }
+    return CL_FALSE;
+}
+
+// ---- progress / timing cells: raytrace.c:155-173 --------------------------------------------------------------------------
+static std::atomic<float> g_progress(0.f);
+static std::atomic<clock_t> g_startTime(0), g_endTime(0);
+cl_float GetProgress(void) { return g_progress.load(); }
+void SetProgress(cl_float p) { g_progress.store(p); }
+clock_t GetStartTime(void) { return g_startTime.load(); }
+clock_t GetEndTime(void) { return g_endTime.load(); }
+void ResetTime(void) {
+    g_startTime = 0;
+    g_endTime = 0;
+}
+
+// ---- extension -----------------------------------------------------------------------------------------------------------
+const char* oclr_last_error(void) { return g_err.c_str(); }
+int oclr_device_count(void) { return device_count(); }
+const char* oclr_version(void) { return "opencl_render_b200 0.1 (sm_100a)"; }
+
+static HostScene to_host(const oclr_scene_desc* d) {
+    HostScene h;
+    h.vertexCount = d->vertexCount;
+    h.vertex = (const float4*)d->vertex;
+    h.triangleCount = d->triangleCount;
+    h.triIdx = (const int32_t*)d->triangleVertexIndex;
+    h.triMat = d->triangleMaterialId;
+    h.triUv = (const float*)d->triangleUv;
+    h.triNormal = (const float4*)d->triangleNormal;
+    h.axesDivCount = d->axesDivCount;
+    h.boxMin = (const float4*)d->sceneBoxMin;
+    h.gridStart = d->scenePixelTriangleListStart;
+    h.gridList = d->scenePixelTriangleList;
+    h.materialCount = d->materialCount;
+    h.matSize = (const uint2*)d->materialImageSize;
+    h.matStart = d->materialImageStart;
+    h.texturesSize = d->texturesSize;
+    h.textures = (const uchar4*)d->textures;
+    h.lightCount = d->lightCount;
+    h.lightType = d->lightType;
+    h.lightPos = (const float4*)d->lightPosition;
+    h.lightDir = (const float4*)d->lightDirection;
+    h.lightColour = (const float4*)d->lightColour;
+    h.lightRadius = d->lightRadius;
+    h.lightHalf = d->lightHalfAttenuationDistance;
+    return h;
+}
+
+oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc) {
+    if (!desc) {
+        fail("oclr_scene_create: null description");
+        return nullptr;
+    }
+    std::string err;
+    Scene* s = scene_create(device, to_host(desc), err);
+    if (!s) {
+        fail("oclr_scene_create: " + err);
+        return nullptr;
+    }
+    oclr_scene* h = new oclr_scene();
+    h->impl = s;
+    return h;
+}
+void oclr_scene_destroy(oclr_scene* scene) {
+    if (!scene) return;
+    scene_destroy(scene->impl);
+    delete scene;
+}
+size_t oclr_scene_device_bytes(const oclr_scene* scene) { return scene ? scene_device_bytes(scene->impl) : 0; }
+
+void oclr_set_camera(oclr_camera* out, const cl_float position[3], const cl_float object[3], const cl_float up[3], cl_float fov,
+                     cl_uint width, cl_uint height) {
+    set_camera(out, position, object, up, fov, width, height);
+}
+
+static Camera to_camera(const oclr_camera* c) {
+    Camera k;
+    memcpy(&k, c, sizeof(Camera));
+    return k;
+}
+
+oclr_frame* oclr_frame_create(oclr_scene* scene, const oclr_camera* camera, const cl_uint* start, const cl_uint* end,
+                              const cl_uint* list, size_t listSize) {
+    if (!scene || !camera) {
+        fail("oclr_frame_create: null scene or camera");
+        return nullptr;
+    }
+    std::string err;
+    Frame* f = frame_create(scene->impl, to_camera(camera), start, end, list, listSize, err);
+    if (!f) {
+        fail("oclr_frame_create: " + err);
+        return nullptr;
+    }
+    oclr_frame* h = new oclr_frame();
+    h->impl = f;
+    h->scene = scene;
+    return h;
+}
+void oclr_frame_destroy(oclr_frame* frame) {
+    if (!frame) return;
+    frame_destroy(frame->impl);
+    delete frame;
+}
+
+static int pick_variant(int v) { return v == OCLR_KERNEL_DEFAULT ? (int)kKernelPersistent : v; }
+
+int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, cl_uint rowEnd, int kernelVariant, int countEvents,
+                      void* cudaStream, oclr_render_stats* stats) {
+    if (!frame) {
+        fail("oclr_frame_render: null frame");
+        return 0;
+    }
+    std::string err;
+    RenderStats rs;
+    if (!frame_render(frame->impl, sampleCount, rowBegin, rowEnd, pick_variant(kernelVariant), countEvents != 0, cudaStream,
+                      stats ? &rs : nullptr, err)) {
+        fail("oclr_frame_render: " + err);
+        return 0;
+    }
+    if (stats) {
+        stats->deviceMs = rs.deviceMs;
+        stats->launches = rs.launches;
+        memcpy(&stats->counters, &rs.counters, sizeof(Counters));
+    }
+    return 1;
+}
+
+int oclr_frame_read(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, cl_ushort* r, cl_ushort* g, cl_ushort* b, void* cudaStream) {
+    if (!frame || !r || !g || !b) {
+        fail("oclr_frame_read: null argument");
+        return 0;
+    }
+    std::string err;
+    if (!frame_read(frame->impl, rowBegin, rowEnd, r, g, b, cudaStream, err)) {
+        fail("oclr_frame_read: " + err);
+        return 0;
+    }
+    return 1;
+}
+
+int oclr_frame_read_primary_ids(oclr_frame* frame, cl_uint* ids) {
+    if (!frame || !ids) {
+        fail("oclr_frame_read_primary_ids: null argument");
+        return 0;
+    }
+    std::string err;
+    if (!frame_read_ids(frame->impl, ids, err)) {
+        fail("oclr_frame_read_primary_ids: " + err);
+        return 0;
+    }
+    return 1;
+}
+
+int oclr_frame_read_flags(oclr_frame* frame, cl_uchar* flags) {
+    if (!frame || !flags) {
+        fail("oclr_frame_read_flags: null argument");
+        return 0;
+    }
+    std::string err;
+    if (!frame_read_flags(frame->impl, flags, err)) {
+        fail("oclr_frame_read_flags: " + err);
+        return 0;
+    }
+    return 1;
+}
+
+void oclr_frame_device_planes(oclr_frame* frame, void** red, void** green, void** blue) {
+    if (frame) frame_device_planes(frame->impl, red, green, blue);
+}
+
+int oclr_band_partition(cl_uint height, cl_uint bandRows, int rank, int worldSize, cl_uint* rows, int maxBands) {
+    if (bandRows == 0 || worldSize < 1 || rank < 0 || rank >= worldSize) return 0;
+    int owned = 0;
+    const cl_uint bands = (height + bandRows - 1) / bandRows;
+    for (cl_uint b = (cl_uint)rank; b < bands; b += (cl_uint)worldSize) {
+        if (rows && owned < maxBands) {
+            rows[2 * owned] = b * bandRows;
+            rows[2 * owned + 1] = (b + 1) * bandRows < height ? (b + 1) * bandRows : height;
+        }
+        ++owned;
+    }
+    return owned;
+}
+
+// ---- one frame on one device: upload, trace, read back ---------------------------------------------------------------------
+static bool render_rows_on_device(int device, const HostScene& h, const Camera& cam, const cl_uint* camStart, const cl_uint* camEnd,
+                                  const cl_uint* camList, size_t camListSize, cl_uint sampleCount, int rank, int world,
+                                  cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
+    Scene* s = scene_create(device, h, err);
+    if (!s) return false;
+    Frame* f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err);
+    bool ok = f != nullptr;
+    if (ok) {
+        const int maxBands = (int)((cam.height + 127) / 128) + 1;
+        std::vector<cl_uint> rows(2 * (size_t)maxBands);
+        const int owned = world > 1 ? oclr_band_partition(cam.height, 128, rank, world, rows.data(), maxBands) : 1;
+        if (world <= 1) {
+            rows[0] = 0;
+            rows[1] = cam.height;
+        }
+        for (int k = 0; ok && k < owned; ++k) {
+            RenderStats rs;
+            ok = frame_render(f, sampleCount, rows[2 * k], rows[2 * k + 1], kKernelPersistent, false, nullptr, &rs, err);
+            if (ok) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
+            if (world <= 1) g_progress.store(0.999f * (float)(k + 1) / (float)owned);
+        }
+    }
+    if (f) frame_destroy(f);
+    scene_destroy(s);
+    return ok;
+}
+
+static cl_bool raytrace_all_impl(cl_uint computationType, const Camera& cam, const HostScene& h, const cl_uint* camStart,
+                                 const cl_uint* camEnd, const cl_uint* camList, ptrdiff_t camListSize, cl_uint sampleCount,
+                                 cl_ushort* r, cl_ushort* g, cl_ushort* b) {
+    if (computationType == 0) {
+        fail("RaytraceAll: computation type 0 (\"Local CPU single thread\") is not implemented by this library -- "
+             "it is a CUDA sm_100a drop-in with no CPU fallback; pick a CUDA device (type >= 1)");
+        return CL_FALSE;
+    }
+    const int devices = device_count();
+    if (devices <= 0) {
+        fail("RaytraceAll: no CUDA device available (no CPU fallback)");
+        return CL_FALSE;
+    }
+    if (!r || !g || !b || camListSize < 0 || sampleCount == 0) {
+        fail("RaytraceAll: bad arguments");
+        return CL_FALSE;
+    }
+    const int type = (int)computationType - 1;
+    const bool allDevices = devices > 1 && type == devices;
+    if (!allDevices && type >= devices) {
+        fail("RaytraceAll: computation type out of range");
+        return CL_FALSE;
+    }
+    g_progress.store(0.f);
+    g_startTime = clock();
+    g_endTime = g_startTime.load();
+    bool ok = true;
+    std::string err;
+    if (!allDevices) {
+        ok = render_rows_on_device(type, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, 0, 1, r, g, b, err);
+    } else {
+        // Scene replicated per GPU, rows dealt in bands of 128; every GPU copies its own rows straight to the
+        // caller's planes (disjoint), so no gather step is needed inside one process.
+        std::vector<std::thread> pool;
+        std::vector<std::string> errs(devices);
+        std::vector<char> oks(devices, 1);
+        for (int d = 0; d < devices; ++d)
+            pool.emplace_back([&, d]() {
+                oks[d] = render_rows_on_device(d, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, d, devices, r, g,
+                                               b, errs[d]);
+            });
+        for (auto& t : pool) t.join();
+        for (int d = 0; d < devices; ++d)
+            if (!oks[d]) {
+                ok = false;
+                err = errs[d];
+            }
+    }
+    g_endTime = clock();
+    if (!ok) {
+        fail("RaytraceAll: " + err);
+        return CL_FALSE;
+    }
+    return CL_TRUE;
+}
+
+cl_bool oclr_raytrace_all_p(cl_uint computationType, const cl_uint* dim, const cl_float* eye, const cl_float* eyeToTopLeft,
+                            const cl_float* leftToRight, const cl_float* topToBottom, cl_float pixelSizeInv,
+                            const oclr_scene_desc* scene, const cl_uint* camStart, const cl_uint* camEnd, const cl_uint* camList,
+                            ptrdiff_t camListSize, cl_uint sampleCount, cl_ushort* r, cl_ushort* g, cl_ushort* b) {
+    if (!dim || !eye || !eyeToTopLeft || !leftToRight || !topToBottom || !scene) {
+        fail("oclr_raytrace_all_p: null argument");
+        return CL_FALSE;
+    }
+    Camera cam;
+    memset(&cam, 0, sizeof(cam));
+    cam.width = dim[0];
+    cam.height = dim[1];
+    for (int i = 0; i < 3; ++i) {
+        cam.eye[i] = eye[i];
+        cam.eyeToTopLeft[i] = eyeToTopLeft[i];
+        cam.leftToRight[i] = leftToRight[i];
+        cam.topToBottom[i] = topToBottom[i];
+    }
+    cam.pixelSizeInv = pixelSizeInv;
+    return raytrace_all_impl(computationType, cam, to_host(scene), camStart, camEnd, camList, camListSize, sampleCount, r, g, b);
+}
+
+cl_bool RaytraceAll(cl_uint computationType, cl_uint2 dim, cl_float3 eye, cl_float3 eyeToTopLeft, cl_float3 leftToRight,
+                    cl_float3 topToBottom, cl_float pixelSizeInv, cl_uint* camStart, cl_uint* camEnd, cl_uint* camList,
+                    ptrdiff_t camListSize, cl_uint sampleCount, cl_uint vertexCount, cl_float3* vertex, cl_uint triangleCount,
+                    cl_int3* triIdx, cl_int* triMat, cl_float2* triUv, cl_float3* triNormal, cl_int axesDivCount,
+                    cl_float3* sceneBoxMin, cl_uint* gridStart, cl_uint* gridList, cl_uint materialCount, cl_uint2* matSize,
+                    cl_int* matStart, cl_uint texturesSize, cl_uchar3* textures, cl_uint lightCount, cl_int* lightType,
+                    cl_float3* lightPos, cl_float3* lightDir, cl_float3* lightColour, cl_float* lightRadius, cl_float* lightHalf,
+                    cl_ushort* outR, cl_ushort* outG, cl_ushort* outB) {
+    oclr_scene_desc d;
+    memset(&d, 0, sizeof(d));
+    d.vertexCount = vertexCount;
+    d.vertex = vertex;
+    d.triangleCount = triangleCount;
+    d.triangleVertexIndex = triIdx;
+    d.triangleMaterialId = triMat;
+    d.triangleUv = triUv;
+    d.triangleNormal = triNormal;
+    d.axesDivCount = axesDivCount;
+    d.sceneBoxMin = sceneBoxMin;
+    d.scenePixelTriangleListStart = gridStart;
+    d.scenePixelTriangleList = gridList;
+    d.materialCount = materialCount;
+    d.materialImageSize = matSize;
+    d.materialImageStart = matStart;
+    d.texturesSize = texturesSize;
+    d.textures = textures;
+    d.lightCount = lightCount;
+    d.lightType = lightType;
+    d.lightPosition = lightPos;
+    d.lightDirection = lightDir;
+    d.lightColour = lightColour;
+    d.lightRadius = lightRadius;
+    d.lightHalfAttenuationDistance = lightHalf;
+    return oclr_raytrace_all_p(computationType, dim.s, eye.s, eyeToTopLeft.s, leftToRight.s, topToBottom.s, pixelSizeInv, &d, camStart,
+                               camEnd, camList, camListSize, sampleCount, outR, outG, outB);
+}
+
+// ---- builders --------------------------------------------------------------------------------------------------------------
+int oclr_build_camera_lists(const oclr_camera* camera, cl_uint vertexCount, const cl_float3* vertex, cl_uint triangleCount,
+                            const cl_int3* triIdx, oclr_camera_lists* out) {
+    if (!camera || !out || (triangleCount && (!vertex || !triIdx))) {
+        fail("oclr_build_camera_lists: null argument");
+        return 0;
+    }
+    memset(out, 0, sizeof(*out));
+    if (!build_camera_lists(camera, vertexCount, (const float4*)vertex, triangleCount, (const int32_t*)triIdx, out)) {
+        fail("oclr_build_camera_lists: out of memory");
+        return 0;
+    }
+    return 1;
+}
+int oclr_build_scene_grid(cl_int axesDivCount, cl_uint vertexCount, const cl_float3* vertex, cl_uint triangleCount,
+                          const cl_int3* triIdx, oclr_scene_grid* out) {
+    if (!out || (triangleCount && (!vertex || !triIdx))) {
+        fail("oclr_build_scene_grid: null argument");
+        return 0;
+    }
+    memset(out, 0, sizeof(*out));
+    if (!build_scene_grid(axesDivCount, vertexCount, (const float4*)vertex, triangleCount, (const int32_t*)triIdx, out)) {
+        fail("oclr_build_scene_grid: bad axesDivCount (power of two <= 1024) or out of memory");
+        return 0;
+    }
+    return 1;
+}
+void oclr_free_camera_lists(oclr_camera_lists* l) {
+    if (!l) return;
+    free(l->start);
+    free(l->end);
+    free(l->list);
+    memset(l, 0, sizeof(*l));
+}
+void oclr_free_scene_grid(oclr_scene_grid* g) {
+    if (!g) return;
+    free(g->boxMin);
+    free(g->start);
+    free(g->list);
+    memset(g, 0, sizeof(*g));
+}

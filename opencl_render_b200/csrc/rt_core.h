@@ -1,0 +1,658 @@
+// rt_core.h -- the arithmetic of the raytrace path, shared by every CUDA kernel of this library.
+//
+// Everything here is `__host__ __device__` so that tests can compile the very same expressions with g++
+// (-ffp-contract=off) and compare them bit-for-bit with the reference on a machine without a GPU; the product
+// library only ever instantiates it inside CUDA kernels (compiled with -fmad=false, IEEE div/sqrt).
+//
+// Bit-exactness contract (SURVEY.md section 7 "Hard parts"): same fp32 operation order as the reference, no FMA
+// contraction, dot = ((a0*b0 + a1*b1) + a2*b2) (source/opencl/raytrace.c:18-20), the libm calls the C path
+// evaluates in double stay in double (raytrace_opencl.c:22, 27, 251-253, 594, 631).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "rt_types.h"
+
+namespace oclr {
+
+struct f3 {
+    float x, y, z;
+};
+
+#if defined(__CUDA_ARCH__)
+#define OCLR_LDG(p) __ldg(p)
+#define OCLR_POPCLL(v) __popcll(v)
+#define OCLR_INF __int_as_float(0x7f800000)
+#else
+#define OCLR_LDG(p) (*(p))
+#define OCLR_POPCLL(v) __builtin_popcountll(v)
+#define OCLR_INF __builtin_inff()
+#endif
+
+OCLR_HD f3 mk3(float x, float y, float z) {
+    f3 r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    return r;
+}
+OCLR_HD f3 mk3(const float* p) { return mk3(p[0], p[1], p[2]); }
+// raytrace.c:18-20
+OCLR_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// raytrace.c:21-27
+OCLR_HD f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// (float)sqrt((double)x): double sqrt then narrowing == correctly rounded single sqrt
+OCLR_HD float sqrt_c(float v) { return sqrtf(v); }
+
+// ---- RNG: raytrace_opencl.c:1-23 -----------------------------------------------------------------------------
+OCLR_HD uint64_t rotl64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
+OCLR_HD uint64_t xorshift64star(uint64_t v) {
+    v ^= v >> 12;
+    v ^= v << 25;
+    v ^= v >> 27;
+    return v * 2685821657736338717ull;
+}
+OCLR_HD float rand_f(uint64_t& s, float lo, float hi) {
+    s ^= xorshift64star((rotl64(s, 55) ^ rotl64(s, 3)) * 0xc23f3c0ad9da6357ull);
+    s ^= xorshift64star((rotl64(s, 35) ^ rotl64(s, 3)) ^ 0xce84d6af03c16b89ull);
+    s ^= xorshift64star((rotl64(s, 63) ^ rotl64(s, 35)) * 0xf097ef8bbe03ddccull);
+    s ^= xorshift64star((rotl64(s, 41) ^ rotl64(s, 12)) ^ 0x48302294fbfe30bfull);
+    s ^= xorshift64star((rotl64(s, 1) ^ rotl64(s, 62)) * 0x79e7425e3f4f147dull);
+    s ^= xorshift64star((rotl64(s, 42) ^ rotl64(s, 29)) ^ 0x14d1d30856e5be9aull);
+    s ^= xorshift64star((rotl64(s, 47) ^ rotl64(s, 45)) * 0x24289d47a66617c3ull);
+    s ^= xorshift64star((rotl64(s, 39) ^ rotl64(s, 6)) ^ 0x5576fb2f80a05d14ull);
+    // (double)state / (double)0xffffffffffffffff: the divisor rounds to 2^64, so the quotient is an exact scaling
+    return lo + (hi - lo) * (float)((double)s * (1.0 / 18446744073709551616.0));
+}
+
+// raytrace_opencl.c:30-45.  The number of draws is state-visible (rejection loop).
+OCLR_HD f3 sphere_point(uint64_t& s, float radius) {
+    f3 p;
+    float len;
+    do {
+        p.x = rand_f(s, -1.f, 1.f);
+        p.y = rand_f(s, -1.f, 1.f);
+        p.z = rand_f(s, -1.f, 1.f);
+        len = sqrt_c(dot3(p, p));
+    } while (len <= 0.f);
+    float tmp = sqrt_c(rand_f(s, 0.f, 1.f)) * radius / len;
+    return mk3(tmp * p.x, tmp * p.y, tmp * p.z);
+}
+
+// raytrace_opencl.c:25-28 (double modf twice)
+OCLR_HD float positive_modf(float v) {
+    double ip;
+    return (float)modf(modf((double)v, &ip) + 1., &ip);
+}
+
+// raytrace_opencl.c:83-101
+OCLR_HD float point_to_line_sq(f3 o, f3 d, f3 p) {
+    f3 od = mk3(d.x - o.x, d.y - o.y, d.z - o.z);
+    float odSq = dot3(od, od);
+    f3 op = mk3(p.x - o.x, p.y - o.y, p.z - o.z);
+    float k = dot3(op, od) / odSq;
+    f3 proj = mk3(o.x + k * od.x, o.y + k * od.y, o.z + k * od.z);
+    f3 dv = mk3(proj.x - p.x, proj.y - p.y, proj.z - p.z);
+    return dot3(dv, dv);
+}
+
+// raytrace_opencl.c:103-122.  `size.x - 1` is unsigned arithmetic in the reference.
+OCLR_HD f3 table_value(const uchar4* table, uint2 size, float u0, float v0, float u1, float v1, float u2, float v2,
+                       float abL, float acL) {
+    float pu = positive_modf(u0 + (u1 - u0) * abL + (u2 - u0) * acL);
+    float pv = positive_modf(v0 + (v1 - v0) * abL + (v2 - v0) * acL);
+    float lx = pu * (float)(size.x - 1u);
+    float ly = pv * (float)(size.y - 1u);
+    int ix = (int)floorf(lx);
+    int iy = (int)floorf(ly);
+    int idx = (int)((uint32_t)ix + (uint32_t)iy * size.x);
+    uchar4 t = OCLR_LDG(table + idx);
+    return mk3((float)t.x / 255.f, (float)t.y / 255.f, (float)t.z / 255.f);
+}
+
+// ---- ray / triangle: raytrace_opencl.c:124-172 against the packed triGeo record --------------------------------
+// Stage 1 reads 32 B (q0,q1), stage 2 another 32 B (q2,q3) only when the plane distance is inside (minD, maxD).
+OCLR_HD bool tri_test(const float4* g, f3 o, f3 r, float minD, float maxD, float& t, float& abL, float& acL) {
+    const float4 q0 = OCLR_LDG(g + 0);
+    const float4 q1 = OCLR_LDG(g + 1);
+    const f3 n = mk3(q0.x, q0.y, q0.z);
+    const f3 a = mk3(q0.w, q1.x, q1.y);
+    const f3 ao = mk3(o.x - a.x, o.y - a.y, o.z - a.z);
+    t = -dot3(n, ao) / dot3(n, r);
+    if (minD < t && t < maxD) {
+        const float4 q2 = OCLR_LDG(g + 2);
+        const float4 q3 = OCLR_LDG(g + 3);
+        const float abab = q1.z, abac = q1.w, acac = q2.w, D = q3.w;
+        const f3 ab = mk3(q2.x, q2.y, q2.z);
+        const f3 ac = mk3(q3.x, q3.y, q3.z);
+        const f3 proj = mk3(o.x + t * r.x, o.y + t * r.y, o.z + t * r.z);
+        const f3 ap = mk3(proj.x - a.x, proj.y - a.y, proj.z - a.z);
+        const float apab = dot3(ap, ab);
+        const float apac = dot3(ap, ac);
+        abL = (abac * apac - acac * apab) * D;
+        acL = (abac * apab - abab * apac) * D;
+        return (0.f <= abL && 0.f <= acL && abL + acL <= 1.f);
+    }
+    return false;
+}
+
+// ---- grid addressing: raytrace_opencl.c:174-193 (binary search, strict <) ---------------------------------------
+OCLR_HD void box_address(int n, const float* px, const float* py, const float* pz, f3 p, int& cx, int& cy, int& cz) {
+    cx = 0;
+    cy = 0;
+    cz = 0;
+    while (1 < n) {
+        n /= 2;
+        if (px[cx + n] < p.x) cx += n;
+        if (py[cy + n] < p.y) cy += n;
+        if (pz[cz + n] < p.z) cz += n;
+    }
+}
+
+// raytrace_opencl.c:265-322.  The caller ignores the return value, so partial moves are kept (:354, :360).
+OCLR_HD void bind_in_cube(f3& p, f3 r, f3 lo, f3 hi) {
+    float t;
+    if (p.x < lo.x) {
+        if (r.x <= 0) return;
+        t = (lo.x - p.x) / r.x;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+    if (hi.x < p.x) {
+        if (0 <= r.x) return;
+        t = (hi.x - p.x) / r.x;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+    if (p.y < lo.y) {
+        if (r.y <= 0) return;
+        t = (lo.y - p.y) / r.y;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+    if (hi.y < p.y) {
+        if (0 <= r.y) return;
+        t = (hi.y - p.y) / r.y;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+    if (p.z < lo.z) {
+        if (r.z <= 0) return;
+        t = (lo.z - p.z) / r.z;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+    if (hi.z < p.z) {
+        if (0 <= r.z) return;
+        t = (hi.z - p.z) / r.z;
+        p.x += t * r.x; p.y += t * r.y; p.z += t * r.z;
+    }
+}
+
+// ---- grid walk state: raytrace_opencl.c:324-401 -------------------------------------------------------------------
+// The reference recomputes all three plane distances every cell (:383-385); each depends only on its own axis'
+// cell index, so only the axis that stepped is re-divided here -- identical values, one IEEE division per step.
+struct GridWalk {
+    f3 o, r;
+    float minD, maxD;
+    uint32_t excl;
+    int cx, cy, cz;
+    int ex, ey, ez;
+    float tx, ty, tz;
+    int curBrick;
+    uint64_t mask;
+    uint32_t rankBase;
+};
+
+OCLR_HD void walk_begin(GridWalk& w, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
+                        float minD, float maxD, uint32_t excl) {
+    const int n = S.n;
+    w.o = o;
+    w.r = r;
+    w.minD = minD;
+    w.maxD = maxD;
+    w.excl = excl;
+    const f3 lo = mk3(px[0], py[0], pz[0]);
+    const f3 hi = mk3(px[n], py[n], pz[n]);
+    f3 start = mk3(o.x + minD * r.x, o.y + minD * r.y, o.z + minD * r.z);
+    bind_in_cube(start, r, lo, hi);
+    box_address(n, px, py, pz, start, w.cx, w.cy, w.cz);
+    w.ex = w.ey = w.ez = -1;
+    if (maxD < OCLR_INF) {
+        f3 end = mk3(o.x + maxD * r.x, o.y + maxD * r.y, o.z + maxD * r.z);
+        bind_in_cube(end, r, lo, hi);
+        box_address(n, px, py, pz, end, w.ex, w.ey, w.ez);
+    }
+    w.tx = (px[w.cx + (0 <= r.x)] - o.x) / r.x;
+    w.ty = (py[w.cy + (0 <= r.y)] - o.y) / r.y;
+    w.tz = (pz[w.cz + (0 <= r.z)] - o.z) / r.z;
+    w.curBrick = -1;
+    w.mask = 0;
+    w.rankBase = 0;
+}
+
+// Occupancy of the current cell; loads the brick record when the walk entered a new brick.
+// Returns true and the list range when the cell has triangles.
+template <bool COUNT>
+OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* cnt) {
+    const int b = (w.cx >> 2) + S.nb * ((w.cy >> 2) + S.nb * (w.cz >> 2));
+    if (b != w.curBrick) {
+        const uint4 br = OCLR_LDG(S.bricks + b);
+        w.mask = (uint64_t)br.x | ((uint64_t)br.y << 32);
+        w.rankBase = br.z;
+        w.curBrick = b;
+        if (COUNT) cnt->bricksLoaded++;
+    }
+    const int bit = (w.cx & 3) | ((w.cy & 3) << 2) | ((w.cz & 3) << 4);
+    if (COUNT) cnt->cells++;
+    if ((w.mask >> bit) & 1ull) {
+        const uint32_t rank = w.rankBase + (uint32_t)OCLR_POPCLL(w.mask & ((1ull << bit) - 1ull));
+        range = OCLR_LDG(S.cellRange + rank);
+        if (COUNT) cnt->cellsNonEmpty++;
+        return true;
+    }
+    return false;
+}
+
+// Advance to the next cell (:383-398).  Returns false when the walk left the grid.
+OCLR_HD bool walk_step(GridWalk& w, int n, const float* px, const float* py, const float* pz) {
+    if ((w.tx < w.ty) & (w.tx < w.tz)) {
+        const int up = (0 <= w.r.x);
+        w.cx += up ? 1 : -1;
+        if (w.cx < 0 || n <= w.cx) return false;
+        w.tx = (px[w.cx + up] - w.o.x) / w.r.x;
+    } else if (w.ty < w.tz) {
+        const int up = (0 <= w.r.y);
+        w.cy += up ? 1 : -1;
+        if (w.cy < 0 || n <= w.cy) return false;
+        w.ty = (py[w.cy + up] - w.o.y) / w.r.y;
+    } else {
+        const int up = (0 <= w.r.z);
+        w.cz += up ? 1 : -1;
+        if (w.cz < 0 || n <= w.cz) return false;
+        w.tz = (pz[w.cz + up] - w.o.z) / w.r.z;
+    }
+    return true;
+}
+
+// Whole traversal for one ray, serial form (one thread walks one ray).  `outT` is reset to maxD in every cell
+// (:366); the walk stops at the first cell that produced any hit (:380), at the end cell (:381) or off the grid.
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace(const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
+                            float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC,
+                            Counters* cnt) {
+    GridWalk w;
+    walk_begin(w, S, px, py, pz, o, r, minD, maxD, excl);
+    if (COUNT) cnt->gridRays++;
+    uint32_t closest = kNoTriangle;
+    for (;;) {
+        uint2 range;
+        outT = maxD;
+        if (walk_cell<COUNT>(w, S, range, cnt)) {
+            for (uint32_t i = range.x; i < range.y; ++i) {
+                const uint32_t tri = OCLR_LDG(S.cellList + i);
+                if (tri != excl) {
+                    float t, ab, ac;
+                    if (COUNT) cnt->gridCandidates++;
+                    if (tri_test(S.triGeo + 4 * (size_t)tri, o, r, minD, outT, t, ab, ac)) {
+                        closest = tri;
+                        outT = t;
+                        outAB = ab;
+                        outAC = ac;
+                    }
+                }
+            }
+        }
+        if (closest != kNoTriangle || (w.cx == w.ex && w.cy == w.ey && w.cz == w.ez)) break;
+        if (!walk_step(w, S.n, px, py, pz)) break;
+    }
+    return closest;
+}
+
+// ---- shading pieces ---------------------------------------------------------------------------------------------
+struct TriShade {
+    f3 a, b, c, nA, nB, nC;
+    float u0, v0, u1, v1, u2, v2;
+    int mat;
+};
+
+OCLR_HD TriShade load_shade(const SceneView& S, uint32_t tri) {
+    const float4* p = S.triShade + 8 * (size_t)tri;
+    const float4 s0 = OCLR_LDG(p + 0), s1 = OCLR_LDG(p + 1), s2 = OCLR_LDG(p + 2), s3 = OCLR_LDG(p + 3);
+    const float4 s4 = OCLR_LDG(p + 4), s5 = OCLR_LDG(p + 5), s6 = OCLR_LDG(p + 6), s7 = OCLR_LDG(p + 7);
+    TriShade t;
+    t.a = mk3(s0.x, s0.y, s0.z);
+#if defined(__CUDA_ARCH__)
+    t.mat = __float_as_int(s0.w);
+#else
+    union { float f; int i; } cv;
+    cv.f = s0.w;
+    t.mat = cv.i;
+#endif
+    t.b = mk3(s1.x, s1.y, s1.z);
+    t.c = mk3(s2.x, s2.y, s2.z);
+    t.nA = mk3(s3.x, s3.y, s3.z);
+    t.nB = mk3(s4.x, s4.y, s4.z);
+    t.nC = mk3(s5.x, s5.y, s5.z);
+    t.u0 = s6.x; t.v0 = s6.y; t.u1 = s6.z; t.v1 = s6.w;
+    t.u2 = s7.x; t.v2 = s7.y;
+    return t;
+}
+
+// Material id + UVs only (transparent-occluder lookups in the shadow loop, :613-619)
+OCLR_HD void load_mat_uv(const SceneView& S, uint32_t tri, int& mat, float& u0, float& v0, float& u1, float& v1,
+                         float& u2, float& v2) {
+    const float4* p = S.triShade + 8 * (size_t)tri;
+    const float4 s0 = OCLR_LDG(p + 0), s6 = OCLR_LDG(p + 6), s7 = OCLR_LDG(p + 7);
+#if defined(__CUDA_ARCH__)
+    mat = __float_as_int(s0.w);
+#else
+    union { float f; int i; } cv;
+    cv.f = s0.w;
+    mat = cv.i;
+#endif
+    u0 = s6.x; v0 = s6.y; u1 = s6.z; v1 = s6.w;
+    u2 = s7.x; v2 = s7.y;
+}
+
+OCLR_HD bool channel_present(const SceneView& S, int mat, int channel, uint2& size) {
+    if (mat < 0 || (uint32_t)mat >= S.materialCount) return false;  // reference reads OOB for mat < 0 (:226 vs :231); guarded
+    size = OCLR_LDG(S.matSize + kMaterialChannels * mat + channel);
+    return 0u < size.x;
+}
+
+OCLR_HD f3 channel_value(const SceneView& S, int mat, int channel, uint2 size, const TriShade& ts, float abL, float acL) {
+    const int start = OCLR_LDG(S.matStart + kMaterialChannels * mat + channel);
+    return table_value(S.textures + start, size, ts.u0, ts.v0, ts.u1, ts.v1, ts.u2, ts.v2, abL, acL);
+}
+
+// raytrace_opencl.c:124-172 on raw vertices (bump-mapping helper rays only, :244, :249): result flag ignored there,
+// abL/acL keep their previous value when the plane distance is outside (0, inf).
+OCLR_HD bool tri_bary_raw(f3 o, f3 r, f3 a, f3 b, f3 c, float& abL, float& acL) {
+    const f3 ab = mk3(b.x - a.x, b.y - a.y, b.z - a.z);
+    const f3 ac = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
+    const f3 ao = mk3(o.x - a.x, o.y - a.y, o.z - a.z);
+    const f3 n = cross3(ac, ab);
+    const float t = -dot3(n, ao) / dot3(n, r);
+    if (0.f < t && t < OCLR_INF) {
+        const float abab = dot3(ab, ab), abac = dot3(ab, ac), acac = dot3(ac, ac);
+        const float D = 1.f / (abac * abac - abab * acac);
+        const f3 proj = mk3(o.x + t * r.x, o.y + t * r.y, o.z + t * r.z);
+        const f3 ap = mk3(proj.x - a.x, proj.y - a.y, proj.z - a.z);
+        const float apab = dot3(ap, ab), apac = dot3(ap, ac);
+        abL = (abac * apac - acac * apab) * D;
+        acL = (abac * apab - abab * apac) * D;
+        return true;
+    }
+    return false;
+}
+
+// raytrace_opencl.c:195-263
+// `undefined` is set when the reference would read uninitialised variables: the first bump helper ray (:244) does not
+// meet the triangle's plane at a positive distance (happens for bounce rays, whose direction is shorter than a pixel
+// step), so abL/acL of :245 are stack garbage there.  This implementation then uses the hit's own abL/acL.
+OCLR_HD f3 triangle_normal(const SceneView& S, const Camera& cam, const TriShade& ts, f3 loc, f3 rayO, f3 rayV, float abL,
+                           float acL, bool& undefined) {
+    const float dab = sqrt_c(point_to_line_sq(ts.a, ts.b, loc));
+    const float dbc = sqrt_c(point_to_line_sq(ts.b, ts.c, loc));
+    const float dca = sqrt_c(point_to_line_sq(ts.c, ts.a, loc));
+    const float inv = 1.f / (dab + dbc + dca);
+    f3 nrm = mk3((dab * ts.nC.x + dbc * ts.nA.x + dca * ts.nB.x) * inv, (dab * ts.nC.y + dbc * ts.nA.y + dca * ts.nB.y) * inv,
+                 (dab * ts.nC.z + dbc * ts.nA.z + dca * ts.nB.z) * inv);
+    uint2 bumpSize;
+    if (channel_present(S, ts.mat, kChBump, bumpSize)) {
+        const f3 tb = mk3(cam.topToBottom), lr = mk3(cam.leftToRight);
+        const f3 h = channel_value(S, ts.mat, kChBump, bumpSize, ts, abL, acL);
+        float bL = abL, cL = acL;  // uninitialised in the reference when the first helper ray misses the plane
+        if (!tri_bary_raw(rayO, mk3(rayV.x + tb.x, rayV.y + tb.y, rayV.z + tb.z), ts.a, ts.b, ts.c, bL, cL)) undefined = true;
+        const f3 hS = channel_value(S, ts.mat, kChBump, bumpSize, ts, bL, cL);
+        tri_bary_raw(rayO, mk3(rayV.x + lr.x, rayV.y + lr.y, rayV.z + lr.z), ts.a, ts.b, ts.c, bL, cL);
+        const f3 hE = channel_value(S, ts.mat, kChBump, bumpSize, ts, bL, cL);
+        const float kPi = 3.14159265f;  // raytrace.h:33 (float macro in the C path)
+        const float aE = (hE.x - h.x) * kPi / 2.f;
+        const float aS = (hS.x - h.x) * kPi / 2.f;
+        const float xPart = (float)sin((double)aE);
+        const float yPart = (float)sin((double)aS);
+        const float nPart = (float)cos((double)aE) * (float)cos((double)aS);
+        nrm.x = nPart * nrm.x / cam.pixelSizeInv + xPart * lr.x + yPart * tb.x;
+        nrm.y = nPart * nrm.y / cam.pixelSizeInv + xPart * lr.y + yPart * tb.y;
+        nrm.z = nPart * nrm.z / cam.pixelSizeInv + xPart * lr.z + yPart * tb.z;
+        const float li = 1.f / sqrt_c(dot3(nrm, nrm));
+        nrm.x *= li;
+        nrm.y *= li;
+        nrm.z *= li;
+    }
+    return nrm;
+}
+
+// (int)f as the x86-64 C path evaluates it (cvttss2si: out-of-range and NaN give INT_MIN), raytrace_opencl.c:729
+OCLR_HD int float_to_int_x86(float f) {
+    if (f >= -2147483648.f && f < 2147483648.f) return (int)f;
+    return (int)0x80000000;
+}
+
+// 16-bit accumulate with the reference's per-sample truncation and clamp (:726-741)
+OCLR_HD uint16_t accumulate16(uint16_t prev, float c, float scale) {
+    int v = (int)prev + float_to_int_x86(c * scale);
+    if (v < 0) v = 0;
+    if (0xFFFF < v) v = 0xFFFF;
+    return (uint16_t)v;
+}
+
+// One light's sample point and shadow-ray interval (:564-607).  Returns false for a light type that is not in the
+// reference's switch (leaves a zero vector and an empty interval, like the omni case :585-588).
+struct LightRay {
+    f3 dir;
+    float minLen, maxLen;
+};
+OCLR_HD void light_ray(const Light& L, f3 loc, uint64_t& rng, LightRay& lr) {
+    lr.dir = mk3(0.f, 0.f, 0.f);
+    lr.minLen = 0.f;
+    lr.maxLen = 0.f;
+    switch (L.type) {
+        case 1: case 2: case 7: case 8: case 9: {  // SPOT, SPOTRECT, TUBE, AREA, PHOTOMETRIC
+            const f3 rl = sphere_point(rng, L.radius);
+            lr.dir = mk3(rl.x + L.pos[0] - loc.x, rl.y + L.pos[1] - loc.y, rl.z + L.pos[2] - loc.z);
+            lr.maxLen = sqrt_c(dot3(lr.dir, lr.dir));
+            const float inv = 1.f / lr.maxLen;
+            lr.dir.x *= inv;
+            lr.dir.y *= inv;
+            lr.dir.z *= inv;
+        } break;
+        case 3: case 4: case 5: case 6: {  // DISTANT, PARALLEL, PARSPOT, PARSPOTRECT
+            f3 d = sphere_point(rng, L.distantRadius);
+            d.x -= L.dir[0];
+            d.y -= L.dir[1];
+            d.z -= L.dir[2];
+            const float inv = 1.f / sqrt_c(dot3(d, d));
+            lr.dir = mk3(d.x * inv, d.y * inv, d.z * inv);
+            lr.maxLen = OCLR_INF;
+        } break;
+        default:  // OMNI (0) and unknown types contribute nothing but still take the ambient path
+            break;
+    }
+}
+
+// :629-635
+OCLR_HD void light_accumulate(const Light& L, f3 nrm, const LightRay& lr, f3 att, f3 face[2]) {
+    const float d = dot3(nrm, lr.dir);
+    const float effect = fabsf(d);
+    const int idx = (int)(0.f <= d);
+    const float x = lr.maxLen / L.halfDistance;
+    const float a = (x == 0.f) ? 1.f : (float)pow(0.5, (double)x);  // pow(0.5f, 0) == 1 exactly
+    const float e = effect * (a == a ? a : 1.f);
+    face[idx].x += (1.f - face[idx].x) * att.x * e * L.colour[0];
+    face[idx].y += (1.f - face[idx].y) * att.y * e * L.colour[1];
+    face[idx].z += (1.f - face[idx].z) * att.z * e * L.colour[2];
+}
+
+// ---- one pixel-sample, serial form: raytrace_opencl.c:452-725 --------------------------------------------------------
+// Ring storage is supplied by the caller (registers/local memory on the simple kernel, shared memory on the
+// persistent kernel) through RingT: fields indexed by slot.
+struct RingLocal {
+    int maxB[kRingSize];
+    uint32_t excl[kRingSize];
+    f3 o[kRingSize], v[kRingSize], mul[kRingSize];
+    bool cam[kRingSize];
+    float minD[kRingSize], maxD[kRingSize];
+};
+
+template <bool COUNT>
+OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px, const float* py, const float* pz,
+                        uint32_t pixel, uint32_t sampleIdx, uint32_t* primaryId, bool& undefinedRef, Counters* cnt) {
+    const Camera& cam = F.cam;
+    uint64_t rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
+    const float fx = (float)(pixel % cam.width);
+    const float fy = (float)(pixel / cam.width);
+    RingLocal ring;
+    f3 colour = mk3(0.f, 0.f, 0.f);
+    int begin = 0, end = 1;
+    float tmp;
+    ring.maxB[0] = kMaxBounces;
+    ring.excl[0] = kNoTriangle;
+    ring.o[0] = mk3(cam.eye);
+    ring.v[0] = mk3(cam.eyeToTopLeft);
+    tmp = fx + rand_f(rng, 0.f, 1.f);
+    ring.v[0].x += cam.leftToRight[0] * tmp;
+    ring.v[0].y += cam.leftToRight[1] * tmp;
+    ring.v[0].z += cam.leftToRight[2] * tmp;
+    tmp = fy + rand_f(rng, 0.f, 1.f);
+    ring.v[0].x += cam.topToBottom[0] * tmp;
+    ring.v[0].y += cam.topToBottom[1] * tmp;
+    ring.v[0].z += cam.topToBottom[2] * tmp;
+    ring.mul[0] = mk3(1.f, 1.f, 1.f);
+    ring.cam[0] = true;
+    ring.minD[0] = 0.f;
+    ring.maxD[0] = OCLR_INF;
+    bool first = true;
+    for (; begin != end; begin = (begin + 1) % kRingSize) {
+        const f3 ro = ring.o[begin], rv = ring.v[begin], rm = ring.mul[begin];
+        float hitT = ring.maxD[begin];
+        uint32_t hit = kNoTriangle;
+        float hitAB = 0.f, hitAC = 0.f;
+        if (COUNT) cnt->segments++;
+        if (ring.cam[begin]) {
+            const uint32_t e = OCLR_LDG(F.camEnd + pixel);
+            for (uint32_t i = OCLR_LDG(F.camStart + pixel); i < e; ++i) {
+                const uint32_t tri = OCLR_LDG(F.camList + i);
+                if (ring.excl[begin] != tri) {
+                    float t, ab, ac;
+                    if (COUNT) cnt->primCandidates++;
+                    if (tri_test(S.triGeo + 4 * (size_t)tri, ro, rv, ring.minD[begin], hitT, t, ab, ac)) {
+                        hitT = t;
+                        hit = tri;
+                        hitAB = ab;
+                        hitAC = ac;
+                    }
+                }
+            }
+        } else {
+            hit = grid_trace<COUNT>(S, px, py, pz, ro, rv, ring.minD[begin], ring.maxD[begin], ring.excl[begin], hitT, hitAB,
+                                    hitAC, cnt);
+        }
+        if (first) {
+            if (primaryId) *primaryId = hit;
+            first = false;
+        }
+        if (hit == kNoTriangle) continue;
+        if (COUNT) cnt->shadedHits++;
+
+        const TriShade ts = load_shade(S, hit);
+        const int m = ts.mat;
+        f3 tex = mk3(0.f, 0.f, 0.f), transp = tex, refl = tex, lum = tex;
+        f3 face[2] = {mk3(0.1f, 0.1f, 0.1f), mk3(0.1f, 0.1f, 0.1f)};
+        const f3 loc = mk3(ro.x + hitT * rv.x, ro.y + hitT * rv.y, ro.z + hitT * rv.z);
+        const f3 nrm = triangle_normal(S, cam, ts, loc, ro, rv, hitAB, hitAC, undefinedRef);
+        {
+            uint2 sz;
+            if (channel_present(S, m, kChColor, sz)) tex = channel_value(S, m, kChColor, sz, ts, hitAB, hitAC);
+            if (channel_present(S, m, kChTransparency, sz)) transp = channel_value(S, m, kChTransparency, sz, ts, hitAB, hitAC);
+            if (channel_present(S, m, kChReflection, sz)) refl = channel_value(S, m, kChReflection, sz, ts, hitAB, hitAC);
+            if (channel_present(S, m, kChLuminance, sz)) lum = channel_value(S, m, kChLuminance, sz, ts, hitAB, hitAC);
+        }
+        for (uint32_t j = 0; j < S.lightCount; ++j) {
+            const Light& L = S.lights[j];
+            LightRay lr;
+            f3 att = mk3(1.f, 1.f, 1.f);
+            light_ray(L, loc, rng, lr);
+            if (lr.minLen < lr.maxLen) {
+                for (;;) {
+                    float t, ab = 0.f, ac = 0.f;
+                    const uint32_t occ = grid_trace<COUNT>(S, px, py, pz, loc, lr.dir, lr.minLen, lr.maxLen, hit, t, ab, ac, cnt);
+                    if (occ == kNoTriangle) break;
+                    int om;
+                    float u0, v0, u1, v1, u2, v2;
+                    load_mat_uv(S, occ, om, u0, v0, u1, v1, u2, v2);
+                    f3 tr = mk3(0.f, 0.f, 0.f);
+                    uint2 sz;
+                    if (channel_present(S, om, kChTransparency, sz)) {
+                        if (COUNT) cnt->occluderLookups++;
+                        const int start = OCLR_LDG(S.matStart + kMaterialChannels * om + kChTransparency);
+                        tr = table_value(S.textures + start, sz, u0, v0, u1, v1, u2, v2, ab, ac);
+                    }
+                    att.x *= tr.x;
+                    att.y *= tr.y;
+                    att.z *= tr.z;
+                    if (!(0.f < att.x && 0.f < att.y && 0.f < att.z)) break;
+                    lr.minLen = t;
+                }
+            }
+            light_accumulate(L, nrm, lr, att, face);
+        }
+        colour.x += (1.f - colour.x) * lum.x * rm.x;
+        colour.y += (1.f - colour.y) * lum.y * rm.y;
+        colour.z += (1.f - colour.z) * lum.z * rm.z;
+        const int front = (int)(dot3(nrm, rv) <= 0.f);
+        const f3 light = face[front];
+        colour.x += (1.f - colour.x) * rm.x * (1.f - transp.x) * tex.x * light.x;
+        colour.y += (1.f - colour.y) * rm.y * (1.f - transp.y) * tex.y * light.y;
+        colour.z += (1.f - colour.z) * rm.z * (1.f - transp.z) * tex.z * light.z;
+
+        if (ring.maxB[begin] <= 0) continue;
+        // max() is the reference's ternary macro (raytrace.h:30), not fmaxf
+        float total = (refl.x + transp.x) > (refl.y + transp.y) ? (refl.x + transp.x) : (refl.y + transp.y);
+        total = total > (refl.z + transp.z) ? total : (refl.z + transp.z);
+        f3 diffuse = mk3(0.f, 0.f, 0.f);
+        if (total < 1.f) diffuse = mk3(1.f - total, 1.f - total, 1.f - total);
+        f3 mul = mk3(rm.x * tex.x * diffuse.x, rm.y * tex.y * diffuse.y, rm.z * tex.z * diffuse.z);
+        if (3.f / 256.f <= mul.x + mul.y + mul.z) {  // diffuse bounce (:667-683)
+            ring.maxB[end] = 0;
+            ring.excl[end] = hit;
+            ring.o[end] = loc;
+            f3 d = sphere_point(rng, 1.f);
+            if (front != (int)(0 <= dot3(d, nrm))) d = mk3(-d.x, -d.y, -d.z);
+            ring.v[end] = d;
+            ring.mul[end] = mul;
+            ring.cam[end] = false;
+            ring.minD[end] = 0.f;
+            ring.maxD[end] = OCLR_INF;
+            end = (end + 1) % kRingSize;
+            if ((end + 1) % kRingSize == begin) continue;
+        }
+        mul = mk3(rm.x * tex.x * refl.x, rm.y * tex.y * refl.y, rm.z * tex.z * refl.z);
+        if (3.f / 256.f <= mul.x + mul.y + mul.z) {  // mirror (:690-705)
+            ring.maxB[end] = ring.maxB[begin] - 1;
+            ring.excl[end] = hit;
+            ring.o[end] = loc;
+            tmp = -2.f * dot3(nrm, rv);
+            ring.v[end] = mk3(rv.x + tmp * nrm.x, rv.y + tmp * nrm.y, rv.z + tmp * nrm.z);
+            ring.mul[end] = mul;
+            ring.cam[end] = false;
+            ring.minD[end] = 0.f;
+            ring.maxD[end] = OCLR_INF;
+            end = (end + 1) % kRingSize;
+            if ((end + 1) % kRingSize == begin) continue;
+        }
+        mul = mk3(rm.x * tex.x * transp.x, rm.y * tex.y * transp.y, rm.z * tex.z * transp.z);
+        if (3.f / 256.f <= mul.x + mul.y + mul.z) {  // glass (:711-722)
+            ring.maxB[end] = ring.maxB[begin] - 1;
+            ring.excl[end] = hit;
+            ring.o[end] = ro;
+            ring.v[end] = rv;
+            ring.mul[end] = mul;
+            ring.cam[end] = ring.cam[begin];
+            ring.minD[end] = hitT;
+            ring.maxD[end] = OCLR_INF;
+            end = (end + 1) % kRingSize;
+            if ((end + 1) % kRingSize == begin) continue;
+        }
+    }
+    return colour;
+}
+
+}  // namespace oclr

@@ -1,0 +1,102 @@
+// rt_types.h -- device-side data layout of the B200 raytrace path (HBM-resident, uploaded once per scene).
+//
+// The reference hands its kernel 35 flat SoA buffers (source/opencl/raytrace_opencl.c:406-450).  They are
+// repacked at upload into the layout below so that every fetch on the hot path is a 128-bit load of data
+// that is consumed whole:
+//
+//   triGeo    4 x float4 per triangle (64 B, two 32 B sectors)
+//               q0 = (n.x, n.y, n.z, a.x)   n = cross(ac, ab)          stage 1 (plane distance) needs q0,q1
+//               q1 = (a.y, a.z, abab, abac)
+//               q2 = (ab.x, ab.y, ab.z, acac)                           stage 2 (barycentrics) needs q2,q3
+//               q3 = (ac.x, ac.y, ac.z, D)  D = 1/(abac*abac - abab*acac)
+//             All of these are ray-independent sub-expressions of RayIntersectsTriangle
+//             (raytrace_opencl.c:131-149) evaluated with the reference's exact fp32 operation order, so
+//             hoisting them out of the per-ray test leaves every result bit-identical.
+//   triShade  8 x float4 per triangle (128 B): a|mat, b, c, nA, nB, nC, (uv0,uv1), (uv2,-) -- read once per hit.
+//   bricks    the reference's 256^3 CSR `Start` array (67 MB, 88 % empty cells) becomes 4x4x4-cell bricks:
+//             one uint4 per brick = {occupancy mask lo, hi, rank of the brick's first non-empty cell, 0}
+//             (4 MB at 256^3).  A DDA walk reads one 16 B record per brick and then steps through up to
+//             ~10 cells of it from registers; empty cells cost one bit test.
+//   cellRange one uint2 {begin,end} per NON-EMPTY cell, in brick-major order, into cellList.
+//   cellList  triangle ids, per-cell order preserved from the reference list (ascending id; the order is
+//             observable through the strict `<` closest-hit rule, raytrace_opencl.c:143, 372-377).
+//   planes    3 x (n+1) floats (x planes, y planes, z planes) -- copied to shared memory by each CTA.
+#pragma once
+#include <stdint.h>
+
+#include <vector_functions.h>
+#include <vector_types.h>  // float4 / uint4 / uint2 / uchar4 (plain C++ header of the CUDA toolkit)
+
+#if defined(__CUDACC__)
+#define OCLR_HD __host__ __device__ __forceinline__
+#else
+#define OCLR_HD inline
+#endif
+
+namespace oclr {
+
+enum { kMaterialChannels = 5, kChColor = 0, kChReflection = 1, kChTransparency = 2, kChBump = 3, kChLuminance = 4 };
+enum { kRingSize = 12, kMaxBounces = 12 };
+enum { kNoTriangle = 0xFFFFFFFFu };
+
+// One light, with the per-light constants of raytrace_opencl.c:594 hoisted (evaluated once at upload in the
+// reference's double-precision expression).
+struct Light {
+    int32_t type;            // _LIGHT_TYPE_* (raytrace_opencl.h:1-12)
+    float radius;            // lightRadius[j]
+    float halfDistance;      // lightHalfAttenuationDistance[j]
+    float distantRadius;     // (float)(sin((radius/2)*M_PIf/180) * sqrt(dot(dir,dir)))   (:594)
+    float pos[4];
+    float dir[4];
+    float colour[4];
+};
+
+struct SceneView {
+    const float4* triGeo;
+    const float4* triShade;
+    const uint4* bricks;
+    const uint2* cellRange;
+    const uint32_t* cellList;
+    const float* planes;      // 3*(n+1)
+    const uint2* matSize;     // 5*materialCount
+    const int32_t* matStart;  // 5*materialCount+1
+    const uchar4* textures;
+    const Light* lights;
+    uint32_t triangleCount;
+    uint32_t materialCount;
+    uint32_t lightCount;
+    int32_t n;                // axesDivCount (power of two)
+    int32_t nb;               // bricks per axis = max(n/4, 1)
+};
+
+struct Camera {
+    uint32_t width, height;
+    float eye[4];
+    float eyeToTopLeft[4];
+    float leftToRight[4];
+    float topToBottom[4];
+    float pixelSizeInv;
+};
+
+struct FrameView {
+    Camera cam;
+    const uint32_t* camStart;
+    const uint32_t* camEnd;
+    const uint32_t* camList;
+    uint32_t sampleCount;
+    uint32_t rowBegin, rowEnd;   // rows rendered by this launch (screen-band partition across GPUs)
+    uint16_t* outR;              // full-frame planes, row-major, width*height
+    uint16_t* outG;
+    uint16_t* outB;
+    uint32_t* idOut;             // optional: primary-hit triangle id per pixel (sample 0), or nullptr
+    uint8_t* flagOut;            // optional: per pixel, bit 0 = the reference's result is undefined here (rt_core.h triangle_normal)
+};
+
+// Per-launch event counters for the algorithmic-bytes figure.  Only the counting build
+// of the kernel touches them.
+struct Counters {
+    unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
+        occluderLookups, bricksLoaded;
+};
+
+}  // namespace oclr

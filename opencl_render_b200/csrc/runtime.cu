@@ -1,0 +1,319 @@
+// runtime.cu -- CUDA host runtime behind the C-ABI.  Replaces the OpenCL host setup of
+// source/opencl/raytrace.c:283-603: where the reference rebuilds a context, JIT-compiles the kernel and wraps 35
+// host arrays as zero-copy buffers on every call, this keeps a Scene resident in HBM (uploaded once, repacked to the
+// layout of rt_types.h) and a Frame (camera lists + three 16-bit planes) per camera.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <thread>
+
+#include "rt_kernels.cuh"
+#include "rt_persistent.cuh"
+#include "runtime.h"
+
+namespace oclr {
+
+#define OCLR_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return false;                                                                            \
+        }                                                                                            \
+    } while (0)
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool alloc(size_t n, std::string& err) {
+        bytes = n;
+        OCLR_CUDA(cudaMalloc(&p, n ? n : 16));
+        return true;
+    }
+    bool upload(const void* src, size_t n, std::string& err, cudaStream_t st = 0) {
+        if (!alloc(n, err)) return false;
+        if (n) OCLR_CUDA(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st));
+        return true;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+struct Scene {
+    int device = 0;
+    DeviceBuffer triGeo, triShade, bricks, cellRange, cellList, planes, matSize, matStart, textures, lights;
+    SceneView view = {};
+    size_t bytes = 0;
+    int smCount = 148;
+};
+
+struct Frame {
+    Scene* scene = nullptr;
+    Camera cam = {};
+    DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+bool device_name(int dev, char* buf, size_t len) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    snprintf(buf, len, "CUDA %s (sm_%d%d, %d SMs) #%d", p.name, p.major, p.minor, p.multiProcessorCount, dev);
+    return true;
+}
+
+static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
+    OCLR_CUDA(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    OCLR_CUDA(cudaGetDeviceProperties(&prop, s->device));
+    if (prop.major < 10) {
+        err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return false;
+    }
+    s->smCount = prop.multiProcessorCount;
+    if (!validate_scene(h, err)) return false;
+
+    const size_t N = h.triangleCount;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int threads = hw ? (int)hw : 1;
+    // pack triangles straight into pinned staging so the H2D copy runs at full PCIe rate
+    float4 *geo = nullptr, *shade = nullptr;
+    OCLR_CUDA(cudaMallocHost((void**)&geo, sizeof(float4) * 4 * (N ? N : 1)));
+    OCLR_CUDA(cudaMallocHost((void**)&shade, sizeof(float4) * 8 * (N ? N : 1)));
+    pack_triangles(h, geo, shade, threads);
+    bool ok = s->triGeo.upload(geo, sizeof(float4) * 4 * N, err) && s->triShade.upload(shade, sizeof(float4) * 8 * N, err);
+    PackedGrid grid;
+    std::vector<Light> lights;
+    if (ok) ok = pack_grid(h, grid, err);
+    if (ok) {
+        pack_lights(h, lights);
+        ok = s->bricks.upload(grid.bricks.data(), sizeof(uint4) * grid.bricks.size(), err) &&
+             s->cellRange.upload(grid.cellRange.data(), sizeof(uint2) * grid.cellRange.size(), err) &&
+             s->cellList.upload(grid.cellList.data(), sizeof(uint32_t) * grid.cellList.size(), err) &&
+             s->planes.upload(grid.planes.data(), sizeof(float) * grid.planes.size(), err) &&
+             s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
+             s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
+             s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
+             s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFreeHost(geo);
+    cudaFreeHost(shade);
+    if (!ok) return false;
+    if (e != cudaSuccess) {
+        err = std::string("scene upload: ") + cudaGetErrorString(e);
+        return false;
+    }
+    SceneView& v = s->view;
+    v.triGeo = (const float4*)s->triGeo.p;
+    v.triShade = (const float4*)s->triShade.p;
+    v.bricks = (const uint4*)s->bricks.p;
+    v.cellRange = (const uint2*)s->cellRange.p;
+    v.cellList = (const uint32_t*)s->cellList.p;
+    v.planes = (const float*)s->planes.p;
+    v.matSize = (const uint2*)s->matSize.p;
+    v.matStart = (const int32_t*)s->matStart.p;
+    v.textures = (const uchar4*)s->textures.p;
+    v.lights = (const Light*)s->lights.p;
+    v.triangleCount = h.triangleCount;
+    v.materialCount = h.materialCount;
+    v.lightCount = h.lightCount;
+    v.n = grid.n;
+    v.nb = grid.nb;
+    s->bytes = s->triGeo.bytes + s->triShade.bytes + s->bricks.bytes + s->cellRange.bytes + s->cellList.bytes + s->planes.bytes +
+               s->matSize.bytes + s->matStart.bytes + s->textures.bytes + s->lights.bytes;
+    return true;
+}
+
+Scene* scene_create(int device, const HostScene& h, std::string& err) {
+    if (device < 0 || device >= device_count()) {
+        err = "no such CUDA device: " + std::to_string(device) + " (the library has no CPU fallback)";
+        return nullptr;
+    }
+    Scene* s = new Scene();
+    s->device = device;
+    if (!scene_upload(s, h, err)) {
+        scene_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+void scene_destroy(Scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->cellList, &s->planes, &s->matSize, &s->matStart,
+                           &s->textures, &s->lights};
+    for (DeviceBuffer* b : all) b->release();
+    delete s;
+}
+
+size_t scene_device_bytes(const Scene* s) { return s->bytes; }
+int scene_device(const Scene* s) { return s->device; }
+
+static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
+                        std::string& err) {
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    if (!camStart || !camEnd || (listSize && !camList)) {
+        err = "camera triangle lists missing";
+        return false;
+    }
+    if (!f->camStart.upload(camStart, sizeof(uint32_t) * P, err)) return false;
+    if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
+    if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
+    if (!f->planesRGB.alloc(sizeof(uint16_t) * 3 * P, err)) return false;
+    if (!f->ids.alloc(sizeof(uint32_t) * P, err)) return false;
+    if (!f->flags.alloc(sizeof(uint8_t) * P, err)) return false;
+    OCLR_CUDA(cudaMemsetAsync(f->flags.p, 0, f->flags.bytes, 0));
+    if (!f->counters.alloc(sizeof(Counters), err)) return false;
+    if (!f->workCounter.alloc(sizeof(uint32_t) * 4, err)) return false;
+    OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
+    OCLR_CUDA(cudaEventCreate(&f->ev0));
+    OCLR_CUDA(cudaEventCreate(&f->ev1));
+    OCLR_CUDA(cudaDeviceSynchronize());
+    return true;
+}
+
+Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
+                    size_t camListSize, std::string& err) {
+    if (!s) {
+        err = "null scene";
+        return nullptr;
+    }
+    if (cam.width == 0 || cam.height == 0 || (uint64_t)cam.width * cam.height > 0xFFFFFFFFull) {
+        err = "bad image dimension";
+        return nullptr;
+    }
+    Frame* f = new Frame();
+    f->scene = s;
+    f->cam = cam;
+    if (!frame_setup(f, camStart, camEnd, camList, camListSize, err)) {
+        frame_destroy(f);
+        return nullptr;
+    }
+    return f;
+}
+
+void frame_destroy(Frame* f) {
+    if (!f) return;
+    cudaSetDevice(f->scene->device);
+    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter};
+    for (DeviceBuffer* b : all) b->release();
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    delete f;
+}
+
+bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
+                  RenderStats* stats, std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    Scene* s = f->scene;
+    OCLR_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rowEnd > f->cam.height) rowEnd = f->cam.height;
+    if (sampleCount == 0 || rowBegin >= rowEnd) {
+        err = "empty render request";
+        return false;
+    }
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    FrameView F;
+    F.cam = f->cam;
+    F.camStart = (const uint32_t*)f->camStart.p;
+    F.camEnd = (const uint32_t*)f->camEnd.p;
+    F.camList = (const uint32_t*)f->camList.p;
+    F.sampleCount = sampleCount;
+    F.rowBegin = rowBegin;
+    F.rowEnd = rowEnd;
+    F.outR = (uint16_t*)f->planesRGB.p;
+    F.outG = F.outR + P;
+    F.outB = F.outG + P;
+    F.idOut = (uint32_t*)f->ids.p;
+    F.flagOut = (uint8_t*)f->flags.p;
+    Counters* dcnt = (Counters*)f->counters.p;
+    if (count) OCLR_CUDA(cudaMemsetAsync(dcnt, 0, sizeof(Counters), st));
+    const size_t shBytes = sizeof(float) * 3 * (s->view.n + 1);
+    uint32_t launches = 0;
+    if (stats) OCLR_CUDA(cudaEventRecord(f->ev0, st));
+    if (variant == kKernelSimple) {
+        dim3 grid((f->cam.width + 15) / 16, (rowEnd - rowBegin + 7) / 8);
+        if (count)
+            raytrace_simple_kernel<true><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
+        else
+            raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
+        launches = 1;
+    } else if (variant == kKernelPersistent) {
+        if (!launch_persistent(s->view, F, s->smCount, (uint32_t*)f->workCounter.p, count ? dcnt : nullptr, st, launches, err)) return false;
+    } else {
+        err = "unknown kernel variant";
+        return false;
+    }
+    OCLR_CUDA(cudaGetLastError());
+    if (stats) {
+        OCLR_CUDA(cudaEventRecord(f->ev1, st));
+        OCLR_CUDA(cudaEventSynchronize(f->ev1));
+        OCLR_CUDA(cudaEventElapsedTime(&stats->deviceMs, f->ev0, f->ev1));
+        stats->launches = launches;
+        if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
+    }
+    return true;
+}
+
+bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
+                std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rowEnd > f->cam.height) rowEnd = f->cam.height;
+    if (rowBegin >= rowEnd) return true;
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    const size_t off = (size_t)rowBegin * f->cam.width, cnt = (size_t)(rowEnd - rowBegin) * f->cam.width;
+    const uint16_t* d = (const uint16_t*)f->planesRGB.p;
+    OCLR_CUDA(cudaMemcpyAsync(outR + off, d + off, cnt * 2, cudaMemcpyDeviceToHost, st));
+    OCLR_CUDA(cudaMemcpyAsync(outG + off, d + P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
+    OCLR_CUDA(cudaMemcpyAsync(outB + off, d + 2 * P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
+    OCLR_CUDA(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool frame_read_ids(Frame* f, uint32_t* ids, std::string& err) {
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    OCLR_CUDA(cudaMemcpy(ids, f->ids.p, f->ids.bytes, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err) {
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    OCLR_CUDA(cudaMemcpy(flags, f->flags.p, f->flags.bytes, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+void frame_device_planes(Frame* f, void** r, void** g, void** b) {
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    uint16_t* d = (uint16_t*)f->planesRGB.p;
+    *r = d;
+    *g = d + P;
+    *b = d + 2 * P;
+}
+
+}  // namespace oclr

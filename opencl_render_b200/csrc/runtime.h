@@ -1,0 +1,95 @@
+// runtime.h -- internal C++ interface between the C-ABI (abi.cpp), the host-side packers/builders (g++) and the CUDA
+// runtime + kernels (nvcc).  Replaces the OpenCL host setup of source/opencl/raytrace.c:283-603 (context, program
+// build, 35 buffers, tile loop) with: one resident Scene per upload, one Frame per camera, kernels launched on a
+// caller-chosen stream.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rt_types.h"
+
+namespace oclr {
+
+// Host arrays exactly as the reference passes them to RaytraceAll (source/opencl/raytrace.h:58-106).
+struct HostScene {
+    uint32_t vertexCount = 0;
+    const float4* vertex = nullptr;          // cl_float3 == 16 B
+    uint32_t triangleCount = 0;
+    const int32_t* triIdx = nullptr;         // cl_int3 == 16 B: 4 ints per triangle
+    const int32_t* triMat = nullptr;
+    const float* triUv = nullptr;            // cl_float2 x 3 per triangle
+    const float4* triNormal = nullptr;       // cl_float3 x 3 per triangle
+    int32_t axesDivCount = 0;
+    const float4* boxMin = nullptr;          // axesDivCount + 1
+    const uint32_t* gridStart = nullptr;     // axesDivCount^3 + 1
+    const uint32_t* gridList = nullptr;
+    uint32_t materialCount = 0;
+    const uint2* matSize = nullptr;          // 5 * materialCount
+    const int32_t* matStart = nullptr;       // 5 * materialCount + 1
+    uint32_t texturesSize = 0;
+    const uchar4* textures = nullptr;
+    uint32_t lightCount = 0;
+    const int32_t* lightType = nullptr;
+    const float4* lightPos = nullptr;
+    const float4* lightDir = nullptr;
+    const float4* lightColour = nullptr;
+    const float* lightRadius = nullptr;
+    const float* lightHalf = nullptr;
+};
+
+// ---- host packers (scene_pack.cpp, g++ -ffp-contract=off) -------------------------------------------------------
+struct PackedGrid {
+    std::vector<uint4> bricks;
+    std::vector<uint2> cellRange;
+    std::vector<uint32_t> cellList;
+    std::vector<float> planes;
+    int32_t n = 0, nb = 0;
+};
+void pack_triangles(const HostScene& h, float4* triGeo /*4N*/, float4* triShade /*8N*/, int threads);
+bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err);
+void pack_lights(const HostScene& h, std::vector<Light>& out);
+bool validate_scene(const HostScene& h, std::string& err);
+
+// ---- device runtime (runtime.cu) -----------------------------------------------------------------------------------
+struct Scene;
+struct Frame;
+
+int device_count();
+bool device_name(int dev, char* buf, size_t len);
+
+Scene* scene_create(int device, const HostScene& h, std::string& err);
+void scene_destroy(Scene* s);
+size_t scene_device_bytes(const Scene* s);
+int scene_device(const Scene* s);
+
+// Camera lists are per-frame inputs (CameraTriangleList::New output, trianglelist.cpp:520-626).  `camStart`/`camEnd`
+// hold width*height entries; only rows [rowBegin,rowEnd) need to be valid (band-partitioned multi-GPU rendering).
+Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
+                    size_t camListSize, std::string& err);
+void frame_destroy(Frame* f);
+
+enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1 };
+
+struct RenderStats {
+    float deviceMs = 0.f;        // CUDA-event time of the trace kernel(s) on the launch stream
+    uint32_t launches = 0;       // kernels launched
+    Counters counters = {};      // filled when `count` was requested
+};
+
+// Renders rows [rowBegin,rowEnd) with `sampleCount` samples into the frame's device planes (zeroed first, like the
+// OpenCL branch raytrace.c:476-486).  `stream` is a cudaStream_t (0 = default stream).  Synchronous w.r.t. the host
+// only when `stats` is non-null (it needs the event time).
+bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
+                  RenderStats* stats, std::string& err);
+// Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
+bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
+                std::string& err);
+bool frame_read_ids(Frame* f, uint32_t* ids, std::string& err);
+bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err);
+// Device pointers of the planes (for NCCL gathers done by the host layer) and of the id plane.
+void frame_device_planes(Frame* f, void** r, void** g, void** b);
+
+}  // namespace oclr

@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Developer check on a GPU box: CUDA path vs the compiled reference (oracle/_ref) on configs 1-2 (+ optional 3),
+device timings and event counters.  Not part of the product; tests/ holds the real parity tests."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from opencl_render_b200 import api, scenes  # noqa: E402
+import ref  # noqa: E402
+
+
+def run(cfg_id, variants=(0, 1), ref_rows=None, reps=5):
+    cfg = scenes.CONFIGS[cfg_id]
+    t = time.time(); sc = cfg["make"](); t_scene = time.time() - t
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+    t = time.time(); lists = api.camera_triangle_list(cam, sc); t_cam = time.time() - t
+    t = time.time(); api.scene_triangle_list(sc, 256); t_grid = time.time() - t
+    print(f"[cfg{cfg_id}] {cfg['name']}: tris={sc.triangle_count} scene {t_scene:.2f}s camlist {t_cam:.2f}s ({lists.list.size} refs) "
+          f"grid {t_grid:.2f}s ({sc.grid_list.size} refs)", flush=True)
+    t = time.time(); ds = api.DeviceScene(sc, 0); fr = api.DeviceFrame(ds, cam, lists); t_up = time.time() - t
+    print(f"  upload {t_up:.2f}s device bytes {ds.device_bytes/1e6:.1f} MB", flush=True)
+    S = cfg["samples"]
+    out = {}
+    for v in variants:
+        ms, launches, cnt = fr.render(S, variant=v, count=True)
+        times = []
+        for _ in range(reps):
+            ms, launches, _ = fr.render(S, variant=v)
+            times.append(ms)
+        img = fr.read()
+        ids = fr.primary_ids()
+        flags = fr.undefined_flags()
+        rays = cfg["width"] * cfg["height"] * S
+        best = min(times)
+        print(f"  variant {v}: device ms {['%.3f' % x for x in times]} -> {rays / best / 1e3:.1f} Mrays/s; launches {launches}", flush=True)
+        print("   per-ray counters:", {k: round(c / rays, 3) for k, c in cnt.items()}, flush=True)
+        out[v] = (img, ids, flags, best)
+    rows = ref_rows or (0, cfg["height"])
+    t = time.time(); R = ref.render(cam, lists, sc, S, rows=rows); t_ref = time.time() - t
+    nref = (rows[1] - rows[0]) * cfg["width"] * S
+    print(f"  reference C kernel on {os.cpu_count()} threads rows {rows}: {t_ref:.2f}s -> {nref / t_ref / 1e6:.3f} Mrays/s", flush=True)
+    for v, (img, ids, flags, best) in out.items():
+        sl = slice(rows[0], rows[1])
+        diff = [(img[c][sl] != R[c][sl]) for c in range(3)]
+        anyd = diff[0] | diff[1] | diff[2]
+        mx = max(int(np.abs(img[c][sl].astype(np.int64) - R[c][sl].astype(np.int64)).max()) for c in range(3))
+        unfl = anyd & (flags[sl] == 0)
+        mse = np.mean([(img[c][sl].astype(np.float64) / 65535 - R[c][sl].astype(np.float64) / 65535) ** 2 for c in range(3)])
+        psnr = float("inf") if mse == 0 else 10 * np.log10(1.0 / mse)
+        print(f"  variant {v} vs reference: differing pixels {int(anyd.sum())} (unflagged {int(unfl.sum())}, flagged px {int(flags[sl].sum())}) "
+              f"max|d|={mx} ({mx / 65535:.2e}) PSNR={psnr:.1f} dB", flush=True)
+    if len(out) == 2:
+        a, b = out[0], out[1]
+        print("  variant0 == variant1:", all(np.array_equal(a[0][c], b[0][c]) for c in range(3)), "ids equal:", np.array_equal(a[1], b[1]))
+    fr.close(); ds.close()
+
+
+if __name__ == "__main__":
+    print("types:", api.computation_types())
+    for cid in [int(x) for x in (sys.argv[1:] or ["1", "2"])]:
+        run(cid, ref_rows=None if cid <= 2 else (1000, 1064))
