@@ -249,6 +249,9 @@ void oclr_frame_destroy(oclr_frame* frame);
  * Returns 1 on success. */
 int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, cl_uint rowEnd, int kernelVariant,
                       int countEvents, void* cudaStream, oclr_render_stats* stats);
+/* Same for the interleaved band set of one rank: the rows y with (y / bandRows) % worldSize == rank, in ONE launch. */
+int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint bandRows, int rank, int worldSize, int kernelVariant,
+                            int countEvents, void* cudaStream, oclr_render_stats* stats);
 /* Copy rows [rowBegin,rowEnd) of the planes to full-frame host arrays. */
 int oclr_frame_read(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, cl_ushort* outputRed, cl_ushort* outputGreen,
                     cl_ushort* outputBlue, void* cudaStream);
@@ -258,6 +261,8 @@ int oclr_frame_read_primary_ids(oclr_frame* frame, cl_uint* ids);
  * barycentrics when a bump-mapped surface is hit by a non-camera ray whose first helper ray, raytrace_opencl.c:244, does
  * not meet the triangle plane); parity checks exclude exactly these pixels. */
 int oclr_frame_read_flags(oclr_frame* frame, cl_uchar* flags);
+/* Number of CUDA kernels the last render call on this frame launched. */
+cl_uint oclr_frame_last_launches(const oclr_frame* frame);
 /* Device addresses of the three planes (W*H cl_ushort each) -- for NCCL gathers issued by the host layer. */
 void oclr_frame_device_planes(oclr_frame* frame, void** red, void** green, void** blue);
 

@@ -67,8 +67,8 @@ EXPORTS = [
     "GetProgress", "SetProgress", "GetStartTime", "GetEndTime", "ResetTime", "RaytraceAll",
     # Part 2: extension
     "oclr_last_error", "oclr_device_count", "oclr_version", "oclr_scene_create", "oclr_scene_destroy", "oclr_scene_device_bytes",
-    "oclr_set_camera", "oclr_frame_create", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_read",
-    "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
+    "oclr_set_camera", "oclr_frame_create", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
+    "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_last_launches", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
     "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_free_camera_lists", "oclr_free_scene_grid",
 ]
 
@@ -109,12 +109,17 @@ def load() -> C.CDLL:
     lib.oclr_frame_render.restype = C.c_int
     lib.oclr_frame_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                       C.POINTER(RenderStats)]
+    lib.oclr_frame_render_bands.restype = C.c_int
+    lib.oclr_frame_render_bands.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.POINTER(RenderStats)]
     lib.oclr_frame_read.restype = C.c_int
     lib.oclr_frame_read.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oclr_frame_read_primary_ids.restype = C.c_int
     lib.oclr_frame_read_primary_ids.argtypes = [C.c_void_p, C.c_void_p]
     lib.oclr_frame_read_flags.restype = C.c_int
     lib.oclr_frame_read_flags.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oclr_frame_last_launches.restype = C.c_uint32
+    lib.oclr_frame_last_launches.argtypes = [C.c_void_p]
     lib.oclr_frame_device_planes.restype = None
     lib.oclr_frame_device_planes.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.oclr_band_partition.restype = C.c_int

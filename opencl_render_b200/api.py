@@ -298,6 +298,16 @@ class DeviceFrame:
             raise OclrError(_lib.last_error())
         return float(stats.deviceMs), int(stats.launches), (stats.counters.as_dict() if count else None)
 
+    def render_bands(self, sample_count: int, band_rows: int, rank: int, world: int, variant: int = KERNEL_DEFAULT,
+                     count: bool = False, stream: int = 0, sync: bool = True):
+        """Trace the rows y with (y // band_rows) % world == rank in one launch."""
+        stats = _lib.RenderStats()
+        ok = self._lib.oclr_frame_render_bands(self.handle, sample_count, band_rows, rank, world, variant, 1 if count else 0,
+                                               C.c_void_p(stream), C.byref(stats) if (sync or count) else None)
+        if not ok:
+            raise OclrError(_lib.last_error())
+        return float(stats.deviceMs), int(stats.launches), (stats.counters.as_dict() if count else None)
+
     def read(self, rows=None, out=None, stream: int = 0):
         h, w = self.camera.height, self.camera.width
         r0, r1 = rows if rows is not None else (0, h)
@@ -319,6 +329,10 @@ class DeviceFrame:
         if not self._lib.oclr_frame_read_flags(self.handle, _ptr(flags)):
             raise OclrError(_lib.last_error())
         return flags
+
+    @property
+    def last_launches(self) -> int:
+        return int(self._lib.oclr_frame_last_launches(self.handle))
 
     def device_planes(self):
         r, g, b = C.c_void_p(), C.c_void_p(), C.c_void_p()

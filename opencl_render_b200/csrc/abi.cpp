@@ -212,6 +212,27 @@ int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, 
     return 1;
 }
 
+int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint bandRows, int rank, int worldSize, int kernelVariant,
+                            int countEvents, void* cudaStream, oclr_render_stats* stats) {
+    if (!frame || rank < 0 || worldSize < 1) {
+        fail("oclr_frame_render_bands: bad argument");
+        return 0;
+    }
+    std::string err;
+    RenderStats rs;
+    if (!frame_render_bands(frame->impl, sampleCount, bandRows, (uint32_t)rank, (uint32_t)worldSize, pick_variant(kernelVariant),
+                            countEvents != 0, cudaStream, stats ? &rs : nullptr, err)) {
+        fail("oclr_frame_render_bands: " + err);
+        return 0;
+    }
+    if (stats) {
+        stats->deviceMs = rs.deviceMs;
+        stats->launches = rs.launches;
+        memcpy(&stats->counters, &rs.counters, sizeof(Counters));
+    }
+    return 1;
+}
+
 int oclr_frame_read(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, cl_ushort* r, cl_ushort* g, cl_ushort* b, void* cudaStream) {
     if (!frame || !r || !g || !b) {
         fail("oclr_frame_read: null argument");
@@ -250,6 +271,8 @@ int oclr_frame_read_flags(oclr_frame* frame, cl_uchar* flags) {
     }
     return 1;
 }
+
+cl_uint oclr_frame_last_launches(const oclr_frame* frame) { return frame ? frame_last_launches(frame->impl) : 0; }
 
 void oclr_frame_device_planes(oclr_frame* frame, void** red, void** green, void** blue) {
     if (frame) frame_device_planes(frame->impl, red, green, blue);

@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(128) raytrace_simple_kernel(SceneView S, Frame
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t y = F.rowBegin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= F.cam.width || y >= F.rowEnd) return;
+    const uint32_t y = map_row(F, blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3));
+    if (x >= F.cam.width || y >= F.cam.height) return;
     const uint32_t pixel = y * F.cam.width + x;
 
     Counters cnt = {};

@@ -7,7 +7,7 @@ inline bool launch_persistent(const SceneView& S, const FrameView& F, int smCoun
                               cudaStream_t st, uint32_t& launches, std::string& err) {
     (void)smCount; (void)workCounter;
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
-    dim3 grid((F.cam.width + 15) / 16, (F.rowEnd - F.rowBegin + 7) / 8);
+    dim3 grid((F.cam.width + 15) / 16, (launch_rows(F) + 7) / 8);
     if (dcnt) raytrace_simple_kernel<true><<<grid, 128, shBytes, st>>>(S, F, dcnt);
     else raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(S, F, dcnt);
     launches = 1;

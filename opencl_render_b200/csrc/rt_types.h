@@ -84,13 +84,24 @@ struct FrameView {
     const uint32_t* camEnd;
     const uint32_t* camList;
     uint32_t sampleCount;
-    uint32_t rowBegin, rowEnd;   // rows rendered by this launch (screen-band partition across GPUs)
+    uint32_t rowBegin, rowEnd;   // rows rendered by this launch when bandWorld <= 1
+    // Screen-band partition across GPUs: when bandWorld > 1 the launch covers the rows y with
+    // (y / bandRows) % bandWorld == bandRank; `ownedRows` of them exist.  Launch-domain row k maps to frame row map_row(k).
+    uint32_t bandRows, bandRank, bandWorld, ownedRows;
     uint16_t* outR;              // full-frame planes, row-major, width*height
     uint16_t* outG;
     uint16_t* outB;
     uint32_t* idOut;             // optional: primary-hit triangle id per pixel (sample 0), or nullptr
     uint8_t* flagOut;            // optional: per pixel, bit 0 = the reference's result is undefined here (rt_core.h triangle_normal)
 };
+
+// Launch-domain row k -> frame row (>= height when k is past the owned rows).
+OCLR_HD uint32_t map_row(const FrameView& F, uint32_t k) {
+    if (F.bandWorld <= 1) return F.rowBegin + k < F.rowEnd ? F.rowBegin + k : 0xFFFFFFFFu;
+    if (k >= F.ownedRows) return 0xFFFFFFFFu;
+    return (k / F.bandRows) * (F.bandRows * F.bandWorld) + F.bandRank * F.bandRows + (k % F.bandRows);
+}
+OCLR_HD uint32_t launch_rows(const FrameView& F) { return F.bandWorld <= 1 ? F.rowEnd - F.rowBegin : F.ownedRows; }
 
 // Per-launch event counters for the algorithmic-bytes figure.  Only the counting build
 // of the kernel touches them.

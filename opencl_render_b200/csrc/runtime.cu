@@ -55,6 +55,7 @@ struct Frame {
     Camera cam = {};
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t lastLaunches = 0;
 };
 
 int device_count() {
@@ -219,29 +220,21 @@ void frame_destroy(Frame* f) {
     delete f;
 }
 
-bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
-                  RenderStats* stats, std::string& err) {
-    if (!f) {
-        err = "null frame";
-        return false;
-    }
+uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint32_t world) {
+    if (world <= 1) return height;
+    uint32_t owned = 0;
+    for (uint32_t b0 = rank * bandRows; b0 < height; b0 += bandRows * world) owned += (b0 + bandRows <= height) ? bandRows : height - b0;
+    return owned;
+}
+
+static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
     Scene* s = f->scene;
-    OCLR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (rowEnd > f->cam.height) rowEnd = f->cam.height;
-    if (sampleCount == 0 || rowBegin >= rowEnd) {
-        err = "empty render request";
-        return false;
-    }
     const size_t P = (size_t)f->cam.width * f->cam.height;
-    FrameView F;
     F.cam = f->cam;
     F.camStart = (const uint32_t*)f->camStart.p;
     F.camEnd = (const uint32_t*)f->camEnd.p;
     F.camList = (const uint32_t*)f->camList.p;
-    F.sampleCount = sampleCount;
-    F.rowBegin = rowBegin;
-    F.rowEnd = rowEnd;
     F.outR = (uint16_t*)f->planesRGB.p;
     F.outG = F.outR + P;
     F.outB = F.outG + P;
@@ -253,7 +246,7 @@ bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t ro
     uint32_t launches = 0;
     if (stats) OCLR_CUDA(cudaEventRecord(f->ev0, st));
     if (variant == kKernelSimple) {
-        dim3 grid((f->cam.width + 15) / 16, (rowEnd - rowBegin + 7) / 8);
+        dim3 grid((f->cam.width + 15) / 16, (launch_rows(F) + 7) / 8);
         if (count)
             raytrace_simple_kernel<true><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         else
@@ -266,6 +259,7 @@ bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t ro
         return false;
     }
     OCLR_CUDA(cudaGetLastError());
+    f->lastLaunches = launches;
     if (stats) {
         OCLR_CUDA(cudaEventRecord(f->ev1, st));
         OCLR_CUDA(cudaEventSynchronize(f->ev1));
@@ -274,6 +268,56 @@ bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t ro
         if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
     }
     return true;
+}
+
+bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
+                  RenderStats* stats, std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    if (rowEnd > f->cam.height) rowEnd = f->cam.height;
+    if (sampleCount == 0 || rowBegin >= rowEnd) {
+        err = "empty render request";
+        return false;
+    }
+    FrameView F = {};
+    F.sampleCount = sampleCount;
+    F.rowBegin = rowBegin;
+    F.rowEnd = rowEnd;
+    F.bandRows = 0;
+    F.bandRank = 0;
+    F.bandWorld = 1;
+    F.ownedRows = rowEnd - rowBegin;
+    return frame_launch(f, F, variant, count, stream, stats, err);
+}
+
+bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, int variant, bool count,
+                        void* stream, RenderStats* stats, std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    if (sampleCount == 0 || bandRows == 0 || world == 0 || rank >= world) {
+        err = "bad band request";
+        return false;
+    }
+    if (world == 1) return frame_render(f, sampleCount, 0, f->cam.height, variant, count, stream, stats, err);
+    FrameView F = {};
+    F.sampleCount = sampleCount;
+    F.rowBegin = 0;
+    F.rowEnd = f->cam.height;
+    F.bandRows = bandRows;
+    F.bandRank = rank;
+    F.bandWorld = world;
+    F.ownedRows = band_owned_rows(f->cam.height, bandRows, rank, world);
+    if (F.ownedRows == 0) {
+        if (stats) *stats = RenderStats();
+        return true;
+    }
+    return frame_launch(f, F, variant, count, stream, stats, err);
 }
 
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
@@ -307,6 +351,8 @@ bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err) {
     OCLR_CUDA(cudaMemcpy(flags, f->flags.p, f->flags.bytes, cudaMemcpyDeviceToHost));
     return true;
 }
+
+uint32_t frame_last_launches(const Frame* f) { return f ? f->lastLaunches : 0; }
 
 void frame_device_planes(Frame* f, void** r, void** g, void** b) {
     const size_t P = (size_t)f->cam.width * f->cam.height;

@@ -84,9 +84,14 @@ struct RenderStats {
 // only when `stats` is non-null (it needs the event time).
 bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
                   RenderStats* stats, std::string& err);
+// Same, for the rows y with (y / bandRows) % world == rank (one launch covers all bands the rank owns).
+bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, int variant, bool count,
+                        void* stream, RenderStats* stats, std::string& err);
+uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint32_t world);
 // Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
                 std::string& err);
+uint32_t frame_last_launches(const Frame* f);
 bool frame_read_ids(Frame* f, uint32_t* ids, std::string& err);
 bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err);
 // Device pointers of the planes (for NCCL gathers done by the host layer) and of the id plane.

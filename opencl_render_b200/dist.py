@@ -1,0 +1,126 @@
+"""Multi-GPU host layer (one process per GPU, torch.distributed over NCCL/NVLink for the plumbing).
+
+The path shards by pixels: the image is cut into row bands dealt round-robin to the ranks, the scene
+is replicated per GPU, and the only exchange step is assembling the three 16-bit planes -- one NCCL all-gather of each
+rank's compact rows.  No collective sits on the trace path itself."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+
+def owned_rows(height: int, rank: int, world: int, band_rows: int) -> np.ndarray:
+    """Frame rows y with (y // band_rows) % world == rank, ascending (mirrors map_row() in csrc/rt_types.h)."""
+    y = np.arange(height)
+    return y[(y // band_rows) % world == rank]
+
+
+class BandPartition:
+    def __init__(self, height: int, width: int, rank: int, world: int, band_rows: int = 16):
+        self.height, self.width, self.rank, self.world, self.band_rows = height, width, rank, world, band_rows
+        self.rows = owned_rows(height, rank, world, band_rows)
+        self.owned_rows = int(self.rows.size)
+        self.max_owned = max(int(owned_rows(height, r, world, band_rows).size) for r in range(world))
+
+    def render(self, frame: api.DeviceFrame, samples: int, variant: int, stream: int) -> int:
+        """Async launch on `stream`; returns the number of kernels launched."""
+        if self.owned_rows == 0:
+            return 0
+        frame.render_bands(samples, self.band_rows, self.rank, self.world, variant=variant, stream=stream, sync=False)
+        return frame.last_launches
+
+    def render_timed(self, frame, samples, variant) -> float:
+        return frame.render_bands(samples, self.band_rows, self.rank, self.world, variant=variant)[0]
+
+    def render_counted(self, frame, samples, variant):
+        return frame.render_bands(samples, self.band_rows, self.rank, self.world, variant=variant, count=True)
+
+
+class _DevPtr:
+    """Exposes a raw device address to torch through __cuda_array_interface__ (int16 view of the ushort planes)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i2", "data": (int(ptr), False), "version": 3}
+
+
+class PlaneGather:
+    """Assembles the full frame on every rank: compact owned rows -> all_gather_into_tensor -> scatter to frame rows."""
+
+    def __init__(self, frame, part: BandPartition, device, planes=None):
+        import torch
+        self.torch = torch
+        self.part = part
+        h, w = part.height, part.width
+        if planes is None:
+            r, g, b = frame.device_planes()
+            assert g == r + 2 * h * w and b == g + 2 * h * w
+            planes = torch.as_tensor(_DevPtr(r, (3, h, w)), device=device)          # the frame's own planes, no copy
+        self.planes = planes
+        self.mine = torch.as_tensor(part.rows, device=device, dtype=torch.long)
+        self.send = torch.zeros((3, part.max_owned, w), dtype=torch.int16, device=device)
+        self.recv = torch.empty((part.world, 3, part.max_owned, w), dtype=torch.int16, device=device)
+        self.full = torch.zeros((3, h, w), dtype=torch.int16, device=device)
+        self.all_rows = [torch.as_tensor(owned_rows(h, r_, part.world, part.band_rows), device=device, dtype=torch.long)
+                         for r_ in range(part.world)]
+        self.launches = 0
+
+    def run(self):
+        import torch.distributed as dist
+        t = self.torch
+        n = self.part.owned_rows
+        if n:
+            t.index_select(self.planes, 1, self.mine, out=self.send[:, :n, :])
+        dist.all_gather_into_tensor(self.recv.view(-1, self.recv.shape[2], self.recv.shape[3]), self.send)                           # NCCL over NVLink: the only exchange step
+        for r_, rows in enumerate(self.all_rows):
+            if rows.numel():
+                self.full.index_copy_(1, rows, self.recv[r_, :, :rows.numel(), :])
+        return self.full
+
+
+class EndToEnd:
+    """The drop-in call with HOST buffers: at world == 1 it is RaytraceAll itself (upload + repack + trace + read back);
+    at world > 1 each rank uploads the scene, traces its bands and reads its rows back through the scene/frame API."""
+
+    def __init__(self, scene: api.HostScene, cam: api.CameraSetup, lists: api.CameraLists, part: BandPartition, device: int):
+        import torch
+        self.scene, self.cam, self.part, self.device = scene, cam, part, device
+
+        def pin(a):
+            a = np.ascontiguousarray(a)
+            if a.size == 0:
+                return a
+            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+            v = t.numpy().view(a.dtype).reshape(a.shape)
+            v[...] = a
+            self._keep.append(t)
+            return v
+
+        self._keep = []
+        for name in ("vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type",
+                     "light_pos", "light_dir", "light_colour", "light_radius", "light_half", "box_min", "grid_start", "grid_list"):
+            setattr(scene, name, pin(getattr(scene, name)))
+        self.lists = api.CameraLists(pin(lists.start), pin(lists.end), pin(lists.list))
+        self.out = tuple(pin(np.zeros((cam.height, cam.width), np.uint16)) for _ in range(3))
+        self.h2d_bytes = int(sum(getattr(scene, n).nbytes for n in (
+            "vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type", "light_pos",
+            "light_dir", "light_colour", "light_radius", "light_half", "box_min", "grid_start", "grid_list")) +
+            self.lists.start.nbytes + self.lists.end.nbytes + self.lists.list.nbytes)
+        self.d2h_bytes = int(6 * part.owned_rows * cam.width)
+
+    def step(self, samples: int):
+        if self.part.world == 1:
+            api.raytrace_all(1 + self.device, self.cam, self.lists, samples, self.scene, out=self.out)
+            return
+        ds = api.DeviceScene(self.scene, self.device)
+        fr = api.DeviceFrame(ds, self.cam, self.lists)
+        fr.render_bands(samples, self.part.band_rows, self.part.rank, self.part.world)
+        rows = self.part.rows
+        if rows.size:      # contiguous runs of owned rows
+            cuts = np.nonzero(np.diff(rows) != 1)[0] + 1
+            for seg in np.split(rows, cuts):
+                fr.read(rows=(int(seg[0]), int(seg[-1]) + 1), out=self.out)
+        fr.close()
+        ds.close()

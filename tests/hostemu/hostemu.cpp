@@ -44,7 +44,7 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     S.lightCount = h.lightCount; S.n = grid.n; S.nb = grid.nb;
     FrameView F;
     memcpy(&F.cam, cam, sizeof(Camera));
-    F.camStart = camStart; F.camEnd = camEnd; F.camList = camList; F.sampleCount = sampleCount; F.rowBegin = rowBegin; F.rowEnd = rowEnd;
+    F.camStart = camStart; F.camEnd = camEnd; F.camList = camList; F.sampleCount = sampleCount; F.rowBegin = rowBegin; F.rowEnd = rowEnd; F.bandRows = 0; F.bandRank = 0; F.bandWorld = 1; F.ownedRows = rowEnd - rowBegin;
     F.outR = outR; F.outG = outG; F.outB = outB; F.idOut = ids; F.flagOut = flags;
     const float* px = S.planes; const float* py = px + (S.n + 1); const float* pz = py + (S.n + 1);
     if (rowEnd > cam->height) rowEnd = cam->height;

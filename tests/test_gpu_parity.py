@@ -1,0 +1,191 @@
+"""GPU parity suite (run with -m gpu on a B200): the CUDA path, called through the C-ABI of libopencl_render_b200.so, against
+the oracle -- golden vectors generated from the reference build, the C port, and (when oracle/_ref travelled) the reference
+itself -- on the same seeded inputs.
+
+Bar (BASELINE.json north_star): primary-hit triangle ids bit-exact; RGB max-abs <= 1e-3 per channel and PSNR >= 60 dB.
+What is asserted is stronger: RGB planes are BIT-EXACT at every pixel where the reference's own result is defined; the
+only excluded pixels are those the library flags as "reference undefined" (uninitialised read in the reference's bump
+mapping, see include/oclr_abi.h oclr_frame_read_flags), and on those the tolerance bar is still checked against the port."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from opencl_render_b200 import api, scenes
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+VARIANTS = [api.KERNEL_SIMPLE, api.KERNEL_PERSISTENT]
+
+
+def _render(sc, cam, lists, samples, variant=api.KERNEL_DEFAULT, rows=None, count=False):
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    ms, launches, cnt = fr.render(samples, rows=rows, variant=variant, count=count)
+    img = fr.read()
+    ids = fr.primary_ids()
+    flags = fr.undefined_flags()
+    fr.close()
+    ds.close()
+    assert launches >= 1 and ms > 0
+    return img, ids, flags, cnt
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_cuda_equals_golden(name, variant):
+    sc, cam, lists, samples = helpers.make_case(name)
+    gold = np.load(GOLDEN / f"{name}.npz")
+    img, ids, flags, _ = _render(sc, cam, lists, samples, variant)
+    res = helpers.compare_rgb(img, (gold["r"], gold["g"], gold["b"]), mask=(flags == 0))
+    assert res["diff_pixels"] == 0, res
+    if samples != 1:
+        ids = _render(sc, cam, lists, 1, variant)[1]
+    mism = int((ids != gold["ids"]).sum())
+    assert mism == 0, f"{mism} primary-hit ids differ"      # shared-edge epsilon population: 0 on these cases
+    if name != "terrain_textured":
+        assert flags.sum() == 0
+    whole = helpers.compare_rgb(img, (gold["r"], gold["g"], gold["b"]))
+    assert whole["diff_pixels"] <= int(flags.sum())
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_cuda_equals_port_with_tolerance_bar(name, port):
+    sc, cam, lists, samples = helpers.make_case(name)
+    img, ids, flags, _ = _render(sc, cam, lists, samples)
+    r, g, b, pid = port.render(cam, lists, sc, samples, want_ids=True)
+    res = helpers.compare_rgb(img, (r, g, b))
+    assert res["max_abs"] <= helpers.RGB_TOL and res["psnr"] >= helpers.PSNR_MIN, res     # the stated tolerance bar ...
+    assert res["diff_pixels"] == 0, res                                                      # ... and in fact bit-exact
+    assert np.array_equal(ids, pid)
+
+
+@pytest.mark.parametrize("name", ["soup", "spheres_mirror", "terrain"])
+def test_cuda_equals_reference_build(name, ref):
+    sc, cam, lists, samples = helpers.make_case(name)
+    img, _, flags, _ = _render(sc, cam, lists, samples)
+    want = ref.render(cam, lists, sc, samples)
+    assert helpers.compare_rgb(img, want, mask=(flags == 0))["diff_pixels"] == 0
+
+
+def test_raytrace_all_host_buffers(port):
+    """The drop-in call itself: host arrays in, host planes out (upload + repack + trace + read back)."""
+    sc, cam, lists, samples = helpers.make_case("spheres")
+    r, g, b = api.raytrace_all(1, cam, lists, samples, sc)
+    want = port.render(cam, lists, sc, samples)
+    assert np.array_equal(r, want[0]) and np.array_equal(g, want[1]) and np.array_equal(b, want[2])
+    with pytest.raises(api.OclrError):
+        api.raytrace_all(0, cam, lists, samples, sc)            # "Local CPU single thread" is refused: no CPU fallback
+    with pytest.raises(api.OclrError):
+        api.raytrace_all(99, cam, lists, samples, sc)
+
+
+def test_id_material_scene_on_cuda_decodes_to_id_plane():
+    """the id-material variant makes the RGB output itself carry the primary ids -- cross-checks the id plane."""
+    sc, cam, lists, _ = helpers.make_case("terrain")
+    idsc = scenes.id_material_variant(sc)
+    img, _, _, _ = _render(idsc, cam, lists, 1)
+    _, ids, _, _ = _render(sc, cam, lists, 1)
+    assert np.array_equal(scenes.decode_id_planes(*img), ids)
+
+
+def test_band_rendering_equals_full_frame():
+    sc, cam, lists, samples = helpers.make_case("spheres")
+    full, ids, _, _ = _render(sc, cam, lists, samples)
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
+    for rank in range(3):
+        for rows in api.band_partition(cam.height, rank, 3, band_rows=32):
+            fr.render(samples, rows=rows)
+            fr.read(rows=rows, out=out)
+    for c in range(3):
+        assert np.array_equal(out[c], full[c])
+
+
+def test_counters_equal_host_emulation(hostemu):
+    sc, cam, lists, samples = helpers.make_case("spheres")
+    _, _, _, cnt = _render(sc, cam, lists, samples, api.KERNEL_SIMPLE, count=True)
+    _, _, _, want = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for k in ("segments", "primCandidates", "gridRays", "cells", "cellsNonEmpty", "gridCandidates", "shadedHits", "occluderLookups"):
+        assert cnt[k] == want[k], k
+
+
+def test_edge_cases(port):
+    # empty scene, no lights, all-miss camera, single triangle, 1x1 image
+    cam = api.set_camera((0, 4.4, -8), (0, 0, 0), (0, 1, 0), 0.9, 40, 30)
+    empty = scenes.soup(0, seed=1)
+    lists = api.camera_triangle_list(cam, empty)
+    api.scene_triangle_list(empty, 16)
+    img, ids, _, _ = _render(empty, cam, lists, 2)
+    assert all((p == 0).all() for p in img) and (ids == 0xFFFFFFFF).all()
+
+    one = scenes.soup(1, seed=4)
+    lists = api.camera_triangle_list(cam, one)
+    api.scene_triangle_list(one, 256)
+    img, ids, _, _ = _render(one, cam, lists, 1)
+    want = port.render(cam, lists, one, 1, want_ids=True)
+    assert all(np.array_equal(img[c], want[c]) for c in range(3)) and np.array_equal(ids, want[3])
+
+    nolight = scenes.soup(50, seed=9)
+    for k in ("light_type", "light_pos", "light_dir", "light_colour", "light_radius", "light_half"):
+        setattr(nolight, k, getattr(nolight, k)[:0])
+    lists = api.camera_triangle_list(cam, nolight)
+    api.scene_triangle_list(nolight, 64)
+    img, _, _, _ = _render(nolight, cam, lists, 1)
+    want = port.render(cam, lists, nolight, 1)
+    assert all(np.array_equal(img[c], want[c]) for c in range(3))
+
+    away = api.set_camera((0, 4.4, -8), (0, 4.4, -20), (0, 1, 0), 0.5, 1, 1)      # looks away from the soup: all miss
+    sc = scenes.soup(50, seed=9)
+    api.scene_triangle_list(sc, 64)
+    lists = api.CameraLists(np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+    img, ids, _, _ = _render(sc, away, lists, 3)
+    assert all((p == 0).all() for p in img) and (ids == 0xFFFFFFFF).all()
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (101 090 triangles, 1920x1080): size-independent properties -- the two kernel
+    variants agree bit for bit, band-split rendering reproduces the full frame, and the id-material decode equals the
+    id plane; plus bit-exact parity with the reference on a band of rows."""
+    cfg = scenes.CONFIGS[2]
+    sc = cfg["make"]()
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+    lists = api.camera_triangle_list(cam, sc)
+    api.scene_triangle_list(sc, 256)
+    assert sc.triangle_count == 101090
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(1, variant=api.KERNEL_SIMPLE)
+    a = fr.read()
+    ida = fr.primary_ids()
+    fr.render(1, variant=api.KERNEL_PERSISTENT)
+    b = fr.read()
+    idb = fr.primary_ids()
+    assert all(np.array_equal(a[c], b[c]) for c in range(3)) and np.array_equal(ida, idb)
+    out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
+    for rank in range(8):
+        for rows in api.band_partition(cam.height, rank, 8):
+            fr.render(1, rows=rows)
+            fr.read(rows=rows, out=out)
+    assert all(np.array_equal(out[c], b[c]) for c in range(3))
+    fr.close()
+    ds.close()
+    idsc = scenes.id_material_variant(sc)
+    ds = api.DeviceScene(idsc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(1)
+    assert np.array_equal(scenes.decode_id_planes(*fr.read()), idb)
+    fr.close()
+    ds.close()
+    try:
+        import ref
+        if ref.available():
+            rows = (500, 540)
+            want = ref.render(cam, lists, sc, 1, rows=rows)
+            for c in range(3):
+                assert np.array_equal(want[c][rows[0]:rows[1]], b[c][rows[0]:rows[1]])
+    except ImportError:
+        pass
