@@ -39,6 +39,10 @@ class BandPartition:
         return frame.render_bands(samples, self.band_rows, self.rank, self.world, variant=variant, count=True)
 
 
+def torch_u8(t):
+    return t.uint8    # byte view: every backend (NCCL, gloo) moves uint8
+
+
 class _DevPtr:
     """Exposes a raw device address to torch through __cuda_array_interface__ (int16 view of the ushort planes)."""
 
@@ -73,7 +77,7 @@ class PlaneGather:
         n = self.part.owned_rows
         if n:
             t.index_select(self.planes, 1, self.mine, out=self.send[:, :n, :])
-        dist.all_gather_into_tensor(self.recv.view(-1, self.recv.shape[2], self.recv.shape[3]), self.send)                           # NCCL over NVLink: the only exchange step
+        dist.all_gather_into_tensor(self.recv.view(torch_u8(t)).view(-1), self.send.view(torch_u8(t)).view(-1))                           # NCCL over NVLink: the only exchange step
         for r_, rows in enumerate(self.all_rows):
             if rows.numel():
                 self.full.index_copy_(1, rows, self.recv[r_, :, :rows.numel(), :])
