@@ -233,6 +233,10 @@ oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);
 void oclr_scene_destroy(oclr_scene* scene);
 size_t oclr_scene_device_bytes(const oclr_scene* scene);
 
+/* Test door: copies one packed device array back to `dst` (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList);
+ * returns its size in bytes (nothing is copied when it exceeds `capacity`). */
+size_t oclr_scene_debug_read(oclr_scene* scene, int which, void* dst, size_t capacity);
+
 /* Camera (SetCamera, source/render.cpp:461-491): position / look-at / up / horizontal fov (radians) / size. */
 void oclr_set_camera(oclr_camera* out, const cl_float position[3], const cl_float object[3], const cl_float up[3],
                      cl_float fov, cl_uint width, cl_uint height);

@@ -263,6 +263,13 @@ class DeviceScene:
     def device_bytes(self) -> int:
         return int(self._lib.oclr_scene_device_bytes(self.handle))
 
+    def debug_read(self, which: int) -> np.ndarray:
+        """Packed device array as bytes (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList)."""
+        n = int(self._lib.oclr_scene_debug_read(self.handle, which, None, 0))
+        out = np.zeros(max(n, 1), np.uint8)
+        self._lib.oclr_scene_debug_read(self.handle, which, _ptr(out), n)
+        return out[:n]
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.oclr_scene_destroy(self.handle)

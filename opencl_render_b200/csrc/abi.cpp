@@ -153,6 +153,9 @@ void oclr_scene_destroy(oclr_scene* scene) {
     scene_destroy(scene->impl);
     delete scene;
 }
+size_t oclr_scene_debug_read(oclr_scene* scene, int which, void* dst, size_t capacity) {
+    return scene ? scene_debug_read(scene->impl, which, dst, capacity) : 0;
+}
 size_t oclr_scene_device_bytes(const oclr_scene* scene) { return scene ? scene_device_bytes(scene->impl) : 0; }
 
 void oclr_set_camera(oclr_camera* out, const cl_float position[3], const cl_float object[3], const cl_float up[3], cl_float fov,

@@ -1,0 +1,115 @@
+// pack_kernels.cuh -- device half of the "scene upload path": the reference arrays are copied to HBM as they are
+// (one cudaMemcpyAsync per array, straight from the caller's memory) and repacked there into the layout of
+// rt_types.h.  Same arithmetic as scene_pack.cpp (the host packer the tests use as the checker), compiled with
+// -fmad=false so the hoisted per-triangle terms are the exact fp32 values of raytrace_opencl.c:131-149.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "rt_core.h"
+
+namespace oclr {
+
+enum PackError { kPackOk = 0, kPackBadVertexIndex = 1, kPackBadMaterial = 2, kPackBadCsr = 4, kPackBadListEntry = 8 };
+
+// One thread per triangle: gathers the 3 vertices (16 B loads), precomputes the plane/Gram terms, writes 4 + 8 float4.
+__global__ void __launch_bounds__(256) pack_triangles_kernel(uint32_t triangleCount, uint32_t vertexCount, uint32_t materialCount,
+                                                             const float4* __restrict__ vertex, const int4* __restrict__ triIdx,
+                                                             const int32_t* __restrict__ triMat, const float2* __restrict__ triUv,
+                                                             const float4* __restrict__ triNormal, float4* __restrict__ geo,
+                                                             float4* __restrict__ shade, uint32_t* __restrict__ error) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= triangleCount) return;
+    const int4 vi = __ldg(triIdx + i);
+    const int32_t mat = __ldg(triMat + i);
+    if ((uint32_t)vi.x >= vertexCount || (uint32_t)vi.y >= vertexCount || (uint32_t)vi.z >= vertexCount) {
+        atomicOr(error, (uint32_t)kPackBadVertexIndex);
+        return;
+    }
+    if (mat >= (int32_t)materialCount) atomicOr(error, (uint32_t)kPackBadMaterial);
+    const float4 A = __ldg(vertex + vi.x), B = __ldg(vertex + vi.y), C = __ldg(vertex + vi.z);
+    const f3 a = mk3(A.x, A.y, A.z), b = mk3(B.x, B.y, B.z), c = mk3(C.x, C.y, C.z);
+    const f3 ab = mk3(b.x - a.x, b.y - a.y, b.z - a.z);
+    const f3 ac = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
+    const f3 n = cross3(ac, ab);
+    const float abab = dot3(ab, ab), abac = dot3(ab, ac), acac = dot3(ac, ac);
+    const float D = 1.f / (abac * abac - abab * acac);
+    float4* g = geo + 4 * (size_t)i;
+    g[0] = make_float4(n.x, n.y, n.z, a.x);
+    g[1] = make_float4(a.y, a.z, abab, abac);
+    g[2] = make_float4(ab.x, ab.y, ab.z, acac);
+    g[3] = make_float4(ac.x, ac.y, ac.z, D);
+    const float4 nA = __ldg(triNormal + 3 * (size_t)i), nB = __ldg(triNormal + 3 * (size_t)i + 1), nC = __ldg(triNormal + 3 * (size_t)i + 2);
+    const float2 u0 = __ldg(triUv + 3 * (size_t)i), u1 = __ldg(triUv + 3 * (size_t)i + 1), u2 = __ldg(triUv + 3 * (size_t)i + 2);
+    float4* s = shade + 8 * (size_t)i;
+    s[0] = make_float4(a.x, a.y, a.z, __int_as_float(mat));
+    s[1] = make_float4(b.x, b.y, b.z, 0.f);
+    s[2] = make_float4(c.x, c.y, c.z, 0.f);
+    s[3] = make_float4(nA.x, nA.y, nA.z, 0.f);
+    s[4] = make_float4(nB.x, nB.y, nB.z, 0.f);
+    s[5] = make_float4(nC.x, nC.y, nC.z, 0.f);
+    s[6] = make_float4(u0.x, u0.y, u1.x, u1.y);
+    s[7] = make_float4(u2.x, u2.y, 0.f, 0.f);
+}
+
+// Pass 1 over the reference CSR (n^3 + 1 starts): one thread per 4x4x4 brick builds its occupancy mask and counts its
+// non-empty cells.  Pass 2 (after an exclusive scan of the counts) writes {mask, rank base} and the {begin,end} ranges.
+__device__ __forceinline__ uint64_t brick_mask(const uint32_t* __restrict__ start, int n, int nb, uint32_t total, int b, uint32_t* error,
+                                               uint2* ranges /* nullable */) {
+    const int side = n >= 4 ? 4 : n;
+    const int bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+    uint64_t mask = 0;
+    int k = 0;
+    for (int z = 0; z < side; ++z)
+        for (int y = 0; y < side; ++y) {
+            const size_t row = (size_t)(bx * 4) + (size_t)n * (by * 4 + y) + (size_t)n * n * (bz * 4 + z);
+            uint32_t s = __ldg(start + row);
+            for (int x = 0; x < side; ++x) {
+                const uint32_t e = __ldg(start + row + x + 1);
+                if (e < s || e > total) atomicOr(error, (uint32_t)kPackBadCsr);
+                if (s < e) {
+                    mask |= 1ull << (x | (y << 2) | (z << 4));
+                    if (ranges) ranges[k] = make_uint2(s, e);
+                    ++k;
+                }
+                s = e;
+            }
+        }
+    return mask;
+}
+
+__global__ void __launch_bounds__(128) brick_count_kernel(const uint32_t* __restrict__ start, int n, int nb, uint32_t total,
+                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ error) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb * nb * nb) return;
+    counts[b] = (uint32_t)__popcll(brick_mask(start, n, nb, total, b, error, nullptr));
+}
+
+__global__ void __launch_bounds__(128) brick_write_kernel(const uint32_t* __restrict__ start, int n, int nb, uint32_t total,
+                                                          const uint32_t* __restrict__ rankBase, uint4* __restrict__ bricks,
+                                                          uint2* __restrict__ cellRange, uint32_t* __restrict__ error) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb * nb * nb) return;
+    const uint32_t base = rankBase[b];
+    const uint64_t mask = brick_mask(start, n, nb, total, b, error, cellRange + base);
+    bricks[b] = make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), base, 0u);
+}
+
+__global__ void __launch_bounds__(256) check_list_kernel(const uint32_t* __restrict__ list, uint32_t total, uint32_t triangleCount,
+                                                         uint32_t* __restrict__ error) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total && __ldg(list + i) >= triangleCount) atomicOr(error, (uint32_t)kPackBadListEntry);
+}
+
+// sceneBoxMin (cl_float3 per plane index) -> three contiguous float arrays
+__global__ void split_planes_kernel(const float4* __restrict__ boxMin, int n, float* __restrict__ planes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const float4 p = boxMin[i];
+    planes[i] = p.x;
+    planes[(n + 1) + i] = p.y;
+    planes[2 * (n + 1) + i] = p.z;
+}
+
+}  // namespace oclr

@@ -18,7 +18,7 @@
 //             (4 MB at 256^3).  A DDA walk reads one 16 B record per brick and then steps through up to
 //             ~10 cells of it from registers; empty cells cost one bit test.
 //   cellRange one uint2 {begin,end} per NON-EMPTY cell, in brick-major order, into cellList.
-//   cellList  triangle ids, per-cell order preserved from the reference list (ascending id; the order is
+//   cellList  the reference's scenePixelTriangleList as uploaded (triangle ids, ascending per cell; the order is
 //             observable through the strict `<` closest-hit rule, raytrace_opencl.c:143, 372-377).
 //   planes    3 x (n+1) floats (x planes, y planes, z planes) -- copied to shared memory by each CTA.
 #pragma once

@@ -8,6 +8,7 @@
 
 #include <thread>
 
+#include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
 #include "rt_persistent.cuh"
 #include "runtime.h"
@@ -23,21 +24,34 @@ namespace oclr {
         }                                                                                            \
     } while (0)
 
+// Device memory comes from the stream-ordered pool of the device with the release threshold lifted, so the
+// alloc/free pairs of repeated RaytraceAll calls are served from memory the pool already holds.
+static void prepare_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
+
 struct DeviceBuffer {
     void* p = nullptr;
     size_t bytes = 0;
-    bool alloc(size_t n, std::string& err) {
+    bool alloc(size_t n, std::string& err, cudaStream_t st = 0) {
         bytes = n;
-        OCLR_CUDA(cudaMalloc(&p, n ? n : 16));
+        OCLR_CUDA(cudaMallocAsync(&p, n ? n : 16, st));
         return true;
     }
     bool upload(const void* src, size_t n, std::string& err, cudaStream_t st = 0) {
-        if (!alloc(n, err)) return false;
+        if (!alloc(n, err, st)) return false;
         if (n) OCLR_CUDA(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st));
         return true;
     }
-    void release() {
-        if (p) cudaFree(p);
+    void release(cudaStream_t st = 0) {
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
     }
 };
@@ -86,37 +100,81 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
         return false;
     }
     s->smCount = prop.multiProcessorCount;
+    prepare_pool(s->device);
     if (!validate_scene(h, err)) return false;
 
     const size_t N = h.triangleCount;
-    unsigned hw = std::thread::hardware_concurrency();
-    const int threads = hw ? (int)hw : 1;
-    // pack triangles straight into pinned staging so the H2D copy runs at full PCIe rate
-    float4 *geo = nullptr, *shade = nullptr;
-    OCLR_CUDA(cudaMallocHost((void**)&geo, sizeof(float4) * 4 * (N ? N : 1)));
-    OCLR_CUDA(cudaMallocHost((void**)&shade, sizeof(float4) * 8 * (N ? N : 1)));
-    pack_triangles(h, geo, shade, threads);
-    bool ok = s->triGeo.upload(geo, sizeof(float4) * 4 * N, err) && s->triShade.upload(shade, sizeof(float4) * 8 * N, err);
-    PackedGrid grid;
-    std::vector<Light> lights;
-    if (ok) ok = pack_grid(h, grid, err);
-    if (ok) {
-        pack_lights(h, lights);
-        ok = s->bricks.upload(grid.bricks.data(), sizeof(uint4) * grid.bricks.size(), err) &&
-             s->cellRange.upload(grid.cellRange.data(), sizeof(uint2) * grid.cellRange.size(), err) &&
-             s->cellList.upload(grid.cellList.data(), sizeof(uint32_t) * grid.cellList.size(), err) &&
-             s->planes.upload(grid.planes.data(), sizeof(float) * grid.planes.size(), err) &&
-             s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
-             s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
-             s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
-             s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err);
+    const int n = h.axesDivCount, nb = n >= 4 ? n / 4 : 1;
+    const size_t cells = (size_t)n * n * n, nBricks = (size_t)nb * nb * nb;
+    const uint32_t total = h.gridStart[cells];
+    if (total && !h.gridList) {
+        err = "scenePixelTriangleList missing";
+        return false;
     }
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFreeHost(geo);
-    cudaFreeHost(shade);
+    std::vector<Light> lights;
+    pack_lights(h, lights);
+
+    // 1. raw reference arrays -> HBM, straight from the caller's memory (async on the default stream)
+    DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag;
+    bool ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
+              triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
+              triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) && boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
+              gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
+              s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err) &&
+              s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
+              s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
+              s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
+              s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&
+              s->triGeo.alloc(sizeof(float4) * 4 * N, err) && s->triShade.alloc(sizeof(float4) * 8 * N, err) &&
+              s->bricks.alloc(sizeof(uint4) * nBricks, err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
+              counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err) &&
+              errFlag.alloc(sizeof(uint32_t) * 2, err);
+    uint32_t nonEmpty = 0, flag = 0;
+    if (ok) {
+        // 2. repack on the device
+        cudaMemsetAsync(errFlag.p, 0, sizeof(uint32_t) * 2, 0);
+        cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (nBricks + 1), 0);
+        if (N)
+            pack_triangles_kernel<<<(unsigned)((N + 255) / 256), 256>>>((uint32_t)N, h.vertexCount, h.materialCount, (const float4*)vertex.p,
+                                                                      (const int4*)triIdx.p, (const int32_t*)triMat.p, (const float2*)triUv.p,
+                                                                      (const float4*)triNormal.p, (float4*)s->triGeo.p,
+                                                                      (float4*)s->triShade.p, (uint32_t*)errFlag.p);
+        split_planes_kernel<<<(n + 1 + 127) / 128, 128>>>((const float4*)boxMin.p, n, (float*)s->planes.p);
+        brick_count_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (uint32_t*)counts.p,
+                                                                      (uint32_t*)errFlag.p);
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (const uint32_t*)counts.p, (uint32_t*)rankBase.p, (int)(nBricks + 1));
+        ok = scanTmp.alloc(tmpBytes, err);
+        if (ok) {
+            cub::DeviceScan::ExclusiveSum(scanTmp.p, tmpBytes, (const uint32_t*)counts.p, (uint32_t*)rankBase.p, (int)(nBricks + 1));
+            if (total) check_list_kernel<<<(total + 255) / 256, 256>>>((const uint32_t*)s->cellList.p, total, (uint32_t)N, (uint32_t*)errFlag.p);
+            cudaMemcpyAsync(&nonEmpty, (const uint32_t*)rankBase.p + nBricks, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+            cudaError_t e = cudaStreamSynchronize(0);
+            if (e != cudaSuccess) {
+                err = std::string("scene repack: ") + cudaGetErrorString(e);
+                ok = false;
+            }
+        }
+        if (ok) ok = s->cellRange.alloc(sizeof(uint2) * (nonEmpty ? nonEmpty : 1), err);
+        if (ok) {
+            brick_write_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (const uint32_t*)rankBase.p,
+                                                                          (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (uint32_t*)errFlag.p);
+            cudaMemcpyAsync(&flag, errFlag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(0);
+    DeviceBuffer* tmp[] = {&vertex, &triIdx, &triMat, &triUv, &triNormal, &boxMin, &gridStart, &counts, &rankBase, &scanTmp, &errFlag};
+    for (DeviceBuffer* b : tmp) b->release();
     if (!ok) return false;
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         err = std::string("scene upload: ") + cudaGetErrorString(e);
+        return false;
+    }
+    if (flag) {
+        err = std::string("scene arrays are inconsistent:") + ((flag & kPackBadVertexIndex) ? " triangleVertexIndex out of range;" : "") +
+              ((flag & kPackBadMaterial) ? " triangleMaterialId out of range;" : "") +
+              ((flag & kPackBadCsr) ? " scenePixelTriangleListStart is not a monotone CSR;" : "") +
+              ((flag & kPackBadListEntry) ? " scenePixelTriangleList entry out of range;" : "");
         return false;
     }
     SceneView& v = s->view;
@@ -133,8 +191,8 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     v.triangleCount = h.triangleCount;
     v.materialCount = h.materialCount;
     v.lightCount = h.lightCount;
-    v.n = grid.n;
-    v.nb = grid.nb;
+    v.n = n;
+    v.nb = nb;
     s->bytes = s->triGeo.bytes + s->triShade.bytes + s->bricks.bytes + s->cellRange.bytes + s->cellList.bytes + s->planes.bytes +
                s->matSize.bytes + s->matStart.bytes + s->textures.bytes + s->lights.bytes;
     return true;
@@ -164,6 +222,16 @@ void scene_destroy(Scene* s) {
 }
 
 size_t scene_device_bytes(const Scene* s) { return s->bytes; }
+
+// Debug/test door: copies one packed device array back (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList).
+size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap) {
+    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->planes, &s->cellList};
+    if (which < 0 || which > 5) return 0;
+    cudaSetDevice(s->device);
+    const size_t n = all[which]->bytes;
+    if (dst && n && n <= cap) cudaMemcpy(dst, all[which]->p, n, cudaMemcpyDeviceToHost);
+    return n;
+}
 int scene_device(const Scene* s) { return s->device; }
 
 static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
@@ -184,9 +252,9 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
     if (!f->counters.alloc(sizeof(Counters), err)) return false;
     if (!f->workCounter.alloc(sizeof(uint32_t) * 4, err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
-    OCLR_CUDA(cudaEventCreate(&f->ev0));
-    OCLR_CUDA(cudaEventCreate(&f->ev1));
-    OCLR_CUDA(cudaDeviceSynchronize());
+    OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
+    OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
+    OCLR_CUDA(cudaStreamSynchronize(0));
     return true;
 }
 

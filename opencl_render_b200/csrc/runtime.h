@@ -64,6 +64,7 @@ Scene* scene_create(int device, const HostScene& h, std::string& err);
 void scene_destroy(Scene* s);
 size_t scene_device_bytes(const Scene* s);
 int scene_device(const Scene* s);
+size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap);
 
 // Camera lists are per-frame inputs (CameraTriangleList::New output, trianglelist.cpp:520-626).  `camStart`/`camEnd`
 // hold width*height entries; only rows [rowBegin,rowEnd) need to be valid (band-partitioned multi-GPU rendering).

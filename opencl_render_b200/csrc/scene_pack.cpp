@@ -34,19 +34,7 @@ bool validate_scene(const HostScene& h, std::string& err) {
         err = "triangle arrays missing";
         return false;
     }
-    for (uint32_t i = 0; i < h.triangleCount; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            const int32_t v = h.triIdx[4 * (size_t)i + k];
-            if (v < 0 || (uint32_t)v >= h.vertexCount) {
-                err = "triangleVertexIndex out of range";
-                return false;
-            }
-        }
-        if (h.triMat[i] >= (int32_t)h.materialCount) {
-            err = "triangleMaterialId out of range";
-            return false;
-        }
-    }
+    // per-element range checks (vertex indices, material ids, CSR monotonicity, list entries) run in the device packers
     if (h.materialCount && (!h.matSize || !h.matStart)) {
         err = "material tables missing";
         return false;
@@ -126,8 +114,12 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
     }
     out.bricks.assign((size_t)nb * nb * nb, make_uint4(0, 0, 0, 0));
     out.cellRange.clear();
-    out.cellList.resize(total);
-    uint32_t cursor = 0;
+    out.cellList.assign(h.gridList, h.gridList + total);   // list kept in the reference's order; ranges point into it
+    for (uint32_t k = 0; k < total; ++k)
+        if (out.cellList[k] >= h.triangleCount) {
+            err = "scenePixelTriangleList entry out of range";
+            return false;
+        }
     const int side = n >= 4 ? 4 : n;
     for (int bz = 0; bz < nb; ++bz)
         for (int by = 0; by < nb; ++by)
@@ -145,15 +137,7 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
                             }
                             if (s < e) {
                                 mask |= 1ull << (x | (y << 2) | (z << 4));
-                                out.cellRange.push_back(make_uint2(cursor, cursor + (e - s)));
-                                for (uint32_t k = s; k < e; ++k) {
-                                    const uint32_t tri = h.gridList[k];
-                                    if (tri >= h.triangleCount) {
-                                        err = "scenePixelTriangleList entry out of range";
-                                        return false;
-                                    }
-                                    out.cellList[cursor++] = tri;
-                                }
+                                out.cellRange.push_back(make_uint2(s, e));
                             }
                         }
                 out.bricks[(size_t)bx + (size_t)nb * (by + (size_t)nb * bz)] =

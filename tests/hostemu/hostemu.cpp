@@ -86,3 +86,24 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     }
     return 1;
 }
+
+// Host packer output for comparison with the device packers (pack_kernels.cuh).  Buffers sized by the caller:
+// geo 64 B/tri, shade 128 B/tri, bricks 16 B/brick, ranges 8 B per non-empty cell (count returned), planes 3*(n+1) floats.
+extern "C" long hostemu_pack(const oclr_scene_desc* d, void* geo, void* shade, void* bricks, void* ranges, size_t rangesCap, void* planes) {
+    HostScene h;
+    h.vertexCount = d->vertexCount; h.vertex = (const float4*)d->vertex;
+    h.triangleCount = d->triangleCount; h.triIdx = (const int32_t*)d->triangleVertexIndex; h.triMat = d->triangleMaterialId;
+    h.triUv = (const float*)d->triangleUv; h.triNormal = (const float4*)d->triangleNormal;
+    h.axesDivCount = d->axesDivCount; h.boxMin = (const float4*)d->sceneBoxMin; h.gridStart = d->scenePixelTriangleListStart;
+    h.gridList = d->scenePixelTriangleList; h.materialCount = d->materialCount; h.matSize = (const uint2*)d->materialImageSize;
+    h.matStart = d->materialImageStart; h.texturesSize = d->texturesSize; h.textures = (const uchar4*)d->textures;
+    std::string err;
+    pack_triangles(h, (float4*)geo, (float4*)shade, 2);
+    PackedGrid grid;
+    if (!pack_grid(h, grid, err)) return -1;
+    memcpy(bricks, grid.bricks.data(), sizeof(uint4) * grid.bricks.size());
+    if (grid.cellRange.size() * sizeof(uint2) > rangesCap) return -2;
+    memcpy(ranges, grid.cellRange.data(), sizeof(uint2) * grid.cellRange.size());
+    memcpy(planes, grid.planes.data(), sizeof(float) * grid.planes.size());
+    return (long)grid.cellRange.size();
+}

@@ -112,6 +112,46 @@ def test_counters_equal_host_emulation(hostemu):
         assert cnt[k] == want[k], k
 
 
+def test_device_packers_equal_host_packers(hostemu):
+    """Scene upload path: the CUDA repack kernels (pack_kernels.cuh) produce byte-identical triGeo / triShade / bricks /
+    cellRange / planes to the host packer compiled by the tests (scene_pack.cpp, g++ -ffp-contract=off)."""
+    import ctypes as C
+    for name in ("spheres", "terrain_textured", "coarse_grid"):
+        sc, cam, lists, _ = helpers.make_case(name)
+        n, N = sc.axes_div, sc.triangle_count
+        nb = max(n // 4, 1)
+        geo, shade = np.zeros(64 * N, np.uint8), np.zeros(128 * N, np.uint8)
+        bricks, planes = np.zeros(16 * nb ** 3, np.uint8), np.zeros(12 * (n + 1), np.uint8)
+        ranges = np.zeros(8 * max(int((np.diff(sc.grid_start) > 0).sum()), 1), np.uint8)
+        d = sc.desc()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        hostemu.hostemu_pack.restype = C.c_long
+        cnt = hostemu.hostemu_pack(C.byref(d), p(geo), p(shade), p(bricks), p(ranges), C.c_size_t(ranges.size), p(planes))
+        assert cnt >= 0
+        ds = api.DeviceScene(sc, 0)
+        assert np.array_equal(ds.debug_read(0), geo) and np.array_equal(ds.debug_read(1), shade)
+        assert np.array_equal(ds.debug_read(2), bricks) and np.array_equal(ds.debug_read(4), planes)
+        assert np.array_equal(ds.debug_read(3)[:8 * cnt], ranges[:8 * cnt])
+        assert np.array_equal(ds.debug_read(5).view(np.uint32), sc.grid_list)
+        ds.close()
+
+
+def test_inconsistent_scene_is_refused():
+    sc, cam, lists, _ = helpers.make_case("soup")
+    bad = sc.tri_idx.copy()
+    bad[5, 1] = sc.vertex_count + 3
+    good = sc.tri_idx
+    sc.tri_idx = bad
+    with pytest.raises(api.OclrError, match="triangleVertexIndex"):
+        api.DeviceScene(sc, 0)
+    sc.tri_idx = good
+    gl = sc.grid_list.copy()
+    gl[7] = sc.triangle_count
+    sc.grid_list = gl
+    with pytest.raises(api.OclrError, match="scenePixelTriangleList"):
+        api.DeviceScene(sc, 0)
+
+
 def test_edge_cases(port):
     # empty scene, no lights, all-miss camera, single triangle, 1x1 image
     cam = api.set_camera((0, 4.4, -8), (0, 0, 0), (0, 1, 0), 0.9, 40, 30)
