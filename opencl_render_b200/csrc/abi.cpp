@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <atomic>
 #include <mutex>
@@ -295,13 +296,24 @@ int oclr_band_partition(cl_uint height, cl_uint bandRows, int rank, int worldSiz
     return owned;
 }
 
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 // ---- one frame on one device: upload, trace, read back ---------------------------------------------------------------------
 static bool render_rows_on_device(int device, const HostScene& h, const Camera& cam, const cl_uint* camStart, const cl_uint* camEnd,
                                   const cl_uint* camList, size_t camListSize, cl_uint sampleCount, int rank, int world,
                                   cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
+    const bool trace = getenv("OCLR_TRACE") != nullptr;
+    const double t0 = now_ms();
     Scene* s = scene_create(device, h, err);
     if (!s) return false;
+    const double t1 = now_ms();
     Frame* f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err);
+    const double t2 = now_ms();
+    double tRender = 0, tRead = 0;
     bool ok = f != nullptr;
     if (ok) {
         const int maxBands = (int)((cam.height + 127) / 128) + 1;
@@ -313,13 +325,21 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
         }
         for (int k = 0; ok && k < owned; ++k) {
             RenderStats rs;
+            const double a = now_ms();
             ok = frame_render(f, sampleCount, rows[2 * k], rows[2 * k + 1], kKernelPersistent, false, nullptr, &rs, err);
+            const double c = now_ms();
             if (ok) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
+            tRender += c - a;
+            tRead += now_ms() - c;
             if (world <= 1) g_progress.store(0.999f * (float)(k + 1) / (float)owned);
         }
     }
+    const double t3 = now_ms();
     if (f) frame_destroy(f);
     scene_destroy(s);
+    if (trace)
+        fprintf(stderr, "[opencl_render_b200] RaytraceAll dev %d: scene upload+repack %.2f ms, camera lists %.2f ms, trace %.2f ms, read back %.2f ms, "
+                        "release %.2f ms\n", device, t1 - t0, t2 - t1, tRender, tRead, now_ms() - t3);
     return ok;
 }
 

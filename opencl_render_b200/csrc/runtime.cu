@@ -93,13 +93,15 @@ bool device_name(int dev, char* buf, size_t len) {
 
 static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     OCLR_CUDA(cudaSetDevice(s->device));
-    cudaDeviceProp prop;
-    OCLR_CUDA(cudaGetDeviceProperties(&prop, s->device));
-    if (prop.major < 10) {
-        err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    int major = 0, minor = 0, sms = 0;   // attribute queries: cudaGetDeviceProperties costs milliseconds per call
+    OCLR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, s->device));
+    OCLR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, s->device));
+    OCLR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (major < 10) {
+        err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(major) + std::to_string(minor);
         return false;
     }
-    s->smCount = prop.multiProcessorCount;
+    s->smCount = sms;
     prepare_pool(s->device);
     if (!validate_scene(h, err)) return false;
 
