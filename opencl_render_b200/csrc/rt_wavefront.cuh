@@ -1,0 +1,482 @@
+// rt_wavefront.cuh -- the production form of the raytrace path on B200: a wavefront pipeline of two kernels.
+//
+// Why: ncu on the one-thread-per-pixel kernel (profiles/r01_simple_kernel_cfg2_details.txt) shows 5.65 active threads
+// per warp instruction -- ray/triangle tests run with ~3 lanes because at any DDA step only ~9 % of the cells a warp
+// looks at hold triangles, and every lane waits for the longest of three consecutive grid walks.  The path is issue-
+// bound with the working set in L2 (DRAM traffic 118 MB per frame), so the cure is lane utilisation, not bytes.
+//
+//   wf_logic_kernel   one thread per pixel-sample "path".  Runs the reference's per-pixel control flow
+//                     (raytrace_opencl.c:452-742: ray-gen, camera-list scan, shading, light sampling, bounce ring, RNG
+//                     in the reference's draw order) as a resumable state machine and SUSPENDS at every call of
+//                     RayIntersectsTriangles (:530 closest hit of a ring segment, :611 shadow/occluder ray), appending
+//                     the path to a ray queue.  Path state lives in HBM as SoA float4 planes: ring (12 slots x 48 B),
+//                     shading carry (112 B), ray (36 B), hit (16 B), rng (8 B), colour (16 B).
+//   wf_trace_kernel   persistent warps (grid = resident CTAs of all 148 SMs) drain the queue.  Each lane owns one ray;
+//                     lanes that finish are refilled from the queue with one warp-aggregated atomic (ballot + shuffle),
+//                     and work inside a warp is phase-batched: a WALK phase advances every lane's DDA to its next
+//                     non-empty cell (one bit test per empty cell from the 4x4x4 brick mask in registers), a TEST phase
+//                     then runs ray/triangle tests with all lanes that found triangles -- vote thresholds decide when
+//                     to switch.  Split planes sit in shared memory; triangle fetches are two 128-bit loads per stage.
+//
+// The host alternates the two kernels until the queue stays empty; the arithmetic is rt_core.h, identical to the
+// simple kernel, so results are bit-identical by construction (tests assert it).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "rt_kernels.cuh"
+
+namespace oclr {
+
+enum WfStage { kWfDone = 0, kWfNew = 1, kWfWaitClosest = 2, kWfWaitShadow = 3 };
+enum { kCarryParts = 7, kRingParts = 3 };
+
+// Path state (device pointers; Q = paths in the launch domain).  All float4 planes are [part][Q].
+struct WfState {
+    uint32_t Q;
+    uint32_t* ctl;       // stage | begin << 4 | end << 8 | light << 12
+    uint64_t* rng;
+    float4* colour;
+    float4* ring;        // [slot * 3 + part][Q]
+    float4* carry;       // [part][Q], part < 7
+    float4* rayO;        // (o.xyz, minD)
+    float4* rayD;        // (d.xyz, maxD)
+    uint32_t* rayExcl;
+    float4* hit;         // (as_float(tri), t, abL, acL)
+    uint32_t* queue;     // path indices waiting for a trace
+    uint32_t* queueCount;
+    uint32_t* queueCursor;
+};
+
+struct Segment {
+    f3 o, v, mul;
+    float minD;
+    int maxB;
+    uint32_t excl;
+    bool cam;
+};
+
+__device__ __forceinline__ void ring_store(const WfState& w, uint32_t q, int slot, const Segment& s) {
+    float4* p = w.ring + (size_t)(slot * kRingParts) * w.Q + q;
+    p[0] = make_float4(s.o.x, s.o.y, s.o.z, s.v.x);
+    p[w.Q] = make_float4(s.v.y, s.v.z, s.mul.x, s.mul.y);
+    p[2 * (size_t)w.Q] = make_float4(s.mul.z, s.minD, __int_as_float((s.maxB & 0xFFFF) | (s.cam ? 0x10000 : 0)), __uint_as_float(s.excl));
+}
+
+__device__ __forceinline__ Segment ring_load(const WfState& w, uint32_t q, int slot) {
+    const float4* p = w.ring + (size_t)(slot * kRingParts) * w.Q + q;
+    const float4 a = p[0], b = p[w.Q], c = p[2 * (size_t)w.Q];
+    Segment s;
+    s.o = mk3(a.x, a.y, a.z);
+    s.v = mk3(a.w, b.x, b.y);
+    s.mul = mk3(b.z, b.w, c.x);
+    s.minD = c.y;
+    const int packed = __float_as_int(c.z);
+    s.maxB = (int)(short)(packed & 0xFFFF);
+    s.cam = (packed & 0x10000) != 0;
+    s.excl = __float_as_uint(c.w);
+    return s;
+}
+
+// Appends path q to the ray queue: one atomic per warp (ballot + popc + shuffle).
+__device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want) {
+    const unsigned m = __ballot_sync(__activemask(), want);
+    if (!want) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(w.queueCount, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    w.queue[base + __popc(m & ((1u << lane) - 1u))] = q;
+}
+
+// ---- logic kernel -----------------------------------------------------------------------------------------------------
+// Thread -> path mapping keeps a warp on an 8x4 pixel tile, so queue entries appended by a warp are spatially coherent.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) wf_logic_kernel(SceneView S, FrameView F, WfState w, uint32_t sampleIdx, uint32_t startSample,
+                                                       Counters* gcnt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t k = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t y = map_row(F, k);
+    const bool valid = x < F.cam.width && y < F.cam.height;
+    const uint32_t q = k * F.cam.width + x;
+    const uint32_t pixel = valid ? y * F.cam.width + x : 0;
+    uint32_t ctl = valid ? (startSample ? (uint32_t)kWfNew : w.ctl[q]) : (uint32_t)kWfDone;
+    int stage = (int)(ctl & 7u);
+    bool want = false;
+    if (stage != kWfDone) {
+        Counters cnt = {};
+        const Camera& cam = F.cam;
+        int begin = (int)((ctl >> 4) & 15u), end = (int)((ctl >> 8) & 15u);
+        uint32_t j = (ctl >> 12) & 0xFFFFu;
+        uint64_t rng;
+        f3 colour;
+        Segment seg;
+        uint32_t hit = kNoTriangle;
+        float hitT = 0.f, hitAB = 0.f, hitAC = 0.f;
+        // shading state
+        f3 loc, nrm, tex, transp, refl, lum, att;
+        f3 face[2];
+        LightRay lr;
+        bool undef = false;
+        bool first = (stage == kWfNew);
+        enum { GO_SEGMENT, GO_SHADE, GO_LIGHTS, GO_FINISH, GO_POP, GO_EXIT } go;
+
+        if (stage == kWfNew) {
+            rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
+            colour = mk3(0.f, 0.f, 0.f);
+            const float fx = (float)(pixel % cam.width), fy = (float)(pixel / cam.width);
+            seg.maxB = kMaxBounces;
+            seg.excl = kNoTriangle;
+            seg.o = mk3(cam.eye);
+            seg.v = mk3(cam.eyeToTopLeft);
+            float tmp = fx + rand_f(rng, 0.f, 1.f);
+            seg.v.x += cam.leftToRight[0] * tmp;
+            seg.v.y += cam.leftToRight[1] * tmp;
+            seg.v.z += cam.leftToRight[2] * tmp;
+            tmp = fy + rand_f(rng, 0.f, 1.f);
+            seg.v.x += cam.topToBottom[0] * tmp;
+            seg.v.y += cam.topToBottom[1] * tmp;
+            seg.v.z += cam.topToBottom[2] * tmp;
+            seg.mul = mk3(1.f, 1.f, 1.f);
+            seg.cam = true;
+            seg.minD = 0.f;
+            begin = 0;
+            end = 1;
+            ring_store(w, q, 0, seg);
+            go = GO_SEGMENT;
+        } else {
+            rng = w.rng[q];
+            const float4 c4 = w.colour[q];
+            colour = mk3(c4.x, c4.y, c4.z);
+            seg = ring_load(w, q, begin);
+            const float4 h = w.hit[q];
+            hit = __float_as_uint(h.x);
+            if (stage == kWfWaitClosest) {
+                hitT = h.y;
+                hitAB = h.z;
+                hitAC = h.w;
+                go = (hit == kNoTriangle) ? GO_POP : GO_SHADE;
+            } else {  // kWfWaitShadow: the occluder query of light j returned
+                const float4* cp = w.carry + q;
+                const float4 k0 = cp[0], k1 = cp[w.Q], k2 = cp[2 * (size_t)w.Q], k3 = cp[3 * (size_t)w.Q], k4 = cp[4 * (size_t)w.Q],
+                             k5 = cp[5 * (size_t)w.Q], k6 = cp[6 * (size_t)w.Q];
+                nrm = mk3(k0.x, k0.y, k0.z);
+                hitT = k0.w;
+                tex = mk3(k1.x, k1.y, k1.z);
+                const uint32_t shaded = __float_as_uint(k1.w);
+                refl = mk3(k2.x, k2.y, k2.z);
+                transp = mk3(k2.w, k3.x, k3.y);
+                lum = mk3(k3.z, k3.w, k4.x);
+                att = mk3(k4.y, k4.z, k4.w);
+                face[0] = mk3(k5.x, k5.y, k5.z);
+                face[1] = mk3(k6.x, k6.y, k6.z);
+                const float4 ro4 = w.rayO[q], rd4 = w.rayD[q];
+                loc = mk3(ro4.x, ro4.y, ro4.z);
+                lr.dir = mk3(rd4.x, rd4.y, rd4.z);
+                lr.minLen = ro4.w;
+                lr.maxLen = rd4.w;
+                const uint32_t occ = hit;
+                hit = shaded;
+                bool again = false;
+                if (occ != kNoTriangle) {  // raytrace_opencl.c:613-625
+                    int om;
+                    float u0, v0, u1, v1, u2, v2;
+                    load_mat_uv(S, occ, om, u0, v0, u1, v1, u2, v2);
+                    f3 tr = mk3(0.f, 0.f, 0.f);
+                    uint2 sz;
+                    if (channel_present(S, om, kChTransparency, sz)) {
+                        if (COUNT) cnt.occluderLookups++;
+                        const int start = __ldg(S.matStart + kMaterialChannels * om + kChTransparency);
+                        tr = table_value(S.textures + start, sz, u0, v0, u1, v1, u2, v2, h.z, h.w);
+                    }
+                    att.x *= tr.x;
+                    att.y *= tr.y;
+                    att.z *= tr.z;
+                    if (0.f < att.x && 0.f < att.y && 0.f < att.z) {
+                        again = true;
+                        w.rayO[q] = make_float4(loc.x, loc.y, loc.z, h.y);  // toLightVectorMinLength = mult
+                        w.carry[4 * (size_t)w.Q + q] = make_float4(lum.z, att.x, att.y, att.z);
+                    }
+                }
+                if (again) {
+                    want = true;
+                    go = GO_EXIT;
+                } else {
+                    light_accumulate(S.lights[j], nrm, lr, att, face);
+                    ++j;
+                    go = GO_LIGHTS;
+                }
+            }
+        }
+
+        while (go != GO_EXIT) {
+            if (go == GO_SEGMENT) {
+                if (COUNT) cnt.segments++;
+                if (seg.cam) {  // raytrace_opencl.c:514-528
+                    hit = kNoTriangle;
+                    hitT = OCLR_INF;
+                    hitAB = hitAC = 0.f;
+                    const uint32_t e = __ldg(F.camEnd + pixel);
+                    for (uint32_t i = __ldg(F.camStart + pixel); i < e; ++i) {
+                        const uint32_t tri = __ldg(F.camList + i);
+                        if (seg.excl != tri) {
+                            float t, ab, ac;
+                            if (COUNT) cnt.primCandidates++;
+                            if (tri_test(S.triGeo + 4 * (size_t)tri, seg.o, seg.v, seg.minD, hitT, t, ab, ac)) {
+                                hitT = t;
+                                hit = tri;
+                                hitAB = ab;
+                                hitAC = ac;
+                            }
+                        }
+                    }
+                    if (first && F.idOut && sampleIdx == 0) F.idOut[pixel] = hit;
+                    first = false;
+                    go = (hit == kNoTriangle) ? GO_POP : GO_SHADE;
+                } else {
+                    w.rayO[q] = make_float4(seg.o.x, seg.o.y, seg.o.z, seg.minD);
+                    w.rayD[q] = make_float4(seg.v.x, seg.v.y, seg.v.z, OCLR_INF);
+                    w.rayExcl[q] = seg.excl;
+                    stage = kWfWaitClosest;
+                    want = true;
+                    go = GO_EXIT;
+                }
+            } else if (go == GO_SHADE) {  // :532-561
+                if (COUNT) cnt.shadedHits++;
+                const TriShade ts = load_shade(S, hit);
+                tex = transp = refl = lum = mk3(0.f, 0.f, 0.f);
+                face[0] = face[1] = mk3(0.1f, 0.1f, 0.1f);
+                loc = mk3(seg.o.x + hitT * seg.v.x, seg.o.y + hitT * seg.v.y, seg.o.z + hitT * seg.v.z);
+                nrm = triangle_normal(S, cam, ts, loc, seg.o, seg.v, hitAB, hitAC, undef);
+                uint2 sz;
+                if (channel_present(S, ts.mat, kChColor, sz)) tex = channel_value(S, ts.mat, kChColor, sz, ts, hitAB, hitAC);
+                if (channel_present(S, ts.mat, kChTransparency, sz)) transp = channel_value(S, ts.mat, kChTransparency, sz, ts, hitAB, hitAC);
+                if (channel_present(S, ts.mat, kChReflection, sz)) refl = channel_value(S, ts.mat, kChReflection, sz, ts, hitAB, hitAC);
+                if (channel_present(S, ts.mat, kChLuminance, sz)) lum = channel_value(S, ts.mat, kChLuminance, sz, ts, hitAB, hitAC);
+                j = 0;
+                go = GO_LIGHTS;
+            } else if (go == GO_LIGHTS) {  // :563-637, suspended at :611
+                go = GO_FINISH;
+                while (j < S.lightCount) {
+                    att = mk3(1.f, 1.f, 1.f);
+                    light_ray(S.lights[j], loc, rng, lr);
+                    if (lr.minLen < lr.maxLen) {
+                        w.rayO[q] = make_float4(loc.x, loc.y, loc.z, lr.minLen);
+                        w.rayD[q] = make_float4(lr.dir.x, lr.dir.y, lr.dir.z, lr.maxLen);
+                        w.rayExcl[q] = hit;
+                        float4* cp = w.carry + q;
+                        cp[0] = make_float4(nrm.x, nrm.y, nrm.z, hitT);
+                        cp[w.Q] = make_float4(tex.x, tex.y, tex.z, __uint_as_float(hit));
+                        cp[2 * (size_t)w.Q] = make_float4(refl.x, refl.y, refl.z, transp.x);
+                        cp[3 * (size_t)w.Q] = make_float4(transp.y, transp.z, lum.x, lum.y);
+                        cp[4 * (size_t)w.Q] = make_float4(lum.z, att.x, att.y, att.z);
+                        cp[5 * (size_t)w.Q] = make_float4(face[0].x, face[0].y, face[0].z, 0.f);
+                        cp[6 * (size_t)w.Q] = make_float4(face[1].x, face[1].y, face[1].z, 0.f);
+                        stage = kWfWaitShadow;
+                        want = true;
+                        go = GO_EXIT;
+                        break;
+                    }
+                    light_accumulate(S.lights[j], nrm, lr, att, face);
+                    ++j;
+                }
+            } else if (go == GO_FINISH) {  // :639-722
+                const f3 rm = seg.mul, rv = seg.v;
+                colour.x += (1.f - colour.x) * lum.x * rm.x;
+                colour.y += (1.f - colour.y) * lum.y * rm.y;
+                colour.z += (1.f - colour.z) * lum.z * rm.z;
+                const int front = (int)(dot3(nrm, rv) <= 0.f);
+                const f3 light = face[front];
+                colour.x += (1.f - colour.x) * rm.x * (1.f - transp.x) * tex.x * light.x;
+                colour.y += (1.f - colour.y) * rm.y * (1.f - transp.y) * tex.y * light.y;
+                colour.z += (1.f - colour.z) * rm.z * (1.f - transp.z) * tex.z * light.z;
+                go = GO_POP;
+                if (seg.maxB > 0) {
+                    float total = (refl.x + transp.x) > (refl.y + transp.y) ? (refl.x + transp.x) : (refl.y + transp.y);
+                    total = total > (refl.z + transp.z) ? total : (refl.z + transp.z);
+                    f3 diffuse = mk3(0.f, 0.f, 0.f);
+                    if (total < 1.f) diffuse = mk3(1.f - total, 1.f - total, 1.f - total);
+                    bool full = false;
+                    Segment ns;
+                    ns.excl = hit;
+                    ns.mul = mk3(rm.x * tex.x * diffuse.x, rm.y * tex.y * diffuse.y, rm.z * tex.z * diffuse.z);
+                    if (3.f / 256.f <= ns.mul.x + ns.mul.y + ns.mul.z) {  // diffuse bounce
+                        f3 d = sphere_point(rng, 1.f);
+                        if (front != (int)(0 <= dot3(d, nrm))) d = mk3(-d.x, -d.y, -d.z);
+                        ns.maxB = 0;
+                        ns.o = loc;
+                        ns.v = d;
+                        ns.cam = false;
+                        ns.minD = 0.f;
+                        ring_store(w, q, end, ns);
+                        end = (end + 1) % kRingSize;
+                        full = ((end + 1) % kRingSize == begin);
+                    }
+                    if (!full) {
+                        ns.mul = mk3(rm.x * tex.x * refl.x, rm.y * tex.y * refl.y, rm.z * tex.z * refl.z);
+                        if (3.f / 256.f <= ns.mul.x + ns.mul.y + ns.mul.z) {  // mirror
+                            const float tmp = -2.f * dot3(nrm, rv);
+                            ns.maxB = seg.maxB - 1;
+                            ns.o = loc;
+                            ns.v = mk3(rv.x + tmp * nrm.x, rv.y + tmp * nrm.y, rv.z + tmp * nrm.z);
+                            ns.cam = false;
+                            ns.minD = 0.f;
+                            ring_store(w, q, end, ns);
+                            end = (end + 1) % kRingSize;
+                            full = ((end + 1) % kRingSize == begin);
+                        }
+                    }
+                    if (!full) {
+                        ns.mul = mk3(rm.x * tex.x * transp.x, rm.y * tex.y * transp.y, rm.z * tex.z * transp.z);
+                        if (3.f / 256.f <= ns.mul.x + ns.mul.y + ns.mul.z) {  // glass
+                            ns.maxB = seg.maxB - 1;
+                            ns.o = seg.o;
+                            ns.v = rv;
+                            ns.cam = seg.cam;
+                            ns.minD = hitT;
+                            ring_store(w, q, end, ns);
+                            end = (end + 1) % kRingSize;
+                        }
+                    }
+                }
+            } else {  // GO_POP
+                begin = (begin + 1) % kRingSize;
+                if (begin == end) {
+                    const float scale = 65535.f / (float)F.sampleCount;
+                    const uint16_t pr = sampleIdx ? F.outR[pixel] : (uint16_t)0;
+                    const uint16_t pg = sampleIdx ? F.outG[pixel] : (uint16_t)0;
+                    const uint16_t pb = sampleIdx ? F.outB[pixel] : (uint16_t)0;
+                    F.outR[pixel] = accumulate16(pr, colour.x, scale);
+                    F.outG[pixel] = accumulate16(pg, colour.y, scale);
+                    F.outB[pixel] = accumulate16(pb, colour.z, scale);
+                    stage = kWfDone;
+                    go = GO_EXIT;
+                } else {
+                    seg = ring_load(w, q, begin);
+                    stage = kWfWaitClosest;  // provisional; GO_SEGMENT decides
+                    go = GO_SEGMENT;
+                }
+            }
+        }
+        if (undef && F.flagOut) F.flagOut[pixel] = 1;
+        if (stage != kWfDone) {
+            w.rng[q] = rng;
+            w.colour[q] = make_float4(colour.x, colour.y, colour.z, 0.f);
+        }
+        w.ctl[q] = (uint32_t)stage | ((uint32_t)begin << 4) | ((uint32_t)end << 8) | (j << 12);
+        if (COUNT) flush_counters(cnt, gcnt);
+    }
+    enqueue(w, q, want);
+}
+
+// ---- trace kernel -------------------------------------------------------------------------------------------------------
+enum { kLaneIdle = 0, kLaneWalk = 1, kLaneTest = 2 };
+
+#ifndef OCLR_WALK_MIN
+#define OCLR_WALK_MIN 10   // keep walking while at least this many lanes of the warp are still looking for triangles
+#endif
+#ifndef OCLR_TEST_MIN
+#define OCLR_TEST_MIN 10   // keep testing while at least this many lanes have candidates pending
+#endif
+#ifndef OCLR_REFILL_MIN
+#define OCLR_REFILL_MIN 8  // refill from the queue once this many lanes are idle
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w, Counters* gcnt) {
+    extern __shared__ float shPlanes[];
+    load_planes(shPlanes, S);
+    const float* px = shPlanes;
+    const float* py = shPlanes + (S.n + 1);
+    const float* pz = shPlanes + 2 * (S.n + 1);
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t count = *w.queueCount;
+    const int n = S.n;
+
+    Counters cnt = {};
+    int st = kLaneIdle;
+    bool exhausted = false;
+    uint32_t path = 0;
+    GridWalk g;
+    uint32_t i = 0, iEnd = 0;
+    uint32_t best = kNoTriangle;
+    float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
+
+    for (;;) {
+        // ---- refill idle lanes from the queue: one atomic per warp ----
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == kLaneIdle);
+        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= OCLR_REFILL_MIN)) {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(w.queueCursor, (uint32_t)nIdle);
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + (uint32_t)nIdle >= count) exhausted = true;
+            if (st == kLaneIdle) {
+                const uint32_t idx = base + (uint32_t)__popc(idle & ltMask);
+                if (idx < count) {
+                    path = w.queue[idx];
+                    const float4 ro = w.rayO[path], rd = w.rayD[path];
+                    walk_begin(g, S, px, py, pz, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w, w.rayExcl[path]);
+                    best = kNoTriangle;
+                    st = kLaneWalk;
+                    if (COUNT) cnt.gridRays++;
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, st != kLaneIdle) == 0u) break;
+
+        // ---- WALK phase: advance to the next non-empty cell (or off the grid / to the end cell) ----
+        for (;;) {
+            if (st == kLaneWalk) {
+                uint2 range;
+                if (walk_cell<COUNT>(g, S, range, &cnt)) {
+                    i = range.x;
+                    iEnd = range.y;
+                    bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
+                    st = kLaneTest;
+                } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step(g, n, px, py, pz)) {
+                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
+                    st = kLaneIdle;
+                }
+            }
+            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneWalk)) < OCLR_WALK_MIN) break;
+        }
+
+        // ---- TEST phase: one candidate per lane per iteration ----
+        for (;;) {
+            if (st == kLaneTest) {
+                const uint32_t tri = __ldg(S.cellList + i);
+                if (tri != g.excl) {
+                    float t, ab, ac;
+                    if (COUNT) cnt.gridCandidates++;
+                    if (tri_test(S.triGeo + 4 * (size_t)tri, g.o, g.r, g.minD, bestT, t, ab, ac)) {
+                        best = tri;
+                        bestT = t;
+                        bestAB = ab;
+                        bestAC = ac;
+                    }
+                }
+                if (++i == iEnd) {
+                    if (best != kNoTriangle) {  // first cell with any hit wins (:380)
+                        w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
+                        st = kLaneIdle;
+                    } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step(g, n, px, py, pz)) {
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
+                        st = kLaneIdle;
+                    } else {
+                        st = kLaneWalk;
+                    }
+                }
+            }
+            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneTest)) < OCLR_TEST_MIN) break;
+        }
+    }
+    if (COUNT) flush_counters(cnt, gcnt);
+}
+
+}  // namespace oclr

@@ -6,11 +6,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <thread>
 
 #include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
-#include "rt_persistent.cuh"
+#include "rt_wavefront.cuh"
 #include "runtime.h"
 
 namespace oclr {
@@ -68,6 +69,10 @@ struct Frame {
     Scene* scene = nullptr;
     Camera cam = {};
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
+    // wavefront path state (allocated on first use, sized for the largest launch domain seen)
+    DeviceBuffer wfCtl, wfRng, wfColour, wfRing, wfCarry, wfRayO, wfRayD, wfRayExcl, wfHit, wfQueue;
+    uint32_t wfCapacity = 0;
+    uint32_t* hostCount = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t lastLaunches = 0;
 };
@@ -283,8 +288,11 @@ Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const
 void frame_destroy(Frame* f) {
     if (!f) return;
     cudaSetDevice(f->scene->device);
-    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter};
+    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter,
+                           &f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl, &f->wfHit,
+                           &f->wfQueue};
     for (DeviceBuffer* b : all) b->release();
+    if (f->hostCount) cudaFreeHost(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     delete f;
@@ -295,6 +303,82 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
     uint32_t owned = 0;
     for (uint32_t b0 = rank * bandRows; b0 < height; b0 += bandRows * world) owned += (b0 + bandRows <= height) ? bandRows : height - b0;
     return owned;
+}
+
+// Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
+static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
+                             uint32_t& launches, std::string& err) {
+    const uint32_t rows = launch_rows(F), W = F.cam.width;
+    const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
+    if (Q64 > 0xFFFFFFF0ull) {
+        err = "launch domain too large";
+        return false;
+    }
+    const uint32_t Q = (uint32_t)Q64;
+    if (Q > f->wfCapacity) {
+        DeviceBuffer* all[] = {&f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl,
+                               &f->wfHit, &f->wfQueue};
+        for (DeviceBuffer* b : all) b->release(st);
+        if (!f->wfCtl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) || !f->wfRng.alloc(sizeof(uint64_t) * (size_t)Q, err, st) ||
+            !f->wfColour.alloc(sizeof(float4) * (size_t)Q, err, st) ||
+            !f->wfRing.alloc(sizeof(float4) * (size_t)Q * kRingSize * kRingParts, err, st) ||
+            !f->wfCarry.alloc(sizeof(float4) * (size_t)Q * kCarryParts, err, st) || !f->wfRayO.alloc(sizeof(float4) * (size_t)Q, err, st) ||
+            !f->wfRayD.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfRayExcl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
+            !f->wfHit.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfQueue.alloc(sizeof(uint32_t) * (size_t)Q, err, st))
+            return false;
+        f->wfCapacity = Q;
+    }
+    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * 2, cudaHostAllocDefault));
+    WfState w;
+    w.Q = Q;
+    w.ctl = (uint32_t*)f->wfCtl.p;
+    w.rng = (uint64_t*)f->wfRng.p;
+    w.colour = (float4*)f->wfColour.p;
+    w.ring = (float4*)f->wfRing.p;
+    w.carry = (float4*)f->wfCarry.p;
+    w.rayO = (float4*)f->wfRayO.p;
+    w.rayD = (float4*)f->wfRayD.p;
+    w.rayExcl = (uint32_t*)f->wfRayExcl.p;
+    w.hit = (float4*)f->wfHit.p;
+    w.queue = (uint32_t*)f->wfQueue.p;
+    w.queueCount = (uint32_t*)f->workCounter.p;
+    w.queueCursor = w.queueCount + 1;
+
+    const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
+    int perSm = 0;
+    if (dcnt)
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<true>, 128, shBytes));
+    else
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
+    if (perSm < 1) perSm = 1;
+    const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
+    const unsigned traceGrid = (unsigned)(smCount * perSm);
+    if (F.flagOut) OCLR_CUDA(cudaMemsetAsync(F.flagOut, 0, (size_t)F.cam.width * F.cam.height, st));
+    for (uint32_t s = 0; s < F.sampleCount; ++s) {
+        for (uint32_t round = 0;; ++round) {
+            OCLR_CUDA(cudaMemsetAsync(w.queueCount, 0, sizeof(uint32_t) * 2, st));
+            if (dcnt)
+                wf_logic_kernel<true><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, dcnt);
+            else
+                wf_logic_kernel<false><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, dcnt);
+            ++launches;
+            OCLR_CUDA(cudaMemcpyAsync(f->hostCount, w.queueCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            OCLR_CUDA(cudaStreamSynchronize(st));
+            const uint32_t waiting = f->hostCount[0];
+            if (waiting == 0) break;
+            const unsigned grid = (unsigned)std::min<uint64_t>(traceGrid, ((uint64_t)waiting + 127) / 128);
+            if (dcnt)
+                wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, dcnt);
+            else
+                wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, dcnt);
+            ++launches;
+            if (round > 100000) {
+                err = "wavefront did not converge";
+                return false;
+            }
+        }
+    }
+    return true;
 }
 
 static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
@@ -323,7 +407,7 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
             raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         launches = 1;
     } else if (variant == kKernelPersistent) {
-        if (!launch_persistent(s->view, F, s->smCount, (uint32_t*)f->workCounter.p, count ? dcnt : nullptr, st, launches, err)) return false;
+        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, err)) return false;
     } else {
         err = "unknown kernel variant";
         return false;
