@@ -63,7 +63,8 @@ def build_workload(cfg_id):
 def algorithmic_bytes(cnt: dict, rays: int) -> float:
     """B = 8*[primary ray] + 68*C_prim + 8*K_cells + 68*C_grid + 212*H + 44*O + 12 per pixel-sample, counted
     in the reference layout; totals per launch."""
-    return (8.0 * rays + 68.0 * cnt["primCandidates"] + 8.0 * cnt["cells"] + 68.0 * cnt["gridCandidates"] + 212.0 * cnt["shadedHits"] +
+    grid_candidates = cnt["gridCandidates"] + cnt.get("mailboxSkips", 0)     # the reference tests these again in every cell
+    return (8.0 * rays + 68.0 * cnt["primCandidates"] + 8.0 * cnt["cells"] + 68.0 * grid_candidates + 212.0 * cnt["shadedHits"] +
             44.0 * cnt["occluderLookups"] + 12.0 * rays)
 
 

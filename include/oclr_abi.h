@@ -217,7 +217,8 @@ typedef struct oclr_frame oclr_frame;
 /* Per-launch event counts behind the algorithmic-bytes figure. */
 typedef struct oclr_counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
-        occluderLookups, bricksLoaded;
+        occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
+        mailboxSkips;
 } oclr_counters;
 
 typedef struct oclr_render_stats {

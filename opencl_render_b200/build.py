@@ -37,7 +37,7 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     stamp = OBJ / "stamp.txt"
-    dig = _digest()
+    dig = _digest() + os.environ.get("OCLR_NVCC_DEFS", "")
     if LIB.is_file() and not force and stamp.is_file() and stamp.read_text() == dig:
         return LIB
     if not (CUDA / "bin" / "nvcc").is_file():
@@ -50,7 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         src = CSRC / name
         obj = OBJ / (name + ".o")
         if tool == "nvcc":
-            cmd = [str(CUDA / "bin" / "nvcc"), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            extra = os.environ.get("OCLR_NVCC_DEFS", "").split()      # experiment knob, e.g. -DOCLR_TRACE_MIN_CTAS=10
+            cmd = [str(CUDA / "bin" / "nvcc"), *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         elif tool == "g++":
             cmd = ["g++", *CXX_FLAGS, "-c", str(src), "-o", str(obj)]
         else:

@@ -240,6 +240,7 @@ OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* 
     }
     const int bit = (w.cx & 3) | ((w.cy & 3) << 2) | ((w.cz & 3) << 4);
     if (COUNT) cnt->cells++;
+    if (COUNT && w.mask == 0ull) cnt->emptyBrickCells++;
     if ((w.mask >> bit) & 1ull) {
         const uint32_t rank = w.rankBase + (uint32_t)OCLR_POPCLL(w.mask & ((1ull << bit) - 1ull));
         range = OCLR_LDG(S.cellRange + rank);
@@ -250,23 +251,26 @@ OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* 
 }
 
 // Advance to the next cell (:383-398).  Returns false when the walk left the grid.
+// Branch-free form of the reference's three-way if/else: the axis is selected first (same comparisons, same tie rule:
+// x only if strictly smallest, else y if strictly smaller than z, else z -- NaNs fall through to z), then ONE step, one
+// shared-memory plane fetch and one IEEE division run for whichever axis was chosen, so the lanes of a warp stay converged.
 OCLR_HD bool walk_step(GridWalk& w, int n, const float* px, const float* py, const float* pz) {
-    if ((w.tx < w.ty) & (w.tx < w.tz)) {
-        const int up = (0 <= w.r.x);
-        w.cx += up ? 1 : -1;
-        if (w.cx < 0 || n <= w.cx) return false;
-        w.tx = (px[w.cx + up] - w.o.x) / w.r.x;
-    } else if (w.ty < w.tz) {
-        const int up = (0 <= w.r.y);
-        w.cy += up ? 1 : -1;
-        if (w.cy < 0 || n <= w.cy) return false;
-        w.ty = (py[w.cy + up] - w.o.y) / w.r.y;
-    } else {
-        const int up = (0 <= w.r.z);
-        w.cz += up ? 1 : -1;
-        if (w.cz < 0 || n <= w.cz) return false;
-        w.tz = (pz[w.cz + up] - w.o.z) / w.r.z;
-    }
+    const bool xmin = (w.tx < w.ty) & (w.tx < w.tz);
+    const bool ymin = (!xmin) & (w.ty < w.tz);
+    int c = xmin ? w.cx : (ymin ? w.cy : w.cz);
+    const float rr = xmin ? w.r.x : (ymin ? w.r.y : w.r.z);
+    const float oo = xmin ? w.o.x : (ymin ? w.o.y : w.o.z);
+    const float* p = xmin ? px : (ymin ? py : pz);
+    const int up = (0 <= rr);
+    c += up ? 1 : -1;
+    if (c < 0 || n <= c) return false;
+    const float t = (p[c + up] - oo) / rr;
+    w.cx = xmin ? c : w.cx;
+    w.tx = xmin ? t : w.tx;
+    w.cy = ymin ? c : w.cy;
+    w.ty = ymin ? t : w.ty;
+    w.cz = (xmin | ymin) ? w.cz : c;
+    w.tz = (xmin | ymin) ? w.tz : t;
     return true;
 }
 

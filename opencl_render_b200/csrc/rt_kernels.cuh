@@ -25,6 +25,12 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     atomicAdd(&g->shadedHits, c.shadedHits);
     atomicAdd(&g->occluderLookups, c.occluderLookups);
     atomicAdd(&g->bricksLoaded, c.bricksLoaded);
+    atomicAdd(&g->emptyBrickCells, c.emptyBrickCells);
+    if (c.walkWarpIters) atomicAdd(&g->walkWarpIters, c.walkWarpIters);
+    if (c.walkLaneIters) atomicAdd(&g->walkLaneIters, c.walkLaneIters);
+    if (c.testWarpIters) atomicAdd(&g->testWarpIters, c.testWarpIters);
+    if (c.testLaneIters) atomicAdd(&g->testLaneIters, c.testLaneIters);
+    if (c.mailboxSkips) atomicAdd(&g->mailboxSkips, c.mailboxSkips);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

@@ -107,7 +107,8 @@ OCLR_HD uint32_t launch_rows(const FrameView& F) { return F.bandWorld <= 1 ? F.r
 // of the kernel touches them.
 struct Counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
-        occluderLookups, bricksLoaded;
+        occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
+        mailboxSkips;
 };
 
 }  // namespace oclr

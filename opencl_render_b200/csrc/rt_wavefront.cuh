@@ -374,20 +374,26 @@ __global__ void __launch_bounds__(128) wf_logic_kernel(SceneView S, FrameView F,
 
 // ---- trace kernel -------------------------------------------------------------------------------------------------------
 enum { kLaneIdle = 0, kLaneWalk = 1, kLaneTest = 2 };
+enum { kMailboxSlots = 16 };
 
-#ifndef OCLR_WALK_MIN
-#define OCLR_WALK_MIN 10   // keep walking while at least this many lanes of the warp are still looking for triangles
+// Vote thresholds of the trace kernel (tunable at run time through OCLR_WALK_MIN / OCLR_TEST_MIN / OCLR_REFILL_MIN).
+#ifndef OCLR_TRACE_MIN_CTAS
+#define OCLR_TRACE_MIN_CTAS 8
 #endif
-#ifndef OCLR_TEST_MIN
-#define OCLR_TEST_MIN 10   // keep testing while at least this many lanes have candidates pending
-#endif
-#ifndef OCLR_REFILL_MIN
-#define OCLR_REFILL_MIN 8  // refill from the queue once this many lanes are idle
-#endif
+struct TraceTuning {
+    int walkMin;     // keep walking while at least this many lanes of the warp are still looking for triangles
+    int testMin;     // keep testing while at least this many lanes have candidates pending
+    int refillMin;   // refill from the queue once this many lanes are idle
+};
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w, Counters* gcnt) {
+__global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(SceneView S, WfState w, TraceTuning tune, Counters* gcnt) {
     extern __shared__ float shPlanes[];
+    // Per-lane mailbox: a direct-mapped cache of the triangle ids this ray has already tested, [slot][thread] so a warp
+    // never bank-conflicts.  Skipping a cached id is EXACT: a cell that did not end the walk produced no hit, so its
+    // in-cell bound stayed at maxDistance (:366) and every triangle tested there failed either the (min, max) range
+    // or the barycentric test -- both ray/triangle properties that do not change in a later cell.
+    __shared__ uint32_t mailbox[kMailboxSlots][128];
     load_planes(shPlanes, S);
     const float* px = shPlanes;
     const float* py = shPlanes + (S.n + 1);
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w
     for (;;) {
         // ---- refill idle lanes from the queue: one atomic per warp ----
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == kLaneIdle);
-        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= OCLR_REFILL_MIN)) {
+        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
             const int nIdle = __popc(idle);
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
@@ -424,6 +430,8 @@ __global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w
                     walk_begin(g, S, px, py, pz, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w, w.rayExcl[path]);
                     best = kNoTriangle;
                     st = kLaneWalk;
+#pragma unroll
+                    for (int k = 0; k < kMailboxSlots; ++k) mailbox[k][threadIdx.x] = kNoTriangle;
                     if (COUNT) cnt.gridRays++;
                 }
             }
@@ -432,6 +440,10 @@ __global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w
 
         // ---- WALK phase: advance to the next non-empty cell (or off the grid / to the end cell) ----
         for (;;) {
+            if (COUNT) {
+                if (lane == 0) cnt.walkWarpIters++;
+                if (st == kLaneWalk) cnt.walkLaneIters++;
+            }
             if (st == kLaneWalk) {
                 uint2 range;
                 if (walk_cell<COUNT>(g, S, range, &cnt)) {
@@ -444,24 +456,35 @@ __global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w
                     st = kLaneIdle;
                 }
             }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneWalk)) < OCLR_WALK_MIN) break;
+            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneWalk)) < tune.walkMin) break;
         }
 
         // ---- TEST phase: one candidate per lane per iteration ----
         for (;;) {
+            if (COUNT) {
+                if (lane == 0) cnt.testWarpIters++;
+                if (st == kLaneTest) cnt.testLaneIters++;
+            }
             if (st == kLaneTest) {
-                const uint32_t tri = __ldg(S.cellList + i);
-                if (tri != g.excl) {
+                uint32_t tri = __ldg(S.cellList + i);
+                // run past the excluded triangle and candidates this ray already tested in an earlier cell
+                while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++i != iEnd) {
+                    if (COUNT && tri != g.excl) cnt.mailboxSkips++;
+                    tri = __ldg(S.cellList + i);
+                }
+                if (i != iEnd) {
                     float t, ab, ac;
                     if (COUNT) cnt.gridCandidates++;
+                    mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] = tri;
                     if (tri_test(S.triGeo + 4 * (size_t)tri, g.o, g.r, g.minD, bestT, t, ab, ac)) {
                         best = tri;
                         bestT = t;
                         bestAB = ab;
                         bestAC = ac;
                     }
+                    ++i;
                 }
-                if (++i == iEnd) {
+                if (i == iEnd) {
                     if (best != kNoTriangle) {  // first cell with any hit wins (:380)
                         w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
                         st = kLaneIdle;
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(128, 4) wf_trace_kernel(SceneView S, WfState w
                     }
                 }
             }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneTest)) < OCLR_TEST_MIN) break;
+            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneTest)) < tune.testMin) break;
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);

@@ -4,6 +4,7 @@
 // layout of rt_types.h) and a Frame (camera lists + three 16-bit planes) per camera.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -351,7 +352,15 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     else
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
+    static TraceTuning tune = {0, 0, 0};
+    if (tune.walkMin == 0) {
+        auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
+        tune.walkMin = env("OCLR_WALK_MIN", 16);
+        tune.testMin = env("OCLR_TEST_MIN", 16);
+        tune.refillMin = env("OCLR_REFILL_MIN", 4);
+    }
     const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
+    if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
     const unsigned traceGrid = (unsigned)(smCount * perSm);
     if (F.flagOut) OCLR_CUDA(cudaMemsetAsync(F.flagOut, 0, (size_t)F.cam.width * F.cam.height, st));
     for (uint32_t s = 0; s < F.sampleCount; ++s) {
@@ -368,9 +377,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
             if (waiting == 0) break;
             const unsigned grid = (unsigned)std::min<uint64_t>(traceGrid, ((uint64_t)waiting + 127) / 128);
             if (dcnt)
-                wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, dcnt);
+                wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
             else
-                wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, dcnt);
+                wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
             ++launches;
             if (round > 100000) {
                 err = "wavefront did not converge";
