@@ -197,6 +197,11 @@ struct GridWalk {
     int curBrick;
     uint64_t mask;
     uint32_t rankBase;
+    // Two-level walk (see walk_enter_coarse): shift == 0 -> (cx,cy,cz) are cells and (tx,ty,tz) the next cell-plane
+    // crossings; shift == 2 -> (cx,cy,cz) are 4x4x4-brick coordinates and (tx,ty,tz) the next BRICK-plane crossings.
+    int shift;
+    int endBrick;   // linear id of the brick holding the end cell (never skipped), or -1
+    bool coarseOk;  // all three direction components non-zero (no NaN crossings possible)
 };
 
 OCLR_HD void walk_begin(GridWalk& w, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
@@ -224,13 +229,16 @@ OCLR_HD void walk_begin(GridWalk& w, const SceneView& S, const float* px, const 
     w.curBrick = -1;
     w.mask = 0;
     w.rankBase = 0;
+    w.shift = 0;
+    w.endBrick = (w.ex < 0) ? -1 : (w.ex >> 2) + S.nb * ((w.ey >> 2) + S.nb * (w.ez >> 2));
+    w.coarseOk = (n >= 4) & (r.x != 0.f) & (r.y != 0.f) & (r.z != 0.f);
 }
 
-// Occupancy of the current cell; loads the brick record when the walk entered a new brick.
-// Returns true and the list range when the cell has triangles.
+// Loads the 16-byte brick record of the current position (cell or brick level) when the walk entered a new brick.
 template <bool COUNT>
-OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* cnt) {
-    const int b = (w.cx >> 2) + S.nb * ((w.cy >> 2) + S.nb * (w.cz >> 2));
+OCLR_HD void walk_load_brick(GridWalk& w, const SceneView& S, Counters* cnt) {
+    const int sh = 2 - w.shift;
+    const int b = (w.cx >> sh) + S.nb * ((w.cy >> sh) + S.nb * (w.cz >> sh));
     if (b != w.curBrick) {
         const uint4 br = OCLR_LDG(S.bricks + b);
         w.mask = (uint64_t)br.x | ((uint64_t)br.y << 32);
@@ -238,6 +246,13 @@ OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* 
         w.curBrick = b;
         if (COUNT) cnt->bricksLoaded++;
     }
+}
+
+// Occupancy of the current cell; loads the brick record when the walk entered a new brick.
+// Returns true and the list range when the cell has triangles.
+template <bool COUNT>
+OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* cnt) {
+    walk_load_brick<COUNT>(w, S, cnt);
     const int bit = (w.cx & 3) | ((w.cy & 3) << 2) | ((w.cz & 3) << 4);
     if (COUNT) cnt->cells++;
     if (COUNT && w.mask == 0ull) cnt->emptyBrickCells++;
@@ -254,17 +269,20 @@ OCLR_HD bool walk_cell(GridWalk& w, const SceneView& S, uint2& range, Counters* 
 // Branch-free form of the reference's three-way if/else: the axis is selected first (same comparisons, same tie rule:
 // x only if strictly smallest, else y if strictly smaller than z, else z -- NaNs fall through to z), then ONE step, one
 // shared-memory plane fetch and one IEEE division run for whichever axis was chosen, so the lanes of a warp stay converged.
-OCLR_HD bool walk_step(GridWalk& w, int n, const float* px, const float* py, const float* pz) {
+// At brick level (w.shift == 2) the very same code steps 4 planes at a time.  `axis`/`tEvent` report the crossing taken.
+OCLR_HD bool walk_step_ex(GridWalk& w, int n, const float* px, const float* py, const float* pz, int& axis, float& tEvent) {
     const bool xmin = (w.tx < w.ty) & (w.tx < w.tz);
     const bool ymin = (!xmin) & (w.ty < w.tz);
+    axis = xmin ? 0 : (ymin ? 1 : 2);
+    tEvent = xmin ? w.tx : (ymin ? w.ty : w.tz);
     int c = xmin ? w.cx : (ymin ? w.cy : w.cz);
     const float rr = xmin ? w.r.x : (ymin ? w.r.y : w.r.z);
     const float oo = xmin ? w.o.x : (ymin ? w.o.y : w.o.z);
     const float* p = xmin ? px : (ymin ? py : pz);
     const int up = (0 <= rr);
     c += up ? 1 : -1;
-    if (c < 0 || n <= c) return false;
-    const float t = (p[c + up] - oo) / rr;
+    if (c < 0 || (n >> w.shift) <= c) return false;
+    const float t = (p[(c + up) << w.shift] - oo) / rr;
     w.cx = xmin ? c : w.cx;
     w.tx = xmin ? t : w.tx;
     w.cy = ymin ? c : w.cy;
@@ -273,13 +291,93 @@ OCLR_HD bool walk_step(GridWalk& w, int n, const float* px, const float* py, con
     w.tz = (xmin | ymin) ? w.tz : t;
     return true;
 }
+OCLR_HD bool walk_step(GridWalk& w, int n, const float* px, const float* py, const float* pz) {
+    int axis;
+    float tEvent;
+    return walk_step_ex(w, n, px, py, pz, axis, tEvent);
+}
+
+// ---- two-level walk: exact skipping of empty 4x4x4 bricks ----------------------------------------------------------------
+// The reference's DDA is a 3-way merge of the per-axis plane-crossing sequences t_a(k) = (plane_a[k] - o_a) / r_a, each
+// non-decreasing along the ray, merged by "smallest first, ties to the later axis" (:387-398).  The crossings of every 4th
+// plane (brick faces) are a sub-sequence of each, so merging only those -- the same comparisons on the same fp32
+// quotients -- visits the bricks in exactly the order the cell walk passes through them.  While the bricks are empty
+// nothing else is needed; on entering a brick that has triangles (or holds the end cell) the exact cell-level state is
+// rebuilt: along the entry axis it is the brick's first cell; along each other axis it is the number of that axis' cell
+// crossings inside the brick that the merge would have taken before the entry crossing E ("t < E" for an axis that wins
+// ties against the entry axis' predecessor rule, "t <= E" otherwise), found with two probes of the three interior planes.
+// Requires all direction components non-zero (then no crossing is NaN and the merge order is a total preorder).
+
+// From a cell inside an empty brick: switch to brick coordinates; the heads become the brick-exit crossings.
+OCLR_HD void walk_enter_coarse(GridWalk& w, const float* px, const float* py, const float* pz) {
+    w.cx >>= 2;
+    w.cy >>= 2;
+    w.cz >>= 2;
+    w.tx = (px[(w.cx + (0 <= w.r.x)) << 2] - w.o.x) / w.r.x;
+    w.ty = (py[(w.cy + (0 <= w.r.y)) << 2] - w.o.y) / w.r.y;
+    w.tz = (pz[(w.cz + (0 <= w.r.z)) << 2] - w.o.z) / w.r.z;
+    w.shift = 2;
+}
+
+// One non-entry axis of the refinement: brick coordinate b, current brick-exit crossing tExit (not yet taken).
+// `strict`: this axis' crossings precede E only when strictly smaller (axis index below the entry axis).
+OCLR_HD void refine_axis(int b, float tExit, float o, float r, const float* p, float E, bool strict, int& cell, float& tNext) {
+    const int up = (0 <= r);
+    const int base = b << 2;
+    // cells in travel order u_j = up ? base + j : base + 3 - j; crossing j leaves u_j through plane u_j + up
+    const int p1 = up ? base + 2 : base + 2;  // plane left by u_1: up -> base+1+1, down -> base+2+0
+    const float t1 = (p[p1] - o) / r;
+    const bool pre1 = strict ? (t1 < E) : (t1 <= E);
+    const int p2 = pre1 ? (up ? base + 3 : base + 1) : (up ? base + 1 : base + 3);  // crossing 2 or crossing 0
+    const float t2 = (p[p2] - o) / r;
+    const bool pre2 = strict ? (t2 < E) : (t2 <= E);
+    int j;
+    if (pre1) {
+        j = pre2 ? 3 : 2;
+        tNext = pre2 ? tExit : t2;
+    } else {
+        j = pre2 ? 1 : 0;
+        tNext = pre2 ? t1 : t2;
+    }
+    cell = up ? base + j : base + 3 - j;
+}
+
+// After a brick-level step along `axis` (crossing value E) into a brick that must be walked cell by cell.
+OCLR_HD void walk_refine(GridWalk& w, int axis, float E, const float* px, const float* py, const float* pz) {
+    int cx, cy, cz;
+    float tx, ty, tz;
+    if (axis == 0) {
+        const int up = (0 <= w.r.x);
+        cx = up ? (w.cx << 2) : (w.cx << 2) + 3;
+        tx = (px[cx + up] - w.o.x) / w.r.x;
+    } else {
+        refine_axis(w.cx, w.tx, w.o.x, w.r.x, px, E, true, cx, tx);  // x precedes y/z crossings only when strictly smaller
+    }
+    if (axis == 1) {
+        const int up = (0 <= w.r.y);
+        cy = up ? (w.cy << 2) : (w.cy << 2) + 3;
+        ty = (py[cy + up] - w.o.y) / w.r.y;
+    } else {
+        refine_axis(w.cy, w.ty, w.o.y, w.r.y, py, E, axis == 2, cy, ty);  // y: "<= E" against x, "< E" against z
+    }
+    if (axis == 2) {
+        const int up = (0 <= w.r.z);
+        cz = up ? (w.cz << 2) : (w.cz << 2) + 3;
+        tz = (pz[cz + up] - w.o.z) / w.r.z;
+    } else {
+        refine_axis(w.cz, w.tz, w.o.z, w.r.z, pz, E, false, cz, tz);  // z wins ties against x and y
+    }
+    w.cx = cx; w.cy = cy; w.cz = cz;
+    w.tx = tx; w.ty = ty; w.tz = tz;
+    w.shift = 0;
+}
 
 // Whole traversal for one ray, serial form (one thread walks one ray).  `outT` is reset to maxD in every cell
 // (:366); the walk stops at the first cell that produced any hit (:380), at the end cell (:381) or off the grid.
 template <bool COUNT>
 OCLR_HD uint32_t grid_trace(const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
                             float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC,
-                            Counters* cnt) {
+                            Counters* cnt, bool hierarchical = false) {
     GridWalk w;
     walk_begin(w, S, px, py, pz, o, r, minD, maxD, excl);
     if (COUNT) cnt->gridRays++;
@@ -287,7 +385,8 @@ OCLR_HD uint32_t grid_trace(const SceneView& S, const float* px, const float* py
     for (;;) {
         uint2 range;
         outT = maxD;
-        if (walk_cell<COUNT>(w, S, range, cnt)) {
+        const bool occupied = walk_cell<COUNT>(w, S, range, cnt);
+        if (occupied) {
             for (uint32_t i = range.x; i < range.y; ++i) {
                 const uint32_t tri = OCLR_LDG(S.cellList + i);
                 if (tri != excl) {
@@ -303,6 +402,26 @@ OCLR_HD uint32_t grid_trace(const SceneView& S, const float* px, const float* py
             }
         }
         if (closest != kNoTriangle || (w.cx == w.ex && w.cy == w.ey && w.cz == w.ez)) break;
+        if (hierarchical && w.coarseOk && w.mask == 0ull && w.curBrick != w.endBrick) {
+            // the whole brick is empty: cross it, and any empty bricks behind it, at brick granularity
+            walk_enter_coarse(w, px, py, pz);
+            bool inside = true;
+            for (;;) {
+                int axis;
+                float E;
+                if (!walk_step_ex(w, S.n, px, py, pz, axis, E)) {
+                    inside = false;
+                    break;
+                }
+                walk_load_brick<COUNT>(w, S, cnt);
+                if (w.mask != 0ull || w.curBrick == w.endBrick) {
+                    walk_refine(w, axis, E, px, py, pz);
+                    break;
+                }
+            }
+            if (!inside) break;
+            continue;
+        }
         if (!walk_step(w, S.n, px, py, pz)) break;
     }
     return closest;
@@ -498,7 +617,8 @@ struct RingLocal {
 
 template <bool COUNT>
 OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px, const float* py, const float* pz,
-                        uint32_t pixel, uint32_t sampleIdx, uint32_t* primaryId, bool& undefinedRef, Counters* cnt) {
+                        uint32_t pixel, uint32_t sampleIdx, uint32_t* primaryId, bool& undefinedRef, Counters* cnt,
+                        bool hierarchical = false) {
     const Camera& cam = F.cam;
     uint64_t rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
     const float fx = (float)(pixel % cam.width);
@@ -547,7 +667,7 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
             }
         } else {
             hit = grid_trace<COUNT>(S, px, py, pz, ro, rv, ring.minD[begin], ring.maxD[begin], ring.excl[begin], hitT, hitAB,
-                                    hitAC, cnt);
+                                    hitAC, cnt, hierarchical);
         }
         if (first) {
             if (primaryId) *primaryId = hit;
@@ -577,7 +697,7 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
             if (lr.minLen < lr.maxLen) {
                 for (;;) {
                     float t, ab = 0.f, ac = 0.f;
-                    const uint32_t occ = grid_trace<COUNT>(S, px, py, pz, loc, lr.dir, lr.minLen, lr.maxLen, hit, t, ab, ac, cnt);
+                    const uint32_t occ = grid_trace<COUNT>(S, px, py, pz, loc, lr.dir, lr.minLen, lr.maxLen, hit, t, ab, ac, cnt, hierarchical);
                     if (occ == kNoTriangle) break;
                     int om;
                     float u0, v0, u1, v1, u2, v2;

@@ -384,6 +384,7 @@ struct TraceTuning {
     int walkMin;     // keep walking while at least this many lanes of the warp are still looking for triangles
     int testMin;     // keep testing while at least this many lanes have candidates pending
     int refillMin;   // refill from the queue once this many lanes are idle
+    int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level DDA)
 };
 
 template <bool COUNT>
@@ -411,6 +412,8 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     uint32_t i = 0, iEnd = 0;
     uint32_t best = kNoTriangle;
     float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
+    int lastAxis = 0;
+    float lastE = 0.f;
 
     for (;;) {
         // ---- refill idle lanes from the queue: one atomic per warp ----
@@ -445,13 +448,32 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                 if (st == kLaneWalk) cnt.walkLaneIters++;
             }
             if (st == kLaneWalk) {
-                uint2 range;
-                if (walk_cell<COUNT>(g, S, range, &cnt)) {
-                    i = range.x;
-                    iEnd = range.y;
-                    bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
-                    st = kLaneTest;
-                } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step(g, n, px, py, pz)) {
+                bool step = false, miss = false;
+                if (g.shift == 0) {  // cell level
+                    uint2 range;
+                    if (walk_cell<COUNT>(g, S, range, &cnt)) {
+                        i = range.x;
+                        iEnd = range.y;
+                        bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
+                        st = kLaneTest;
+                    } else if (g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) {
+                        miss = true;
+                    } else {
+                        // whole brick empty: cross it (and the empty bricks behind it) at brick granularity -- exact, see
+                        // walk_enter_coarse in rt_core.h.  The counting build walks cell by cell (reference accounting).
+                        if (!COUNT && tune.hierarchical && g.coarseOk && g.mask == 0ull && g.curBrick != g.endBrick)
+                            walk_enter_coarse(g, px, py, pz);
+                        step = true;
+                    }
+                } else {  // brick level: look at the brick just entered
+                    walk_load_brick<COUNT>(g, S, &cnt);
+                    if (g.mask != 0ull || g.curBrick == g.endBrick)
+                        walk_refine(g, lastAxis, lastE, px, py, pz);  // the next iteration examines the entry cell
+                    else
+                        step = true;
+                }
+                if (step && !walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) miss = true;
+                if (miss) {
                     w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
                     st = kLaneIdle;
                 }

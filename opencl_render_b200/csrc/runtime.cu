@@ -352,12 +352,13 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     else
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
-    static TraceTuning tune = {0, 0, 0};
+    static TraceTuning tune = {0, 0, 0, 1};
     if (tune.walkMin == 0) {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
         tune.walkMin = env("OCLR_WALK_MIN", 16);
         tune.testMin = env("OCLR_TEST_MIN", 16);
         tune.refillMin = env("OCLR_REFILL_MIN", 4);
+        tune.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
     }
     const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));

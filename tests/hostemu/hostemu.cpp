@@ -3,6 +3,7 @@
 // instantiate) and the scene packer for the HOST, so that the packed layout + restated control flow can be compared
 // bit-for-bit with the reference on a machine without a GPU.  It is built into tests/_build/ by tests/conftest.py and is
 // never part of, nor reachable from, libopencl_render_b200.so (which has no CPU compute path).
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -50,6 +51,7 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     if (rowEnd > cam->height) rowEnd = cam->height;
     std::atomic<uint32_t> nextRow(rowBegin);
     std::vector<Counters> cnts(threads > 0 ? threads : 1);
+    const bool hier = getenv("HOSTEMU_HIERARCHICAL") != nullptr;   // exercise the two-level (brick-skipping) walk
     auto worker = [&](int tid) {
         Counters& cnt = cnts[tid];
         memset(&cnt, 0, sizeof(cnt));
@@ -63,7 +65,7 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
                 bool undef = false;
                 for (uint32_t s = 0; s < sampleCount; ++s) {
                     uint32_t pid;
-                    const f3 c = trace_sample<true>(S, F, px, py, pz, pixel, s, &pid, undef, &cnt);
+                    const f3 c = trace_sample<true>(S, F, px, py, pz, pixel, s, &pid, undef, &cnt, hier);
                     if (s == 0 && ids) ids[pixel] = pid;
                     r = accumulate16(r, c.x, scale); g = accumulate16(g, c.y, scale); b = accumulate16(b, c.z, scale);
                 }

@@ -43,3 +43,20 @@ def test_hostemu_counters_match_reference_accounting(hostemu):
     assert cnt["cellsNonEmpty"] <= cnt["cells"] and cnt["bricksLoaded"] <= cnt["cells"]
     assert cnt["gridRays"] > 0 and cnt["primCandidates"] > 0 and cnt["shadedHits"] <= cnt["segments"]
     assert cnt["segments"] >= rays
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_two_level_walk_is_exact(name, hostemu, monkeypatch):
+    """The brick-granular (two-level) DDA of rt_core.h -- the trace kernel's way through empty 4x4x4 bricks -- visits the same
+    bricks and returns bit-identical planes and ids, while touching far fewer cells."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "1")
+    hier = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], hier[0][c])
+    assert np.array_equal(flat[1], hier[1]) and np.array_equal(flat[2], hier[2])
+    assert hier[3]["bricksLoaded"] == flat[3]["bricksLoaded"]          # same brick sequence
+    assert hier[3]["gridCandidates"] == flat[3]["gridCandidates"] and hier[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
+    assert hier[3]["cells"] <= flat[3]["cells"]
