@@ -62,7 +62,39 @@ def run(cfg_id, variants=(0, 1), ref_rows=None, reps=5):
     fr.close(); ds.close()
 
 
+def run_sweep(cfg_id=5, check_frames=(0, 21, 42)):
+    """Config 5: scene uploaded once, 64 cameras on a circle, per-frame camera lists; mirror chains up to depth 12."""
+    cfg = scenes.CONFIGS[cfg_id]
+    sc = cfg["make"]()
+    api.scene_triangle_list(sc, 256)
+    t = time.time(); ds = api.DeviceScene(sc, 0); t_up = time.time() - t
+    print(f"[cfg{cfg_id}] {cfg['name']}: tris={sc.triangle_count} upload once {t_up:.2f}s ({ds.device_bytes/1e6:.1f} MB)", flush=True)
+    cams = scenes.sweep_cameras(sc, cfg["frames"])
+    total_ms, total_rays, t_lists, worst = 0.0, 0, 0.0, 0
+    for k, m in enumerate(cams):
+        cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+        t = time.time(); lists = api.camera_triangle_list(cam, sc); t_lists += time.time() - t
+        fr = api.DeviceFrame(ds, cam, lists)
+        ms, launches, _ = fr.render(cfg["samples"], variant=1)
+        total_ms += ms; total_rays += cfg["width"] * cfg["height"] * cfg["samples"]
+        if k in check_frames:
+            img = fr.read(); flags = fr.undefined_flags()
+            rows = (500, 532)
+            R = ref.render(cam, lists, sc, cfg["samples"], rows=rows)
+            sl = slice(*rows)
+            d = sum(int(((img[c][sl] != R[c][sl]) & (flags[sl] == 0)).sum()) for c in range(3))
+            worst = max(worst, d)
+            print(f"  frame {k}: {ms:.2f} ms, {launches} launches, lit {int((img[0] > 0).sum())}, diff vs reference rows {rows}: {d}", flush=True)
+        fr.close()
+    print(f"  {len(cams)} frames: device {total_ms:.1f} ms total -> {total_rays / total_ms / 1e3:.1f} Mrays/s; host camera lists {t_lists:.1f}s; worst diff {worst}")
+    ds.close()
+
+
 if __name__ == "__main__":
     print("types:", api.computation_types())
-    for cid in [int(x) for x in (sys.argv[1:] or ["1", "2"])]:
-        run(cid, ref_rows=None if cid <= 2 else (1000, 1064))
+    for cid in [x for x in (sys.argv[1:] or ["1", "2"])]:
+        if cid == "5s":
+            run_sweep(5)
+        else:
+            cid = int(cid)
+            run(cid, ref_rows=None if cid <= 2 else (1000, 1064), reps=5 if cid <= 3 else 2)

@@ -1,0 +1,42 @@
+"""Calling-convention check of include/oclr_abi.h: a C caller compiled against OUR header drives the REFERENCE's compiled
+`RaytraceAll` (oracle/_ref) with by-value OpenCL vector unions; the image must equal the pointer-door result.  (CPU only.)"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_header_calling_convention_matches_reference(ref):
+    import ref as refmod
+    out = ROOT / "tests" / "_build"
+    out.mkdir(exist_ok=True)
+    lib = out / "libabi_caller.so"
+    subprocess.run(["gcc", "-O1", "-std=gnu11", "-fPIC", "-shared", str(ROOT / "tests" / "abi_caller.c"), str(refmod.LIB),
+                    f"-Wl,-rpath,{refmod.LIB.parent}", "-o", str(lib)], check=True)
+    caller = C.CDLL(str(lib))
+    sc, cam, lists, samples = helpers.make_case("soup_s4")
+    want = ref.raytrace_all(cam, lists, sc, samples)
+    h, w = cam.height, cam.width
+    got = [np.zeros((h, w), np.uint16) for _ in range(3)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    f4 = lambda v: np.ascontiguousarray(v, np.float32)
+    dim = np.array([w, h], np.uint32)
+    keep = [f4(cam.eye), f4(cam.eye_to_top_left), f4(cam.left_to_right), f4(cam.top_to_bottom)]
+    caller.abi_call_by_value.restype = C.c_uint32
+    ok = caller.abi_call_by_value(p(dim), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), C.c_float(cam.pixel_size_inv),
+                                  p(lists.start), p(lists.end), p(lists.list), C.c_uint32(samples), p(sc.vertex),
+                                  C.c_uint32(sc.triangle_count), p(sc.tri_idx), p(sc.tri_mat), p(sc.tri_uv), p(sc.tri_normal),
+                                  C.c_int32(sc.axes_div), p(sc.box_min), p(sc.grid_start), p(sc.grid_list), p(sc.mat_size),
+                                  p(sc.mat_start), p(sc.textures), C.c_uint32(sc.light_count), p(sc.light_type), p(sc.light_pos),
+                                  p(sc.light_dir), p(sc.light_colour), p(sc.light_radius), p(sc.light_half), p(got[0]), p(got[1]),
+                                  p(got[2]))
+    assert ok == 1
+    for c in range(3):
+        assert np.array_equal(got[c], want[c])
+    assert int((got[0] > 0).sum()) > 100
