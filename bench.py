@@ -238,7 +238,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (rank 0's share of the frame) -----------------------------------------------------
     roof = cpu = None
     if rank == 0:
-        ms_k, _, cnt = part.render_counted(fr, S, args.variant)
+        ms_k, _, cnt = part.render_counted(fr, S, 0)      # event counts in the reference's accounting: the per-pixel kernel
         times = []
         for _ in range(5):
             flush.zero_()

@@ -218,7 +218,7 @@ typedef struct oclr_frame oclr_frame;
 typedef struct oclr_counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
-        mailboxSkips;
+        mailboxSkips, coarseSteps, coarseEnters;
 } oclr_counters;
 
 typedef struct oclr_render_stats {

@@ -31,6 +31,8 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     if (c.testWarpIters) atomicAdd(&g->testWarpIters, c.testWarpIters);
     if (c.testLaneIters) atomicAdd(&g->testLaneIters, c.testLaneIters);
     if (c.mailboxSkips) atomicAdd(&g->mailboxSkips, c.mailboxSkips);
+    if (c.coarseSteps) atomicAdd(&g->coarseSteps, c.coarseSteps);
+    if (c.coarseEnters) atomicAdd(&g->coarseEnters, c.coarseEnters);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

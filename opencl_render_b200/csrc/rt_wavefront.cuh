@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
     int lastAxis = 0;
     float lastE = 0.f;
+    uint32_t nextTri = 0;
 
     for (;;) {
         // ---- refill idle lanes from the queue: one atomic per warp ----
@@ -441,60 +442,79 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
         }
         if (__ballot_sync(0xFFFFFFFFu, st != kLaneIdle) == 0u) break;
 
-        // ---- WALK phase: advance to the next non-empty cell (or off the grid / to the end cell) ----
+        // ---- WALK phase: advance to the next cell that holds an UNTESTED triangle (or off the grid / to the end cell) ----
+        // One control path for both levels of the walk: classify the current position from the brick record, then either
+        // leave the phase (candidates found / walk over), change level (rare) or take one branch-free DDA step.
         for (;;) {
             if (COUNT) {
                 if (lane == 0) cnt.walkWarpIters++;
                 if (st == kLaneWalk) cnt.walkLaneIters++;
             }
             if (st == kLaneWalk) {
-                bool step = false, miss = false;
-                if (g.shift == 0) {  // cell level
-                    uint2 range;
-                    if (walk_cell<COUNT>(g, S, range, &cnt)) {
-                        i = range.x;
-                        iEnd = range.y;
+                walk_load_brick<COUNT>(g, S, &cnt);
+                const bool coarse = g.shift != 0;
+                const int bit = (g.cx & 3) | ((g.cy & 3) << 2) | ((g.cz & 3) << 4);
+                const bool occupied = (!coarse) & (((g.mask >> bit) & 1ull) != 0ull);
+                const bool atEnd = (!coarse) & (g.cx == g.ex) & (g.cy == g.ey) & (g.cz == g.ez);
+                bool pending = false;
+                if (COUNT && !coarse) {
+                    cnt.cells++;
+                    if (g.mask == 0ull) cnt.emptyBrickCells++;
+                }
+                if (occupied) {
+                    const uint32_t rank = g.rankBase + (uint32_t)__popcll(g.mask & ((1ull << bit) - 1ull));
+                    const uint2 range = __ldg(S.cellRange + rank);
+                    if (COUNT) cnt.cellsNonEmpty++;
+                    // pre-filter: the excluded triangle and ids this ray already tested need no test (exact, see mailbox)
+                    i = range.x;
+                    iEnd = range.y;
+                    uint32_t tri = __ldg(S.cellList + i);
+                    while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++i != iEnd) {
+                        if (COUNT && tri != g.excl) cnt.mailboxSkips++;
+                        tri = __ldg(S.cellList + i);
+                    }
+                    if (i != iEnd) {
+                        nextTri = tri;
                         bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
                         st = kLaneTest;
-                    } else if (g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) {
-                        miss = true;
+                        pending = true;
+                    } else if (COUNT && tri != g.excl) {
+                        cnt.mailboxSkips++;
+                    }
+                }
+                if (!pending) {
+                    if (coarse & ((g.mask != 0ull) | (g.curBrick == g.endBrick))) {
+                        walk_refine(g, lastAxis, lastE, px, py, pz);  // brick needs a cell walk: rebuild the exact cell state
+                    } else if (atEnd) {
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
+                        st = kLaneIdle;
                     } else {
                         // whole brick empty: cross it (and the empty bricks behind it) at brick granularity -- exact, see
-                        // walk_enter_coarse in rt_core.h.  The counting build walks cell by cell (reference accounting).
-                        if (!COUNT && tune.hierarchical && g.coarseOk && g.mask == 0ull && g.curBrick != g.endBrick)
+                        // walk_enter_coarse in rt_core.h.  (`cells` counts only the cells examined one by one.)
+                        if ((!coarse) & (tune.hierarchical != 0) & g.coarseOk & (g.mask == 0ull) & (g.curBrick != g.endBrick)) {
                             walk_enter_coarse(g, px, py, pz);
-                        step = true;
+                            if (COUNT) cnt.coarseEnters++;
+                        }
+                        if (COUNT && g.shift) cnt.coarseSteps++;
+                        if (!walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) {
+                            w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
+                            st = kLaneIdle;
+                        }
                     }
-                } else {  // brick level: look at the brick just entered
-                    walk_load_brick<COUNT>(g, S, &cnt);
-                    if (g.mask != 0ull || g.curBrick == g.endBrick)
-                        walk_refine(g, lastAxis, lastE, px, py, pz);  // the next iteration examines the entry cell
-                    else
-                        step = true;
-                }
-                if (step && !walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) miss = true;
-                if (miss) {
-                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
-                    st = kLaneIdle;
                 }
             }
             if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneWalk)) < tune.walkMin) break;
         }
 
-        // ---- TEST phase: one candidate per lane per iteration ----
+        // ---- TEST phase: one real ray/triangle test per lane per iteration ----
         for (;;) {
             if (COUNT) {
                 if (lane == 0) cnt.testWarpIters++;
                 if (st == kLaneTest) cnt.testLaneIters++;
             }
             if (st == kLaneTest) {
-                uint32_t tri = __ldg(S.cellList + i);
-                // run past the excluded triangle and candidates this ray already tested in an earlier cell
-                while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++i != iEnd) {
-                    if (COUNT && tri != g.excl) cnt.mailboxSkips++;
-                    tri = __ldg(S.cellList + i);
-                }
-                if (i != iEnd) {
+                {
+                    const uint32_t tri = nextTri;
                     float t, ab, ac;
                     if (COUNT) cnt.gridCandidates++;
                     mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] = tri;
@@ -504,13 +524,21 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                         bestAB = ab;
                         bestAC = ac;
                     }
-                    ++i;
+                }
+                // advance to the next candidate that needs a test
+                while (++i != iEnd) {
+                    const uint32_t tri = __ldg(S.cellList + i);
+                    if (tri != g.excl && mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] != tri) {
+                        nextTri = tri;
+                        break;
+                    }
+                    if (COUNT && tri != g.excl) cnt.mailboxSkips++;
                 }
                 if (i == iEnd) {
                     if (best != kNoTriangle) {  // first cell with any hit wins (:380)
                         w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
                         st = kLaneIdle;
-                    } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step(g, n, px, py, pz)) {
+                    } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) {
                         w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
                         st = kLaneIdle;
                     } else {
