@@ -387,6 +387,13 @@ struct TraceTuning {
     int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level DDA)
 };
 
+// Lane bookkeeping: the walker runs AHEAD of the tests.  A lane's DDA keeps walking while the cells it found wait in a
+// small per-lane queue (shared memory) for the next TEST phase; cells are tested in walk order and the first cell with a
+// hit ends the ray (:380), discarding whatever the walker found beyond it.  The speculation is bounded by the queue
+// depth; it keeps ~all lanes busy in both phases instead of parking a lane the moment it finds triangles.
+enum { kPendingDepth = 2 };
+enum { kWalkNone = 0, kWalkRunning = 1, kWalkFinished = 2 };
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(SceneView S, WfState w, TraceTuning tune, Counters* gcnt) {
     extern __shared__ float shPlanes[];
@@ -395,6 +402,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     // in-cell bound stayed at maxDistance (:366) and every triangle tested there failed either the (min, max) range
     // or the barycentric test -- both ray/triangle properties that do not change in a later cell.
     __shared__ uint32_t mailbox[kMailboxSlots][128];
+    __shared__ uint2 pending[kPendingDepth][128];
     load_planes(shPlanes, S);
     const float* px = shPlanes;
     const float* py = shPlanes + (S.n + 1);
@@ -405,20 +413,21 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     const int n = S.n;
 
     Counters cnt = {};
-    int st = kLaneIdle;
+    int wst = kWalkNone;      // walker status
+    int qHead = 0, qCount = 0;
+    bool testing = false;     // a popped cell is being tested (i, iEnd, nextTri valid)
     bool exhausted = false;
     uint32_t path = 0;
     GridWalk g;
-    uint32_t i = 0, iEnd = 0;
+    uint32_t i = 0, iEnd = 0, nextTri = 0;
     uint32_t best = kNoTriangle;
     float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
     int lastAxis = 0;
     float lastE = 0.f;
-    uint32_t nextTri = 0;
 
     for (;;) {
         // ---- refill idle lanes from the queue: one atomic per warp ----
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == kLaneIdle);
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, wst == kWalkNone);
         if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
             const int nIdle = __popc(idle);
             const int leader = __ffs(idle) - 1;
@@ -426,37 +435,39 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
             if (lane == leader) base = atomicAdd(w.queueCursor, (uint32_t)nIdle);
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (base + (uint32_t)nIdle >= count) exhausted = true;
-            if (st == kLaneIdle) {
+            if (wst == kWalkNone) {
                 const uint32_t idx = base + (uint32_t)__popc(idle & ltMask);
                 if (idx < count) {
                     path = w.queue[idx];
                     const float4 ro = w.rayO[path], rd = w.rayD[path];
                     walk_begin(g, S, px, py, pz, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w, w.rayExcl[path]);
                     best = kNoTriangle;
-                    st = kLaneWalk;
+                    wst = kWalkRunning;
+                    qHead = qCount = 0;
+                    testing = false;
 #pragma unroll
                     for (int k = 0; k < kMailboxSlots; ++k) mailbox[k][threadIdx.x] = kNoTriangle;
                     if (COUNT) cnt.gridRays++;
                 }
             }
         }
-        if (__ballot_sync(0xFFFFFFFFu, st != kLaneIdle) == 0u) break;
+        if (__ballot_sync(0xFFFFFFFFu, wst != kWalkNone) == 0u) break;
 
-        // ---- WALK phase: advance to the next cell that holds an UNTESTED triangle (or off the grid / to the end cell) ----
-        // One control path for both levels of the walk: classify the current position from the brick record, then either
-        // leave the phase (candidates found / walk over), change level (rare) or take one branch-free DDA step.
+        // ---- WALK phase ------------------------------------------------------------------------------------------------
+        // One control path for both levels of the walk: classify the current position from the brick record, queue the cell
+        // if it holds an untested triangle, then change level (rare) or take one branch-free DDA step.
         for (;;) {
+            const bool walking = (wst == kWalkRunning) & (qCount < kPendingDepth);
             if (COUNT) {
                 if (lane == 0) cnt.walkWarpIters++;
-                if (st == kLaneWalk) cnt.walkLaneIters++;
+                if (walking) cnt.walkLaneIters++;
             }
-            if (st == kLaneWalk) {
+            if (walking) {
                 walk_load_brick<COUNT>(g, S, &cnt);
                 const bool coarse = g.shift != 0;
                 const int bit = (g.cx & 3) | ((g.cy & 3) << 2) | ((g.cz & 3) << 4);
                 const bool occupied = (!coarse) & (((g.mask >> bit) & 1ull) != 0ull);
                 const bool atEnd = (!coarse) & (g.cx == g.ex) & (g.cy == g.ey) & (g.cz == g.ez);
-                bool pending = false;
                 if (COUNT && !coarse) {
                     cnt.cells++;
                     if (g.mask == 0ull) cnt.emptyBrickCells++;
@@ -466,54 +477,73 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                     const uint2 range = __ldg(S.cellRange + rank);
                     if (COUNT) cnt.cellsNonEmpty++;
                     // pre-filter: the excluded triangle and ids this ray already tested need no test (exact, see mailbox)
-                    i = range.x;
-                    iEnd = range.y;
-                    uint32_t tri = __ldg(S.cellList + i);
-                    while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++i != iEnd) {
+                    uint32_t k = range.x;
+                    uint32_t tri = __ldg(S.cellList + k);
+                    while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++k != range.y) {
                         if (COUNT && tri != g.excl) cnt.mailboxSkips++;
-                        tri = __ldg(S.cellList + i);
+                        tri = __ldg(S.cellList + k);
                     }
-                    if (i != iEnd) {
-                        nextTri = tri;
-                        bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
-                        st = kLaneTest;
-                        pending = true;
+                    if (k != range.y) {
+                        int slot = qHead + qCount;
+                        slot = slot >= kPendingDepth ? slot - kPendingDepth : slot;
+                        pending[slot][threadIdx.x] = make_uint2(k, range.y);
+                        ++qCount;
                     } else if (COUNT && tri != g.excl) {
                         cnt.mailboxSkips++;
                     }
                 }
-                if (!pending) {
-                    if (coarse & ((g.mask != 0ull) | (g.curBrick == g.endBrick))) {
-                        walk_refine(g, lastAxis, lastE, px, py, pz);  // brick needs a cell walk: rebuild the exact cell state
-                    } else if (atEnd) {
-                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
-                        st = kLaneIdle;
-                    } else {
-                        // whole brick empty: cross it (and the empty bricks behind it) at brick granularity -- exact, see
-                        // walk_enter_coarse in rt_core.h.  (`cells` counts only the cells examined one by one.)
-                        if ((!coarse) & (tune.hierarchical != 0) & g.coarseOk & (g.mask == 0ull) & (g.curBrick != g.endBrick)) {
-                            walk_enter_coarse(g, px, py, pz);
-                            if (COUNT) cnt.coarseEnters++;
+                if (coarse & ((g.mask != 0ull) | (g.curBrick == g.endBrick))) {
+                    walk_refine(g, lastAxis, lastE, px, py, pz);  // brick needs a cell walk: rebuild the exact cell state
+                } else if (atEnd) {
+                    wst = kWalkFinished;
+                } else {
+                    // whole brick empty: cross it (and the empty bricks behind it) at brick granularity -- exact, see
+                    // walk_enter_coarse in rt_core.h.  (`cells` counts only the cells examined one by one.)
+                    if ((!coarse) & (tune.hierarchical != 0) & g.coarseOk & (g.mask == 0ull) & (g.curBrick != g.endBrick)) {
+                        walk_enter_coarse(g, px, py, pz);
+                        if (COUNT) cnt.coarseEnters++;
+                    }
+                    if (COUNT && g.shift) cnt.coarseSteps++;
+                    if (!walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) wst = kWalkFinished;
+                }
+            }
+            if (__popc(__ballot_sync(0xFFFFFFFFu, (wst == kWalkRunning) & (qCount < kPendingDepth))) < tune.walkMin) break;
+        }
+
+        // ---- TEST phase: one real ray/triangle test per lane per iteration, cells in walk order -----------------------------
+        for (;;) {
+            const bool active = testing | (qCount > 0);
+            if (COUNT) {
+                if (lane == 0) cnt.testWarpIters++;
+                if (active) cnt.testLaneIters++;
+            }
+            if (active) {
+                bool have = true;
+                if (!testing) {  // next queued cell
+                    const uint2 r = pending[qHead][threadIdx.x];
+                    qHead = qHead + 1 >= kPendingDepth ? 0 : qHead + 1;
+                    --qCount;
+                    i = r.x;
+                    iEnd = r.y;
+                    bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
+                    testing = true;
+                    // the first candidate was untested when the cell was queued; a cell tested since may have covered it
+                    nextTri = __ldg(S.cellList + i);
+                    while (mailbox[nextTri & (kMailboxSlots - 1)][threadIdx.x] == nextTri) {
+                        if (COUNT) cnt.mailboxSkips++;
+                        if (++i == iEnd) {
+                            have = false;
+                            break;
                         }
-                        if (COUNT && g.shift) cnt.coarseSteps++;
-                        if (!walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) {
-                            w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
-                            st = kLaneIdle;
+                        nextTri = __ldg(S.cellList + i);
+                        while (nextTri == g.excl && ++i != iEnd) nextTri = __ldg(S.cellList + i);
+                        if (i == iEnd) {
+                            have = false;
+                            break;
                         }
                     }
                 }
-            }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneWalk)) < tune.walkMin) break;
-        }
-
-        // ---- TEST phase: one real ray/triangle test per lane per iteration ----
-        for (;;) {
-            if (COUNT) {
-                if (lane == 0) cnt.testWarpIters++;
-                if (st == kLaneTest) cnt.testLaneIters++;
-            }
-            if (st == kLaneTest) {
-                {
+                if (have) {
                     const uint32_t tri = nextTri;
                     float t, ab, ac;
                     if (COUNT) cnt.gridCandidates++;
@@ -524,29 +554,32 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                         bestAB = ab;
                         bestAC = ac;
                     }
-                }
-                // advance to the next candidate that needs a test
-                while (++i != iEnd) {
-                    const uint32_t tri = __ldg(S.cellList + i);
-                    if (tri != g.excl && mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] != tri) {
-                        nextTri = tri;
-                        break;
+                    // advance to the next candidate that needs a test
+                    while (++i != iEnd) {
+                        const uint32_t nt = __ldg(S.cellList + i);
+                        if (nt != g.excl && mailbox[nt & (kMailboxSlots - 1)][threadIdx.x] != nt) {
+                            nextTri = nt;
+                            break;
+                        }
+                        if (COUNT && nt != g.excl) cnt.mailboxSkips++;
                     }
-                    if (COUNT && tri != g.excl) cnt.mailboxSkips++;
                 }
-                if (i == iEnd) {
-                    if (best != kNoTriangle) {  // first cell with any hit wins (:380)
+                if (i == iEnd) {  // cell done
+                    testing = false;
+                    if (best != kNoTriangle) {  // first cell with any hit wins (:380); later cells are discarded
                         w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
-                        st = kLaneIdle;
-                    } else if ((g.cx == g.ex && g.cy == g.ey && g.cz == g.ez) || !walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) {
-                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
-                        st = kLaneIdle;
-                    } else {
-                        st = kLaneWalk;
+                        wst = kWalkNone;
+                        qCount = 0;
                     }
                 }
             }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, st == kLaneTest)) < tune.testMin) break;
+            if (__popc(__ballot_sync(0xFFFFFFFFu, testing | (qCount > 0))) < tune.testMin) break;
+        }
+
+        // walk over, nothing left to test, no hit: miss
+        if ((wst == kWalkFinished) & (!testing) & (qCount == 0)) {
+            w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
+            wst = kWalkNone;
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
