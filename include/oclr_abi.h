@@ -234,7 +234,8 @@ oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);
 void oclr_scene_destroy(oclr_scene* scene);
 size_t oclr_scene_device_bytes(const oclr_scene* scene);
 
-/* Test door: copies one packed device array back to `dst` (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList);
+/* Test door: copies one packed device array back to `dst` (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList,
+ * 6 faceMask);
  * returns its size in bytes (nothing is copied when it exceeds `capacity`). */
 size_t oclr_scene_debug_read(oclr_scene* scene, int which, void* dst, size_t capacity);
 

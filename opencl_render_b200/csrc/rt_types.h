@@ -20,6 +20,10 @@
 //   cellRange one uint2 {begin,end} per NON-EMPTY cell, in brick-major order, into cellList.
 //   cellList  the reference's scenePixelTriangleList as uploaded (triangle ids, ascending per cell; the order is
 //             observable through the strict `<` closest-hit rule, raytrace_opencl.c:143, 372-377).
+//   faceMask  6 x uint32 per non-empty cell, face = axis*2 + (entered moving towards +axis): bit k set when the k-th
+//             list entry (k < 32) does not occur in the list of the neighbour cell the DDA just left.  A ray that steps
+//             from cell N into cell C has already examined every triangle of N, so only the masked-in entries of C
+//             can be new to it -- the trace kernel jumps straight to them instead of scanning the whole list.
 //   planes    3 x (n+1) floats (x planes, y planes, z planes) -- copied to shared memory by each CTA.
 #pragma once
 #include <stdint.h>
@@ -57,6 +61,7 @@ struct SceneView {
     const uint4* bricks;
     const uint2* cellRange;
     const uint32_t* cellList;
+    const uint32_t* faceMask;  // 6 per non-empty cell: bit k of [rank*6 + face] = list entry k is NOT in the face neighbour's list
     const float* planes;      // 3*(n+1)
     const uint2* matSize;     // 5*materialCount
     const int32_t* matStart;  // 5*materialCount+1

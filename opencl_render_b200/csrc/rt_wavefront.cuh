@@ -394,6 +394,28 @@ struct TraceTuning {
 enum { kPendingDepth = 2 };
 enum { kWalkNone = 0, kWalkRunning = 1, kWalkFinished = 2 };
 
+// Next list entry at or after k that this ray still has to test: entries whose face-mask bit is clear were in the cell the
+// walk just left (already examined), the excluded triangle and mailbox hits are skipped too.  Returns false at the end.
+template <bool COUNT>
+__device__ __forceinline__ bool next_candidate(const uint32_t* __restrict__ list, uint32_t begin, uint32_t end, uint32_t m, uint32_t excl,
+                                               const uint32_t (*mb)[128], uint32_t& k, uint32_t& tri, Counters& cnt) {
+    for (;;) {
+        const uint32_t rel = k - begin;
+        if (rel < 32u) {
+            const uint32_t mm = m >> rel;
+            k = mm ? k + (uint32_t)(__ffs((int)mm) - 1) : begin + 32u;
+        }
+        if (k >= end) {
+            k = end;
+            return false;
+        }
+        tri = __ldg(list + k);
+        if (tri != excl && mb[tri & (kMailboxSlots - 1)][threadIdx.x] != tri) return true;
+        if (COUNT && tri != excl) cnt.mailboxSkips++;
+        ++k;
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(SceneView S, WfState w, TraceTuning tune, Counters* gcnt) {
     extern __shared__ float shPlanes[];
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     // in-cell bound stayed at maxDistance (:366) and every triangle tested there failed either the (min, max) range
     // or the barycentric test -- both ray/triangle properties that do not change in a later cell.
     __shared__ uint32_t mailbox[kMailboxSlots][128];
-    __shared__ uint2 pending[kPendingDepth][128];
+    __shared__ uint4 pending[kPendingDepth][128];  // {next entry, end, face mask, begin}
     load_planes(shPlanes, S);
     const float* px = shPlanes;
     const float* py = shPlanes + (S.n + 1);
@@ -419,7 +441,8 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     bool exhausted = false;
     uint32_t path = 0;
     GridWalk g;
-    uint32_t i = 0, iEnd = 0, nextTri = 0;
+    uint32_t i = 0, iEnd = 0, nextTri = 0, curMask = 0, curBegin = 0;
+    int face = -1;  // face through which the walker entered the current cell by a cell-level step (-1: none)
     uint32_t best = kNoTriangle;
     float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
     int lastAxis = 0;
@@ -445,6 +468,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                     wst = kWalkRunning;
                     qHead = qCount = 0;
                     testing = false;
+                    face = -1;
 #pragma unroll
                     for (int k = 0; k < kMailboxSlots; ++k) mailbox[k][threadIdx.x] = kNoTriangle;
                     if (COUNT) cnt.gridRays++;
@@ -476,24 +500,20 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                     const uint32_t rank = g.rankBase + (uint32_t)__popcll(g.mask & ((1ull << bit) - 1ull));
                     const uint2 range = __ldg(S.cellRange + rank);
                     if (COUNT) cnt.cellsNonEmpty++;
-                    // pre-filter: the excluded triangle and ids this ray already tested need no test (exact, see mailbox)
-                    uint32_t k = range.x;
-                    uint32_t tri = __ldg(S.cellList + k);
-                    while ((tri == g.excl || mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] == tri) && ++k != range.y) {
-                        if (COUNT && tri != g.excl) cnt.mailboxSkips++;
-                        tri = __ldg(S.cellList + k);
-                    }
-                    if (k != range.y) {
+                    // pre-filter (exact): entries shared with the cell just left, the excluded triangle and ids this ray
+                    // already tested need no test; a cell with nothing new is treated like an empty one
+                    const uint32_t m = face >= 0 ? __ldg(S.faceMask + 6 * (size_t)rank + face) : 0xFFFFFFFFu;
+                    uint32_t k = range.x, tri;
+                    if (next_candidate<COUNT>(S.cellList, range.x, range.y, m, g.excl, mailbox, k, tri, cnt)) {
                         int slot = qHead + qCount;
                         slot = slot >= kPendingDepth ? slot - kPendingDepth : slot;
-                        pending[slot][threadIdx.x] = make_uint2(k, range.y);
+                        pending[slot][threadIdx.x] = make_uint4(k, range.y, m, range.x);
                         ++qCount;
-                    } else if (COUNT && tri != g.excl) {
-                        cnt.mailboxSkips++;
                     }
                 }
                 if (coarse & ((g.mask != 0ull) | (g.curBrick == g.endBrick))) {
                     walk_refine(g, lastAxis, lastE, px, py, pz);  // brick needs a cell walk: rebuild the exact cell state
+                    face = -1;
                 } else if (atEnd) {
                     wst = kWalkFinished;
                 } else {
@@ -505,6 +525,8 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                     }
                     if (COUNT && g.shift) cnt.coarseSteps++;
                     if (!walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) wst = kWalkFinished;
+                    const float rs = lastAxis == 0 ? g.r.x : (lastAxis == 1 ? g.r.y : g.r.z);
+                    face = g.shift ? -1 : lastAxis * 2 + (0 <= rs ? 1 : 0);
                 }
             }
             if (__popc(__ballot_sync(0xFFFFFFFFu, (wst == kWalkRunning) & (qCount < kPendingDepth))) < tune.walkMin) break;
@@ -518,32 +540,20 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                 if (active) cnt.testLaneIters++;
             }
             if (active) {
-                bool have = true;
                 if (!testing) {  // next queued cell
-                    const uint2 r = pending[qHead][threadIdx.x];
+                    const uint4 r = pending[qHead][threadIdx.x];
                     qHead = qHead + 1 >= kPendingDepth ? 0 : qHead + 1;
                     --qCount;
                     i = r.x;
                     iEnd = r.y;
+                    curMask = r.z;
+                    curBegin = r.w;
                     bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
                     testing = true;
-                    // the first candidate was untested when the cell was queued; a cell tested since may have covered it
-                    nextTri = __ldg(S.cellList + i);
-                    while (mailbox[nextTri & (kMailboxSlots - 1)][threadIdx.x] == nextTri) {
-                        if (COUNT) cnt.mailboxSkips++;
-                        if (++i == iEnd) {
-                            have = false;
-                            break;
-                        }
-                        nextTri = __ldg(S.cellList + i);
-                        while (nextTri == g.excl && ++i != iEnd) nextTri = __ldg(S.cellList + i);
-                        if (i == iEnd) {
-                            have = false;
-                            break;
-                        }
-                    }
+                    // its first candidate was untested when the cell was queued; a cell tested since may have covered it
+                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, g.excl, mailbox, i, nextTri, cnt);
                 }
-                if (have) {
+                if (i != iEnd) {
                     const uint32_t tri = nextTri;
                     float t, ab, ac;
                     if (COUNT) cnt.gridCandidates++;
@@ -554,15 +564,8 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
                         bestAB = ab;
                         bestAC = ac;
                     }
-                    // advance to the next candidate that needs a test
-                    while (++i != iEnd) {
-                        const uint32_t nt = __ldg(S.cellList + i);
-                        if (nt != g.excl && mailbox[nt & (kMailboxSlots - 1)][threadIdx.x] != nt) {
-                            nextTri = nt;
-                            break;
-                        }
-                        if (COUNT && nt != g.excl) cnt.mailboxSkips++;
-                    }
+                    ++i;
+                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, g.excl, mailbox, i, nextTri, cnt);
                 }
                 if (i == iEnd) {  // cell done
                     testing = false;

@@ -60,7 +60,7 @@ struct DeviceBuffer {
 
 struct Scene {
     int device = 0;
-    DeviceBuffer triGeo, triShade, bricks, cellRange, cellList, planes, matSize, matStart, textures, lights;
+    DeviceBuffer triGeo, triShade, bricks, cellRange, cellList, faceMask, planes, matSize, matStart, textures, lights;
     SceneView view = {};
     size_t bytes = 0;
     int smCount = 148;
@@ -164,9 +164,11 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
             }
         }
         if (ok) ok = s->cellRange.alloc(sizeof(uint2) * (nonEmpty ? nonEmpty : 1), err);
+        if (ok) ok = s->faceMask.alloc(sizeof(uint32_t) * 6 * (size_t)(nonEmpty ? nonEmpty : 1), err);
         if (ok) {
             brick_write_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (const uint32_t*)rankBase.p,
-                                                                          (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (uint32_t*)errFlag.p);
+                                                                          (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (const uint32_t*)s->cellList.p,
+                                                                          (uint32_t*)s->faceMask.p, (uint32_t*)errFlag.p);
             cudaMemcpyAsync(&flag, errFlag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
         }
     }
@@ -191,6 +193,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     v.bricks = (const uint4*)s->bricks.p;
     v.cellRange = (const uint2*)s->cellRange.p;
     v.cellList = (const uint32_t*)s->cellList.p;
+    v.faceMask = (const uint32_t*)s->faceMask.p;
     v.planes = (const float*)s->planes.p;
     v.matSize = (const uint2*)s->matSize.p;
     v.matStart = (const int32_t*)s->matStart.p;
@@ -201,7 +204,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     v.lightCount = h.lightCount;
     v.n = n;
     v.nb = nb;
-    s->bytes = s->triGeo.bytes + s->triShade.bytes + s->bricks.bytes + s->cellRange.bytes + s->cellList.bytes + s->planes.bytes +
+    s->bytes = s->triGeo.bytes + s->triShade.bytes + s->bricks.bytes + s->cellRange.bytes + s->cellList.bytes + s->faceMask.bytes + s->planes.bytes +
                s->matSize.bytes + s->matStart.bytes + s->textures.bytes + s->lights.bytes;
     return true;
 }
@@ -223,8 +226,8 @@ Scene* scene_create(int device, const HostScene& h, std::string& err) {
 void scene_destroy(Scene* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->cellList, &s->planes, &s->matSize, &s->matStart,
-                           &s->textures, &s->lights};
+    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->cellList, &s->faceMask, &s->planes, &s->matSize,
+                           &s->matStart, &s->textures, &s->lights};
     for (DeviceBuffer* b : all) b->release();
     delete s;
 }
@@ -233,8 +236,8 @@ size_t scene_device_bytes(const Scene* s) { return s->bytes; }
 
 // Debug/test door: copies one packed device array back (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList).
 size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap) {
-    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->planes, &s->cellList};
-    if (which < 0 || which > 5) return 0;
+    DeviceBuffer* all[] = {&s->triGeo, &s->triShade, &s->bricks, &s->cellRange, &s->planes, &s->cellList, &s->faceMask};
+    if (which < 0 || which > 6) return 0;
     cudaSetDevice(s->device);
     const size_t n = all[which]->bytes;
     if (dst && n && n <= cap) cudaMemcpy(dst, all[which]->p, n, cudaMemcpyDeviceToHost);

@@ -45,6 +45,7 @@ struct PackedGrid {
     std::vector<uint4> bricks;
     std::vector<uint2> cellRange;
     std::vector<uint32_t> cellList;
+    std::vector<uint32_t> faceMask;
     std::vector<float> planes;
     int32_t n = 0, nb = 0;
 };

@@ -114,6 +114,7 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
     }
     out.bricks.assign((size_t)nb * nb * nb, make_uint4(0, 0, 0, 0));
     out.cellRange.clear();
+    out.faceMask.clear();
     out.cellList.assign(h.gridList, h.gridList + total);   // list kept in the reference's order; ranges point into it
     for (uint32_t k = 0; k < total; ++k)
         if (out.cellList[k] >= h.triangleCount) {
@@ -138,12 +139,31 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
                             if (s < e) {
                                 mask |= 1ull << (x | (y << 2) | (z << 4));
                                 out.cellRange.push_back(make_uint2(s, e));
+                                const int c[3] = {bx * 4 + x, by * 4 + y, bz * 4 + z};
+                                for (int face = 0; face < 6; ++face) {  // face = axis*2 + (entered moving towards +axis)
+                                    int q[3] = {c[0], c[1], c[2]};
+                                    q[face >> 1] += (face & 1) ? -1 : 1;  // the cell the walk came from
+                                    uint32_t m = 0xFFFFFFFFu;
+                                    if (q[face >> 1] >= 0 && q[face >> 1] < n) {
+                                        const size_t nid = (size_t)q[0] + (size_t)n * q[1] + (size_t)n * n * q[2];
+                                        const uint32_t ns = h.gridStart[nid], ne = h.gridStart[nid + 1];
+                                        for (uint32_t k = 0; k < 32 && s + k < e; ++k) {
+                                            bool found = false;
+                                            for (uint32_t j = ns; j < ne && !found; ++j) found = h.gridList[j] == h.gridList[s + k];
+                                            if (found) m &= ~(1u << k);
+                                        }
+                                    }
+                                    out.faceMask.push_back(m);
+                                }
                             }
                         }
                 out.bricks[(size_t)bx + (size_t)nb * (by + (size_t)nb * bz)] =
                     make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), rankBase, 0);
             }
-    if (out.cellRange.empty()) out.cellRange.push_back(make_uint2(0, 0));
+    if (out.cellRange.empty()) {
+        out.cellRange.push_back(make_uint2(0, 0));
+        out.faceMask.assign(6, 0xFFFFFFFFu);
+    }
     return true;
 }
 

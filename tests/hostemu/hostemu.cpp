@@ -40,7 +40,7 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     pack_lights(h, lights);
     SceneView S;
     S.triGeo = geo.data(); S.triShade = shade.data(); S.bricks = grid.bricks.data(); S.cellRange = grid.cellRange.data();
-    S.cellList = grid.cellList.data(); S.planes = grid.planes.data(); S.matSize = h.matSize; S.matStart = h.matStart;
+    S.cellList = grid.cellList.data(); S.faceMask = grid.faceMask.data(); S.planes = grid.planes.data(); S.matSize = h.matSize; S.matStart = h.matStart;
     S.textures = h.textures; S.lights = lights.data(); S.triangleCount = h.triangleCount; S.materialCount = h.materialCount;
     S.lightCount = h.lightCount; S.n = grid.n; S.nb = grid.nb;
     FrameView F;
@@ -91,7 +91,8 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
 
 // Host packer output for comparison with the device packers (pack_kernels.cuh).  Buffers sized by the caller:
 // geo 64 B/tri, shade 128 B/tri, bricks 16 B/brick, ranges 8 B per non-empty cell (count returned), planes 3*(n+1) floats.
-extern "C" long hostemu_pack(const oclr_scene_desc* d, void* geo, void* shade, void* bricks, void* ranges, size_t rangesCap, void* planes) {
+extern "C" long hostemu_pack(const oclr_scene_desc* d, void* geo, void* shade, void* bricks, void* ranges, size_t rangesCap, void* planes,
+                             void* faceMask) {
     HostScene h;
     h.vertexCount = d->vertexCount; h.vertex = (const float4*)d->vertex;
     h.triangleCount = d->triangleCount; h.triIdx = (const int32_t*)d->triangleVertexIndex; h.triMat = d->triangleMaterialId;
@@ -107,5 +108,6 @@ extern "C" long hostemu_pack(const oclr_scene_desc* d, void* geo, void* shade, v
     if (grid.cellRange.size() * sizeof(uint2) > rangesCap) return -2;
     memcpy(ranges, grid.cellRange.data(), sizeof(uint2) * grid.cellRange.size());
     memcpy(planes, grid.planes.data(), sizeof(float) * grid.planes.size());
+    if (faceMask) memcpy(faceMask, grid.faceMask.data(), sizeof(uint32_t) * 6 * grid.cellRange.size());
     return (long)grid.cellRange.size();
 }

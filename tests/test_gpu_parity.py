@@ -126,13 +126,15 @@ def test_device_packers_equal_host_packers(hostemu):
         d = sc.desc()
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         hostemu.hostemu_pack.restype = C.c_long
-        cnt = hostemu.hostemu_pack(C.byref(d), p(geo), p(shade), p(bricks), p(ranges), C.c_size_t(ranges.size), p(planes))
+        masks = np.zeros(3 * ranges.size, np.uint8)
+        cnt = hostemu.hostemu_pack(C.byref(d), p(geo), p(shade), p(bricks), p(ranges), C.c_size_t(ranges.size), p(planes), p(masks))
         assert cnt >= 0
         ds = api.DeviceScene(sc, 0)
         assert np.array_equal(ds.debug_read(0), geo) and np.array_equal(ds.debug_read(1), shade)
         assert np.array_equal(ds.debug_read(2), bricks) and np.array_equal(ds.debug_read(4), planes)
         assert np.array_equal(ds.debug_read(3)[:8 * cnt], ranges[:8 * cnt])
         assert np.array_equal(ds.debug_read(5).view(np.uint32), sc.grid_list)
+        assert np.array_equal(ds.debug_read(6)[:24 * cnt], masks[:24 * cnt])
         ds.close()
 
 
