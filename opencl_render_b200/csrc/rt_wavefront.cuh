@@ -391,7 +391,10 @@ struct TraceTuning {
 // small per-lane queue (shared memory) for the next TEST phase; cells are tested in walk order and the first cell with a
 // hit ends the ray (:380), discarding whatever the walker found beyond it.  The speculation is bounded by the queue
 // depth; it keeps ~all lanes busy in both phases instead of parking a lane the moment it finds triangles.
-enum { kPendingDepth = 2 };
+#ifndef OCLR_PENDING_DEPTH
+#define OCLR_PENDING_DEPTH 4
+#endif
+enum { kPendingDepth = OCLR_PENDING_DEPTH };
 enum { kWalkNone = 0, kWalkRunning = 1, kWalkFinished = 2 };
 
 // Next list entry at or after k that this ray still has to test: entries whose face-mask bit is clear were in the cell the
