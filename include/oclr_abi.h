@@ -224,6 +224,8 @@ typedef struct oclr_counters {
 typedef struct oclr_render_stats {
     float deviceMs;        /* CUDA-event time of the trace kernels on the launch stream */
     cl_uint launches;      /* kernels launched by this call */
+    float traceMs;         /* CUDA-event time of the wf_trace_kernel launches alone (dominant kernel) */
+    cl_uint traceLaunches;
     oclr_counters counters;
 } oclr_render_stats;
 

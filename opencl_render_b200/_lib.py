@@ -48,7 +48,8 @@ class Counters(C.Structure):
 
 class RenderStats(C.Structure):
     """oclr_render_stats"""
-    _fields_ = [("deviceMs", C.c_float), ("launches", C.c_uint32), ("counters", Counters)]
+    _fields_ = [("deviceMs", C.c_float), ("launches", C.c_uint32), ("traceMs", C.c_float), ("traceLaunches", C.c_uint32),
+                ("counters", Counters)]
 
 
 class CameraLists(C.Structure):

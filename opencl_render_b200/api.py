@@ -303,6 +303,7 @@ class DeviceFrame:
                                          C.byref(stats) if (sync or count) else None)
         if not ok:
             raise OclrError(_lib.last_error())
+        self.last_trace_ms, self.last_trace_launches = float(stats.traceMs), int(stats.traceLaunches)
         return float(stats.deviceMs), int(stats.launches), (stats.counters.as_dict() if count else None)
 
     def render_bands(self, sample_count: int, band_rows: int, rank: int, world: int, variant: int = KERNEL_DEFAULT,
@@ -313,6 +314,7 @@ class DeviceFrame:
                                                C.c_void_p(stream), C.byref(stats) if (sync or count) else None)
         if not ok:
             raise OclrError(_lib.last_error())
+        self.last_trace_ms, self.last_trace_launches = float(stats.traceMs), int(stats.traceLaunches)
         return float(stats.deviceMs), int(stats.launches), (stats.counters.as_dict() if count else None)
 
     def read(self, rows=None, out=None, stream: int = 0):

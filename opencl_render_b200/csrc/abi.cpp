@@ -211,6 +211,8 @@ int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, 
     if (stats) {
         stats->deviceMs = rs.deviceMs;
         stats->launches = rs.launches;
+        stats->traceMs = rs.traceMs;
+        stats->traceLaunches = rs.traceLaunches;
         memcpy(&stats->counters, &rs.counters, sizeof(Counters));
     }
     return 1;
@@ -232,6 +234,8 @@ int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint band
     if (stats) {
         stats->deviceMs = rs.deviceMs;
         stats->launches = rs.launches;
+        stats->traceMs = rs.traceMs;
+        stats->traceLaunches = rs.traceLaunches;
         memcpy(&stats->counters, &rs.counters, sizeof(Counters));
     }
     return 1;

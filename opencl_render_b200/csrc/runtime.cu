@@ -76,6 +76,8 @@ struct Frame {
     uint32_t* hostCount = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t lastLaunches = 0;
+    std::vector<cudaEvent_t> traceEvents;   // pairs around the trace launches of the last timed render
+    uint32_t traceEventsUsed = 0;
 };
 
 int device_count() {
@@ -299,6 +301,7 @@ void frame_destroy(Frame* f) {
     if (f->hostCount) cudaFreeHost(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
+    for (cudaEvent_t e : f->traceEvents) cudaEventDestroy(e);
     delete f;
 }
 
@@ -311,7 +314,8 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
-                             uint32_t& launches, std::string& err) {
+                             uint32_t& launches, bool timeTrace, std::string& err) {
+    f->traceEventsUsed = 0;
     const uint32_t rows = launch_rows(F), W = F.cam.width;
     const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
     if (Q64 > 0xFFFFFFF0ull) {
@@ -380,10 +384,22 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
             const uint32_t waiting = f->hostCount[0];
             if (waiting == 0) break;
             const unsigned grid = (unsigned)std::min<uint64_t>(traceGrid, ((uint64_t)waiting + 127) / 128);
+            if (timeTrace) {
+                while (f->traceEvents.size() < (size_t)f->traceEventsUsed + 2) {
+                    cudaEvent_t e;
+                    OCLR_CUDA(cudaEventCreate(&e));
+                    f->traceEvents.push_back(e);
+                }
+                OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
+            }
             if (dcnt)
                 wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
             else
                 wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
+            if (timeTrace) {
+                OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed + 1], st));
+                f->traceEventsUsed += 2;
+            }
             ++launches;
             if (round > 100000) {
                 err = "wavefront did not converge";
@@ -420,7 +436,7 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
             raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         launches = 1;
     } else if (variant == kKernelPersistent) {
-        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, err)) return false;
+        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, err)) return false;
     } else {
         err = "unknown kernel variant";
         return false;
@@ -432,6 +448,13 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         OCLR_CUDA(cudaEventSynchronize(f->ev1));
         OCLR_CUDA(cudaEventElapsedTime(&stats->deviceMs, f->ev0, f->ev1));
         stats->launches = launches;
+        stats->traceMs = 0.f;
+        stats->traceLaunches = variant == kKernelPersistent ? f->traceEventsUsed / 2 : 0;
+        for (uint32_t k = 0; variant == kKernelPersistent && k + 1 < f->traceEventsUsed; k += 2) {
+            float ms = 0.f;
+            OCLR_CUDA(cudaEventElapsedTime(&ms, f->traceEvents[k], f->traceEvents[k + 1]));
+            stats->traceMs += ms;
+        }
         if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
     }
     return true;

@@ -78,6 +78,8 @@ enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1 };
 struct RenderStats {
     float deviceMs = 0.f;        // CUDA-event time of the trace kernel(s) on the launch stream
     uint32_t launches = 0;       // kernels launched
+    float traceMs = 0.f;         // CUDA-event time of the wf_trace_kernel launches alone (the dominant kernel)
+    uint32_t traceLaunches = 0;
     Counters counters = {};      // filled when `count` was requested
 };
 
