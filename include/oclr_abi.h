@@ -218,7 +218,7 @@ typedef struct oclr_frame oclr_frame;
 typedef struct oclr_counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
-        mailboxSkips, coarseSteps, coarseEnters;
+        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters;
 } oclr_counters;
 
 typedef struct oclr_render_stats {
@@ -229,7 +229,7 @@ typedef struct oclr_render_stats {
     oclr_counters counters;
 } oclr_render_stats;
 
-enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PERSISTENT = 1, OCLR_KERNEL_DEFAULT = -1 };
+enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PERSISTENT = 1, OCLR_KERNEL_PACKED = 2, OCLR_KERNEL_DEFAULT = -1 };
 
 /* Upload + repack a scene into the HBM of CUDA device `device`.  NULL on failure. */
 oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);

@@ -193,7 +193,14 @@ void oclr_frame_destroy(oclr_frame* frame) {
     delete frame;
 }
 
-static int pick_variant(int v) { return v == OCLR_KERNEL_DEFAULT ? (int)kKernelPersistent : v; }
+static int default_variant() {
+    static const int v = [] {
+        const char* e = getenv("OCLR_KERNEL_VARIANT");   // experiment knob
+        return e ? atoi(e) : (int)kKernelPersistent;
+    }();
+    return v;
+}
+static int pick_variant(int v) { return v == OCLR_KERNEL_DEFAULT ? default_variant() : v; }
 
 int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, cl_uint rowEnd, int kernelVariant, int countEvents,
                       void* cudaStream, oclr_render_stats* stats) {
@@ -330,7 +337,7 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
         for (int k = 0; ok && k < owned; ++k) {
             RenderStats rs;
             const double a = now_ms();
-            ok = frame_render(f, sampleCount, rows[2 * k], rows[2 * k + 1], kKernelPersistent, false, nullptr, &rs, err);
+            ok = frame_render(f, sampleCount, rows[2 * k], rows[2 * k + 1], default_variant(), false, nullptr, &rs, err);
             const double c = now_ms();
             if (ok) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
             tRender += c - a;

@@ -55,24 +55,8 @@ __global__ void __launch_bounds__(256) pack_triangles_kernel(uint32_t triangleCo
 
 // Pass 1 over the reference CSR (n^3 + 1 starts): one thread per 4x4x4 brick builds its occupancy mask and counts its
 // non-empty cells.  Pass 2 (after an exclusive scan of the counts) writes {mask, rank base} and the {begin,end} ranges.
-// bit k set = list entry k of cell [s,e) is absent from the (sorted) list [ns,ne) of the cell the walk came from
-__device__ __forceinline__ uint32_t face_mask(const uint32_t* __restrict__ list, uint32_t s, uint32_t e, uint32_t ns, uint32_t ne) {
-    uint32_t m = 0xFFFFFFFFu;
-    for (uint32_t k = 0; k < 32u && s + k < e; ++k) {
-        const uint32_t tri = __ldg(list + s + k);
-        uint32_t lo = ns, hi = ne;  // lower bound in the ascending neighbour list
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(list + mid) < tri) lo = mid + 1; else hi = mid;
-        }
-        if (lo < ne && __ldg(list + lo) == tri) m &= ~(1u << k);
-    }
-    return m;
-}
-
 __device__ __forceinline__ uint64_t brick_mask(const uint32_t* __restrict__ start, int n, int nb, uint32_t total, int b, uint32_t* error,
-                                               uint2* ranges /* nullable */, const uint32_t* __restrict__ list = nullptr,
-                                               uint32_t* faceMask = nullptr) {
+                                               uint2* ranges /* nullable */, uint32_t* cellIds = nullptr /* linear cell id per non-empty cell */) {
     const int side = n >= 4 ? 4 : n;
     const int bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
     uint64_t mask = 0;
@@ -87,20 +71,7 @@ __device__ __forceinline__ uint64_t brick_mask(const uint32_t* __restrict__ star
                 if (s < e) {
                     mask |= 1ull << (x | (y << 2) | (z << 4));
                     if (ranges) ranges[k] = make_uint2(s, e);
-                    if (faceMask && e <= total) {
-                        const int c[3] = {bx * 4 + x, by * 4 + y, bz * 4 + z};
-                        for (int face = 0; face < 6; ++face) {  // face = axis*2 + (entered moving towards +axis)
-                            int q[3] = {c[0], c[1], c[2]};
-                            q[face >> 1] += (face & 1) ? -1 : 1;
-                            uint32_t m = 0xFFFFFFFFu;
-                            if (q[face >> 1] >= 0 && q[face >> 1] < n) {
-                                const size_t nid = (size_t)q[0] + (size_t)n * q[1] + (size_t)n * n * q[2];
-                                const uint32_t ns = __ldg(start + nid), ne = __ldg(start + nid + 1);
-                                if (ns <= ne && ne <= total) m = face_mask(list, s, e, ns, ne);
-                            }
-                            faceMask[6 * (size_t)k + face] = m;
-                        }
-                    }
+                    if (cellIds) cellIds[k] = (uint32_t)(row + x);
                     ++k;
                 }
                 s = e;
@@ -118,13 +89,43 @@ __global__ void __launch_bounds__(128) brick_count_kernel(const uint32_t* __rest
 
 __global__ void __launch_bounds__(128) brick_write_kernel(const uint32_t* __restrict__ start, int n, int nb, uint32_t total,
                                                           const uint32_t* __restrict__ rankBase, uint4* __restrict__ bricks,
-                                                          uint2* __restrict__ cellRange, const uint32_t* __restrict__ list,
-                                                          uint32_t* __restrict__ faceMask, uint32_t* __restrict__ error) {
+                                                          uint2* __restrict__ cellRange, uint32_t* __restrict__ cellIds,
+                                                          uint32_t* __restrict__ error) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb * nb * nb) return;
     const uint32_t base = rankBase[b];
-    const uint64_t mask = brick_mask(start, n, nb, total, b, error, cellRange + base, list, faceMask + 6 * (size_t)base);
+    const uint64_t mask = brick_mask(start, n, nb, total, b, error, cellRange + base, cellIds + base);
     bricks[b] = make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), base, 0u);
+}
+
+// Face masks (rt_types.h): bit e set = list entry e of the cell is absent from the list of the neighbour the walk comes from.
+// One thread per (non-empty cell, face): the work of the face masks sits in the ~10 % of bricks that hold triangles, so it is
+// spread over cells x faces instead of being done by the brick's thread.  Both lists are ascending: one merge pass.
+__global__ void __launch_bounds__(256) face_mask_kernel(const uint32_t* __restrict__ start, int n, uint32_t total, uint32_t nonEmpty,
+                                                        const uint32_t* __restrict__ cellIds, const uint2* __restrict__ cellRange,
+                                                        const uint32_t* __restrict__ list, uint32_t* __restrict__ faceMask) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nonEmpty * 6u) return;
+    const uint32_t k = t / 6u, face = t - 6u * k;   // face = axis*2 + (entered moving towards +axis)
+    const uint32_t id = cellIds[k];
+    int q[3] = {(int)(id % (uint32_t)n), (int)((id / (uint32_t)n) % (uint32_t)n), (int)(id / ((uint32_t)n * (uint32_t)n))};
+    q[face >> 1] += (face & 1) ? -1 : 1;
+    uint32_t m = 0xFFFFFFFFu;
+    if (q[face >> 1] >= 0 && q[face >> 1] < n) {
+        const size_t nid = (size_t)q[0] + (size_t)n * q[1] + (size_t)n * n * q[2];
+        const uint32_t ns = __ldg(start + nid), ne = __ldg(start + nid + 1);
+        const uint2 r = cellRange[k];
+        if (ns < ne && ne <= total && r.y <= total) {
+            uint32_t j = ns;
+            uint32_t other = __ldg(list + j);
+            for (uint32_t e = 0; e < 32u && r.x + e < r.y; ++e) {
+                const uint32_t tri = __ldg(list + r.x + e);
+                while (other < tri && j + 1 < ne) other = __ldg(list + (++j));
+                if (other == tri) m &= ~(1u << e);
+            }
+        }
+    }
+    faceMask[t] = m;
 }
 
 __global__ void __launch_bounds__(256) check_list_kernel(const uint32_t* __restrict__ list, uint32_t total, uint32_t triangleCount,

@@ -604,6 +604,18 @@ OCLR_HD void light_accumulate(const Light& L, f3 nrm, const LightRay& lr, f3 att
     face[idx].z += (1.f - face[idx].z) * att.z * e * L.colour[2];
 }
 
+// rt_walk.h: the walk in the trace kernel's packed formulation (walkMode 2 of trace_sample exercises it on the host)
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl,
+                                   float& outT, float& outAB, float& outAC, Counters* cnt);
+
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_mode(int walkMode, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
+                                 float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC, Counters* cnt) {
+    if (walkMode == 2) return grid_trace_packed<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);  // px = base of all planes
+    return grid_trace<COUNT>(S, px, py, pz, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode == 1);
+}
+
 // ---- one pixel-sample, serial form: raytrace_opencl.c:452-725 --------------------------------------------------------
 // Ring storage is supplied by the caller (registers/local memory on the simple kernel, shared memory on the
 // persistent kernel) through RingT: fields indexed by slot.
@@ -618,7 +630,7 @@ struct RingLocal {
 template <bool COUNT>
 OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px, const float* py, const float* pz,
                         uint32_t pixel, uint32_t sampleIdx, uint32_t* primaryId, bool& undefinedRef, Counters* cnt,
-                        bool hierarchical = false) {
+                        int walkMode = 0 /* 0 cell walk, 1 two-level walk, 2 packed two-level walk (rt_walk.h) */) {
     const Camera& cam = F.cam;
     uint64_t rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
     const float fx = (float)(pixel % cam.width);
@@ -666,8 +678,8 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
                 }
             }
         } else {
-            hit = grid_trace<COUNT>(S, px, py, pz, ro, rv, ring.minD[begin], ring.maxD[begin], ring.excl[begin], hitT, hitAB,
-                                    hitAC, cnt, hierarchical);
+            hit = grid_trace_mode<COUNT>(walkMode, S, px, py, pz, ro, rv, ring.minD[begin], ring.maxD[begin], ring.excl[begin], hitT,
+                                         hitAB, hitAC, cnt);
         }
         if (first) {
             if (primaryId) *primaryId = hit;
@@ -697,7 +709,7 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
             if (lr.minLen < lr.maxLen) {
                 for (;;) {
                     float t, ab = 0.f, ac = 0.f;
-                    const uint32_t occ = grid_trace<COUNT>(S, px, py, pz, loc, lr.dir, lr.minLen, lr.maxLen, hit, t, ab, ac, cnt, hierarchical);
+                    const uint32_t occ = grid_trace_mode<COUNT>(walkMode, S, px, py, pz, loc, lr.dir, lr.minLen, lr.maxLen, hit, t, ab, ac, cnt);
                     if (occ == kNoTriangle) break;
                     int om;
                     float u0, v0, u1, v1, u2, v2;
@@ -780,3 +792,5 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
 }
 
 }  // namespace oclr
+
+#include "rt_walk.h"

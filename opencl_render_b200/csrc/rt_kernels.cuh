@@ -33,6 +33,8 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     if (c.mailboxSkips) atomicAdd(&g->mailboxSkips, c.mailboxSkips);
     if (c.coarseSteps) atomicAdd(&g->coarseSteps, c.coarseSteps);
     if (c.coarseEnters) atomicAdd(&g->coarseEnters, c.coarseEnters);
+    if (c.switchWarpIters) atomicAdd(&g->switchWarpIters, c.switchWarpIters);
+    if (c.switchLaneIters) atomicAdd(&g->switchLaneIters, c.switchLaneIters);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

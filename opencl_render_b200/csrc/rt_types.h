@@ -113,7 +113,7 @@ OCLR_HD uint32_t launch_rows(const FrameView& F) { return F.bandWorld <= 1 ? F.r
 struct Counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
-        mailboxSkips, coarseSteps, coarseEnters;
+        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters;
 };
 
 }  // namespace oclr

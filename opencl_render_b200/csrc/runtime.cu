@@ -12,6 +12,7 @@
 
 #include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
+#include "rt_trace.cuh"
 #include "rt_wavefront.cuh"
 #include "runtime.h"
 
@@ -72,6 +73,7 @@ struct Frame {
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
     // wavefront path state (allocated on first use, sized for the largest launch domain seen)
     DeviceBuffer wfCtl, wfRng, wfColour, wfRing, wfCarry, wfRayO, wfRayD, wfRayExcl, wfHit, wfQueue;
+    DeviceBuffer recO, recD, recS0, recS1;   // walk records in queue order (rt_trace.cuh)
     uint32_t wfCapacity = 0;
     uint32_t* hostCount = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -125,7 +127,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     pack_lights(h, lights);
 
     // 1. raw reference arrays -> HBM, straight from the caller's memory (async on the default stream)
-    DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag;
+    DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag, cellIds;
     bool ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
               triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
               triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) && boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
@@ -165,17 +167,28 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
                 ok = false;
             }
         }
+        if (ok && nonEmpty >= (1u << 29)) {
+            err = "too many non-empty grid cells (>= 2^29)";
+            ok = false;
+        }
         if (ok) ok = s->cellRange.alloc(sizeof(uint2) * (nonEmpty ? nonEmpty : 1), err);
         if (ok) ok = s->faceMask.alloc(sizeof(uint32_t) * 6 * (size_t)(nonEmpty ? nonEmpty : 1), err);
+        if (ok) ok = cellIds.alloc(sizeof(uint32_t) * (size_t)(nonEmpty ? nonEmpty : 1), err);
         if (ok) {
             brick_write_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (const uint32_t*)rankBase.p,
-                                                                          (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (const uint32_t*)s->cellList.p,
-                                                                          (uint32_t*)s->faceMask.p, (uint32_t*)errFlag.p);
+                                                                          (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (uint32_t*)cellIds.p,
+                                                                          (uint32_t*)errFlag.p);
+            if (nonEmpty)
+                face_mask_kernel<<<(unsigned)(((size_t)nonEmpty * 6 + 255) / 256), 256>>>((const uint32_t*)gridStart.p, n, total, nonEmpty,
+                                                                                         (const uint32_t*)cellIds.p, (const uint2*)s->cellRange.p,
+                                                                                         (const uint32_t*)s->cellList.p, (uint32_t*)s->faceMask.p);
+            else
+                cudaMemsetAsync(s->faceMask.p, 0xFF, sizeof(uint32_t) * 6, 0);
             cudaMemcpyAsync(&flag, errFlag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
         }
     }
     cudaError_t e = cudaStreamSynchronize(0);
-    DeviceBuffer* tmp[] = {&vertex, &triIdx, &triMat, &triUv, &triNormal, &boxMin, &gridStart, &counts, &rankBase, &scanTmp, &errFlag};
+    DeviceBuffer* tmp[] = {&vertex, &triIdx, &triMat, &triUv, &triNormal, &boxMin, &gridStart, &counts, &rankBase, &scanTmp, &errFlag, &cellIds};
     for (DeviceBuffer* b : tmp) b->release();
     if (!ok) return false;
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
@@ -296,7 +309,7 @@ void frame_destroy(Frame* f) {
     cudaSetDevice(f->scene->device);
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter,
                            &f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl, &f->wfHit,
-                           &f->wfQueue};
+                           &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1};
     for (DeviceBuffer* b : all) b->release();
     if (f->hostCount) cudaFreeHost(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
@@ -314,7 +327,7 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
-                             uint32_t& launches, bool timeTrace, std::string& err) {
+                             uint32_t& launches, bool timeTrace, bool packed, std::string& err) {
     f->traceEventsUsed = 0;
     const uint32_t rows = launch_rows(F), W = F.cam.width;
     const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
@@ -325,14 +338,16 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     const uint32_t Q = (uint32_t)Q64;
     if (Q > f->wfCapacity) {
         DeviceBuffer* all[] = {&f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl,
-                               &f->wfHit, &f->wfQueue};
+                               &f->wfHit, &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1};
         for (DeviceBuffer* b : all) b->release(st);
         if (!f->wfCtl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) || !f->wfRng.alloc(sizeof(uint64_t) * (size_t)Q, err, st) ||
             !f->wfColour.alloc(sizeof(float4) * (size_t)Q, err, st) ||
             !f->wfRing.alloc(sizeof(float4) * (size_t)Q * kRingSize * kRingParts, err, st) ||
             !f->wfCarry.alloc(sizeof(float4) * (size_t)Q * kCarryParts, err, st) || !f->wfRayO.alloc(sizeof(float4) * (size_t)Q, err, st) ||
             !f->wfRayD.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfRayExcl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
-            !f->wfHit.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfQueue.alloc(sizeof(uint32_t) * (size_t)Q, err, st))
+            !f->wfHit.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfQueue.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
+            !f->recO.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recD.alloc(sizeof(float4) * (size_t)Q, err, st) ||
+            !f->recS0.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recS1.alloc(sizeof(uint4) * (size_t)Q, err, st))
             return false;
         f->wfCapacity = Q;
     }
@@ -351,21 +366,38 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     w.queue = (uint32_t*)f->wfQueue.p;
     w.queueCount = (uint32_t*)f->workCounter.p;
     w.queueCursor = w.queueCount + 1;
+    WalkRecords rec;
+    rec.o = (float4*)f->recO.p;
+    rec.d = (float4*)f->recD.p;
+    rec.s0 = (float4*)f->recS0.p;
+    rec.s1 = (uint4*)f->recS1.p;
+    if (packed && S.n > 1024) {
+        err = "axesDivCount > 1024 is not supported by the packed walk";
+        return false;
+    }
 
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
-    if (dcnt)
+    if (packed) {
+        if (dcnt)
+            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace2_kernel<true>, 128, shBytes));
+        else
+            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace2_kernel<false>, 128, shBytes));
+    } else if (dcnt)
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<true>, 128, shBytes));
     else
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
-    static TraceTuning tune = {0, 0, 0, 1};
+    static TraceTuning tune = {0, 0, 0, 1, 0, 0, 0};
     if (tune.walkMin == 0) {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
         tune.walkMin = env("OCLR_WALK_MIN", 16);
         tune.testMin = env("OCLR_TEST_MIN", 16);
         tune.refillMin = env("OCLR_REFILL_MIN", 4);
         tune.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
+        tune.wWalk = env("OCLR_W_WALK", 2);
+        tune.wTest = env("OCLR_W_TEST", 3);
+        tune.wSwitch = env("OCLR_W_SWITCH", 6);
     }
     const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -392,7 +424,15 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
                 }
                 OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
             }
-            if (dcnt)
+            if (packed) {
+                const unsigned setupGrid = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)waiting + 255) / 256);
+                wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
+                ++launches;
+                if (dcnt)
+                    wf_trace2_kernel<true><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                else
+                    wf_trace2_kernel<false><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+            } else if (dcnt)
                 wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
             else
                 wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
@@ -435,8 +475,9 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         else
             raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         launches = 1;
-    } else if (variant == kKernelPersistent) {
-        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, err)) return false;
+    } else if (variant == kKernelPersistent || variant == kKernelPacked) {
+        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, variant == kKernelPacked, err))
+            return false;
     } else {
         err = "unknown kernel variant";
         return false;
@@ -449,8 +490,8 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         OCLR_CUDA(cudaEventElapsedTime(&stats->deviceMs, f->ev0, f->ev1));
         stats->launches = launches;
         stats->traceMs = 0.f;
-        stats->traceLaunches = variant == kKernelPersistent ? f->traceEventsUsed / 2 : 0;
-        for (uint32_t k = 0; variant == kKernelPersistent && k + 1 < f->traceEventsUsed; k += 2) {
+        stats->traceLaunches = variant != kKernelSimple ? f->traceEventsUsed / 2 : 0;
+        for (uint32_t k = 0; variant != kKernelSimple && k + 1 < f->traceEventsUsed; k += 2) {
             float ms = 0.f;
             OCLR_CUDA(cudaEventElapsedTime(&ms, f->traceEvents[k], f->traceEvents[k + 1]));
             stats->traceMs += ms;

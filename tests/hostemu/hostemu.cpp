@@ -51,7 +51,8 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     if (rowEnd > cam->height) rowEnd = cam->height;
     std::atomic<uint32_t> nextRow(rowBegin);
     std::vector<Counters> cnts(threads > 0 ? threads : 1);
-    const bool hier = getenv("HOSTEMU_HIERARCHICAL") != nullptr;   // exercise the two-level (brick-skipping) walk
+    // walk mode: unset = the reference's cell walk, 1 = two-level (brick-skipping) walk, 2 = the trace kernel's packed form (rt_walk.h)
+    const int hier = getenv("HOSTEMU_HIERARCHICAL") ? (atoi(getenv("HOSTEMU_HIERARCHICAL")) == 2 ? 2 : 1) : 0;
     auto worker = [&](int tid) {
         Counters& cnt = cnts[tid];
         memset(&cnt, 0, sizeof(cnt));

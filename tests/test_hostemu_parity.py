@@ -60,3 +60,22 @@ def test_two_level_walk_is_exact(name, hostemu, monkeypatch):
     assert hier[3]["bricksLoaded"] == flat[3]["bricksLoaded"]          # same brick sequence
     assert hier[3]["gridCandidates"] == flat[3]["gridCandidates"] and hier[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
     assert hier[3]["cells"] <= flat[3]["cells"]
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_packed_walk_is_exact(name, hostemu, monkeypatch):
+    """rt_walk.h -- the walk as the production trace kernel runs it (packed coordinates, incremental brick ids, face masks and
+    mailbox skipping) -- against the reference's cell walk: identical planes, ids and flags, same brick sequence, same set of
+    non-empty cells; triangle tests can only go down (entries shared with the previous cell / already tested are skipped)."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "2")
+    packed = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], packed[0][c])
+    assert np.array_equal(flat[1], packed[1]) and np.array_equal(flat[2], packed[2])
+    assert packed[3]["bricksLoaded"] == flat[3]["bricksLoaded"]
+    assert packed[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
+    assert packed[3]["gridCandidates"] <= flat[3]["gridCandidates"]
+    assert packed[3]["cells"] <= flat[3]["cells"]
