@@ -235,7 +235,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = rays_frame * e2e_steps / float(t.item()) / 1e6
 
-    # ---- roofline of the dominant kernel, wf_trace_kernel (rank 0's share of the frame) ------------------------------------------
+    # ---- roofline of the dominant kernel, wf_pipe_kernel (rank 0's share of the frame) ------------------------------------------
     roof = cpu = None
     if rank == 0:
         _, _, cnt = part.render_counted(fr, S, 0)      # event counts in the reference's accounting: the per-pixel kernel
@@ -253,7 +253,7 @@ def run_b200(args):
         algo_trace = 8.0 * cnt["cells"] + 68.0 * cnt["gridCandidates"] + 52.0 * cnt["gridRays"]
         peak, which = hbm_peak()
         achieved = (algo_trace / n_trace) / (ms_trace / n_trace * 1e-3) / 1e9
-        roof = {"kernel": "wf_trace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roof = {"kernel": "wf_pipe_kernel (+ wf_setup_kernel)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": which, "launches_per_step": n_trace, "avg_launch_ms": ms_trace / n_trace,
                 "algorithmic_bytes_per_launch": algo_trace / n_trace,
                 "note": "working set is L2-resident (DRAM traffic << algorithmic bytes, see traffic); the kernel is issue-bound, "

@@ -218,18 +218,19 @@ typedef struct oclr_frame oclr_frame;
 typedef struct oclr_counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
-        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters;
+        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
+        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters;
 } oclr_counters;
 
 typedef struct oclr_render_stats {
     float deviceMs;        /* CUDA-event time of the trace kernels on the launch stream */
     cl_uint launches;      /* kernels launched by this call */
-    float traceMs;         /* CUDA-event time of the wf_trace_kernel launches alone (dominant kernel) */
+    float traceMs;         /* CUDA-event time of the trace-stage launches alone (dominant kernel) */
     cl_uint traceLaunches;
     oclr_counters counters;
 } oclr_render_stats;
 
-enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PERSISTENT = 1, OCLR_KERNEL_PACKED = 2, OCLR_KERNEL_DEFAULT = -1 };
+enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PERSISTENT = 1, OCLR_KERNEL_PIPE = 2, OCLR_KERNEL_DEFAULT = -1 };
 
 /* Upload + repack a scene into the HBM of CUDA device `device`.  NULL on failure. */
 oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);

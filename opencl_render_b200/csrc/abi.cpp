@@ -196,7 +196,7 @@ void oclr_frame_destroy(oclr_frame* frame) {
 static int default_variant() {
     static const int v = [] {
         const char* e = getenv("OCLR_KERNEL_VARIANT");   // experiment knob
-        return e ? atoi(e) : (int)kKernelPersistent;
+        return e ? atoi(e) : (int)kKernelPipe;
     }();
     return v;
 }

@@ -35,6 +35,11 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     if (c.coarseEnters) atomicAdd(&g->coarseEnters, c.coarseEnters);
     if (c.switchWarpIters) atomicAdd(&g->switchWarpIters, c.switchWarpIters);
     if (c.switchLaneIters) atomicAdd(&g->switchLaneIters, c.switchLaneIters);
+    if (c.walkIdleLanes) atomicAdd(&g->walkIdleLanes, c.walkIdleLanes);
+    if (c.walkParkedLanes) atomicAdd(&g->walkParkedLanes, c.walkParkedLanes);
+    if (c.walkFinishedLanes) atomicAdd(&g->walkFinishedLanes, c.walkFinishedLanes);
+    if (c.walkLowIters) atomicAdd(&g->walkLowIters, c.walkLowIters);
+    if (c.walkExhaustedIters) atomicAdd(&g->walkExhaustedIters, c.walkExhaustedIters);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

@@ -1,18 +1,15 @@
-// rt_trace.cuh -- production trace stage of the wavefront pipeline (rt_wavefront.cuh has the logic kernel and the first
-// trace kernel, kept for A/B): a setup kernel + a persistent trace kernel built on the packed walk of rt_walk.h.
+// rt_trace.cuh -- production trace stage of the wavefront pipeline: a setup kernel + a persistent trace kernel organised as a
+// warp-level pipeline (rt_wavefront.cuh has the logic kernel and the first-generation trace kernel, kept for A/B).
 //
-// What ncu said about the first trace kernel (profiles/r01_wf_trace_cfg2_*): issue-bound (66-69 % of issue slots), 14 of 32
-// lanes active per instruction.  Per-line attribution: the common path of one walk iteration was ~125 instructions at 22 lanes,
-// and on top of it every iteration paid ~65 instructions for "open the cell" work at ~6 lanes, ~90 for level switches of the
-// two-level walk at 1.4 lanes, and every refill ran BindInCube/GetBoxAddress with a handful of lanes.  Hence:
+// What ncu said about the first trace kernel (profiles/r01_wf_trace_cfg2_*): issue-bound (66-69 % of issue slots) with 14 of 32
+// lanes active per instruction.  By phase: the walk ran at ~21 lanes, but "open the cell + scan its list + test" -- 37 % of all
+// instructions -- ran with 5-6 lanes, the level switches of the two-level walk with <2, and every refill ran
+// BindInCube/GetBoxAddress with a handful of lanes.  Hence:
 //
 //   wf_setup_kernel   one thread per queued ray, all lanes busy: BindInCube + GetBoxAddress + first crossings
 //                     (raytrace_opencl.c:350-362), written as 64-byte records in QUEUE order, so the trace kernel's refill is
 //                     four coalesced 128-bit loads per lane instead of a gather plus ~400 divergent instructions.
-//   wf_trace2_kernel  WALK phase: one select-based step on packed coordinates (rt_walk.h), an occupied cell costs one
-//                     shared-memory store (its rank + entry face go to the lane's pending queue; range, face mask and
-//                     candidate scan happen when the cell is popped in the TEST phase, with the lanes that test);
-//                     level switches (enter-coarse / refine) are parked and run batched once several lanes need one.
+//   wf_pipe_kernel    see the comment above the kernel.
 //
 // Results are bit-identical to the other kernels by construction (same rt_core.h / rt_walk.h arithmetic; tests assert it).
 #pragma once
@@ -53,37 +50,75 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 #endif
 }
 
-#ifndef OCLR_PENDING2_DEPTH
-#define OCLR_PENDING2_DEPTH 8
+// ---- wf_pipe_kernel: warp-level pipeline ----------------------------------------------------------------------------------
+// ncu on the lane-owned trace kernels: 37 % of all instructions are the
+// lane-owned test work (open cell, scan its list, test) executed with 5-6 of 32 lanes, because at any moment only a few of a
+// warp's rays sit on a cell with untested triangles.  Only the WALK is inherently per-ray; opening a cell and testing a
+// (ray, triangle) pair are independent work items, so they are decoupled from the lane that owns the ray:
+//
+//   WALK    lanes own rays; an occupied cell is appended to the WARP's cell queue {rank, entry face, owner lane, seq}
+//           (one ballot + one store); seq = position of the cell along that ray's walk within the current batch;
+//   OPEN    any lane takes any queued cell: range + face mask, then the warp enumerates the untested entries round by round
+//           into the warp's pair queue {triangle, owner, seq};
+//   TEST    any lane takes any pair: ray constants from the owner's row of a shared table, the full test against the ray's
+//           ORIGINAL (minD, maxD), result folded with a 64-bit shared atomicMin on key = seq | t | pair index.  That is the
+//           reference's rule exactly: first cell (in walk order) with any hit wins (:380); inside a cell the in-cell bound
+//           shrinks with a strict `<` (:143, :372-377), i.e. smallest t, earliest list entry on ties -- pair indices grow in
+//           list order.  t > 0 (minD >= 0 for every ray the path produces), so the float's bit pattern orders like the value;
+//   RESOLVE after a drain every owner looks at its key: hit -> write (tri, t, abL, acL) and free the lane; walk finished and
+//           nothing found -> miss.  Rays keep walking between drains (bounded speculation: a batch is ~one cell per lane).
+//
+// No mailbox here: pairs of one ray are tested concurrently, and face masks already remove the repeats between adjacent cells
+// (the mailbox removed 6 % more).
+#ifndef OCLR_CELLQ_CAP
+#define OCLR_CELLQ_CAP 96
 #endif
+enum { kCellQCap = OCLR_CELLQ_CAP, kPairQCap = 64 };
+
+struct WarpPipe {
+    float ray[8][32];               // [o.x o.y o.z r.x r.y r.z minD maxD][owner lane]
+    uint32_t excl[32];
+    unsigned long long bestKey[32];
+    uint32_t bestTri[32];
+    float bestAB[32], bestAC[32];
+    uint32_t cellQ[2][kCellQCap];   // [0] rank | face << 29, [1] owner | seq << 8
+    uint32_t pairQ[2][kPairQCap];   // [0] triangle, [1] owner | seq << 8
+};
+
+__device__ __forceinline__ uint32_t next_entry(uint32_t begin, uint32_t end, uint32_t fm, uint32_t k) {
+    const uint32_t rel = k - begin;
+    if (rel < 32u) {
+        const uint32_t mm = fm >> rel;
+        k = mm ? k + (uint32_t)(__ffs((int)mm) - 1) : begin + 32u;
+    }
+    return k < end ? k : end;
+}
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace2_kernel(SceneView S, WfState w, WalkRecords rec, TraceTuning tune,
+__global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(SceneView S, WfState w, WalkRecords rec, TraceTuning tune,
                                                                             Counters* gcnt) {
-    enum { DEPTH = OCLR_PENDING2_DEPTH };
     extern __shared__ float shPlanes[];
-    __shared__ uint32_t mailbox[kMailboxSlots][128];   // per-lane direct-mapped cache of tested triangle ids (exact, see rt_wavefront.cuh)
-    __shared__ uint32_t pending[DEPTH][128];           // per-lane FIFO of occupied cells found by the walker: rank | entry face << 29
+    __shared__ WarpPipe pipes[4];
     load_planes(shPlanes, S);
     const int lane = threadIdx.x & 31;
+    WarpPipe& P = pipes[threadIdx.x >> 5];
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t count = *w.queueCount;
     const int n = S.n;
     const int nbShift = 31 - __clz(S.nb);
+    const unsigned long long kEmptyKey = ~0ull;
 
     Counters cnt = {};
     PackedWalk g;
     g.level = 0;
-    float minD = 0.f, maxD = 0.f;
-    uint32_t excl = kNoTriangle, path = 0;
+    float maxD = 0.f;
+    uint32_t path = 0;
     int ws = kWsNone;
-    int qHead = 0, qCount = 0;
-    bool testing = false, exhausted = false;
-    uint32_t i = 0, iEnd = 0, nextTri = 0, curMask = 0, curBegin = 0;
-    uint32_t best = kNoTriangle;
-    float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
+    bool exhausted = false;
     int face = kFaceNone, lastAxis = 0;
     float lastE = 0.f;
+    uint32_t seqNext = 0;   // cells this ray has in the current batch
+    uint32_t cq = 0;        // warp-uniform: cells queued
 
     for (;;) {
         // ---- refill idle lanes: one atomic per warp, records read in queue order ----
@@ -102,14 +137,22 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace2_kernel(Sce
                     const uint4 s1 = rec.s1[idx];
                     g.o = mk3(ro.x, ro.y, ro.z);
                     g.r = mk3(rd.x, rd.y, rd.z);
-                    minD = ro.w;
                     maxD = rd.w;
+                    P.ray[0][lane] = ro.x;
+                    P.ray[1][lane] = ro.y;
+                    P.ray[2][lane] = ro.z;
+                    P.ray[3][lane] = rd.x;
+                    P.ray[4][lane] = rd.y;
+                    P.ray[5][lane] = rd.z;
+                    P.ray[6][lane] = ro.w;
+                    P.ray[7][lane] = rd.w;
+                    P.excl[lane] = s1.y;
+                    P.bestKey[lane] = kEmptyKey;
                     g.tx = s0.x;
                     g.ty = s0.y;
                     g.tz = s0.z;
                     g.cpk = __float_as_uint(s0.w);
                     g.epk = s1.x;
-                    excl = s1.y;
                     path = s1.z;
                     g.coarseOk = s1.w != 0u;
                     g.level = 0;
@@ -118,13 +161,9 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace2_kernel(Sce
                                      ? -1
                                      : ((pk_get(g.epk, 0) >> 2) + (((pk_get(g.epk, 1) >> 2) + ((pk_get(g.epk, 2) >> 2) << nbShift)) << nbShift));
                     pwalk_load_brick(g, S.bricks);
-                    best = kNoTriangle;
                     ws = kWsRun;
-                    qHead = qCount = 0;
-                    testing = false;
                     face = kFaceNone;
-#pragma unroll
-                    for (int k = 0; k < kMailboxSlots; ++k) mailbox[k][threadIdx.x] = kNoTriangle;
+                    seqNext = 0;
                     if (COUNT) {
                         cnt.gridRays++;
                         cnt.bricksLoaded++;
@@ -133,41 +172,45 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace2_kernel(Sce
             }
         }
         if (__ballot_sync(0xFFFFFFFFu, ws != kWsNone) == 0u) break;
+        __syncwarp();
 
-        // ---- pick ONE kind of work for this iteration: the one most lanes are ready for (weighted) -------------------------------
-        // walk-ready: walking and room in the pending queue; test-ready: a cell being tested or queued; switch: parked for a
-        // level switch.  Every live lane is in at least one set, so some score is > 0 and the warp always makes progress.
-        const bool rdyWalk = (ws == kWsRun) & (qCount < DEPTH);
-        const bool rdyTest = testing | (qCount > 0);
-        const bool rdySwitch = (ws == kWsRefine) | (ws == kWsEnter);
-        const int sWalk = __popc(__ballot_sync(0xFFFFFFFFu, rdyWalk)) * tune.wWalk;
-        const int sTest = __popc(__ballot_sync(0xFFFFFFFFu, rdyTest)) * tune.wTest;
-        const int sSwitch = __popc(__ballot_sync(0xFFFFFFFFu, rdySwitch)) * tune.wSwitch;
-
-        if (sWalk >= sTest && sWalk >= sSwitch && sWalk > 0) {
-            // ---- WALK: one step of every walk-ready lane ----------------------------------------------------------------------
+        // ---- WALK burst: step every walking lane until the cell queue is worth draining or too few lanes still walk ----------------
+        for (;;) {
+            const bool walking = ws == kWsRun;
             if (COUNT) {
                 if (lane == 0) cnt.walkWarpIters++;
-                if (rdyWalk) cnt.walkLaneIters++;
+                if (walking) cnt.walkLaneIters++;
+                if (ws == kWsNone) cnt.walkIdleLanes++;
+                if ((ws == kWsRefine) | (ws == kWsEnter)) cnt.walkParkedLanes++;
+                if (ws == kWsFinished) cnt.walkFinishedLanes++;
+                if (lane == 0 && exhausted) cnt.walkExhaustedIters++;
             }
-            if (rdyWalk) {
+            if (COUNT) {
+                const int nw = __popc(__ballot_sync(0xFFFFFFFFu, walking));
+                if (lane == 0 && nw <= 8) cnt.walkLowIters++;
+            }
+            bool occupied = false;
+            int bit = 0;
+            if (walking) {
+                bit = pwalk_bit(g.cpk);
+                occupied = (g.level == 0) & pwalk_occupied(g, bit);
+            }
+            const unsigned occ = __ballot_sync(0xFFFFFFFFu, occupied);
+            if (occupied) {
+                const uint32_t pos = cq + (uint32_t)__popc(occ & ltMask);
+                P.cellQ[0][pos] = pwalk_rank(g, bit) | ((uint32_t)face << 29);
+                P.cellQ[1][pos] = (uint32_t)lane | (seqNext << 8);
+                ++seqNext;
+                if (COUNT) cnt.cellsNonEmpty++;
+            }
+            cq += (uint32_t)__popc(occ);
+            if (walking) {
                 const bool coarse = g.level != 0;
                 const bool brickEmpty = (g.maskLo | g.maskHi) == 0u;
                 const bool inEnd = g.brick == g.endBrick;
-                const int bit = pwalk_bit(g.cpk);
-                const bool occupied = (!coarse) & pwalk_occupied(g, bit);
                 if (COUNT && !coarse) {
                     cnt.cells++;
                     if (brickEmpty) cnt.emptyBrickCells++;
-                }
-                if (occupied) {
-                    int slot = qHead + qCount;
-                    slot = slot >= DEPTH ? slot - DEPTH : slot;
-                    const uint32_t rank = pwalk_rank(g, bit);
-                    pending[slot][threadIdx.x] = rank | ((uint32_t)face << 29);
-                    ++qCount;
-                    prefetch_l1(S.cellRange + rank);
-                    if (COUNT) cnt.cellsNonEmpty++;
                 }
                 const bool atEnd = (!coarse) & (g.cpk == g.epk);
                 const bool needRefine = coarse & ((!brickEmpty) | inEnd);
@@ -190,75 +233,121 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace2_kernel(Sce
                         }
                     }
                 }
-            }
-        } else if (sSwitch > sTest) {
-            // ---- SWITCH: parked level switches of the two-level walk, run together -----------------------------------------------
-            if (COUNT) {
-                if (lane == 0) cnt.switchWarpIters++;
-                if (rdySwitch) cnt.switchLaneIters++;
-            }
-            if (ws == kWsEnter) {
-                pwalk_enter_coarse(g, n, shPlanes);
-                ws = kWsRun;
-                if (COUNT) cnt.coarseEnters++;
-            } else if (ws == kWsRefine) {
-                pwalk_refine(g, n, shPlanes, lastAxis, lastE);
-                face = kFaceNone;
-                ws = kWsRun;
-            }
-        } else {
-            // ---- TEST: pop cells in walk order, one real ray/triangle test per lane -----------------------------------------------
-            if (COUNT) {
-                if (lane == 0) cnt.testWarpIters++;
-                if (rdyTest) cnt.testLaneIters++;
-            }
-            if (rdyTest) {
-                if (!testing) {  // open the next queued cell
-                    const uint32_t e = pending[qHead][threadIdx.x];
-                    qHead = qHead + 1 >= DEPTH ? 0 : qHead + 1;
-                    --qCount;
-                    const uint32_t rank = e & 0x1FFFFFFFu;
-                    const uint32_t f = e >> 29;
-                    const uint2 range = __ldg(S.cellRange + rank);
-                    // entries shared with the cell the walk came from were examined there (exact, rt_types.h faceMask)
-                    curMask = f != (uint32_t)kFaceNone ? __ldg(S.faceMask + 6 * (size_t)rank + f) : 0xFFFFFFFFu;
-                    i = curBegin = range.x;
-                    iEnd = range.y;
-                    bestT = maxD;  // *outRayMult = maxDistance at every cell (:366)
-                    testing = true;
-                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, excl, mailbox, i, nextTri, cnt);
-                    if (i != iEnd) prefetch_l1(S.triGeo + 4 * (size_t)nextTri);
-                }
-                if (i != iEnd) {
-                    const uint32_t tri = nextTri;
-                    float t, ab, ac;
-                    if (COUNT) cnt.gridCandidates++;
-                    mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] = tri;
-                    ++i;
-                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, excl, mailbox, i, nextTri, cnt);
-                    if (i != iEnd) prefetch_l1(S.triGeo + 4 * (size_t)nextTri);
-                    if (tri_test(S.triGeo + 4 * (size_t)tri, g.o, g.r, minD, bestT, t, ab, ac)) {
-                        best = tri;
-                        bestT = t;
-                        bestAB = ab;
-                        bestAC = ac;
-                    }
-                }
-                if (i == iEnd) {  // cell done
-                    testing = false;
-                    if (best != kNoTriangle) {  // first cell with any hit wins (:380); whatever the walker found beyond it is dropped
-                        w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
-                        ws = kWsNone;
-                        qCount = 0;
-                    }
+                if ((ws == kWsFinished) & (seqNext == 0u)) {  // walk over and nothing of this ray awaits a test: miss
+                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                    ws = kWsNone;
                 }
             }
+            const int nSwitch = __popc(__ballot_sync(0xFFFFFFFFu, (ws == kWsRefine) | (ws == kWsEnter)));
+            const int nWalk = __popc(__ballot_sync(0xFFFFFFFFu, ws == kWsRun));
+            if (cq >= (uint32_t)tune.drainMin) break;   // (checked before anything that loops back: the queue holds drainMin + 31 cells)
+            if (nSwitch != 0 && (nSwitch >= tune.switchMin || nWalk < tune.walkMin3)) {
+                // ---- SWITCH: parked level switches of the two-level walk, run together
+                if (COUNT) {
+                    if (lane == 0) cnt.switchWarpIters++;
+                    if ((ws == kWsRefine) | (ws == kWsEnter)) cnt.switchLaneIters++;
+                }
+                if (ws == kWsEnter) {
+                    pwalk_enter_coarse(g, n, shPlanes);
+                    ws = kWsRun;
+                    if (COUNT) cnt.coarseEnters++;
+                } else if (ws == kWsRefine) {
+                    pwalk_refine(g, n, shPlanes, lastAxis, lastE);
+                    face = kFaceNone;
+                    ws = kWsRun;
+                }
+                continue;
+            }
+            if (nWalk < tune.walkMin3) break;
         }
 
-        // walk over, nothing left to test, no hit: miss
-        if ((ws == kWsFinished) & (!testing) & (qCount == 0)) {
-            w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
-            ws = kWsNone;
+        // ---- DRAIN: open every queued cell, test every pair, any lane for any ray ---------------------------------------------------
+        if (cq != 0u) {
+            __syncwarp();
+            uint32_t pqHead = 0, pqTail = 0;   // absolute pair indices of this drain (warp-uniform)
+            // TEST round: lanes [0, take) each take one (ray, triangle) pair
+            auto test_round = [&](uint32_t take) {
+                __syncwarp();
+                bool hit = false;
+                unsigned long long key = kEmptyKey;
+                uint32_t owner = 0, ptri = 0;
+                float ab = 0.f, ac = 0.f;
+                if (COUNT) {
+                    if (lane == 0) cnt.testWarpIters++;
+                    if ((uint32_t)lane < take) {
+                        cnt.testLaneIters++;
+                        cnt.gridCandidates++;
+                    }
+                }
+                if ((uint32_t)lane < take) {
+                    const uint32_t pidx = pqHead + (uint32_t)lane;
+                    ptri = P.pairQ[0][pidx & (kPairQCap - 1)];
+                    const uint32_t os = P.pairQ[1][pidx & (kPairQCap - 1)];
+                    owner = os & 31u;
+                    const f3 o = mk3(P.ray[0][owner], P.ray[1][owner], P.ray[2][owner]);
+                    const f3 r = mk3(P.ray[3][owner], P.ray[4][owner], P.ray[5][owner]);
+                    float t;
+                    hit = tri_test(S.triGeo + 4 * (size_t)ptri, o, r, P.ray[6][owner], P.ray[7][owner], t, ab, ac);
+                    if (hit) {
+                        key = ((unsigned long long)(os >> 8) << 56) | ((unsigned long long)__float_as_uint(t) << 24) |
+                              (unsigned long long)(pidx & 0xFFFFFFu);
+                        atomicMin(&P.bestKey[owner], key);
+                    }
+                }
+                __syncwarp();
+                if (hit && P.bestKey[owner] == key) {
+                    P.bestTri[owner] = ptri;
+                    P.bestAB[owner] = ab;
+                    P.bestAC[owner] = ac;
+                }
+                pqHead += take;
+            };
+            for (uint32_t base = 0; base < cq; base += 32u) {
+                uint32_t k = 0, kEnd = 0, kBegin = 0, fm = 0, ownerSeq = 0, excl = kNoTriangle;
+                if (base + (uint32_t)lane < cq) {  // OPEN one cell per lane
+                    const uint32_t e = P.cellQ[0][base + lane];
+                    ownerSeq = P.cellQ[1][base + lane];
+                    const uint32_t rank = e & 0x1FFFFFFFu, f = e >> 29;
+                    const uint2 range = __ldg(S.cellRange + rank);
+                    fm = f != (uint32_t)kFaceNone ? __ldg(S.faceMask + 6 * (size_t)rank + f) : 0xFFFFFFFFu;
+                    excl = P.excl[ownerSeq & 31u];
+                    kBegin = range.x;
+                    kEnd = range.y;
+                    k = next_entry(kBegin, kEnd, fm, kBegin);
+                }
+                // enumerate the untested entries, one per lane per round, into the pair queue (list order per cell)
+                while (__any_sync(0xFFFFFFFFu, k < kEnd)) {
+                    const bool more = k < kEnd;
+                    uint32_t tri = 0;
+                    if (more) tri = __ldg(S.cellList + k);
+                    const bool valid = more & (tri != excl);
+                    const unsigned vb = __ballot_sync(0xFFFFFFFFu, valid);
+                    if (valid) {
+                        const uint32_t pos = (pqTail + (uint32_t)__popc(vb & ltMask)) & (kPairQCap - 1);
+                        P.pairQ[0][pos] = tri;
+                        P.pairQ[1][pos] = ownerSeq;
+                    }
+                    pqTail += (uint32_t)__popc(vb);
+                    if (more) k = next_entry(kBegin, kEnd, fm, k + 1u);
+                    if (pqTail - pqHead >= 32u) test_round(32u);
+                }
+            }
+            while (pqTail != pqHead) test_round(pqTail - pqHead < 32u ? pqTail - pqHead : 32u);
+            __syncwarp();
+            cq = 0;
+        }
+
+        // ---- RESOLVE ----------------------------------------------------------------------------------------------------------------
+        if (ws != kWsNone) {
+            const unsigned long long key = P.bestKey[lane];
+            if (key != kEmptyKey) {  // first cell with any hit wins (:380); whatever the walker found beyond it is dropped
+                w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
+                ws = kWsNone;
+            } else if (ws == kWsFinished) {
+                w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                ws = kWsNone;
+            }
+            seqNext = 0;
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);

@@ -113,7 +113,8 @@ OCLR_HD uint32_t launch_rows(const FrameView& F) { return F.bandWorld <= 1 ? F.r
 struct Counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
-        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters;
+        mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
+        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters;   // lanes of a walk iteration that were not walking, by reason
 };
 
 }  // namespace oclr

@@ -385,7 +385,7 @@ struct TraceTuning {
     int testMin;     // keep testing while at least this many lanes have candidates pending
     int refillMin;   // refill from the queue once this many lanes are idle
     int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level DDA)
-    int wWalk, wTest, wSwitch;  // rt_trace.cuh: per iteration the warp runs the kind of work with the largest (ready lanes x weight)
+    int drainMin, walkMin3, switchMin;  // wf_pipe_kernel: drain the cell queue at this size; end a walk burst below this many walkers; run parked level switches at this count
 };
 
 // Lane bookkeeping: the walker runs AHEAD of the tests.  A lane's DDA keeps walking while the cells it found wait in a

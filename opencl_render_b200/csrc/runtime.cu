@@ -327,7 +327,7 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
-                             uint32_t& launches, bool timeTrace, bool packed, std::string& err) {
+                             uint32_t& launches, bool timeTrace, bool packed /* false: wf_trace_kernel (first generation), true: wf_setup_kernel + wf_pipe_kernel */, std::string& err) {
     f->traceEventsUsed = 0;
     const uint32_t rows = launch_rows(F), W = F.cam.width;
     const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
@@ -380,9 +380,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     int perSm = 0;
     if (packed) {
         if (dcnt)
-            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace2_kernel<true>, 128, shBytes));
+            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<true>, 128, shBytes));
         else
-            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace2_kernel<false>, 128, shBytes));
+            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false>, 128, shBytes));
     } else if (dcnt)
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<true>, 128, shBytes));
     else
@@ -395,9 +395,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
         tune.testMin = env("OCLR_TEST_MIN", 16);
         tune.refillMin = env("OCLR_REFILL_MIN", 4);
         tune.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
-        tune.wWalk = env("OCLR_W_WALK", 2);
-        tune.wTest = env("OCLR_W_TEST", 3);
-        tune.wSwitch = env("OCLR_W_SWITCH", 6);
+        tune.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
+        tune.walkMin3 = env("OCLR_WALK_MIN3", 8);
+        tune.switchMin = env("OCLR_SWITCH_MIN", 6);
     }
     const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -429,9 +429,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
                 wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
                 ++launches;
                 if (dcnt)
-                    wf_trace2_kernel<true><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                    wf_pipe_kernel<true><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
                 else
-                    wf_trace2_kernel<false><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                    wf_pipe_kernel<false><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
             } else if (dcnt)
                 wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
             else
@@ -475,8 +475,8 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         else
             raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         launches = 1;
-    } else if (variant == kKernelPersistent || variant == kKernelPacked) {
-        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, variant == kKernelPacked, err))
+    } else if (variant == kKernelPersistent || variant == kKernelPipe) {
+        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, variant == kKernelPipe, err))
             return false;
     } else {
         err = "unknown kernel variant";

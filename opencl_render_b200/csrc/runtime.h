@@ -73,7 +73,7 @@ Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const
                     size_t camListSize, std::string& err);
 void frame_destroy(Frame* f);
 
-enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1, kKernelPacked = 2 };
+enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1, kKernelPipe = 2 };
 
 struct RenderStats {
     float deviceMs = 0.f;        // CUDA-event time of the trace kernel(s) on the launch stream

@@ -29,3 +29,7 @@ for v in variants:
             c["testWarpIters"] / c["gridRays"], c["cells"] / c["gridRays"], c["gridCandidates"] / c["gridRays"], c["coarseSteps"] / c["gridRays"]))
         if c["switchWarpIters"]:
             print("   switch util %.3f (%.2f warp iters/ray)" % (c["switchLaneIters"] / c["switchWarpIters"] / 32, c["switchWarpIters"] / c["gridRays"]))
+        if c.get("walkIdleLanes") is not None and c["walkWarpIters"]:
+            wl = c["walkWarpIters"] * 32
+            print("   walk-iteration lanes: walking %.3f idle %.3f parked %.3f finished %.3f" % (c["walkLaneIters"] / wl, c["walkIdleLanes"] / wl, c["walkParkedLanes"] / wl, c["walkFinishedLanes"] / wl))
+            print("   walk iterations with <= 8 walkers: %.3f; after the queue ran dry: %.3f" % (c["walkLowIters"] / c["walkWarpIters"], c["walkExhaustedIters"] / c["walkWarpIters"]))
