@@ -160,6 +160,7 @@ def run_reference(args):
 
 
 def run_b200(args):
+    os.environ["NCCL_DEBUG"] = os.environ.get("OCLR_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
     import torch
     import torch.distributed as dist
     from opencl_render_b200 import api, dist as odist

@@ -17,28 +17,79 @@
 
 namespace oclr {
 
-// Walk records written by wf_setup_kernel, indexed by queue slot.
+// Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
+enum { kLengthClasses = 4 };
 struct WalkRecords {
     float4* o;    // (o.xyz, minD)
     float4* d;    // (r.xyz, maxD)
     float4* s0;   // (tx, ty, tz, as_float(cpk))
     uint4* s1;    // (epk, excl, path, coarseOk)
+    // Longest-first scheduling: a trace launch cannot end before its longest walk does, and one lane walking 500 cells alone
+    // takes ~0.3 ms -- if that ray is taken from the queue last it is all tail.  The setup kernel therefore sorts the queue
+    // slots into length classes (estimated cells between start and end / exit cell) and the trace kernel drains the classes
+    // longest first.  order[c * Q + k] = k-th queue slot of class c; classCount[c] = slots in class c.
+    uint32_t* order;
+    uint32_t* classCount;
+    uint32_t Q;
 };
+
+// Estimated number of cells between the start cell and the end cell (finite rays) or the cell where the ray leaves the grid.
+// Only used to ORDER the work, never for a result: approximate arithmetic is fine here.
+__device__ __forceinline__ int walk_length_estimate(const PackedWalk& g, int n, const float* px, const float* py, const float* pz) {
+    int ex, ey, ez;
+    if (g.epk != kPkNone) {
+        ex = pk_get(g.epk, 0);
+        ey = pk_get(g.epk, 1);
+        ez = pk_get(g.epk, 2);
+    } else {
+        const float bx = g.r.x >= 0.f ? px[n] : px[0], by = g.r.y >= 0.f ? py[n] : py[0], bz = g.r.z >= 0.f ? pz[n] : pz[0];
+        float t = OCLR_INF;
+        if (g.r.x != 0.f) t = fminf(t, (bx - g.o.x) / g.r.x);
+        if (g.r.y != 0.f) t = fminf(t, (by - g.o.y) / g.r.y);
+        if (g.r.z != 0.f) t = fminf(t, (bz - g.o.z) / g.r.z);
+        if (!(t < OCLR_INF) || t < 0.f) t = 0.f;
+        box_address(n, px, py, pz, mk3(g.o.x + t * g.r.x, g.o.y + t * g.r.y, g.o.z + t * g.r.z), ex, ey, ez);
+    }
+    return abs(ex - pk_get(g.cpk, 0)) + abs(ey - pk_get(g.cpk, 1)) + abs(ez - pk_get(g.cpk, 2));
+}
 
 __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, WalkRecords rec) {
     extern __shared__ float shPlanes[];
+    const uint32_t count = *w.queueCount;
+    if (blockIdx.x * blockDim.x >= count) return;
     load_planes(shPlanes, S);
     const int n = S.n;
-    const uint32_t count = *w.queueCount;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
-        const uint32_t path = w.queue[idx];
-        const float4 ro = w.rayO[path], rd = w.rayD[path];
-        PackedWalk g;
-        pwalk_setup(g, n, S.nb, shPlanes, shPlanes + (n + 1), shPlanes + 2 * (n + 1), mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w);
-        rec.o[idx] = ro;
-        rec.d[idx] = rd;
-        rec.s0[idx] = make_float4(g.tx, g.ty, g.tz, __uint_as_float(g.cpk));
-        rec.s1[idx] = make_uint4(g.epk, w.rayExcl[path], path, g.coarseOk ? 1u : 0u);
+    const int lane = threadIdx.x & 31;
+    const float* px = shPlanes;
+    const float* py = shPlanes + (n + 1);
+    const float* pz = shPlanes + 2 * (n + 1);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+        const uint32_t idx = base + threadIdx.x;
+        const bool valid = idx < count;
+        int cls = -1;
+        if (valid) {
+            const uint32_t path = w.queue[idx];
+            const float4 ro = w.rayO[path], rd = w.rayD[path];
+            PackedWalk g;
+            pwalk_setup(g, n, S.nb, px, py, pz, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w);
+            rec.o[idx] = ro;
+            rec.d[idx] = rd;
+            rec.s0[idx] = make_float4(g.tx, g.ty, g.tz, __uint_as_float(g.cpk));
+            rec.s1[idx] = make_uint4(g.epk, w.rayExcl[path], path, g.coarseOk ? 1u : 0u);
+            const int len = walk_length_estimate(g, n, px, py, pz);
+            // classes by quarters of n, longest first (a walk can be up to 3n cells long; 8 classes measured no better than 4)
+            cls = kLengthClasses - 1 - min(kLengthClasses - 1, (len * kLengthClasses) / (n > 0 ? n : 1));
+        }
+#pragma unroll
+        for (int c = 0; c < kLengthClasses; ++c) {  // one atomic per warp and class
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+            if (m == 0u) continue;
+            const int leader = __ffs(m) - 1;
+            uint32_t pos = 0;
+            if (lane == leader) pos = atomicAdd(rec.classCount + c, (uint32_t)__popc(m));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+            if (cls == c) rec.order[(size_t)c * rec.Q + pos + (uint32_t)__popc(m & ((1u << lane) - 1u))] = idx;
+        }
     }
 }
 
@@ -99,7 +150,16 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                                                                             Counters* gcnt) {
     extern __shared__ float shPlanes[];
     __shared__ WarpPipe pipes[4];
-    load_planes(shPlanes, S);
+    __shared__ uint32_t classOff[kLengthClasses];   // first queue position of each length class (longest class first)
+    if (blockIdx.x * 128u >= *w.queueCount) return;   // launched with the full persistent grid: the host does not know the count
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < kLengthClasses; ++c) {
+            classOff[c] = acc;
+            acc += rec.classCount[c];
+        }
+    }
+    load_planes(shPlanes, S);   // (ends with __syncthreads)
     const int lane = threadIdx.x & 31;
     WarpPipe& P = pipes[threadIdx.x >> 5];
     const unsigned ltMask = (1u << lane) - 1u;
@@ -107,6 +167,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     const int n = S.n;
     const int nbShift = 31 - __clz(S.nb);
     const unsigned long long kEmptyKey = ~0ull;
+
 
     Counters cnt = {};
     PackedWalk g;
@@ -131,8 +192,12 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (base + (uint32_t)nIdle >= count) exhausted = true;
             if (ws == kWsNone) {
-                const uint32_t idx = base + (uint32_t)__popc(idle & ltMask);
-                if (idx < count) {
+                const uint32_t pos = base + (uint32_t)__popc(idle & ltMask);
+                if (pos < count) {
+                    uint32_t cls = 0;
+#pragma unroll
+                    for (int c = 1; c < kLengthClasses; ++c) cls += pos >= classOff[c];
+                    const uint32_t idx = rec.order[(size_t)cls * rec.Q + (pos - classOff[cls])];
                     const float4 ro = rec.o[idx], rd = rec.d[idx], s0 = rec.s0[idx];
                     const uint4 s1 = rec.s1[idx];
                     g.o = mk3(ro.x, ro.y, ro.z);

@@ -95,7 +95,9 @@ __device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want)
 // Thread -> path mapping keeps a warp on an 8x4 pixel tile, so queue entries appended by a warp are spatially coherent.
 template <bool COUNT>
 __global__ void __launch_bounds__(128) wf_logic_kernel(SceneView S, FrameView F, WfState w, uint32_t sampleIdx, uint32_t startSample,
-                                                       Counters* gcnt) {
+                                                       const uint32_t* prevCount, Counters* gcnt) {
+    // Rounds are enqueued ahead without a host round trip; a round whose predecessor traced no ray has nothing to resume.
+    if (prevCount != nullptr && *prevCount == 0u) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t k = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -429,6 +431,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(Scen
     // or the barycentric test -- both ray/triangle properties that do not change in a later cell.
     __shared__ uint32_t mailbox[kMailboxSlots][128];
     __shared__ uint4 pending[kPendingDepth][128];  // {next entry, end, face mask, begin}
+    if (blockIdx.x * 128u >= *w.queueCount) return;   // launched with the full persistent grid: the host does not know the count
     load_planes(shPlanes, S);
     const float* px = shPlanes;
     const float* py = shPlanes + (S.n + 1);

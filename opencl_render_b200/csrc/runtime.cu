@@ -73,11 +73,12 @@ struct Frame {
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
     // wavefront path state (allocated on first use, sized for the largest launch domain seen)
     DeviceBuffer wfCtl, wfRng, wfColour, wfRing, wfCarry, wfRayO, wfRayD, wfRayExcl, wfHit, wfQueue;
-    DeviceBuffer recO, recD, recS0, recS1;   // walk records in queue order (rt_trace.cuh)
+    DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
     uint32_t wfCapacity = 0;
     uint32_t* hostCount = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t lastLaunches = 0;
+    uint32_t lastRounds = 4;         // rounds the previous sample needed (first chunk of the next one)
     std::vector<cudaEvent_t> traceEvents;   // pairs around the trace launches of the last timed render
     uint32_t traceEventsUsed = 0;
 };
@@ -276,7 +277,7 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
     if (!f->flags.alloc(sizeof(uint8_t) * P, err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->flags.p, 0, f->flags.bytes, 0));
     if (!f->counters.alloc(sizeof(Counters), err)) return false;
-    if (!f->workCounter.alloc(sizeof(uint32_t) * 4, err)) return false;
+    if (!f->workCounter.alloc(sizeof(uint32_t) * 2 * (2 + kLengthClasses), err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
@@ -309,7 +310,7 @@ void frame_destroy(Frame* f) {
     cudaSetDevice(f->scene->device);
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter,
                            &f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl, &f->wfHit,
-                           &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1};
+                           &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1, &f->recOrder};
     for (DeviceBuffer* b : all) b->release();
     if (f->hostCount) cudaFreeHost(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
@@ -338,7 +339,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     const uint32_t Q = (uint32_t)Q64;
     if (Q > f->wfCapacity) {
         DeviceBuffer* all[] = {&f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl,
-                               &f->wfHit, &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1};
+                               &f->wfHit, &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1, &f->recOrder};
         for (DeviceBuffer* b : all) b->release(st);
         if (!f->wfCtl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) || !f->wfRng.alloc(sizeof(uint64_t) * (size_t)Q, err, st) ||
             !f->wfColour.alloc(sizeof(float4) * (size_t)Q, err, st) ||
@@ -347,7 +348,8 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
             !f->wfRayD.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfRayExcl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
             !f->wfHit.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfQueue.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
             !f->recO.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recD.alloc(sizeof(float4) * (size_t)Q, err, st) ||
-            !f->recS0.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recS1.alloc(sizeof(uint4) * (size_t)Q, err, st))
+            !f->recS0.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recS1.alloc(sizeof(uint4) * (size_t)Q, err, st) ||
+            !f->recOrder.alloc(sizeof(uint32_t) * (size_t)Q * kLengthClasses, err, st))
             return false;
         f->wfCapacity = Q;
     }
@@ -364,13 +366,13 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     w.rayExcl = (uint32_t*)f->wfRayExcl.p;
     w.hit = (float4*)f->wfHit.p;
     w.queue = (uint32_t*)f->wfQueue.p;
-    w.queueCount = (uint32_t*)f->workCounter.p;
-    w.queueCursor = w.queueCount + 1;
     WalkRecords rec;
     rec.o = (float4*)f->recO.p;
     rec.d = (float4*)f->recD.p;
     rec.s0 = (float4*)f->recS0.p;
     rec.s1 = (uint4*)f->recS1.p;
+    rec.order = (uint32_t*)f->recOrder.p;
+    rec.Q = Q;
     if (packed && S.n > 1024) {
         err = "axesDivCount > 1024 is not supported by the packed walk";
         return false;
@@ -403,49 +405,60 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
     const unsigned traceGrid = (unsigned)(smCount * perSm);
     if (F.flagOut) OCLR_CUDA(cudaMemsetAsync(F.flagOut, 0, (size_t)F.cam.width * F.cam.height, st));
+    // Rounds (logic -> setup -> trace) are enqueued ahead in chunks without a host round trip: every kernel reads the ray count
+    // of its round from device memory and returns at once when there is nothing to do.  The host looks at the count of the last
+    // enqueued round once per chunk; the first chunk is as long as the previous sample / frame needed.
+    uint32_t* counters = (uint32_t*)f->workCounter.p;   // {count, cursor, class counts} x 2, alternating between rounds
+    const unsigned setupGrid = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)Q + 255) / 256);
     for (uint32_t s = 0; s < F.sampleCount; ++s) {
-        for (uint32_t round = 0;; ++round) {
-            OCLR_CUDA(cudaMemsetAsync(w.queueCount, 0, sizeof(uint32_t) * 2, st));
-            if (dcnt)
-                wf_logic_kernel<true><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, dcnt);
-            else
-                wf_logic_kernel<false><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, dcnt);
-            ++launches;
-            OCLR_CUDA(cudaMemcpyAsync(f->hostCount, w.queueCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            OCLR_CUDA(cudaStreamSynchronize(st));
-            const uint32_t waiting = f->hostCount[0];
-            if (waiting == 0) break;
-            const unsigned grid = (unsigned)std::min<uint64_t>(traceGrid, ((uint64_t)waiting + 127) / 128);
-            if (timeTrace) {
-                while (f->traceEvents.size() < (size_t)f->traceEventsUsed + 2) {
-                    cudaEvent_t e;
-                    OCLR_CUDA(cudaEventCreate(&e));
-                    f->traceEvents.push_back(e);
-                }
-                OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
-            }
-            if (packed) {
-                const unsigned setupGrid = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)waiting + 255) / 256);
-                wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
-                ++launches;
+        uint32_t round = 0;
+        for (;;) {
+            const uint32_t chunk = round == 0 ? std::max<uint32_t>(f->lastRounds, 2) : 2;
+            for (uint32_t k = 0; k < chunk; ++k, ++round) {
+                w.queueCount = counters + (2 + kLengthClasses) * (round & 1u);
+                w.queueCursor = w.queueCount + 1;
+                rec.classCount = w.queueCount + 2;
+                const uint32_t* prev = round ? counters + (2 + kLengthClasses) * ((round - 1) & 1u) : nullptr;
+                OCLR_CUDA(cudaMemsetAsync(w.queueCount, 0, sizeof(uint32_t) * (2 + kLengthClasses), st));
                 if (dcnt)
-                    wf_pipe_kernel<true><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                    wf_logic_kernel<true><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, prev, dcnt);
                 else
-                    wf_pipe_kernel<false><<<grid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
-            } else if (dcnt)
-                wf_trace_kernel<true><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
-            else
-                wf_trace_kernel<false><<<grid, 128, shBytes, st>>>(S, w, tune, dcnt);
-            if (timeTrace) {
-                OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed + 1], st));
-                f->traceEventsUsed += 2;
+                    wf_logic_kernel<false><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, prev, dcnt);
+                ++launches;
+                if (timeTrace) {
+                    while (f->traceEvents.size() < (size_t)f->traceEventsUsed + 2) {
+                        cudaEvent_t e;
+                        OCLR_CUDA(cudaEventCreate(&e));
+                        f->traceEvents.push_back(e);
+                    }
+                    OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
+                }
+                if (packed) {
+                    wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
+                    ++launches;
+                    if (dcnt)
+                        wf_pipe_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                    else
+                        wf_pipe_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
+                } else if (dcnt)
+                    wf_trace_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, tune, dcnt);
+                else
+                    wf_trace_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, tune, dcnt);
+                if (timeTrace) {
+                    OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed + 1], st));
+                    f->traceEventsUsed += 2;
+                }
+                ++launches;
             }
-            ++launches;
+            OCLR_CUDA(cudaMemcpyAsync(f->hostCount, counters + (2 + kLengthClasses) * ((round - 1) & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            OCLR_CUDA(cudaStreamSynchronize(st));
+            if (f->hostCount[0] == 0) break;   // the last enqueued round found no path waiting for a ray: the sample is complete
             if (round > 100000) {
                 err = "wavefront did not converge";
                 return false;
             }
         }
+        f->lastRounds = round;
     }
     return true;
 }
