@@ -92,7 +92,7 @@ def load() -> C.CDLL:
     if not LIB_PATH.is_file():
         raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m opencl_render_b200.build` "
                            "(there is no Python/CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(os.environ.get("OCLR_LIB") or str(LIB_PATH))     # OCLR_LIB: developer knob for A/B builds of the same library
     lib.oclr_last_error.restype = C.c_char_p
     lib.oclr_version.restype = C.c_char_p
     lib.oclr_device_count.restype = C.c_int

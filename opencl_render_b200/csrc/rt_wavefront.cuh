@@ -93,8 +93,11 @@ __device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want)
 
 // ---- logic kernel -----------------------------------------------------------------------------------------------------
 // Thread -> path mapping keeps a warp on an 8x4 pixel tile, so queue entries appended by a warp are spatially coherent.
+#ifndef OCLR_LOGIC_MIN_CTAS
+#define OCLR_LOGIC_MIN_CTAS 5   /* 94 registers, no spills; 6 (80 registers) spills and measures slower */
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) wf_logic_kernel(SceneView S, FrameView F, WfState w, uint32_t sampleIdx, uint32_t startSample,
+__global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(SceneView S, FrameView F, WfState w, uint32_t sampleIdx, uint32_t startSample,
                                                        const uint32_t* prevCount, Counters* gcnt) {
     // Rounds are enqueued ahead without a host round trip; a round whose predecessor traced no ray has nothing to resume.
     if (prevCount != nullptr && *prevCount == 0u) return;

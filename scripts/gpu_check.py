@@ -15,7 +15,7 @@ from opencl_render_b200 import api, scenes  # noqa: E402
 import ref  # noqa: E402
 
 
-def run(cfg_id, variants=(0, 1), ref_rows=None, reps=5):
+def run(cfg_id, variants=(0, 2), ref_rows=None, reps=5):
     cfg = scenes.CONFIGS[cfg_id]
     t = time.time(); sc = cfg["make"](); t_scene = time.time() - t
     m = sc.meta["camera"]
@@ -57,8 +57,8 @@ def run(cfg_id, variants=(0, 1), ref_rows=None, reps=5):
         print(f"  variant {v} vs reference: differing pixels {int(anyd.sum())} (unflagged {int(unfl.sum())}, flagged px {int(flags[sl].sum())}) "
               f"max|d|={mx} ({mx / 65535:.2e}) PSNR={psnr:.1f} dB", flush=True)
     if len(out) == 2:
-        a, b = out[0], out[1]
-        print("  variant0 == variant1:", all(np.array_equal(a[0][c], b[0][c]) for c in range(3)), "ids equal:", np.array_equal(a[1], b[1]))
+        a, b = out[variants[0]], out[variants[1]]
+        print(f"  variant{variants[0]} == variant{variants[1]}:", all(np.array_equal(a[0][c], b[0][c]) for c in range(3)), "ids equal:", np.array_equal(a[1], b[1]))
     fr.close(); ds.close()
 
 
@@ -75,7 +75,7 @@ def run_sweep(cfg_id=5, check_frames=(0, 21, 42)):
         cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
         t = time.time(); lists = api.camera_triangle_list(cam, sc); t_lists += time.time() - t
         fr = api.DeviceFrame(ds, cam, lists)
-        ms, launches, _ = fr.render(cfg["samples"], variant=1)
+        ms, launches, _ = fr.render(cfg["samples"])
         total_ms += ms; total_rays += cfg["width"] * cfg["height"] * cfg["samples"]
         if k in check_frames:
             img = fr.read(); flags = fr.undefined_flags()
