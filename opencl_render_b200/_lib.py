@@ -69,7 +69,8 @@ EXPORTS = [
     "GetProgress", "SetProgress", "GetStartTime", "GetEndTime", "ResetTime", "RaytraceAll",
     # Part 2: extension
     "oclr_last_error", "oclr_device_count", "oclr_version", "oclr_scene_create", "oclr_scene_destroy", "oclr_scene_device_bytes", "oclr_scene_debug_read",
-    "oclr_set_camera", "oclr_frame_create", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
+    "oclr_set_camera", "oclr_frame_create", "oclr_frame_create_device_lists", "oclr_frame_camera_list_size",
+    "oclr_frame_read_camera_lists", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
     "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_last_launches", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
     "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_free_camera_lists", "oclr_free_scene_grid",
 ]
@@ -108,6 +109,12 @@ def load() -> C.CDLL:
     lib.oclr_set_camera.argtypes = [C.POINTER(Camera), c_float_p, c_float_p, c_float_p, C.c_float, C.c_uint32, C.c_uint32]
     lib.oclr_frame_create.restype = C.c_void_p
     lib.oclr_frame_create.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.oclr_frame_create_device_lists.restype = C.c_void_p
+    lib.oclr_frame_create_device_lists.argtypes = [C.c_void_p, C.POINTER(Camera)]
+    lib.oclr_frame_camera_list_size.restype = C.c_size_t
+    lib.oclr_frame_camera_list_size.argtypes = [C.c_void_p]
+    lib.oclr_frame_read_camera_lists.restype = C.c_int
+    lib.oclr_frame_read_camera_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oclr_frame_destroy.argtypes = [C.c_void_p]
     lib.oclr_frame_destroy.restype = None
     lib.oclr_frame_render.restype = C.c_int

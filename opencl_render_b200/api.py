@@ -282,17 +282,31 @@ class DeviceScene:
 class DeviceFrame:
     """One camera on a resident scene: camera lists + three 16-bit planes in HBM."""
 
-    def __init__(self, scene: DeviceScene, camera: CameraSetup, lists: CameraLists):
+    def __init__(self, scene: DeviceScene, camera: CameraSetup, lists: CameraLists | None = None):
+        """`lists` = CameraTriangleList::New output built on the host, or None: the lists are built on the device from the
+        resident scene (entry-for-entry the same; see camera_lists())."""
         self._lib = _lib.load()
         self.scene = scene
         self.camera = camera
         cam = camera.c()
-        start = _c(lists.start, np.uint32)
-        end = _c(lists.end, np.uint32)
-        lst = _c(lists.list, np.uint32)
-        self.handle = self._lib.oclr_frame_create(scene.handle, C.byref(cam), _ptr(start), _ptr(end), _ptr(lst), int(lst.size))
+        if lists is None:
+            self.handle = self._lib.oclr_frame_create_device_lists(scene.handle, C.byref(cam))
+        else:
+            start = _c(lists.start, np.uint32)
+            end = _c(lists.end, np.uint32)
+            lst = _c(lists.list, np.uint32)
+            self.handle = self._lib.oclr_frame_create(scene.handle, C.byref(cam), _ptr(start), _ptr(end), _ptr(lst), int(lst.size))
         if not self.handle:
             raise OclrError(_lib.last_error())
+
+    def camera_lists(self) -> "CameraLists":
+        """Copies the frame's camera lists (uploaded or device-built) back to the host."""
+        P = self.camera.width * self.camera.height
+        n = int(self._lib.oclr_frame_camera_list_size(self.handle))
+        start, end, lst = np.empty(P, np.uint32), np.empty(P, np.uint32), np.empty(max(n, 1), np.uint32)
+        if not self._lib.oclr_frame_read_camera_lists(self.handle, _ptr(start), _ptr(end), _ptr(lst)):
+            raise OclrError(_lib.last_error())
+        return CameraLists(start, end, lst[:n])
 
     def render(self, sample_count: int = 1, rows=None, variant: int = KERNEL_DEFAULT, count: bool = False, stream: int = 0,
                sync: bool = True):

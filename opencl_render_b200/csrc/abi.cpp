@@ -176,6 +176,10 @@ oclr_frame* oclr_frame_create(oclr_scene* scene, const oclr_camera* camera, cons
         fail("oclr_frame_create: null scene or camera");
         return nullptr;
     }
+    if (!start || !end) {
+        fail("oclr_frame_create: camera triangle lists missing (oclr_frame_create_device_lists builds them on the device)");
+        return nullptr;
+    }
     std::string err;
     Frame* f = frame_create(scene->impl, to_camera(camera), start, end, list, listSize, err);
     if (!f) {
@@ -186,6 +190,31 @@ oclr_frame* oclr_frame_create(oclr_scene* scene, const oclr_camera* camera, cons
     h->impl = f;
     h->scene = scene;
     return h;
+}
+oclr_frame* oclr_frame_create_device_lists(oclr_scene* scene, const oclr_camera* camera) {
+    if (!scene || !camera) {
+        fail("oclr_frame_create_device_lists: null scene or camera");
+        return nullptr;
+    }
+    std::string err;
+    Frame* f = frame_create(scene->impl, to_camera(camera), nullptr, nullptr, nullptr, 0, err);
+    if (!f) {
+        fail("oclr_frame_create_device_lists: " + err);
+        return nullptr;
+    }
+    oclr_frame* h = new oclr_frame();
+    h->impl = f;
+    h->scene = scene;
+    return h;
+}
+size_t oclr_frame_camera_list_size(const oclr_frame* frame) { return frame ? frame_camera_list_size(frame->impl) : 0; }
+int oclr_frame_read_camera_lists(oclr_frame* frame, cl_uint* start, cl_uint* end, cl_uint* list) {
+    std::string err;
+    if (!frame || !frame_read_camera_lists(frame->impl, start, end, list, err)) {
+        fail("oclr_frame_read_camera_lists: " + (frame ? err : std::string("null frame")));
+        return 0;
+    }
+    return 1;
 }
 void oclr_frame_destroy(oclr_frame* frame) {
     if (!frame) return;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <thread>
 
+#include "cam_builder.cuh"
 #include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
 #include "rt_trace.cuh"
@@ -78,6 +79,7 @@ struct Frame {
     uint32_t* hostCount = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t lastLaunches = 0;
+    size_t camListSize = 0;
     uint32_t lastRounds = 4;         // rounds the previous sample needed (first chunk of the next one)
     std::vector<cudaEvent_t> traceEvents;   // pairs around the trace launches of the last timed render
     uint32_t traceEventsUsed = 0;
@@ -261,17 +263,8 @@ size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap) {
 }
 int scene_device(const Scene* s) { return s->device; }
 
-static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
-                        std::string& err) {
-    OCLR_CUDA(cudaSetDevice(f->scene->device));
+static bool frame_setup_common(Frame* f, std::string& err) {
     const size_t P = (size_t)f->cam.width * f->cam.height;
-    if (!camStart || !camEnd || (listSize && !camList)) {
-        err = "camera triangle lists missing";
-        return false;
-    }
-    if (!f->camStart.upload(camStart, sizeof(uint32_t) * P, err)) return false;
-    if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
-    if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
     if (!f->planesRGB.alloc(sizeof(uint16_t) * 3 * P, err)) return false;
     if (!f->ids.alloc(sizeof(uint32_t) * P, err)) return false;
     if (!f->flags.alloc(sizeof(uint8_t) * P, err)) return false;
@@ -283,6 +276,133 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
     OCLR_CUDA(cudaStreamSynchronize(0));
     return true;
+}
+
+static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
+                        std::string& err) {
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    if (!camStart || !camEnd || (listSize && !camList)) {
+        err = "camera triangle lists missing";
+        return false;
+    }
+    if (!f->camStart.upload(camStart, sizeof(uint32_t) * P, err)) return false;
+    if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
+    if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
+    f->camListSize = listSize;
+    return frame_setup_common(f, err);
+}
+
+// CameraTriangleList::New on the device (cam_builder.cuh): the frame's camera lists are built from the resident scene.
+static bool frame_build_camera_lists(Frame* f, std::string& err) {
+    Scene* s = f->scene;
+    OCLR_CUDA(cudaSetDevice(s->device));
+    const uint32_t W = f->cam.width, H = f->cam.height, N = s->view.triangleCount;
+    const uint32_t P = W * H;
+    if ((uint64_t)W * H >= 0xFFFFFFFFull) {
+        err = "image too large for the device camera-list builder";
+        return false;
+    }
+    CamProjD c;
+    c.eye = mk3(f->cam.eye);
+    c.tl = mk3(f->cam.eyeToTopLeft);
+    c.lr = mk3(f->cam.leftToRight);
+    c.tb = mk3(f->cam.topToBottom);
+    c.screenN = cross3(c.lr, c.tb);        // host arithmetic, g++/nvcc host side with -ffp-contract=off like builders.cpp
+    c.tlDotN = dot3(c.tl, c.screenN);
+    c.psiSq = f->cam.pixelSizeInv * f->cam.pixelSizeInv;
+    c.W = W;
+    c.H = H;
+    DeviceBuffer screen, slots, offsets, largeList, small, keysA, keysB, pixelCount, startInc, tmp, listRaw, parent, keptLen, keptStart;
+    DeviceBuffer* all[] = {&screen, &slots, &offsets, &largeList, &small, &keysA, &keysB, &pixelCount, &startInc, &tmp, &listRaw, &parent, &keptLen, &keptStart};
+    auto done = [&](bool ok) {
+        for (DeviceBuffer* b : all) b->release();
+        return ok;
+    };
+    const size_t Nz = N ? N : 1;
+    if (!screen.alloc(sizeof(TriScreen) * Nz, err) || !slots.alloc(sizeof(uint64_t) * (Nz + 1), err) ||
+        !offsets.alloc(sizeof(uint64_t) * (Nz + 1), err) || !largeList.alloc(sizeof(uint32_t) * Nz, err) ||
+        !small.alloc(sizeof(uint32_t) * 4, err) || !pixelCount.alloc(sizeof(uint32_t) * ((size_t)P + 1), err) ||
+        !startInc.alloc(sizeof(uint32_t) * ((size_t)P + 1), err))
+        return done(false);
+    cudaMemsetAsync(small.p, 0, sizeof(uint32_t) * 4, 0);
+    cudaMemsetAsync(slots.p, 0, sizeof(uint64_t) * (Nz + 1), 0);
+    cudaMemsetAsync(pixelCount.p, 0, sizeof(uint32_t) * ((size_t)P + 1), 0);
+    uint32_t* largeCount = (uint32_t*)small.p;
+    if (N)
+        cam_project_kernel<<<(N + 255) / 256, 256>>>(c, N, s->view.triShade, (TriScreen*)screen.p, (uint64_t*)slots.p, (uint32_t*)largeList.p,
+                                                    largeCount);
+    size_t tmpBytes = 0, need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    tmpBytes = need;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint32_t*)pixelCount.p, (uint32_t*)startInc.p, (int)(P + 1));
+    tmpBytes = std::max(tmpBytes, need);
+    if (!tmp.alloc(tmpBytes, err)) return done(false);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    uint64_t total = 0;
+    uint32_t nLarge = 0;
+    cudaMemcpyAsync(&total, (const uint64_t*)offsets.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(&nLarge, largeCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    OCLR_CUDA(cudaStreamSynchronize(0));
+    if (total > (1ull << 31)) {
+        err = "camera-list builder: more than 2^31 (triangle, pixel) candidates";
+        return done(false);
+    }
+    const size_t totalZ = total ? (size_t)total : 1;
+    if (!keysA.alloc(sizeof(uint64_t) * totalZ, err) || !keysB.alloc(sizeof(uint64_t) * totalZ, err)) return done(false);
+    const uint64_t sentinel = (uint64_t)P * (uint64_t)(N ? N : 1);
+    if (N) {
+        cam_raster_small_kernel<<<(N + 127) / 128, 128>>>(N, W, sentinel, (const TriScreen*)screen.p, (const uint64_t*)offsets.p,
+                                                         (uint64_t*)keysA.p, (uint32_t*)pixelCount.p);
+        if (nLarge)
+            cam_raster_large_kernel<<<dim3(nLarge, 32), 256>>>(N, W, sentinel, (const TriScreen*)screen.p, (const uint64_t*)offsets.p,
+                                                              (const uint32_t*)largeList.p, (uint64_t*)keysA.p, (uint32_t*)pixelCount.p);
+    }
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint32_t*)pixelCount.p, (uint32_t*)startInc.p, (int)(P + 1));
+    uint32_t real = 0;
+    cudaMemcpyAsync(&real, (const uint32_t*)startInc.p + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    int endBit = 1;
+    while (endBit < 64 && (sentinel >> endBit) != 0) ++endBit;
+    size_t sortBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    DeviceBuffer sortTmp;
+    if (!sortTmp.alloc(sortBytes, err)) return done(false);
+    cub::DeviceRadixSort::SortKeys(sortTmp.p, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    cudaError_t e = cudaStreamSynchronize(0);
+    sortTmp.release();
+    if (e != cudaSuccess) {
+        err = std::string("camera-list builder: ") + cudaGetErrorString(e);
+        return done(false);
+    }
+    const size_t realZ = real ? real : 1;
+    if (!listRaw.alloc(sizeof(uint32_t) * realZ, err) || !parent.alloc(sizeof(uint32_t) * (size_t)P, err) ||
+        !keptLen.alloc(sizeof(uint32_t) * ((size_t)P + 1), err) || !keptStart.alloc(sizeof(uint32_t) * ((size_t)P + 1), err))
+        return done(false);
+    if (real) cam_split_kernel<<<(unsigned)((real + 255) / 256), 256>>>((const uint64_t*)keysB.p, real, N, (uint32_t*)listRaw.p);
+    // storage compression against the left / upper neighbour
+    cudaMemsetAsync(keptLen.p, 0, sizeof(uint32_t) * ((size_t)P + 1), 0);
+    cam_equal_kernel<<<(P + 255) / 256, 256>>>(W, P, (const uint32_t*)startInc.p, (const uint32_t*)listRaw.p, (uint32_t*)parent.p,
+                                              (uint32_t*)keptLen.p);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint32_t*)keptLen.p, (uint32_t*)keptStart.p, (int)(P + 1));
+    uint32_t kept = 0;
+    cudaMemcpyAsync(&kept, (const uint32_t*)keptStart.p + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    int jumps = 1;
+    while ((1u << jumps) < W + H) ++jumps;
+    for (int k = 0; k < jumps; ++k) cam_jump_kernel<<<(P + 255) / 256, 256>>>(P, (uint32_t*)parent.p, largeCount + 1);
+    OCLR_CUDA(cudaStreamSynchronize(0));
+    if (!f->camStart.alloc(sizeof(uint32_t) * (size_t)P, err) || !f->camEnd.alloc(sizeof(uint32_t) * (size_t)P, err) ||
+        !f->camList.alloc(sizeof(uint32_t) * (size_t)(kept ? kept : 1), err))
+        return done(false);
+    cam_finish_kernel<<<(P + 255) / 256, 256>>>(P, (const uint32_t*)startInc.p, (const uint32_t*)parent.p, (const uint32_t*)keptStart.p,
+                                               (const uint32_t*)listRaw.p, (uint32_t*)f->camStart.p, (uint32_t*)f->camEnd.p,
+                                               (uint32_t*)f->camList.p);
+    f->camListSize = kept;
+    e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        err = std::string("camera-list builder: ") + cudaGetErrorString(e);
+        return done(false);
+    }
+    return done(true);
 }
 
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
@@ -298,11 +418,28 @@ Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const
     Frame* f = new Frame();
     f->scene = s;
     f->cam = cam;
-    if (!frame_setup(f, camStart, camEnd, camList, camListSize, err)) {
+    const bool ok = camStart ? frame_setup(f, camStart, camEnd, camList, camListSize, err)
+                             : (frame_build_camera_lists(f, err) && frame_setup_common(f, err));   // no lists given: build them on the device
+    if (!ok) {
         frame_destroy(f);
         return nullptr;
     }
     return f;
+}
+
+size_t frame_camera_list_size(const Frame* f) { return f ? f->camListSize : 0; }
+
+bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t* list, std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    OCLR_CUDA(cudaMemcpy(start, f->camStart.p, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost));
+    OCLR_CUDA(cudaMemcpy(end, f->camEnd.p, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost));
+    if (f->camListSize) OCLR_CUDA(cudaMemcpy(list, f->camList.p, sizeof(uint32_t) * f->camListSize, cudaMemcpyDeviceToHost));
+    return true;
 }
 
 void frame_destroy(Frame* f) {

@@ -72,6 +72,10 @@ size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap);
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
                     size_t camListSize, std::string& err);
 void frame_destroy(Frame* f);
+// camStart == nullptr: CameraTriangleList::New runs on the device from the resident scene (cam_builder.cuh).  The lists a frame
+// holds (uploaded or device-built) can be copied back: `list` needs frame_camera_list_size() entries.
+size_t frame_camera_list_size(const Frame* f);
+bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t* list, std::string& err);
 
 enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1, kKernelPipe = 2 };
 

@@ -73,12 +73,15 @@ def run_sweep(cfg_id=5, check_frames=(0, 21, 42)):
     total_ms, total_rays, t_lists, worst = 0.0, 0, 0.0, 0
     for k, m in enumerate(cams):
         cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
-        t = time.time(); lists = api.camera_triangle_list(cam, sc); t_lists += time.time() - t
-        fr = api.DeviceFrame(ds, cam, lists)
+        t = time.time(); fr = api.DeviceFrame(ds, cam); t_lists += time.time() - t       # camera lists built on the device
+        lists = None
         ms, launches, _ = fr.render(cfg["samples"])
         total_ms += ms; total_rays += cfg["width"] * cfg["height"] * cfg["samples"]
         if k in check_frames:
             img = fr.read(); flags = fr.undefined_flags()
+            lists = api.camera_triangle_list(cam, sc)                # host builder, for the reference run only
+            got = fr.camera_lists()
+            assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
             rows = (500, 532)
             R = ref.render(cam, lists, sc, cfg["samples"], rows=rows)
             sl = slice(*rows)
@@ -86,7 +89,7 @@ def run_sweep(cfg_id=5, check_frames=(0, 21, 42)):
             worst = max(worst, d)
             print(f"  frame {k}: {ms:.2f} ms, {launches} launches, lit {int((img[0] > 0).sum())}, diff vs reference rows {rows}: {d}", flush=True)
         fr.close()
-    print(f"  {len(cams)} frames: device {total_ms:.1f} ms total -> {total_rays / total_ms / 1e3:.1f} Mrays/s; host camera lists {t_lists:.1f}s; worst diff {worst}")
+    print(f"  {len(cams)} frames: device {total_ms:.1f} ms total -> {total_rays / total_ms / 1e3:.1f} Mrays/s; frame creation incl. device camera lists {t_lists:.2f}s; worst diff {worst}")
     ds.close()
 
 

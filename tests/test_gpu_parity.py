@@ -234,3 +234,39 @@ def test_full_size_config2_properties():
                 assert np.array_equal(want[c][rows[0]:rows[1]], b[c][rows[0]:rows[1]])
     except ImportError:
         pass
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_device_camera_lists_equal_host_builder(name):
+    """SURVEY 8f-1: CameraTriangleList::New on the device (csrc/cam_builder.cuh) -- Start, End and the compressed list are
+    entry-for-entry the host builder's (itself list-for-list the reference's, tests/test_builders.py), and rendering from
+    them gives the same planes."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    ds = api.DeviceScene(sc, 0)
+    fd = api.DeviceFrame(ds, cam)                    # lists built on the device
+    got = fd.camera_lists()
+    assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end)
+    assert got.list.size == lists.list.size and np.array_equal(got.list, lists.list)
+    fh = api.DeviceFrame(ds, cam, lists)
+    fd.render(samples)
+    fh.render(samples)
+    a, b = fd.read(), fh.read()
+    assert all(np.array_equal(a[c], b[c]) for c in range(3))
+    fd.close()
+    fh.close()
+    ds.close()
+
+
+def test_device_camera_lists_full_size_config2():
+    cfg = scenes.CONFIGS[2]
+    sc = cfg["make"]()
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+    lists = api.camera_triangle_list(cam, sc)
+    api.scene_triangle_list(sc, 256)
+    ds = api.DeviceScene(sc, 0)
+    fd = api.DeviceFrame(ds, cam)
+    got = fd.camera_lists()
+    assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
+    fd.close()
+    ds.close()
