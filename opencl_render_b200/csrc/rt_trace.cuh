@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             const int nSwitch = __popc(__ballot_sync(0xFFFFFFFFu, (ws == kWsRefine) | (ws == kWsEnter)));
             const int nWalk = __popc(__ballot_sync(0xFFFFFFFFu, ws == kWsRun));
             if (cq >= (uint32_t)tune.drainMin) break;   // (checked before anything that loops back: the queue holds drainMin + 31 cells)
+            // Tail of the launch (queue dry, a few long rays left): the launch cannot end before its longest walk does, so what
+            // counts now is that ray's latency.  Draining after every step would put a full open + test round trip between two
+            // steps; let a few cells accumulate instead (they are opened and tested side by side in one drain).
+            const bool tail = exhausted & (nWalk != 0) & (cq < (uint32_t)tune.tailDrain);
             if (nSwitch != 0 && (nSwitch >= tune.switchMin || nWalk < tune.walkMin3)) {
                 // ---- SWITCH: parked level switches of the two-level walk, run together
                 if (COUNT) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 }
                 continue;
             }
-            if (nWalk < tune.walkMin3) break;
+            if (nWalk < tune.walkMin3 && !tail) break;
         }
 
         // ---- DRAIN: open every queued cell, test every pair, any lane for any ray ---------------------------------------------------

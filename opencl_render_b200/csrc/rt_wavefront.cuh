@@ -390,6 +390,7 @@ struct TraceTuning {
     int testMin;     // keep testing while at least this many lanes have candidates pending
     int refillMin;   // refill from the queue once this many lanes are idle
     int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level DDA)
+    int tailDrain;   // wf_pipe_kernel, queue dry: drain only once this many cells wait (latency of the last long rays)
     int drainMin, walkMin3, switchMin;  // wf_pipe_kernel: drain the cell queue at this size; end a walk burst below this many walkers; run parked level switches at this count
 };
 

@@ -527,7 +527,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     else
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
-    static TraceTuning tune = {0, 0, 0, 1, 0, 0, 0};
+    static TraceTuning tune = {0, 0, 0, 1, 0, 0, 0, 0};
     if (tune.walkMin == 0) {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
         tune.walkMin = env("OCLR_WALK_MIN", 16);
@@ -537,6 +537,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
         tune.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
         tune.walkMin3 = env("OCLR_WALK_MIN3", 8);
         tune.switchMin = env("OCLR_SWITCH_MIN", 6);
+        tune.tailDrain = env("OCLR_TAIL_DRAIN", 8);
     }
     const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
