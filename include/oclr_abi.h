@@ -230,7 +230,8 @@ typedef struct oclr_render_stats {
     oclr_counters counters;
 } oclr_render_stats;
 
-enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PERSISTENT = 1, OCLR_KERNEL_PIPE = 2, OCLR_KERNEL_DEFAULT = -1 };
+/* 0: one thread per pixel (baseline, also the counting kernel of the reference accounting); 2: wavefront pipeline (production) */
+enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PIPE = 2, OCLR_KERNEL_DEFAULT = -1 };
 
 /* Upload + repack a scene into the HBM of CUDA device `device`.  NULL on failure. */
 oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);

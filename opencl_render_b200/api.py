@@ -21,7 +21,7 @@ MATERIAL_CHANNEL_COUNT = 5   # raytrace_opencl.h:14-22
 CH_COLOR, CH_REFLECTION, CH_TRANSPARENCY, CH_BUMP, CH_LUMINANCE = range(5)
 LIGHT_OMNI, LIGHT_SPOT, LIGHT_SPOTRECT, LIGHT_DISTANT, LIGHT_PARALLEL, LIGHT_PARSPOT, LIGHT_PARSPOTRECT, LIGHT_TUBE, \
     LIGHT_AREA, LIGHT_PHOTOMETRIC = range(10)
-KERNEL_SIMPLE, KERNEL_PERSISTENT, KERNEL_PIPE, KERNEL_DEFAULT = 0, 1, 2, -1
+KERNEL_SIMPLE, KERNEL_PIPE, KERNEL_DEFAULT = 0, 2, -1
 NO_TRIANGLE = 0xFFFFFFFF
 
 

@@ -610,9 +610,14 @@ OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o
                                    float& outT, float& outAB, float& outAC, Counters* cnt);
 
 template <bool COUNT>
+OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                  float& outAB, float& outAC, Counters* cnt, int partCells);
+
+template <bool COUNT>
 OCLR_HD uint32_t grid_trace_mode(int walkMode, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
                                  float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC, Counters* cnt) {
     if (walkMode == 2) return grid_trace_packed<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);  // px = base of all planes
+    if (walkMode >= 3) return grid_trace_split<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode);  // parts of `walkMode` cells
     return grid_trace<COUNT>(S, px, py, pz, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode == 1);
 }
 
@@ -630,7 +635,7 @@ struct RingLocal {
 template <bool COUNT>
 OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px, const float* py, const float* pz,
                         uint32_t pixel, uint32_t sampleIdx, uint32_t* primaryId, bool& undefinedRef, Counters* cnt,
-                        int walkMode = 0 /* 0 cell walk, 1 two-level walk, 2 packed two-level walk (rt_walk.h) */) {
+                        int walkMode = 0 /* 0 cell walk, 1 two-level walk, 2 packed two-level walk (rt_walk.h), >= 3 packed walk cut into parts of that many cells */) {
     const Camera& cam = F.cam;
     uint64_t rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
     const float fx = (float)(pixel % cam.width);

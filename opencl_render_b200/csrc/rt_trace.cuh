@@ -1,7 +1,8 @@
 // rt_trace.cuh -- production trace stage of the wavefront pipeline: a setup kernel + a persistent trace kernel organised as a
-// warp-level pipeline (rt_wavefront.cuh has the logic kernel and the first-generation trace kernel, kept for A/B).
+// warp-level pipeline (rt_wavefront.cuh has the logic kernel).
 //
-// What ncu said about the first trace kernel (profiles/r01_wf_trace_cfg2_*): issue-bound (66-69 % of issue slots) with 14 of 32
+// What ncu said about the first-generation trace kernel, in which a lane owned a ray from queue to result
+// (profiles/r01_wf_trace_cfg2_*; the kernel itself is retired, git history has it): issue-bound (66-69 % of issue slots) with 14 of 32
 // lanes active per instruction.  By phase: the walk ran at ~21 lanes, but "open the cell + scan its list + test" -- 37 % of all
 // instructions -- ran with 5-6 lanes, the level switches of the two-level walk with <2, and every refill ran
 // BindInCube/GetBoxAddress with a handful of lanes.  Hence:
@@ -16,6 +17,20 @@
 #include "rt_wavefront.cuh"
 
 namespace oclr {
+
+#ifndef OCLR_TRACE_MIN_CTAS
+#define OCLR_TRACE_MIN_CTAS 8
+#endif
+// Scheduling knobs of wf_pipe_kernel (run-time tunable through OCLR_DRAIN_MIN / OCLR_WALK_MIN3 / OCLR_SWITCH_MIN / OCLR_REFILL_MIN /
+// OCLR_TAIL_DRAIN / OCLR_HIERARCHICAL; the defaults are the measured optimum on config 2, flat within a few per cent).
+struct TraceTuning {
+    int refillMin;     // refill from the queue once this many lanes are idle
+    int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level walk)
+    int tailDrain;     // queue dry: drain only once this many cells wait (latency of the last long rays)
+    int drainMin;      // drain the warp's cell queue at this size
+    int walkMin3;      // end a walk burst below this many walking lanes
+    int switchMin;     // run parked level switches once this many lanes wait for one
+};
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
 enum { kLengthClasses = 4 };
@@ -95,12 +110,6 @@ __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, W
 
 enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#ifndef OCLR_NO_PREFETCH
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-
 // ---- wf_pipe_kernel: warp-level pipeline ----------------------------------------------------------------------------------
 // ncu on the lane-owned trace kernels: 37 % of all instructions are the
 // lane-owned test work (open cell, scan its list, test) executed with 5-6 of 32 lanes, because at any moment only a few of a
@@ -120,7 +129,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 //           nothing found -> miss.  Rays keep walking between drains (bounded speculation: a batch is ~one cell per lane).
 //
 // No mailbox here: pairs of one ray are tested concurrently, and face masks already remove the repeats between adjacent cells
-// (the mailbox removed 6 % more).
+// (a per-lane mailbox removed 6 % more in the lane-owned kernel).
 #ifndef OCLR_CELLQ_CAP
 #define OCLR_CELLQ_CAP 96
 #endif
@@ -136,6 +145,10 @@ struct WarpPipe {
     uint32_t pairQ[2][kPairQCap];   // [0] triangle, [1] owner | seq << 8
 };
 
+// Next list entry at or after k that this ray still has to test: entries whose face-mask bit is clear were in the cell the walk
+// just left (already examined).  Lists longer than 32 entries are scanned in full beyond the mask.  (A variant with one bit
+// per list entry -- no 32-entry limit -- measured 7 % slower on configs 2-3 and saved only 9 % of the tests on config 4, whose
+// neighbouring cells share few triangles; it was dropped.)
 __device__ __forceinline__ uint32_t next_entry(uint32_t begin, uint32_t end, uint32_t fm, uint32_t k) {
     const uint32_t rel = k - begin;
     if (rel < 32u) {
@@ -378,6 +391,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     ownerSeq = P.cellQ[1][base + lane];
                     const uint32_t rank = e & 0x1FFFFFFFu, f = e >> 29;
                     const uint2 range = __ldg(S.cellRange + rank);
+                    // entries shared with the cell the walk came from were examined there (exact, rt_types.h faceMask)
                     fm = f != (uint32_t)kFaceNone ? __ldg(S.faceMask + 6 * (size_t)rank + f) : 0xFFFFFFFFu;
                     excl = P.excl[ownerSeq & 31u];
                     kBegin = range.x;

@@ -177,22 +177,102 @@ OCLR_HD uint32_t pwalk_next_entry(uint32_t begin, uint32_t end, uint32_t faceBit
     return k < end ? k : end;
 }
 
-// Whole traversal for one ray in the trace kernel's formulation, serial (test infrastructure for the host; the kernel
-// runs the same functions with the work of 32 rays interleaved).  Face masks skip entries shared with the cell just left;
-// a small direct-mapped mailbox skips triangles this ray already tested -- both exact (rt_wavefront.cuh).
+// ---- exact random access into the walk --------------------------------------------------------------------------------------------
+// The walk is a 3-way merge of per-axis crossing sequences t_b(k) = (plane_b[k] - o_b) / r_b (rt_core.h, walk_enter_coarse).
+// With all direction components non-zero the merge order of two crossings of DIFFERENT axes is decided by their values and the
+// reference's tie rule alone (:387-398): an x crossing goes first only when strictly smaller; y goes before z only when strictly
+// smaller; otherwise the later axis goes first.  So the state of the walk right after it crosses into cell index B along axis a
+// (crossing value E) is known without walking: along every other axis b it has taken exactly the crossings that precede E,
+// a monotone predicate over the sorted planes -> binary search, one division per probe (walk_refine is the 4-plane case).
+// Used to cut a long walk into parts that different lanes walk concurrently (rt_trace.cuh, wf_setup_kernel).
+
+// Number of crossings of axis b, starting in cell c0, that precede the crossing value E of another axis.  `exits`: the crossing
+// that leaves the grid precedes E too (the walk ends before E).
+OCLR_HD int pwalk_count_before(int n, const float* pb, float o, float r, int c0, float E, bool strict, bool& exits) {
+    const int up = (0 <= r) ? 1 : 0;
+    const int kmax = up ? (n - 1 - c0) : c0;   // crossings 0 .. kmax-1 stay inside the grid, crossing kmax leaves it
+    int lo = 0, hi = kmax + 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float t = (pb[c0 + up + (up ? mid : -mid)] - o) / r;
+        const bool pre = strict ? (t < E) : (t <= E);
+        if (pre) lo = mid + 1; else hi = mid;
+    }
+    exits = lo > kmax;
+    return lo;
+}
+
+// State of the walk that started in cell (c0x, c0y, c0z) right after it crosses into cell index B along `axis`.
+// Returns false when the walk leaves the grid before that crossing.  Requires r.x, r.y, r.z != 0.
+OCLR_HD bool pwalk_jump(PackedWalk& w, int n, int nb, const float* px, const float* py, const float* pz, f3 o, f3 r, int c0x, int c0y,
+                        int c0z, int axis, int B) {
+    const float* pa = axis == 0 ? px : (axis == 1 ? py : pz);
+    const float oa = axis == 0 ? o.x : (axis == 1 ? o.y : o.z), ra = axis == 0 ? r.x : (axis == 1 ? r.y : r.z);
+    const int upa = (0 <= ra) ? 1 : 0;
+    const float E = (pa[B + (upa ? 0 : 1)] - oa) / ra;
+    int c[3] = {c0x, c0y, c0z};
+    bool exits = false;
+    if (axis != 0) {  // x goes before y / z only when strictly smaller
+        const int k = pwalk_count_before(n, px, o.x, r.x, c0x, E, true, exits);
+        if (exits) return false;
+        c[0] = c0x + ((0 <= r.x) ? k : -k);
+    }
+    if (axis != 1) {  // y: before x on ties, before z only when strictly smaller
+        const int k = pwalk_count_before(n, py, o.y, r.y, c0y, E, axis == 2, exits);
+        if (exits) return false;
+        c[1] = c0y + ((0 <= r.y) ? k : -k);
+    }
+    if (axis != 2) {  // z wins ties against x and y
+        const int k = pwalk_count_before(n, pz, o.z, r.z, c0z, E, false, exits);
+        if (exits) return false;
+        c[2] = c0z + ((0 <= r.z) ? k : -k);
+    }
+    c[axis] = B;
+    w.o = o;
+    w.r = r;
+    w.cpk = pk_make(c[0], c[1], c[2]);
+    w.tx = (px[c[0] + (0 <= r.x)] - o.x) / r.x;
+    w.ty = (py[c[1] + (0 <= r.y)] - o.y) / r.y;
+    w.tz = (pz[c[2] + (0 <= r.z)] - o.z) / r.z;
+    w.brick = (c[0] >> 2) + nb * ((c[1] >> 2) + nb * (c[2] >> 2));
+    w.level = 0;
+    w.coarseOk = (n >= 4);
+    w.maskLo = w.maskHi = w.rankBase = 0;
+    return true;
+}
+
+// Cuts of one walk into parts along its dominant axis: at most kMaxWalkParts parts of about `partCells` cells (Manhattan
+// estimate between the start cell and (ex, ey, ez) = end cell or estimated exit cell).  cutIndex[j] (j >= 1) = cell index along
+// `axis` whose entry starts part j.
+enum { kMaxWalkParts = 8 };
+OCLR_HD int pwalk_plan_parts(int c0x, int c0y, int c0z, int ex, int ey, int ez, int partCells, int& axis, int cutIndex[kMaxWalkParts]) {
+    const int dx = ex - c0x, dy = ey - c0y, dz = ez - c0z;
+    const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+    axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    const int span = axis == 0 ? ax : (axis == 1 ? ay : az), sgn = (axis == 0 ? dx : (axis == 1 ? dy : dz)) < 0 ? -1 : 1;
+    const int c0 = axis == 0 ? c0x : (axis == 1 ? c0y : c0z);
+    int parts = (ax + ay + az + partCells - 1) / partCells;
+    if (parts > kMaxWalkParts) parts = kMaxWalkParts;
+    if (parts > span) parts = span;   // every cut needs its own cell index strictly between start and end
+    if (parts < 1) parts = 1;
+    cutIndex[0] = c0;
+    for (int j = 1; j < parts; ++j) cutIndex[j] = c0 + sgn * (int)(((long long)span * j) / parts);
+    return parts;
+}
+
+// The walk proper from an initialised state (brick record not yet loaded).  Serial form of the trace kernel's per-ray logic
+// (test infrastructure for the host; the kernel runs the same functions with the work of 32 rays interleaved).  Face masks skip
+// entries shared with the cell just left; a small direct-mapped mailbox skips triangles this ray already tested -- both exact
+// (rt_wavefront.cuh).
 template <bool COUNT>
-OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl,
-                                   float& outT, float& outAB, float& outAC, Counters* cnt) {
+OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, PackedWalk w, float minD, float maxD, uint32_t excl, float& outT,
+                                  float& outAB, float& outAC, Counters* cnt) {
     const int n = S.n;
     int nbShift = 0;
     while ((1 << nbShift) < S.nb) ++nbShift;
-    PackedWalk w;
-    pwalk_setup(w, n, S.nb, planes, planes + (n + 1), planes + 2 * (n + 1), o, r, minD, maxD);
+    const f3 o = w.o, r = w.r;
     pwalk_load_brick(w, S.bricks);
-    if (COUNT) {
-        cnt->gridRays++;
-        cnt->bricksLoaded++;
-    }
+    if (COUNT) cnt->bricksLoaded++;
     uint32_t mailbox[16];
     for (int k = 0; k < 16; ++k) mailbox[k] = kNoTriangle;
     int face = kFaceNone, lastAxis = 0;
@@ -251,6 +331,83 @@ OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o
             pwalk_load_brick(w, S.bricks);
             if (COUNT) cnt->bricksLoaded++;
         }
+    }
+    outT = maxD;
+    return kNoTriangle;
+}
+
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl,
+                                   float& outT, float& outAB, float& outAC, Counters* cnt) {
+    const int n = S.n;
+    PackedWalk w;
+    pwalk_setup(w, n, S.nb, planes, planes + (n + 1), planes + 2 * (n + 1), o, r, minD, maxD);
+    if (COUNT) cnt->gridRays++;
+    return grid_walk_packed<COUNT>(S, planes, w, minD, maxD, excl, outT, outAB, outAC, cnt);
+}
+
+// End cell of a part = the cell the walk is in right before it crosses into the next part: the next part's start cell moved
+// back one cell along the cut axis.
+OCLR_HD void pwalk_part_end(const PackedWalk& next, int nb, int axis, f3 r, uint32_t& epk, int& endBrick) {
+    int c[3] = {pk_get(next.cpk, 0), pk_get(next.cpk, 1), pk_get(next.cpk, 2)};
+    const float ra = axis == 0 ? r.x : (axis == 1 ? r.y : r.z);
+    c[axis] -= (0 <= ra) ? 1 : -1;
+    epk = pk_make(c[0], c[1], c[2]);
+    endBrick = (c[0] >> 2) + nb * ((c[1] >> 2) + nb * (c[2] >> 2));
+}
+
+// Approximate cell where an unbounded ray leaves the grid (ordering / planning only, never a result).
+OCLR_HD void pwalk_exit_estimate(int n, const float* px, const float* py, const float* pz, f3 o, f3 r, int& ex, int& ey, int& ez) {
+    const float bx = r.x >= 0.f ? px[n] : px[0], by = r.y >= 0.f ? py[n] : py[0], bz = r.z >= 0.f ? pz[n] : pz[0];
+    float t = OCLR_INF;
+    if (r.x != 0.f) { const float q = (bx - o.x) / r.x; t = q < t ? q : t; }
+    if (r.y != 0.f) { const float q = (by - o.y) / r.y; t = q < t ? q : t; }
+    if (r.z != 0.f) { const float q = (bz - o.z) / r.z; t = q < t ? q : t; }
+    if (!(t < OCLR_INF) || t < 0.f) t = 0.f;
+    box_address(n, px, py, pz, mk3(o.x + t * r.x, o.y + t * r.y, o.z + t * r.z), ex, ey, ez);
+}
+
+// The same traversal with the walk cut into parts (the trace stage's way of bounding the longest work item): every part is
+// walked on its own, the first part (in walk order) with a hit gives the result.  Exactly the uncut walk (tests assert it).
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                  float& outAB, float& outAC, Counters* cnt, int partCells) {
+    const int n = S.n;
+    const float* px = planes;
+    const float* py = planes + (n + 1);
+    const float* pz = planes + 2 * (n + 1);
+    PackedWalk first;
+    pwalk_setup(first, n, S.nb, px, py, pz, o, r, minD, maxD);
+    if (COUNT) cnt->gridRays++;
+    const bool splittable = (n >= 4) & (r.x != 0.f) & (r.y != 0.f) & (r.z != 0.f);
+    if (!splittable) return grid_walk_packed<COUNT>(S, planes, first, minD, maxD, excl, outT, outAB, outAC, cnt);
+    const int c0x = pk_get(first.cpk, 0), c0y = pk_get(first.cpk, 1), c0z = pk_get(first.cpk, 2);
+    int ex, ey, ez;
+    if (first.epk != kPkNone) {
+        ex = pk_get(first.epk, 0);
+        ey = pk_get(first.epk, 1);
+        ez = pk_get(first.epk, 2);
+    } else {
+        pwalk_exit_estimate(n, px, py, pz, o, r, ex, ey, ez);
+    }
+    int axis, cut[kMaxWalkParts];
+    const int parts = pwalk_plan_parts(c0x, c0y, c0z, ex, ey, ez, partCells, axis, cut);
+    PackedWalk cur = first;
+    for (int j = 0; j < parts; ++j) {
+        PackedWalk next;
+        bool haveNext = false;
+        if (j + 1 < parts) haveNext = pwalk_jump(next, n, S.nb, px, py, pz, o, r, c0x, c0y, c0z, axis, cut[j + 1]);
+        PackedWalk part = cur;
+        if (haveNext) {
+            pwalk_part_end(next, S.nb, axis, r, part.epk, part.endBrick);
+        } else {  // last part (or the walk leaves the grid before the next cut): the ray's own end condition
+            part.epk = first.epk;
+            part.endBrick = first.endBrick;
+        }
+        const uint32_t hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt);
+        if (hit != kNoTriangle) return hit;
+        if (!haveNext) break;
+        cur = next;
     }
     outT = maxD;
     return kNoTriangle;

@@ -1,25 +1,20 @@
-// rt_wavefront.cuh -- the production form of the raytrace path on B200: a wavefront pipeline of two kernels.
+// rt_wavefront.cuh -- the production form of the raytrace path on B200: a wavefront pipeline.
 //
 // Why: ncu on the one-thread-per-pixel kernel (profiles/r01_simple_kernel_cfg2_details.txt) shows 5.65 active threads
 // per warp instruction -- ray/triangle tests run with ~3 lanes because at any DDA step only ~9 % of the cells a warp
 // looks at hold triangles, and every lane waits for the longest of three consecutive grid walks.  The path is issue-
 // bound with the working set in L2 (DRAM traffic 118 MB per frame), so the cure is lane utilisation, not bytes.
 //
-//   wf_logic_kernel   one thread per pixel-sample "path".  Runs the reference's per-pixel control flow
+//   wf_logic_kernel   (this file) one thread per pixel-sample "path".  Runs the reference's per-pixel control flow
 //                     (raytrace_opencl.c:452-742: ray-gen, camera-list scan, shading, light sampling, bounce ring, RNG
 //                     in the reference's draw order) as a resumable state machine and SUSPENDS at every call of
 //                     RayIntersectsTriangles (:530 closest hit of a ring segment, :611 shadow/occluder ray), appending
 //                     the path to a ray queue.  Path state lives in HBM as SoA float4 planes: ring (12 slots x 48 B),
 //                     shading carry (112 B), ray (36 B), hit (16 B), rng (8 B), colour (16 B).
-//   wf_trace_kernel   persistent warps (grid = resident CTAs of all 148 SMs) drain the queue.  Each lane owns one ray;
-//                     lanes that finish are refilled from the queue with one warp-aggregated atomic (ballot + shuffle),
-//                     and work inside a warp is phase-batched: a WALK phase advances every lane's DDA to its next
-//                     non-empty cell (one bit test per empty cell from the 4x4x4 brick mask in registers), a TEST phase
-//                     then runs ray/triangle tests with all lanes that found triangles -- vote thresholds decide when
-//                     to switch.  Split planes sit in shared memory; triangle fetches are two 128-bit loads per stage.
+//   wf_setup_kernel / wf_pipe_kernel   (rt_trace.cuh) drain the queue: the trace stage.
 //
-// The host alternates the two kernels until the queue stays empty; the arithmetic is rt_core.h, identical to the
-// simple kernel, so results are bit-identical by construction (tests assert it).
+// The host enqueues rounds of (logic, setup, trace) ahead until a round finds no path waiting; the arithmetic is rt_core.h /
+// rt_walk.h, identical to the simple kernel, so results are bit-identical by construction (tests assert it).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -375,228 +370,6 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
         if (COUNT) flush_counters(cnt, gcnt);
     }
     enqueue(w, q, want);
-}
-
-// ---- trace kernel -------------------------------------------------------------------------------------------------------
-enum { kLaneIdle = 0, kLaneWalk = 1, kLaneTest = 2 };
-enum { kMailboxSlots = 16 };
-
-// Vote thresholds of the trace kernel (tunable at run time through OCLR_WALK_MIN / OCLR_TEST_MIN / OCLR_REFILL_MIN).
-#ifndef OCLR_TRACE_MIN_CTAS
-#define OCLR_TRACE_MIN_CTAS 8
-#endif
-struct TraceTuning {
-    int walkMin;     // keep walking while at least this many lanes of the warp are still looking for triangles
-    int testMin;     // keep testing while at least this many lanes have candidates pending
-    int refillMin;   // refill from the queue once this many lanes are idle
-    int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level DDA)
-    int tailDrain;   // wf_pipe_kernel, queue dry: drain only once this many cells wait (latency of the last long rays)
-    int drainMin, walkMin3, switchMin;  // wf_pipe_kernel: drain the cell queue at this size; end a walk burst below this many walkers; run parked level switches at this count
-};
-
-// Lane bookkeeping: the walker runs AHEAD of the tests.  A lane's DDA keeps walking while the cells it found wait in a
-// small per-lane queue (shared memory) for the next TEST phase; cells are tested in walk order and the first cell with a
-// hit ends the ray (:380), discarding whatever the walker found beyond it.  The speculation is bounded by the queue
-// depth; it keeps ~all lanes busy in both phases instead of parking a lane the moment it finds triangles.
-#ifndef OCLR_PENDING_DEPTH
-#define OCLR_PENDING_DEPTH 4
-#endif
-enum { kPendingDepth = OCLR_PENDING_DEPTH };
-enum { kWalkNone = 0, kWalkRunning = 1, kWalkFinished = 2 };
-
-// Next list entry at or after k that this ray still has to test: entries whose face-mask bit is clear were in the cell the
-// walk just left (already examined), the excluded triangle and mailbox hits are skipped too.  Returns false at the end.
-template <bool COUNT>
-__device__ __forceinline__ bool next_candidate(const uint32_t* __restrict__ list, uint32_t begin, uint32_t end, uint32_t m, uint32_t excl,
-                                               const uint32_t (*mb)[128], uint32_t& k, uint32_t& tri, Counters& cnt) {
-    for (;;) {
-        const uint32_t rel = k - begin;
-        if (rel < 32u) {
-            const uint32_t mm = m >> rel;
-            k = mm ? k + (uint32_t)(__ffs((int)mm) - 1) : begin + 32u;
-        }
-        if (k >= end) {
-            k = end;
-            return false;
-        }
-        tri = __ldg(list + k);
-        if (tri != excl && mb[tri & (kMailboxSlots - 1)][threadIdx.x] != tri) return true;
-        if (COUNT && tri != excl) cnt.mailboxSkips++;
-        ++k;
-    }
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_trace_kernel(SceneView S, WfState w, TraceTuning tune, Counters* gcnt) {
-    extern __shared__ float shPlanes[];
-    // Per-lane mailbox: a direct-mapped cache of the triangle ids this ray has already tested, [slot][thread] so a warp
-    // never bank-conflicts.  Skipping a cached id is EXACT: a cell that did not end the walk produced no hit, so its
-    // in-cell bound stayed at maxDistance (:366) and every triangle tested there failed either the (min, max) range
-    // or the barycentric test -- both ray/triangle properties that do not change in a later cell.
-    __shared__ uint32_t mailbox[kMailboxSlots][128];
-    __shared__ uint4 pending[kPendingDepth][128];  // {next entry, end, face mask, begin}
-    if (blockIdx.x * 128u >= *w.queueCount) return;   // launched with the full persistent grid: the host does not know the count
-    load_planes(shPlanes, S);
-    const float* px = shPlanes;
-    const float* py = shPlanes + (S.n + 1);
-    const float* pz = shPlanes + 2 * (S.n + 1);
-    const int lane = threadIdx.x & 31;
-    const unsigned ltMask = (1u << lane) - 1u;
-    const uint32_t count = *w.queueCount;
-    const int n = S.n;
-
-    Counters cnt = {};
-    int wst = kWalkNone;      // walker status
-    int qHead = 0, qCount = 0;
-    bool testing = false;     // a popped cell is being tested (i, iEnd, nextTri valid)
-    bool exhausted = false;
-    uint32_t path = 0;
-    GridWalk g;
-    uint32_t i = 0, iEnd = 0, nextTri = 0, curMask = 0, curBegin = 0;
-    int face = -1;  // face through which the walker entered the current cell by a cell-level step (-1: none)
-    uint32_t best = kNoTriangle;
-    float bestT = 0.f, bestAB = 0.f, bestAC = 0.f;
-    int lastAxis = 0;
-    float lastE = 0.f;
-
-    for (;;) {
-        // ---- refill idle lanes from the queue: one atomic per warp ----
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, wst == kWalkNone);
-        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
-            const int nIdle = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(w.queueCursor, (uint32_t)nIdle);
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (base + (uint32_t)nIdle >= count) exhausted = true;
-            if (wst == kWalkNone) {
-                const uint32_t idx = base + (uint32_t)__popc(idle & ltMask);
-                if (idx < count) {
-                    path = w.queue[idx];
-                    const float4 ro = w.rayO[path], rd = w.rayD[path];
-                    walk_begin(g, S, px, py, pz, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, rd.w, w.rayExcl[path]);
-                    best = kNoTriangle;
-                    wst = kWalkRunning;
-                    qHead = qCount = 0;
-                    testing = false;
-                    face = -1;
-#pragma unroll
-                    for (int k = 0; k < kMailboxSlots; ++k) mailbox[k][threadIdx.x] = kNoTriangle;
-                    if (COUNT) cnt.gridRays++;
-                }
-            }
-        }
-        if (__ballot_sync(0xFFFFFFFFu, wst != kWalkNone) == 0u) break;
-
-        // ---- WALK phase ------------------------------------------------------------------------------------------------
-        // One control path for both levels of the walk: classify the current position from the brick record, queue the cell
-        // if it holds an untested triangle, then change level (rare) or take one branch-free DDA step.
-        for (;;) {
-            const bool walking = (wst == kWalkRunning) & (qCount < kPendingDepth);
-            if (COUNT) {
-                if (lane == 0) cnt.walkWarpIters++;
-                if (walking) cnt.walkLaneIters++;
-            }
-            if (walking) {
-                walk_load_brick<COUNT>(g, S, &cnt);
-                const bool coarse = g.shift != 0;
-                const int bit = (g.cx & 3) | ((g.cy & 3) << 2) | ((g.cz & 3) << 4);
-                const bool occupied = (!coarse) & (((g.mask >> bit) & 1ull) != 0ull);
-                const bool atEnd = (!coarse) & (g.cx == g.ex) & (g.cy == g.ey) & (g.cz == g.ez);
-                if (COUNT && !coarse) {
-                    cnt.cells++;
-                    if (g.mask == 0ull) cnt.emptyBrickCells++;
-                }
-                if (occupied) {
-                    const uint32_t rank = g.rankBase + (uint32_t)__popcll(g.mask & ((1ull << bit) - 1ull));
-                    const uint2 range = __ldg(S.cellRange + rank);
-                    if (COUNT) cnt.cellsNonEmpty++;
-                    // pre-filter (exact): entries shared with the cell just left, the excluded triangle and ids this ray
-                    // already tested need no test; a cell with nothing new is treated like an empty one
-                    const uint32_t m = face >= 0 ? __ldg(S.faceMask + 6 * (size_t)rank + face) : 0xFFFFFFFFu;
-                    uint32_t k = range.x, tri;
-                    if (next_candidate<COUNT>(S.cellList, range.x, range.y, m, g.excl, mailbox, k, tri, cnt)) {
-                        int slot = qHead + qCount;
-                        slot = slot >= kPendingDepth ? slot - kPendingDepth : slot;
-                        pending[slot][threadIdx.x] = make_uint4(k, range.y, m, range.x);
-                        ++qCount;
-                    }
-                }
-                if (coarse & ((g.mask != 0ull) | (g.curBrick == g.endBrick))) {
-                    walk_refine(g, lastAxis, lastE, px, py, pz);  // brick needs a cell walk: rebuild the exact cell state
-                    face = -1;
-                } else if (atEnd) {
-                    wst = kWalkFinished;
-                } else {
-                    // whole brick empty: cross it (and the empty bricks behind it) at brick granularity -- exact, see
-                    // walk_enter_coarse in rt_core.h.  (`cells` counts only the cells examined one by one.)
-                    if ((!coarse) & (tune.hierarchical != 0) & g.coarseOk & (g.mask == 0ull) & (g.curBrick != g.endBrick)) {
-                        walk_enter_coarse(g, px, py, pz);
-                        if (COUNT) cnt.coarseEnters++;
-                    }
-                    if (COUNT && g.shift) cnt.coarseSteps++;
-                    if (!walk_step_ex(g, n, px, py, pz, lastAxis, lastE)) wst = kWalkFinished;
-                    const float rs = lastAxis == 0 ? g.r.x : (lastAxis == 1 ? g.r.y : g.r.z);
-                    face = g.shift ? -1 : lastAxis * 2 + (0 <= rs ? 1 : 0);
-                }
-            }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, (wst == kWalkRunning) & (qCount < kPendingDepth))) < tune.walkMin) break;
-        }
-
-        // ---- TEST phase: one real ray/triangle test per lane per iteration, cells in walk order -----------------------------
-        for (;;) {
-            const bool active = testing | (qCount > 0);
-            if (COUNT) {
-                if (lane == 0) cnt.testWarpIters++;
-                if (active) cnt.testLaneIters++;
-            }
-            if (active) {
-                if (!testing) {  // next queued cell
-                    const uint4 r = pending[qHead][threadIdx.x];
-                    qHead = qHead + 1 >= kPendingDepth ? 0 : qHead + 1;
-                    --qCount;
-                    i = r.x;
-                    iEnd = r.y;
-                    curMask = r.z;
-                    curBegin = r.w;
-                    bestT = g.maxD;  // *outRayMult = maxDistance at every cell (:366)
-                    testing = true;
-                    // its first candidate was untested when the cell was queued; a cell tested since may have covered it
-                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, g.excl, mailbox, i, nextTri, cnt);
-                }
-                if (i != iEnd) {
-                    const uint32_t tri = nextTri;
-                    float t, ab, ac;
-                    if (COUNT) cnt.gridCandidates++;
-                    mailbox[tri & (kMailboxSlots - 1)][threadIdx.x] = tri;
-                    if (tri_test(S.triGeo + 4 * (size_t)tri, g.o, g.r, g.minD, bestT, t, ab, ac)) {
-                        best = tri;
-                        bestT = t;
-                        bestAB = ab;
-                        bestAC = ac;
-                    }
-                    ++i;
-                    next_candidate<COUNT>(S.cellList, curBegin, iEnd, curMask, g.excl, mailbox, i, nextTri, cnt);
-                }
-                if (i == iEnd) {  // cell done
-                    testing = false;
-                    if (best != kNoTriangle) {  // first cell with any hit wins (:380); later cells are discarded
-                        w.hit[path] = make_float4(__uint_as_float(best), bestT, bestAB, bestAC);
-                        wst = kWalkNone;
-                        qCount = 0;
-                    }
-                }
-            }
-            if (__popc(__ballot_sync(0xFFFFFFFFu, testing | (qCount > 0))) < tune.testMin) break;
-        }
-
-        // walk over, nothing left to test, no hit: miss
-        if ((wst == kWalkFinished) & (!testing) & (qCount == 0)) {
-            w.hit[path] = make_float4(__uint_as_float(kNoTriangle), g.maxD, 0.f, 0.f);
-            wst = kWalkNone;
-        }
-    }
-    if (COUNT) flush_counters(cnt, gcnt);
 }
 
 }  // namespace oclr

@@ -465,7 +465,7 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
-                             uint32_t& launches, bool timeTrace, bool packed /* false: wf_trace_kernel (first generation), true: wf_setup_kernel + wf_pipe_kernel */, std::string& err) {
+                             uint32_t& launches, bool timeTrace, std::string& err) {
     f->traceEventsUsed = 0;
     const uint32_t rows = launch_rows(F), W = F.cam.width;
     const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
@@ -510,28 +510,21 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
     rec.s1 = (uint4*)f->recS1.p;
     rec.order = (uint32_t*)f->recOrder.p;
     rec.Q = Q;
-    if (packed && S.n > 1024) {
+    if (S.n > 1024) {
         err = "axesDivCount > 1024 is not supported by the packed walk";
         return false;
     }
 
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
-    if (packed) {
-        if (dcnt)
-            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<true>, 128, shBytes));
-        else
-            OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false>, 128, shBytes));
-    } else if (dcnt)
-        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<true>, 128, shBytes));
+    if (dcnt)
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<true>, 128, shBytes));
     else
-        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_trace_kernel<false>, 128, shBytes));
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
-    static TraceTuning tune = {0, 0, 0, 1, 0, 0, 0, 0};
-    if (tune.walkMin == 0) {
+    static TraceTuning tune = {0, 1, 0, 0, 0, 0};
+    if (tune.refillMin == 0) {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        tune.walkMin = env("OCLR_WALK_MIN", 16);
-        tune.testMin = env("OCLR_TEST_MIN", 16);
         tune.refillMin = env("OCLR_REFILL_MIN", 4);
         tune.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
         tune.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
@@ -571,17 +564,12 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
                     }
                     OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
                 }
-                if (packed) {
-                    wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
-                    ++launches;
-                    if (dcnt)
-                        wf_pipe_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
-                    else
-                        wf_pipe_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
-                } else if (dcnt)
-                    wf_trace_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, tune, dcnt);
+                wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
+                ++launches;
+                if (dcnt)
+                    wf_pipe_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
                 else
-                    wf_trace_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, tune, dcnt);
+                    wf_pipe_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
                 if (timeTrace) {
                     OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed + 1], st));
                     f->traceEventsUsed += 2;
@@ -626,9 +614,8 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         else
             raytrace_simple_kernel<false><<<grid, 128, shBytes, st>>>(s->view, F, dcnt);
         launches = 1;
-    } else if (variant == kKernelPersistent || variant == kKernelPipe) {
-        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, variant == kKernelPipe, err))
-            return false;
+    } else if (variant == kKernelPipe) {
+        if (!launch_wavefront(f, s->view, F, s->smCount, count ? dcnt : nullptr, st, launches, stats != nullptr, err)) return false;
     } else {
         err = "unknown kernel variant";
         return false;

@@ -77,7 +77,7 @@ void frame_destroy(Frame* f);
 size_t frame_camera_list_size(const Frame* f);
 bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t* list, std::string& err);
 
-enum KernelVariant { kKernelSimple = 0, kKernelPersistent = 1, kKernelPipe = 2 };
+enum KernelVariant { kKernelSimple = 0, kKernelPipe = 2 };   // (1 was the lane-owned wavefront kernel, retired)
 
 struct RenderStats {
     float deviceMs = 0.f;        // CUDA-event time of the trace kernel(s) on the launch stream

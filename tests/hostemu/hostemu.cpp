@@ -52,7 +52,9 @@ extern "C" int hostemu_render(const oclr_scene_desc* d, const oclr_camera* cam, 
     std::atomic<uint32_t> nextRow(rowBegin);
     std::vector<Counters> cnts(threads > 0 ? threads : 1);
     // walk mode: unset = the reference's cell walk, 1 = two-level (brick-skipping) walk, 2 = the trace kernel's packed form (rt_walk.h)
-    const int hier = getenv("HOSTEMU_HIERARCHICAL") ? (atoi(getenv("HOSTEMU_HIERARCHICAL")) == 2 ? 2 : 1) : 0;
+    // >= 3 = the packed walk cut into parts of that many cells (exact random access into the walk, rt_walk.h pwalk_jump)
+    const int hierEnv = getenv("HOSTEMU_HIERARCHICAL") ? atoi(getenv("HOSTEMU_HIERARCHICAL")) : 0;
+    const int hier = getenv("HOSTEMU_HIERARCHICAL") ? (hierEnv >= 2 ? hierEnv : 1) : 0;
     auto worker = [&](int tid) {
         Counters& cnt = cnts[tid];
         memset(&cnt, 0, sizeof(cnt));

@@ -16,7 +16,7 @@ from tests import helpers
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
-VARIANTS = [api.KERNEL_SIMPLE, api.KERNEL_PERSISTENT, api.KERNEL_PIPE]
+VARIANTS = [api.KERNEL_SIMPLE, api.KERNEL_PIPE]
 
 
 def _render(sc, cam, lists, samples, variant=api.KERNEL_DEFAULT, rows=None, count=False):
@@ -203,13 +203,10 @@ def test_full_size_config2_properties():
     fr.render(1, variant=api.KERNEL_SIMPLE)
     a = fr.read()
     ida = fr.primary_ids()
-    fr.render(1, variant=api.KERNEL_PERSISTENT)
+    fr.render(1, variant=api.KERNEL_PIPE)
     b = fr.read()
     idb = fr.primary_ids()
     assert all(np.array_equal(a[c], b[c]) for c in range(3)) and np.array_equal(ida, idb)
-    fr.render(1, variant=api.KERNEL_PIPE)
-    b2 = fr.read()
-    assert all(np.array_equal(a[c], b2[c]) for c in range(3)) and np.array_equal(ida, fr.primary_ids())
     out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
     for rank in range(8):
         for rows in api.band_partition(cam.height, rank, 8):

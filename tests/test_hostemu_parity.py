@@ -79,3 +79,21 @@ def test_packed_walk_is_exact(name, hostemu, monkeypatch):
     assert packed[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
     assert packed[3]["gridCandidates"] <= flat[3]["gridCandidates"]
     assert packed[3]["cells"] <= flat[3]["cells"]
+
+
+@pytest.mark.parametrize("part_cells", [3, 7, 40])
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_split_walk_is_exact(name, part_cells, hostemu, monkeypatch):
+    """Exact random access into the walk (rt_walk.h pwalk_jump): every walk cut into parts of ~part_cells cells along its dominant
+    axis, each part walked on its own from a state computed WITHOUT walking (binary search over the crossing values), first part
+    with a hit wins -- planes, ids and flags identical to the uncut reference walk, and the parts together visit exactly the
+    non-empty cells the uncut walk visits."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", str(part_cells))
+    split = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], split[0][c])
+    assert np.array_equal(flat[1], split[1]) and np.array_equal(flat[2], split[2])
+    assert split[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
