@@ -226,7 +226,7 @@ typedef struct oclr_render_stats {
     float deviceMs;        /* CUDA-event time of the trace kernels on the launch stream */
     cl_uint launches;      /* kernels launched by this call */
     float traceMs;         /* CUDA-event time of the trace-stage launches alone (dominant kernel) */
-    cl_uint traceLaunches;
+    cl_uint traceLaunches; /* trace-stage rounds that had rays (rounds enqueued ahead that found none are not counted) */
     oclr_counters counters;
 } oclr_render_stats;
 

@@ -628,11 +628,12 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         OCLR_CUDA(cudaEventElapsedTime(&stats->deviceMs, f->ev0, f->ev1));
         stats->launches = launches;
         stats->traceMs = 0.f;
-        stats->traceLaunches = variant != kKernelSimple ? f->traceEventsUsed / 2 : 0;
+        stats->traceLaunches = 0;
         for (uint32_t k = 0; variant != kKernelSimple && k + 1 < f->traceEventsUsed; k += 2) {
             float ms = 0.f;
             OCLR_CUDA(cudaEventElapsedTime(&ms, f->traceEvents[k], f->traceEvents[k + 1]));
             stats->traceMs += ms;
+            if (ms > 0.015f) ++stats->traceLaunches;   // rounds enqueued ahead that found no ray return at once (~6 us): not counted
         }
         if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
     }
