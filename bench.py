@@ -189,6 +189,8 @@ def run_b200(args):
         if timed_events is not None:
             timed_events[0].record()
         launches = part.render(fr, S, args.variant, stream)
+        if timed_events is not None:
+            timed_events[2].record()                         # trace done, gather not yet: "gather excluded" figure
         if gather is not None:
             gather.run()
             launches += gather.launches
@@ -202,7 +204,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    events = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     launches = 0
     with ClockSampler(local) as clocks:
         for k in range(args.steps):
@@ -211,11 +213,12 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms_total = sum(a.elapsed_time(b) for a, b in events)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    ms_total = sum(a.elapsed_time(b) for a, b, _ in events)
+    ms_render = sum(a.elapsed_time(c) for a, _, c in events)
+    t = torch.tensor([ms_total, ms_render], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, ms_render = float(t[0].item()), float(t[1].item())
     ms_step = ms_total / args.steps
     value = rays_frame / ms_step / 1e3
 
@@ -261,7 +264,11 @@ def run_b200(args):
                         "profiles/ has issue-slot and lane-utilisation counters",
                 "whole_step": {"ms": ms_frame, "algorithmic_bytes": algo_frame, "achieved_gbs": algo_frame / (ms_frame * 1e-3) / 1e9,
                                "frac": algo_frame / (ms_frame * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_ray": algo_frame / rays_rank},
-                "per_ray_events": {k: v / rays_rank for k, v in cnt.items() if v}}
+                "per_ray_events": {k: v / rays_rank for k, v in cnt.items() if v},
+                # comparable with other tracers: ring segments and grid traversals (segments' closest-hit walks +
+                # shadow / occluder walks) per second, rank 0's share at its own frame time
+                "rates": {"segments_per_s": cnt["segments"] / (ms_frame * 1e-3), "traversals_per_s": cnt["gridRays"] / (ms_frame * 1e-3),
+                          "triangle_tests_per_s_reference_accounting": (cnt["primCandidates"] + cnt["gridCandidates"]) / (ms_frame * 1e-3)}}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(prof):
             try:
@@ -286,6 +293,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": e2e.h2d_bytes, "d2h_bytes_per_step": e2e.d2h_bytes,
                     "steps": e2e_steps, "call": "RaytraceAll (C-ABI, host buffers)" if world == 1 else "oclr scene/frame API, rank-local rows"},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
+            "gather": {"included_in_value": world > 1, "ms_per_step": (ms_total - ms_render) / args.steps,
+                       "value_without_gather": rays_frame / (ms_render / args.steps) / 1e3},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -23,6 +23,12 @@ enum { kFaceNone = 7 };
 OCLR_HD uint32_t pk_make(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << kPkBits) | ((uint32_t)z << (2 * kPkBits)); }
 OCLR_HD int pk_get(uint32_t pk, int axis) { return (int)((pk >> (axis * kPkBits)) & kPkMask); }
 
+// A walk that is one PART of a longer walk (see pwalk_jump) ends at a plane instead of a cell: PackedWalk::epk then holds
+// 10b | axis << 10 | cell index -- the part is over the moment a step along `axis` enters that cell index (the cell belongs to
+// the next part).  The index is the first cell of its brick in travel direction, so a brick-level step lands on it too.
+OCLR_HD uint32_t pk_stop(int axis, int cellIndex) { return 0x80000000u | ((uint32_t)axis << kPkBits) | (uint32_t)cellIndex; }
+OCLR_HD bool pk_is_stop(uint32_t epk) { return (epk >> 30) == 2u; }
+
 struct PackedWalk {
     f3 o, r;
     float tx, ty, tz;    // next crossing per axis at the current level
@@ -113,6 +119,14 @@ OCLR_HD bool pwalk_step(PackedWalk& w, int n, int nbShift, const float* planes, 
     crossed = (w.level != 0) | (((c ^ cn) & ~3) != 0);
     if (crossed) w.brick += dir * (1 << (axis * nbShift));
     return true;
+}
+
+// After a successful step along `axis`: did the walk just cross into the cell index at which this part ends?
+OCLR_HD bool pwalk_stopped(const PackedWalk& w, int axis, int up) {
+    if (!pk_is_stop(w.epk) || (int)((w.epk >> kPkBits) & 3u) != axis) return false;
+    const int c = pk_get(w.cpk, axis);
+    const int cell = w.level ? (up ? (c << 2) : (c << 2) + 3) : c;
+    return cell == (int)(w.epk & kPkMask);
 }
 
 // Level 0 -> level 1 inside an empty brick: coordinates become brick coordinates, the heads become the brick-exit crossings.
@@ -243,20 +257,25 @@ OCLR_HD bool pwalk_jump(PackedWalk& w, int n, int nb, const float* px, const flo
 
 // Cuts of one walk into parts along its dominant axis: at most kMaxWalkParts parts of about `partCells` cells (Manhattan
 // estimate between the start cell and (ex, ey, ez) = end cell or estimated exit cell).  cutIndex[j] (j >= 1) = cell index along
-// `axis` whose entry starts part j.
+// `axis` whose entry starts part j (and ends part j - 1, pk_stop).
 enum { kMaxWalkParts = 8 };
 OCLR_HD int pwalk_plan_parts(int c0x, int c0y, int c0z, int ex, int ey, int ez, int partCells, int& axis, int cutIndex[kMaxWalkParts]) {
     const int dx = ex - c0x, dy = ey - c0y, dz = ez - c0z;
     const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
     axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
     const int span = axis == 0 ? ax : (axis == 1 ? ay : az), sgn = (axis == 0 ? dx : (axis == 1 ? dy : dz)) < 0 ? -1 : 1;
-    const int c0 = axis == 0 ? c0x : (axis == 1 ? c0y : c0z);
-    int parts = (ax + ay + az + partCells - 1) / partCells;
-    if (parts > kMaxWalkParts) parts = kMaxWalkParts;
-    if (parts > span) parts = span;   // every cut needs its own cell index strictly between start and end
-    if (parts < 1) parts = 1;
+    const int c0 = axis == 0 ? c0x : (axis == 1 ? c0y : c0z), e = c0 + sgn * span;
+    int want = (ax + ay + az + partCells - 1) / partCells;
+    if (want > kMaxWalkParts) want = kMaxWalkParts;
     cutIndex[0] = c0;
-    for (int j = 1; j < parts; ++j) cutIndex[j] = c0 + sgn * (int)(((long long)span * j) / parts);
+    int parts = 1;
+    for (int j = 1; j < want; ++j) {
+        int B = c0 + sgn * (int)(((long long)span * j) / want);
+        B = sgn > 0 ? (B & ~3) : (B | 3);   // first cell of its brick in travel direction: brick-level steps land on it
+        // strictly between the previous cut and the end, in travel order
+        const bool ok = sgn > 0 ? (B > cutIndex[parts - 1] && B < e) : (B < cutIndex[parts - 1] && B > e);
+        if (ok) cutIndex[parts++] = B;
+    }
     return parts;
 }
 
@@ -326,6 +345,7 @@ OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, Packe
         bool crossed;
         if (COUNT && w.level) cnt->coarseSteps++;
         if (!pwalk_step(w, n, nbShift, planes, lastAxis, up, lastE, crossed)) break;
+        if (pwalk_stopped(w, lastAxis, up)) break;   // this part of the walk ends here; the cell belongs to the next part
         face = w.level ? (int)kFaceNone : lastAxis * 2 + up;
         if (crossed) {
             pwalk_load_brick(w, S.bricks);
@@ -344,16 +364,6 @@ OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o
     pwalk_setup(w, n, S.nb, planes, planes + (n + 1), planes + 2 * (n + 1), o, r, minD, maxD);
     if (COUNT) cnt->gridRays++;
     return grid_walk_packed<COUNT>(S, planes, w, minD, maxD, excl, outT, outAB, outAC, cnt);
-}
-
-// End cell of a part = the cell the walk is in right before it crosses into the next part: the next part's start cell moved
-// back one cell along the cut axis.
-OCLR_HD void pwalk_part_end(const PackedWalk& next, int nb, int axis, f3 r, uint32_t& epk, int& endBrick) {
-    int c[3] = {pk_get(next.cpk, 0), pk_get(next.cpk, 1), pk_get(next.cpk, 2)};
-    const float ra = axis == 0 ? r.x : (axis == 1 ? r.y : r.z);
-    c[axis] -= (0 <= ra) ? 1 : -1;
-    epk = pk_make(c[0], c[1], c[2]);
-    endBrick = (c[0] >> 2) + nb * ((c[1] >> 2) + nb * (c[2] >> 2));
 }
 
 // Approximate cell where an unbounded ray leaves the grid (ordering / planning only, never a result).
@@ -392,22 +402,20 @@ OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o,
     }
     int axis, cut[kMaxWalkParts];
     const int parts = pwalk_plan_parts(c0x, c0y, c0z, ex, ey, ez, partCells, axis, cut);
-    PackedWalk cur = first;
     for (int j = 0; j < parts; ++j) {
-        PackedWalk next;
-        bool haveNext = false;
-        if (j + 1 < parts) haveNext = pwalk_jump(next, n, S.nb, px, py, pz, o, r, c0x, c0y, c0z, axis, cut[j + 1]);
-        PackedWalk part = cur;
-        if (haveNext) {
-            pwalk_part_end(next, S.nb, axis, r, part.epk, part.endBrick);
-        } else {  // last part (or the walk leaves the grid before the next cut): the ray's own end condition
+        PackedWalk part = first;
+        // a part starts where the walk crosses into its cut (state computed without walking); when the walk leaves the grid
+        // before that crossing there is nothing left to visit
+        if (j > 0 && !pwalk_jump(part, n, S.nb, px, py, pz, o, r, c0x, c0y, c0z, axis, cut[j])) break;
+        if (j + 1 < parts) {  // ends at the next cut
+            part.epk = pk_stop(axis, cut[j + 1]);
+            part.endBrick = -1;
+        } else {  // last part: the ray's own end condition
             part.epk = first.epk;
             part.endBrick = first.endBrick;
         }
         const uint32_t hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt);
         if (hit != kNoTriangle) return hit;
-        if (!haveNext) break;
-        cur = next;
     }
     outT = maxD;
     return kNoTriangle;
