@@ -311,6 +311,10 @@ int oclr_build_camera_lists(const oclr_camera* camera, cl_uint vertexCount, cons
                             const cl_int3* triangleVertexIndex, oclr_camera_lists* out);
 int oclr_build_scene_grid(cl_int axesDivCount, cl_uint vertexCount, const cl_float3* vertex, cl_uint triangleCount,
                           const cl_int3* triangleVertexIndex, oclr_scene_grid* out);
+/* SceneTriangleList::New (source/util/trianglelist.cpp:655-737) on CUDA device `device`: same output as oclr_build_scene_grid,
+ * entry for entry (the reference needs 10 s at 101 k triangles, the host builder 0.3 s, this tens of milliseconds). */
+int oclr_build_scene_grid_device(int device, cl_int axesDivCount, cl_uint vertexCount, const cl_float3* vertex, cl_uint triangleCount,
+                                 const cl_int3* triangleVertexIndex, oclr_scene_grid* out);
 void oclr_free_camera_lists(oclr_camera_lists* lists);
 void oclr_free_scene_grid(oclr_scene_grid* grid);
 

@@ -72,7 +72,7 @@ EXPORTS = [
     "oclr_set_camera", "oclr_frame_create", "oclr_frame_create_device_lists", "oclr_frame_camera_list_size",
     "oclr_frame_read_camera_lists", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
     "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_last_launches", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
-    "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_free_camera_lists", "oclr_free_scene_grid",
+    "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_build_scene_grid_device", "oclr_free_camera_lists", "oclr_free_scene_grid",
 ]
 
 _lib = None
@@ -143,6 +143,8 @@ def load() -> C.CDLL:
     lib.oclr_build_camera_lists.argtypes = [C.POINTER(Camera), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(CameraLists)]
     lib.oclr_build_scene_grid.restype = C.c_int
     lib.oclr_build_scene_grid.argtypes = [C.c_int32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SceneGrid)]
+    lib.oclr_build_scene_grid_device.restype = C.c_int
+    lib.oclr_build_scene_grid_device.argtypes = [C.c_int, C.c_int32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SceneGrid)]
     lib.oclr_free_camera_lists.argtypes = [C.POINTER(CameraLists)]
     lib.oclr_free_camera_lists.restype = None
     lib.oclr_free_scene_grid.argtypes = [C.POINTER(SceneGrid)]

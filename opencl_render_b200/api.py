@@ -192,13 +192,18 @@ def camera_triangle_list(camera: CameraSetup, scene: HostScene) -> CameraLists:
     return CameraLists(start, end, lst)
 
 
-def scene_triangle_list(scene: HostScene, axes_div: int = AXES_DIVISION) -> HostScene:
-    """SceneTriangleList::New (trianglelist.cpp:655-737): fills scene.box_min / grid_start / grid_list."""
+def scene_triangle_list(scene: HostScene, axes_div: int = AXES_DIVISION, device: int | None = None) -> HostScene:
+    """SceneTriangleList::New (trianglelist.cpp:655-737): fills scene.box_min / grid_start / grid_list.  `device` = a CUDA device
+    index: the builder runs on the GPU (same output, entry for entry); None: the host builder."""
     lib = _lib.load()
     scene.normalise()
     out = _lib.SceneGrid()
-    if not lib.oclr_build_scene_grid(axes_div, scene.vertex_count, _ptr(scene.vertex), scene.triangle_count,
-                                     _ptr(scene.tri_idx), C.byref(out)):
+    if device is None:
+        ok = lib.oclr_build_scene_grid(axes_div, scene.vertex_count, _ptr(scene.vertex), scene.triangle_count, _ptr(scene.tri_idx), C.byref(out))
+    else:
+        ok = lib.oclr_build_scene_grid_device(device, axes_div, scene.vertex_count, _ptr(scene.vertex), scene.triangle_count,
+                                              _ptr(scene.tri_idx), C.byref(out))
+    if not ok:
         raise OclrError(_lib.last_error())
     try:
         n = int(out.axesDivCount)

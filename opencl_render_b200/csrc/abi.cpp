@@ -525,6 +525,29 @@ int oclr_build_scene_grid(cl_int axesDivCount, cl_uint vertexCount, const cl_flo
     }
     return 1;
 }
+int oclr_build_scene_grid_device(int device, cl_int axesDivCount, cl_uint vertexCount, const cl_float3* vertex, cl_uint triangleCount,
+                                 const cl_int3* triIdx, oclr_scene_grid* out) {
+    if (!out || (triangleCount && (!vertex || !triIdx))) {
+        fail("oclr_build_scene_grid_device: null argument");
+        return 0;
+    }
+    memset(out, 0, sizeof(*out));
+    std::string err;
+    float4* box = nullptr;
+    uint32_t *start = nullptr, *list = nullptr;
+    size_t listSize = 0;
+    if (!build_scene_grid_device(device, axesDivCount, vertexCount, (const float4*)vertex, triangleCount, (const int32_t*)triIdx, &box, &start, &list,
+                                 &listSize, err)) {
+        fail("oclr_build_scene_grid_device: " + err);
+        return 0;
+    }
+    out->axesDivCount = axesDivCount;
+    out->boxMin = (cl_float3*)box;
+    out->start = start;
+    out->list = list;
+    out->listSize = listSize;
+    return 1;
+}
 void oclr_free_camera_lists(oclr_camera_lists* l) {
     if (!l) return;
     free(l->start);

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/oclr_abi.h"
+#include "rt_clip.h"
 #include "rt_core.h"
 
 namespace oclr {
@@ -250,47 +251,7 @@ bool build_camera_lists(const oclr_camera* cam, uint32_t vertexCount, const floa
 }
 
 // ---- scene grid ----------------------------------------------------------------------------------------------------------
-// Clip `poly` against the half-space on one side of `limit` along `dim` (trianglelist.cpp:381-430).  Crossing edges
-// get an interpolated vertex; original vertices strictly outside are dropped; vertices on the plane stay.
-static bool clip_axis(bool keepBelow, float limit, int dim, int& count, float poly[16][3]) {
-    bool fresh[16] = {false};
-    for (int i = 0; i < count; ++i) {
-        const int nx = (i + 1) % count;
-        const float di = limit - poly[i][dim], dn = limit - poly[nx][dim];
-        if (di * dn < 0.f) {
-            const float ex = poly[nx][0] - poly[i][0], ey = poly[nx][1] - poly[i][1], ez = poly[nx][2] - poly[i][2];
-            const float edge[3] = {ex, ey, ez};
-            const float k = di / edge[dim];
-            const int at = i + 1;
-            for (int j = count++; at < j; --j) memcpy(poly[j], poly[j - 1], sizeof(float) * 3);
-            poly[at][0] = poly[i][0] + k * ex;
-            poly[at][1] = poly[i][1] + k * ey;
-            poly[at][2] = poly[i][2] + k * ez;
-            fresh[at] = true;
-            i = at;
-        }
-    }
-    for (int i = 0; i < count; ++i) {
-        const bool outside = keepBelow ? (limit < poly[i][dim]) : (poly[i][dim] < limit);
-        if (!fresh[i] && outside) {
-            for (int j = i + 1; j < count; ++j) {
-                memcpy(poly[j - 1], poly[j], sizeof(float) * 3);
-                fresh[j - 1] = fresh[j];
-            }
-            --count;
-            --i;
-        }
-    }
-    return 0 < count;
-}
-
-// trianglelist.cpp:433-449
-static bool box_hits_triangle(const float lo[3], const float hi[3], const float4& a, const float4& b, const float4& c) {
-    float poly[16][3] = {{a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}};
-    int count = 3;
-    return clip_axis(false, lo[0], 0, count, poly) && clip_axis(false, lo[1], 1, count, poly) && clip_axis(false, lo[2], 2, count, poly) &&
-           clip_axis(true, hi[0], 0, count, poly) && clip_axis(true, hi[1], 1, count, poly) && clip_axis(true, hi[2], 2, count, poly);
-}
+// BoxIntersectsTriangle / Cull: rt_clip.h (shared with the device builder)
 
 bool build_scene_grid(int32_t n, uint32_t vertexCount, const float4* vertex, uint32_t triangleCount, const int32_t* triIdx,
                       oclr_scene_grid* out) {
@@ -349,7 +310,7 @@ bool build_scene_grid(int32_t n, uint32_t vertexCount, const float4* vertex, uin
                         const float slo = lo[k], shi = hi[k];
                         lo[k] = pl[k][nc];
                         hi[k] = pl[k][nc + 1];
-                        if (box_hits_triangle(lo, hi, A, B, C)) {
+                        if (box_hits_triangle(lo, hi, mk3(A.x, A.y, A.z), mk3(B.x, B.y, B.z), mk3(C.x, C.y, C.z))) {
                             seen[nid >> 3] |= (uint8_t)(1u << (nid & 7));
                             queue.push_back(nid);
                         }

@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "cam_builder.cuh"
+#include "grid_builder.cuh"
 #include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
 #include "rt_trace.cuh"
@@ -720,6 +721,132 @@ bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err) {
     OCLR_CUDA(cudaSetDevice(f->scene->device));
     OCLR_CUDA(cudaMemcpy(flags, f->flags.p, f->flags.bytes, cudaMemcpyDeviceToHost));
     return true;
+}
+
+// SceneTriangleList::New on the device (grid_builder.cuh).  Outputs are malloc'ed host arrays like the host builder's.
+bool build_scene_grid_device(int device, int32_t n, uint32_t V, const float4* vertex, uint32_t N, const int32_t* triIdx, float4** outBoxMin,
+                             uint32_t** outStart, uint32_t** outList, size_t* outListSize, std::string& err) {
+    if (n < 1 || (n & (n - 1)) || n > 1024) {
+        err = "axesDivCount must be a power of two <= 1024";
+        return false;
+    }
+    if (device < 0 || device >= device_count()) {
+        err = "no such CUDA device: " + std::to_string(device);
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(device));
+    prepare_pool(device);
+    const size_t cells = (size_t)n * n * n;
+    DeviceBuffer dVertex, dIdx, coord, sorted, planes, triCells, slots, offsets, largeList, small, state, queue, keysA, keysB, cellCount, start, tmp,
+        sortTmp, list, boxMin;
+    DeviceBuffer* all[] = {&dVertex, &dIdx, &coord, &sorted, &planes, &triCells, &slots, &offsets, &largeList, &small, &state, &queue, &keysA, &keysB,
+                           &cellCount, &start, &tmp, &sortTmp, &list, &boxMin};
+    auto done = [&](bool ok) {
+        for (DeviceBuffer* b : all) b->release();
+        return ok;
+    };
+    const size_t Vz = V ? V : 1, Nz = N ? N : 1;
+    if (!dVertex.upload(vertex, sizeof(float4) * V, err) || !dIdx.upload(triIdx, sizeof(int32_t) * 4 * (size_t)N, err) ||
+        !coord.alloc(sizeof(float) * Vz, err) || !sorted.alloc(sizeof(float) * Vz, err) || !planes.alloc(sizeof(float) * 3 * (n + 1), err) ||
+        !triCells.alloc(sizeof(TriCells) * Nz, err) || !slots.alloc(sizeof(uint64_t) * (Nz + 1), err) ||
+        !offsets.alloc(sizeof(uint64_t) * (Nz + 1), err) || !largeList.alloc(sizeof(uint32_t) * Nz, err) || !small.alloc(sizeof(uint32_t) * 4, err) ||
+        !cellCount.alloc(sizeof(uint32_t) * (cells + 1), err) || !start.alloc(sizeof(uint32_t) * (cells + 1), err) ||
+        !boxMin.alloc(sizeof(float4) * (n + 1), err))
+        return done(false);
+    cudaMemsetAsync(planes.p, 0, sizeof(float) * 3 * (n + 1), 0);
+    cudaMemsetAsync(small.p, 0, sizeof(uint32_t) * 4, 0);
+    cudaMemsetAsync(slots.p, 0, sizeof(uint64_t) * (Nz + 1), 0);
+    cudaMemsetAsync(cellCount.p, 0, sizeof(uint32_t) * (cells + 1), 0);
+    // 1. split planes at vertex quantiles
+    size_t need = 0, tmpBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, (const float*)coord.p, (float*)sorted.p, (int)V);
+    tmpBytes = need;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    tmpBytes = std::max(tmpBytes, need);
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
+    tmpBytes = std::max(tmpBytes, need);
+    if (!tmp.alloc(tmpBytes, err)) return done(false);
+    if (V)
+        for (int axis = 0; axis < 3; ++axis) {
+            grid_coord_kernel<<<(V + 255) / 256, 256>>>(V, (const float4*)dVertex.p, axis, (float*)coord.p);
+            cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, (const float*)coord.p, (float*)sorted.p, (int)V);
+            grid_planes_kernel<<<(n + 1 + 127) / 128, 128>>>(V, (const float*)sorted.p, n, (float*)planes.p + (size_t)axis * (n + 1));
+        }
+    grid_boxmin_kernel<<<(n + 1 + 127) / 128, 128>>>(n, (const float*)planes.p, (float4*)boxMin.p);
+    // 2. candidate blocks, slot offsets
+    uint32_t* largeCount = (uint32_t*)small.p;
+    if (N)
+        grid_range_kernel<<<(N + 255) / 256, 256>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p, (TriCells*)triCells.p,
+                                                   (uint64_t*)slots.p, (uint32_t*)largeList.p, largeCount);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    uint64_t total = 0;
+    uint32_t nLarge = 0;
+    cudaMemcpyAsync(&total, (const uint64_t*)offsets.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(&nLarge, largeCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    OCLR_CUDA(cudaStreamSynchronize(0));
+    if (total > (1ull << 31)) {
+        err = "scene-grid builder: more than 2^31 (triangle, cell) candidates";
+        return done(false);
+    }
+    const size_t totalZ = total ? (size_t)total : 1;
+    if (!state.alloc(totalZ, err) || !queue.alloc(sizeof(uint16_t) * totalZ, err) || !keysA.alloc(sizeof(uint64_t) * totalZ, err) ||
+        !keysB.alloc(sizeof(uint64_t) * totalZ, err))
+        return done(false);
+    // 3. flood fills -> keys
+    const uint64_t sentinel = (uint64_t)cells * (uint64_t)Nz;
+    if (N) {
+        grid_fill_small_kernel<<<(N + 127) / 128, 128>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p,
+                                                        (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (uint8_t*)state.p, (uint16_t*)queue.p,
+                                                        sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
+        if (nLarge)
+            grid_fill_large_kernel<<<nLarge, 256>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p,
+                                                   (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (const uint32_t*)largeList.p,
+                                                   (uint8_t*)state.p, sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
+    }
+    // 4. CSR
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
+    uint32_t real = 0;
+    cudaMemcpyAsync(&real, (const uint32_t*)start.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    int endBit = 1;
+    while (endBit < 64 && (sentinel >> endBit) != 0) ++endBit;
+    size_t sortBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    if (!sortTmp.alloc(sortBytes, err)) return done(false);
+    cub::DeviceRadixSort::SortKeys(sortTmp.p, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
+        return done(false);
+    }
+    if (!list.alloc(sizeof(uint32_t) * (size_t)(real ? real : 1), err)) return done(false);
+    if (real) grid_split_kernel<<<(unsigned)((real + 255) / 256), 256>>>((const uint64_t*)keysB.p, real, N, (uint32_t*)list.p);
+    // 5. back to the caller
+    float4* hBox = (float4*)malloc(sizeof(float4) * (n + 1));
+    uint32_t* hStart = (uint32_t*)malloc(sizeof(uint32_t) * (cells + 1));
+    uint32_t* hList = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(real ? real : 1));
+    bool ok = hBox && hStart && hList;
+    if (ok) {
+        e = cudaMemcpy(hBox, boxMin.p, sizeof(float4) * (n + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hStart, start.p, sizeof(uint32_t) * (cells + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && real) e = cudaMemcpy(hList, list.p, sizeof(uint32_t) * (size_t)real, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
+            ok = false;
+        }
+    } else {
+        err = "out of host memory";
+    }
+    if (!ok) {
+        free(hBox);
+        free(hStart);
+        free(hList);
+        return done(false);
+    }
+    *outBoxMin = hBox;
+    *outStart = hStart;
+    *outList = hList;
+    *outListSize = real;
+    return done(true);
 }
 
 uint32_t frame_last_launches(const Frame* f) { return f ? f->lastLaunches : 0; }

@@ -99,6 +99,9 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 // Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
                 std::string& err);
+// SceneTriangleList::New on CUDA device `device` (grid_builder.cuh); outputs are malloc'ed host arrays, entry-for-entry the host builder's.
+bool build_scene_grid_device(int device, int32_t n, uint32_t vertexCount, const float4* vertex, uint32_t triangleCount, const int32_t* triIdx,
+                             float4** outBoxMin, uint32_t** outStart, uint32_t** outList, size_t* outListSize, std::string& err);
 uint32_t frame_last_launches(const Frame* f);
 bool frame_read_ids(Frame* f, uint32_t* ids, std::string& err);
 bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err);

@@ -267,3 +267,17 @@ def test_device_camera_lists_full_size_config2():
     assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
     fd.close()
     ds.close()
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_device_scene_grid_equals_host_builder(name):
+    """SURVEY 8f-1: SceneTriangleList::New on the device (csrc/grid_builder.cuh) -- split planes, CSR starts and the list are
+    entry-for-entry the host builder's (itself list-for-list the reference's, tests/test_builders.py)."""
+    import copy
+    sc, cam, lists, samples = helpers.make_case(name)           # host-built grid inside
+    dev = copy.copy(sc)
+    api.scene_triangle_list(dev, sc.axes_div, device=0)
+    assert dev.axes_div == sc.axes_div
+    assert np.array_equal(dev.box_min.view(np.uint32), sc.box_min.view(np.uint32))
+    assert np.array_equal(dev.grid_start, sc.grid_start)
+    assert dev.grid_list.size == sc.grid_list.size and np.array_equal(dev.grid_list, sc.grid_list)
