@@ -233,7 +233,9 @@ typedef struct oclr_render_stats {
 /* 0: one thread per pixel (baseline, also the counting kernel of the reference accounting); 2: wavefront pipeline (production) */
 enum { OCLR_KERNEL_SIMPLE = 0, OCLR_KERNEL_PIPE = 2, OCLR_KERNEL_DEFAULT = -1 };
 
-/* Upload + repack a scene into the HBM of CUDA device `device`.  NULL on failure. */
+/* Upload + repack a scene into the HBM of CUDA device `device`.  NULL on failure.  With sceneBoxMin ==
+ * scenePixelTriangleListStart == NULL the grid (SceneTriangleList::New, axesDivCount cells per axis) is built on the device during
+ * the upload and never exists on the host. */
 oclr_scene* oclr_scene_create(int device, const oclr_scene_desc* desc);
 void oclr_scene_destroy(oclr_scene* scene);
 size_t oclr_scene_device_bytes(const oclr_scene* scene);

@@ -101,8 +101,8 @@ class HostScene:
     def light_count(self) -> int:
         return int(self.light_type.shape[0])
 
-    def desc(self) -> _lib.SceneDesc:
-        if self.box_min is None:
+    def desc(self, allow_missing_grid: bool = False) -> _lib.SceneDesc:
+        if self.box_min is None and not allow_missing_grid:
             raise OclrError("scene has no grid: call scene_triangle_list(scene) first")
         d = _lib.SceneDesc()
         d.vertexCount = self.vertex_count
@@ -113,9 +113,10 @@ class HostScene:
         d.triangleUv = _ptr(self.tri_uv)
         d.triangleNormal = _ptr(self.tri_normal)
         d.axesDivCount = self.axes_div
-        d.sceneBoxMin = _ptr(self.box_min)
-        d.scenePixelTriangleListStart = _ptr(self.grid_start)
-        d.scenePixelTriangleList = _ptr(self.grid_list)
+        if self.box_min is not None:
+            d.sceneBoxMin = _ptr(self.box_min)
+            d.scenePixelTriangleListStart = _ptr(self.grid_start)
+            d.scenePixelTriangleList = _ptr(self.grid_list)
         d.materialCount = self.material_count
         d.materialImageSize = _ptr(self.mat_size)
         d.materialImageStart = _ptr(self.mat_start)
@@ -254,10 +255,14 @@ def raytrace_all(computation_type: int, camera: CameraSetup, lists: CameraLists,
 class DeviceScene:
     """Resident scene (extension): uploaded and repacked once, rendered many times."""
 
-    def __init__(self, scene: HostScene, device: int = 0):
+    def __init__(self, scene: HostScene, device: int = 0, axes_div: int | None = None):
+        """A scene without a grid (scene_triangle_list not called) is accepted: SceneTriangleList::New then runs on the device
+        during the upload and the grid never exists on the host (`axes_div` = its axesDivCount, default 256)."""
         self._lib = _lib.load()
         scene.normalise()
-        d = scene.desc()
+        if scene.box_min is None:
+            scene.axes_div = axes_div or AXES_DIVISION
+        d = scene.desc(allow_missing_grid=True)
         self.handle = self._lib.oclr_scene_create(device, C.byref(d))
         if not self.handle:
             raise OclrError(_lib.last_error())

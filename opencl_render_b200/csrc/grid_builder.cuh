@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) grid_fill_small_kernel(uint32_t N, const 
 
 // Large blocks: one CTA per triangle.  The clip test is evaluated for every block cell in parallel (state 3 = passes, not yet
 // reached), then the fill grows from the seed by frontier sweeps until a sweep adds nothing.
-__global__ void __launch_bounds__(256) grid_fill_large_kernel(uint32_t N, const float4* __restrict__ vertex, const int4* __restrict__ triIdx, int n,
+__global__ void __launch_bounds__(1024) grid_fill_large_kernel(uint32_t N, const float4* __restrict__ vertex, const int4* __restrict__ triIdx, int n,
                                                               const float* __restrict__ planes, const TriCells* __restrict__ cells,
                                                               const uint64_t* __restrict__ offset, const uint32_t* __restrict__ largeList,
                                                               uint8_t* __restrict__ state, uint64_t sentinel, uint64_t* __restrict__ keys,
@@ -177,19 +177,27 @@ __global__ void __launch_bounds__(256) grid_fill_large_kernel(uint32_t N, const 
     for (uint64_t k = threadIdx.x; k < total; k += blockDim.x) st[k] = (k == t.seed) ? 1 : (cell_hits(t, (uint32_t)k, n, planes, a, b, c) ? 3 : 2);
     __syncthreads();
     const int64_t sx = 1, sy = t.dx, sz = (int64_t)t.dx * t.dy;
+    // Every thread owns a contiguous run of cells and sweeps it forwards, then backwards (raster-scan style): a frontier crosses
+    // a whole run in one sweep instead of advancing one cell per sweep.  A cell promoted in a sweep may already serve its
+    // neighbours in the same sweep: the fixed point -- the connected component of the seed -- is the same.
+    const uint64_t chunk = (total + blockDim.x - 1) / blockDim.x;
+    const uint64_t kBegin = (uint64_t)threadIdx.x * chunk, kEnd = kBegin + chunk < total ? kBegin + chunk : total;
+    auto grow = [&](uint64_t k) {
+        if (st[k] != 3) return;
+        const int cx = (int)(k % (uint64_t)t.dx), cy = (int)((k / (uint64_t)t.dx) % (uint64_t)t.dy), cz = (int)(k / (uint64_t)sz);
+        const bool reach = (cx > 0 && st[k - sx] == 1) || (cx + 1 < t.dx && st[k + sx] == 1) || (cy > 0 && st[k - sy] == 1) ||
+                           (cy + 1 < t.dy && st[k + sy] == 1) || (cz > 0 && st[k - sz] == 1) || (cz + 1 < t.dz && st[k + sz] == 1);
+        if (reach) {
+            st[k] = 1;
+            changed = 1;
+        }
+    };
     for (;;) {
         if (threadIdx.x == 0) changed = 0;
         __syncthreads();
-        for (uint64_t k = threadIdx.x; k < total; k += blockDim.x) {
-            if (st[k] != 3) continue;
-            const int cx = (int)(k % (uint64_t)t.dx), cy = (int)((k / (uint64_t)t.dx) % (uint64_t)t.dy), cz = (int)(k / (uint64_t)sz);
-            const bool reach = (cx > 0 && st[k - sx] == 1) || (cx + 1 < t.dx && st[k + sx] == 1) || (cy > 0 && st[k - sy] == 1) ||
-                               (cy + 1 < t.dy && st[k + sy] == 1) || (cz > 0 && st[k - sz] == 1) || (cz + 1 < t.dz && st[k + sz] == 1);
-            if (reach) {
-                st[k] = 1;   // (a cell promoted in this sweep may already serve its neighbours: the fixed point is the same)
-                changed = 1;
-            }
-        }
+        for (uint64_t k = kBegin; k < kEnd; ++k) grow(k);
+        __syncthreads();
+        for (uint64_t k = kEnd; k > kBegin; --k) grow(k - 1);
         __syncthreads();
         if (!changed) break;
         __syncthreads();

@@ -105,6 +105,163 @@ bool device_name(int dev, char* buf, size_t len) {
     return true;
 }
 
+// SceneTriangleList::New on the device (grid_builder.cuh) from device-resident vertices / indices; the grid stays in HBM.
+struct DeviceGrid {
+    DeviceBuffer boxMin, start, list;   // float4 x (n+1), uint32 x (n^3+1), uint32 x total
+    uint32_t total = 0;
+    void release() {
+        boxMin.release();
+        start.release();
+        list.release();
+    }
+};
+
+static bool grid_build_on_device(int32_t n, uint32_t V, const float4* dVertexP, uint32_t N, const int4* dIdxP, DeviceGrid& out, std::string& err) {
+    const size_t cells = (size_t)n * n * n;
+    DeviceBuffer coord, sorted, planes, triCells, slots, offsets, largeList, small, state, queue, keysA, keysB, cellCount, tmp, sortTmp;
+    DeviceBuffer &start = out.start, &list = out.list, &boxMin = out.boxMin;
+    DeviceBuffer* all[] = {&coord, &sorted, &planes, &triCells, &slots, &offsets, &largeList, &small, &state, &queue, &keysA, &keysB, &cellCount, &tmp, &sortTmp};
+    auto done = [&](bool ok) {
+        for (DeviceBuffer* b : all) b->release();
+        if (!ok) out.release();
+        return ok;
+    };
+    const size_t Vz = V ? V : 1, Nz = N ? N : 1;
+    if (!coord.alloc(sizeof(float) * Vz, err) || !sorted.alloc(sizeof(float) * Vz, err) || !planes.alloc(sizeof(float) * 3 * (n + 1), err) ||
+        !triCells.alloc(sizeof(TriCells) * Nz, err) || !slots.alloc(sizeof(uint64_t) * (Nz + 1), err) ||
+        !offsets.alloc(sizeof(uint64_t) * (Nz + 1), err) || !largeList.alloc(sizeof(uint32_t) * Nz, err) || !small.alloc(sizeof(uint32_t) * 4, err) ||
+        !cellCount.alloc(sizeof(uint32_t) * (cells + 1), err) || !start.alloc(sizeof(uint32_t) * (cells + 1), err) ||
+        !boxMin.alloc(sizeof(float4) * (n + 1), err))
+        return done(false);
+    cudaMemsetAsync(planes.p, 0, sizeof(float) * 3 * (n + 1), 0);
+    cudaMemsetAsync(small.p, 0, sizeof(uint32_t) * 4, 0);
+    cudaMemsetAsync(slots.p, 0, sizeof(uint64_t) * (Nz + 1), 0);
+    cudaMemsetAsync(cellCount.p, 0, sizeof(uint32_t) * (cells + 1), 0);
+    // 1. split planes at vertex quantiles
+    size_t need = 0, tmpBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, (const float*)coord.p, (float*)sorted.p, (int)V);
+    tmpBytes = need;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    tmpBytes = std::max(tmpBytes, need);
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
+    tmpBytes = std::max(tmpBytes, need);
+    if (!tmp.alloc(tmpBytes, err)) return done(false);
+    if (V)
+        for (int axis = 0; axis < 3; ++axis) {
+            grid_coord_kernel<<<(V + 255) / 256, 256>>>(V, dVertexP, axis, (float*)coord.p);
+            cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, (const float*)coord.p, (float*)sorted.p, (int)V);
+            grid_planes_kernel<<<(n + 1 + 127) / 128, 128>>>(V, (const float*)sorted.p, n, (float*)planes.p + (size_t)axis * (n + 1));
+        }
+    grid_boxmin_kernel<<<(n + 1 + 127) / 128, 128>>>(n, (const float*)planes.p, (float4*)boxMin.p);
+    // 2. candidate blocks, slot offsets
+    uint32_t* largeCount = (uint32_t*)small.p;
+    if (N)
+        grid_range_kernel<<<(N + 255) / 256, 256>>>(N, dVertexP, dIdxP, n, (const float*)planes.p, (TriCells*)triCells.p,
+                                                   (uint64_t*)slots.p, (uint32_t*)largeList.p, largeCount);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
+    uint64_t total = 0;
+    uint32_t nLarge = 0;
+    cudaMemcpyAsync(&total, (const uint64_t*)offsets.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(&nLarge, largeCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    OCLR_CUDA(cudaStreamSynchronize(0));
+    if (total > (1ull << 31)) {
+        err = "scene-grid builder: more than 2^31 (triangle, cell) candidates";
+        return done(false);
+    }
+    const size_t totalZ = total ? (size_t)total : 1;
+    if (!state.alloc(totalZ, err) || !queue.alloc(sizeof(uint16_t) * totalZ, err) || !keysA.alloc(sizeof(uint64_t) * totalZ, err) ||
+        !keysB.alloc(sizeof(uint64_t) * totalZ, err))
+        return done(false);
+    // 3. flood fills -> keys
+    const uint64_t sentinel = (uint64_t)cells * (uint64_t)Nz;
+    if (N) {
+        grid_fill_small_kernel<<<(N + 127) / 128, 128>>>(N, dVertexP, dIdxP, n, (const float*)planes.p,
+                                                        (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (uint8_t*)state.p, (uint16_t*)queue.p,
+                                                        sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
+        if (nLarge)
+            grid_fill_large_kernel<<<nLarge, 1024>>>(N, dVertexP, dIdxP, n, (const float*)planes.p,
+                                                   (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (const uint32_t*)largeList.p,
+                                                   (uint8_t*)state.p, sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
+    }
+    // 4. CSR
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
+    uint32_t real = 0;
+    cudaMemcpyAsync(&real, (const uint32_t*)start.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    int endBit = 1;
+    while (endBit < 64 && (sentinel >> endBit) != 0) ++endBit;
+    size_t sortBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    if (!sortTmp.alloc(sortBytes, err)) return done(false);
+    cub::DeviceRadixSort::SortKeys(sortTmp.p, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
+        return done(false);
+    }
+    if (!list.alloc(sizeof(uint32_t) * (size_t)(real ? real : 1), err)) return done(false);
+    if (real) grid_split_kernel<<<(unsigned)((real + 255) / 256), 256>>>((const uint64_t*)keysB.p, real, N, (uint32_t*)list.p);
+    out.total = real;
+    e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
+        return done(false);
+    }
+    return done(true);
+}
+
+// Same, from host arrays to malloc'ed host arrays (the drop-in form of the host builder).
+bool build_scene_grid_device(int device, int32_t n, uint32_t V, const float4* vertex, uint32_t N, const int32_t* triIdx, float4** outBoxMin,
+                             uint32_t** outStart, uint32_t** outList, size_t* outListSize, std::string& err) {
+    if (n < 1 || (n & (n - 1)) || n > 1024) {
+        err = "axesDivCount must be a power of two <= 1024";
+        return false;
+    }
+    if (device < 0 || device >= device_count()) {
+        err = "no such CUDA device: " + std::to_string(device);
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(device));
+    prepare_pool(device);
+    const size_t cells = (size_t)n * n * n;
+    DeviceBuffer dVertex, dIdx;
+    DeviceGrid grid;
+    auto done = [&](bool ok) {
+        dVertex.release();
+        dIdx.release();
+        grid.release();
+        return ok;
+    };
+    if (!dVertex.upload(vertex, sizeof(float4) * V, err) || !dIdx.upload(triIdx, sizeof(int32_t) * 4 * (size_t)N, err)) return done(false);
+    if (!grid_build_on_device(n, V, (const float4*)dVertex.p, N, (const int4*)dIdx.p, grid, err)) return done(false);
+    const uint32_t real = grid.total;
+    float4* hBox = (float4*)malloc(sizeof(float4) * (n + 1));
+    uint32_t* hStart = (uint32_t*)malloc(sizeof(uint32_t) * (cells + 1));
+    uint32_t* hList = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(real ? real : 1));
+    bool ok = hBox && hStart && hList;
+    if (ok) {
+        cudaError_t e = cudaMemcpy(hBox, grid.boxMin.p, sizeof(float4) * (n + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hStart, grid.start.p, sizeof(uint32_t) * (cells + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && real) e = cudaMemcpy(hList, grid.list.p, sizeof(uint32_t) * (size_t)real, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
+            ok = false;
+        }
+    } else {
+        err = "out of host memory";
+    }
+    if (!ok) {
+        free(hBox);
+        free(hStart);
+        free(hList);
+        return done(false);
+    }
+    *outBoxMin = hBox;
+    *outStart = hStart;
+    *outList = hList;
+    *outListSize = real;
+    return done(true);
+}
+
 static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     OCLR_CUDA(cudaSetDevice(s->device));
     int major = 0, minor = 0, sms = 0;   // attribute queries: cudaGetDeviceProperties costs milliseconds per call
@@ -117,12 +274,13 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     }
     s->smCount = sms;
     prepare_pool(s->device);
-    if (!validate_scene(h, err)) return false;
+    if (!validate_scene(h, err, true)) return false;
+    const bool buildGrid = !h.gridStart;   // no grid given: SceneTriangleList::New runs on the device (grid_builder.cuh)
 
     const size_t N = h.triangleCount;
     const int n = h.axesDivCount, nb = n >= 4 ? n / 4 : 1;
     const size_t cells = (size_t)n * n * n, nBricks = (size_t)nb * nb * nb;
-    const uint32_t total = h.gridStart[cells];
+    uint32_t total = buildGrid ? 0u : h.gridStart[cells];
     if (total && !h.gridList) {
         err = "scenePixelTriangleList missing";
         return false;
@@ -134,9 +292,10 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag, cellIds;
     bool ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
               triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
-              triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) && boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
-              gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
-              s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err) &&
+              triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) &&
+              (buildGrid || (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
+                             gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
+                             s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err))) &&
               s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
               s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
               s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
@@ -146,6 +305,23 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
               counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err) &&
               errFlag.alloc(sizeof(uint32_t) * 2, err);
     uint32_t nonEmpty = 0, flag = 0;
+    if (ok && buildGrid) {
+        for (size_t i = 0; ok && i < N; ++i) {  // the builder gathers vertices by index before the packers have validated them
+            const int32_t* vi = h.triIdx + 4 * i;
+            ok = (uint32_t)vi[0] < h.vertexCount && (uint32_t)vi[1] < h.vertexCount && (uint32_t)vi[2] < h.vertexCount;
+        }
+        if (!ok) err = "scene arrays are inconsistent: triangleVertexIndex out of range;";
+    }
+    if (ok && buildGrid) {
+        DeviceGrid grid;
+        ok = grid_build_on_device(n, h.vertexCount, (const float4*)vertex.p, (uint32_t)N, (const int4*)triIdx.p, grid, err);
+        if (ok) {  // hand the three arrays over: same buffers an uploaded grid would occupy
+            boxMin = grid.boxMin;
+            gridStart = grid.start;
+            s->cellList = grid.list;
+            total = grid.total;
+        }
+    }
     if (ok) {
         // 2. repack on the device
         cudaMemsetAsync(errFlag.p, 0, sizeof(uint32_t) * 2, 0);
@@ -721,132 +897,6 @@ bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err) {
     OCLR_CUDA(cudaSetDevice(f->scene->device));
     OCLR_CUDA(cudaMemcpy(flags, f->flags.p, f->flags.bytes, cudaMemcpyDeviceToHost));
     return true;
-}
-
-// SceneTriangleList::New on the device (grid_builder.cuh).  Outputs are malloc'ed host arrays like the host builder's.
-bool build_scene_grid_device(int device, int32_t n, uint32_t V, const float4* vertex, uint32_t N, const int32_t* triIdx, float4** outBoxMin,
-                             uint32_t** outStart, uint32_t** outList, size_t* outListSize, std::string& err) {
-    if (n < 1 || (n & (n - 1)) || n > 1024) {
-        err = "axesDivCount must be a power of two <= 1024";
-        return false;
-    }
-    if (device < 0 || device >= device_count()) {
-        err = "no such CUDA device: " + std::to_string(device);
-        return false;
-    }
-    OCLR_CUDA(cudaSetDevice(device));
-    prepare_pool(device);
-    const size_t cells = (size_t)n * n * n;
-    DeviceBuffer dVertex, dIdx, coord, sorted, planes, triCells, slots, offsets, largeList, small, state, queue, keysA, keysB, cellCount, start, tmp,
-        sortTmp, list, boxMin;
-    DeviceBuffer* all[] = {&dVertex, &dIdx, &coord, &sorted, &planes, &triCells, &slots, &offsets, &largeList, &small, &state, &queue, &keysA, &keysB,
-                           &cellCount, &start, &tmp, &sortTmp, &list, &boxMin};
-    auto done = [&](bool ok) {
-        for (DeviceBuffer* b : all) b->release();
-        return ok;
-    };
-    const size_t Vz = V ? V : 1, Nz = N ? N : 1;
-    if (!dVertex.upload(vertex, sizeof(float4) * V, err) || !dIdx.upload(triIdx, sizeof(int32_t) * 4 * (size_t)N, err) ||
-        !coord.alloc(sizeof(float) * Vz, err) || !sorted.alloc(sizeof(float) * Vz, err) || !planes.alloc(sizeof(float) * 3 * (n + 1), err) ||
-        !triCells.alloc(sizeof(TriCells) * Nz, err) || !slots.alloc(sizeof(uint64_t) * (Nz + 1), err) ||
-        !offsets.alloc(sizeof(uint64_t) * (Nz + 1), err) || !largeList.alloc(sizeof(uint32_t) * Nz, err) || !small.alloc(sizeof(uint32_t) * 4, err) ||
-        !cellCount.alloc(sizeof(uint32_t) * (cells + 1), err) || !start.alloc(sizeof(uint32_t) * (cells + 1), err) ||
-        !boxMin.alloc(sizeof(float4) * (n + 1), err))
-        return done(false);
-    cudaMemsetAsync(planes.p, 0, sizeof(float) * 3 * (n + 1), 0);
-    cudaMemsetAsync(small.p, 0, sizeof(uint32_t) * 4, 0);
-    cudaMemsetAsync(slots.p, 0, sizeof(uint64_t) * (Nz + 1), 0);
-    cudaMemsetAsync(cellCount.p, 0, sizeof(uint32_t) * (cells + 1), 0);
-    // 1. split planes at vertex quantiles
-    size_t need = 0, tmpBytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, need, (const float*)coord.p, (float*)sorted.p, (int)V);
-    tmpBytes = need;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
-    tmpBytes = std::max(tmpBytes, need);
-    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
-    tmpBytes = std::max(tmpBytes, need);
-    if (!tmp.alloc(tmpBytes, err)) return done(false);
-    if (V)
-        for (int axis = 0; axis < 3; ++axis) {
-            grid_coord_kernel<<<(V + 255) / 256, 256>>>(V, (const float4*)dVertex.p, axis, (float*)coord.p);
-            cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, (const float*)coord.p, (float*)sorted.p, (int)V);
-            grid_planes_kernel<<<(n + 1 + 127) / 128, 128>>>(V, (const float*)sorted.p, n, (float*)planes.p + (size_t)axis * (n + 1));
-        }
-    grid_boxmin_kernel<<<(n + 1 + 127) / 128, 128>>>(n, (const float*)planes.p, (float4*)boxMin.p);
-    // 2. candidate blocks, slot offsets
-    uint32_t* largeCount = (uint32_t*)small.p;
-    if (N)
-        grid_range_kernel<<<(N + 255) / 256, 256>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p, (TriCells*)triCells.p,
-                                                   (uint64_t*)slots.p, (uint32_t*)largeList.p, largeCount);
-    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint64_t*)slots.p, (uint64_t*)offsets.p, (int)(N + 1));
-    uint64_t total = 0;
-    uint32_t nLarge = 0;
-    cudaMemcpyAsync(&total, (const uint64_t*)offsets.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, 0);
-    cudaMemcpyAsync(&nLarge, largeCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
-    OCLR_CUDA(cudaStreamSynchronize(0));
-    if (total > (1ull << 31)) {
-        err = "scene-grid builder: more than 2^31 (triangle, cell) candidates";
-        return done(false);
-    }
-    const size_t totalZ = total ? (size_t)total : 1;
-    if (!state.alloc(totalZ, err) || !queue.alloc(sizeof(uint16_t) * totalZ, err) || !keysA.alloc(sizeof(uint64_t) * totalZ, err) ||
-        !keysB.alloc(sizeof(uint64_t) * totalZ, err))
-        return done(false);
-    // 3. flood fills -> keys
-    const uint64_t sentinel = (uint64_t)cells * (uint64_t)Nz;
-    if (N) {
-        grid_fill_small_kernel<<<(N + 127) / 128, 128>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p,
-                                                        (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (uint8_t*)state.p, (uint16_t*)queue.p,
-                                                        sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
-        if (nLarge)
-            grid_fill_large_kernel<<<nLarge, 256>>>(N, (const float4*)dVertex.p, (const int4*)dIdx.p, n, (const float*)planes.p,
-                                                   (const TriCells*)triCells.p, (const uint64_t*)offsets.p, (const uint32_t*)largeList.p,
-                                                   (uint8_t*)state.p, sentinel, (uint64_t*)keysA.p, (uint32_t*)cellCount.p);
-    }
-    // 4. CSR
-    cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, (const uint32_t*)cellCount.p, (uint32_t*)start.p, (int)(cells + 1));
-    uint32_t real = 0;
-    cudaMemcpyAsync(&real, (const uint32_t*)start.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
-    int endBit = 1;
-    while (endBit < 64 && (sentinel >> endBit) != 0) ++endBit;
-    size_t sortBytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
-    if (!sortTmp.alloc(sortBytes, err)) return done(false);
-    cub::DeviceRadixSort::SortKeys(sortTmp.p, sortBytes, (const uint64_t*)keysA.p, (uint64_t*)keysB.p, (int64_t)total, 0, endBit);
-    cudaError_t e = cudaStreamSynchronize(0);
-    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
-        err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
-        return done(false);
-    }
-    if (!list.alloc(sizeof(uint32_t) * (size_t)(real ? real : 1), err)) return done(false);
-    if (real) grid_split_kernel<<<(unsigned)((real + 255) / 256), 256>>>((const uint64_t*)keysB.p, real, N, (uint32_t*)list.p);
-    // 5. back to the caller
-    float4* hBox = (float4*)malloc(sizeof(float4) * (n + 1));
-    uint32_t* hStart = (uint32_t*)malloc(sizeof(uint32_t) * (cells + 1));
-    uint32_t* hList = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(real ? real : 1));
-    bool ok = hBox && hStart && hList;
-    if (ok) {
-        e = cudaMemcpy(hBox, boxMin.p, sizeof(float4) * (n + 1), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(hStart, start.p, sizeof(uint32_t) * (cells + 1), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && real) e = cudaMemcpy(hList, list.p, sizeof(uint32_t) * (size_t)real, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            err = std::string("scene-grid builder: ") + cudaGetErrorString(e);
-            ok = false;
-        }
-    } else {
-        err = "out of host memory";
-    }
-    if (!ok) {
-        free(hBox);
-        free(hStart);
-        free(hList);
-        return done(false);
-    }
-    *outBoxMin = hBox;
-    *outStart = hStart;
-    *outList = hList;
-    *outListSize = real;
-    return done(true);
 }
 
 uint32_t frame_last_launches(const Frame* f) { return f ? f->lastLaunches : 0; }

@@ -52,7 +52,8 @@ struct PackedGrid {
 void pack_triangles(const HostScene& h, float4* triGeo /*4N*/, float4* triShade /*8N*/, int threads);
 bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err);
 void pack_lights(const HostScene& h, std::vector<Light>& out);
-bool validate_scene(const HostScene& h, std::string& err);
+// gridMayBeMissing: sceneBoxMin == scenePixelTriangleListStart == NULL is accepted (the device runtime then builds the grid itself)
+bool validate_scene(const HostScene& h, std::string& err, bool gridMayBeMissing = false);
 
 // ---- device runtime (runtime.cu) -----------------------------------------------------------------------------------
 struct Scene;

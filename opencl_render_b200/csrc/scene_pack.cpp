@@ -17,7 +17,7 @@ static inline float int_bits_as_float(int32_t i) {
     return f;
 }
 
-bool validate_scene(const HostScene& h, std::string& err) {
+bool validate_scene(const HostScene& h, std::string& err, bool gridMayBeMissing) {
     if (h.axesDivCount < 1 || (h.axesDivCount & (h.axesDivCount - 1)) != 0) {
         err = "axesDivCount must be a power of two (GetBoxAddress is a binary search, raytrace_opencl.c:174-193)";
         return false;
@@ -26,7 +26,7 @@ bool validate_scene(const HostScene& h, std::string& err) {
         err = "axesDivCount > 1024 is not supported";
         return false;
     }
-    if (!h.boxMin || !h.gridStart) {
+    if ((!h.boxMin || !h.gridStart) && !(gridMayBeMissing && !h.boxMin && !h.gridStart)) {
         err = "scene grid (sceneBoxMin / scenePixelTriangleListStart) is missing";
         return false;
     }

@@ -281,3 +281,22 @@ def test_device_scene_grid_equals_host_builder(name):
     assert np.array_equal(dev.box_min.view(np.uint32), sc.box_min.view(np.uint32))
     assert np.array_equal(dev.grid_start, sc.grid_start)
     assert dev.grid_list.size == sc.grid_list.size and np.array_equal(dev.grid_list, sc.grid_list)
+
+
+def test_scene_upload_builds_grid_on_device():
+    """A scene uploaded WITHOUT a grid gets SceneTriangleList::New on the device during the upload: the packed arrays are
+    byte-identical to those of the same scene uploaded with the host-built grid, and so is the rendering."""
+    import copy
+    sc, cam, lists, samples = helpers.make_case("spheres_mirror")
+    bare = copy.copy(sc)
+    bare.box_min = bare.grid_start = bare.grid_list = None
+    a = api.DeviceScene(sc, 0)
+    b = api.DeviceScene(bare, 0, axes_div=sc.axes_div)
+    for which in range(7):
+        assert np.array_equal(a.debug_read(which), b.debug_read(which)), which
+    fa, fb = api.DeviceFrame(a, cam), api.DeviceFrame(b, cam)
+    fa.render(samples)
+    fb.render(samples)
+    assert all(np.array_equal(x, y) for x, y in zip(fa.read(), fb.read()))
+    for h in (fa, fb, a, b):
+        h.close()
