@@ -421,4 +421,172 @@ OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o,
     return kNoTriangle;
 }
 
+// ---- warp-cooperative walk of ONE ray ------------------------------------------------------------------------------------------
+// (Groundwork, exercised by the host tests only: a first wiring into wf_pipe_kernel's tail mode was bit-exact but no faster --
+// at the low occupancy of a launch's tail a burst costs about as much latency as the steps it replaces)
+// A lone lane stepping through 500 cells is the critical path of a trace launch (~0.3 ms): each step is ~170 dependent
+// instructions.  When few rays are left, the warp can walk one ray together instead: 32 lanes take the next 11 / 11 / 10 plane
+// crossings of the x / y / z axis (one division each), and the merge order of the reference's walk gives every crossing its
+// position directly -- crossing (a, k) is preceded by its own k predecessors plus, per other axis b, the b-crossings t' with
+// t' < t, or t' == t and b > a (the tie rule of :387-398; see pwalk_jump).  The cell entered by a crossing follows from the same
+// counts, so ~25 cells are classified per burst with no serial dependency.  Requires all direction components non-zero.
+//
+// The arithmetic below is per crossing ("virtual lane" v = 0..31: axis v % 3, index v / 3) so that the kernel (one real lane per
+// crossing) and the host emulation (a loop) share it.
+enum { kCoopLanes = 32 };
+OCLR_HD int coop_candidates(int axis) { return axis == 2 ? 10 : 11; }   // lanes 0..31: axis = lane % 3
+
+struct CoopRay {   // what every lane knows about the ray being walked
+    f3 o, r;
+    int c0[3];      // current cell (already classified)
+    uint32_t epk;   // end cell / stop plane / none
+};
+
+// Crossing value of candidate (axis, k): the k-th next crossing of that axis; +inf when the walk has left the grid before it.
+// kmax = crossings that stay inside the grid; crossing kmax itself is the one that leaves it.
+OCLR_HD float coop_crossing(const CoopRay& ray, int n, const float* planes, int axis, int k, int& kmax) {
+    const float o = axis == 0 ? ray.o.x : (axis == 1 ? ray.o.y : ray.o.z), r = axis == 0 ? ray.r.x : (axis == 1 ? ray.r.y : ray.r.z);
+    const int up = (0 <= r) ? 1 : 0, c0 = ray.c0[axis];
+    kmax = up ? (n - 1 - c0) : c0;
+    if (k > kmax) return OCLR_INF;
+    return (planes[axis * (n + 1) + c0 + up + (up ? k : -k)] - o) / r;
+}
+// does a crossing of axis b with value tb precede a crossing of axis a (a != b) with value ta?
+OCLR_HD bool coop_precedes(int b, float tb, int a, float ta) { return (tb < ta) | ((tb == ta) & (b > a)); }
+
+// Serial emulation of one burst (test infrastructure): appends the cells the walk enters, in order, to cells[] / faces[]
+// (at most 31); returns their number.  `finished`: the walk ended inside the burst (left the grid, reached its end cell or its
+// stop plane).  On return ray.c0 is the last cell entered (when the walk goes on).
+OCLR_HD int coop_burst_serial(CoopRay& ray, int n, const float* planes, uint32_t* cells, int* faces, bool& finished) {
+    float t[3][11];
+    int kmax[3];
+    for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 11; ++k) t[a][k] = k < coop_candidates(a) ? coop_crossing(ray, n, planes, a, k, kmax[a]) : OCLR_INF;
+    int rank[kCoopLanes], cnt[kCoopLanes][3];
+    int R = kCoopLanes, exitRank = 1 << 20, endRank = 1 << 20;
+    uint32_t cellOf[kCoopLanes];
+    for (int v = 0; v < kCoopLanes; ++v) {
+        const int a = v % 3, k = v / 3;
+        rank[v] = k;
+        for (int b = 0; b < 3; ++b) {
+            cnt[v][b] = b == a ? k + 1 : 0;
+            if (b == a) continue;
+            for (int kk = 0; kk < coop_candidates(b); ++kk) cnt[v][b] += coop_precedes(b, t[b][kk], a, t[a][k]) ? 1 : 0;
+            rank[v] += cnt[v][b];
+        }
+        const bool present = k <= kmax[a];
+        if (k == coop_candidates(a) - 1 && kmax[a] >= coop_candidates(a) && rank[v] + 1 < R) R = rank[v] + 1;   // more crossings of a may follow
+        if (present && k == kmax[a] && rank[v] < exitRank) exitRank = rank[v];
+        int c[3];
+        for (int b = 0; b < 3; ++b) {
+            const float rb = b == 0 ? ray.r.x : (b == 1 ? ray.r.y : ray.r.z);
+            c[b] = ray.c0[b] + ((0 <= rb) ? cnt[v][b] : -cnt[v][b]);
+        }
+        cellOf[v] = present && k < kmax[a] ? pk_make(c[0] & kPkMask, c[1] & kPkMask, c[2] & kPkMask) : kPkNone;
+        bool ends = false;
+        if (present && k < kmax[a]) {
+            if (pk_is_stop(ray.epk)) {   // this part of a cut walk is over when a step along the stop axis enters the stop index
+                ends = (int)((ray.epk >> kPkBits) & 3u) == a && c[a] == (int)(ray.epk & kPkMask);
+                if (ends && rank[v] < exitRank) exitRank = rank[v];   // like leaving the grid: the cell is not visited
+                ends = false;
+            } else {
+                ends = cellOf[v] == ray.epk;
+            }
+        }
+        if (ends && rank[v] < endRank) endRank = rank[v];
+    }
+    // crossings with rank < R are certain (no crossing beyond the candidates can precede them); an exit / end crossing only
+    // counts when it lies inside that prefix
+    int limit = R;
+    finished = false;
+    if (exitRank < limit) {
+        limit = exitRank;   // the crossing that leaves the grid (or enters the stop index) enters no cell
+        finished = true;
+    }
+    if (endRank < limit) {
+        limit = endRank + 1;   // the end cell is visited, then the walk stops (:381)
+        finished = true;
+    }
+    int count = 0;
+    for (int q = 0; q < limit; ++q)
+        for (int v = 0; v < kCoopLanes; ++v)
+            if (rank[v] == q && cellOf[v] != kPkNone) {
+                cells[count] = cellOf[v];
+                faces[count] = (v % 3) * 2 + ((0 <= ((v % 3) == 0 ? ray.r.x : ((v % 3) == 1 ? ray.r.y : ray.r.z))) ? 1 : 0);
+                ++count;
+            }
+    if (count > 0) {
+        ray.c0[0] = pk_get(cells[count - 1], 0);
+        ray.c0[1] = pk_get(cells[count - 1], 1);
+        ray.c0[2] = pk_get(cells[count - 1], 2);
+    }
+    return count;
+}
+
+// The traversal walked entirely by cooperative bursts (host test of the burst arithmetic against the reference's cell walk).
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_coop(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                 float& outAB, float& outAC, Counters* cnt) {
+    const int n = S.n;
+    PackedWalk w;
+    pwalk_setup(w, n, S.nb, planes, planes + (n + 1), planes + 2 * (n + 1), o, r, minD, maxD);
+    if (!w.coarseOk) return grid_trace_packed<COUNT>(S, planes, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);
+    if (COUNT) cnt->gridRays++;
+    auto test_cell = [&](uint32_t cpk, int face, uint32_t& closest) {
+        const int cx = pk_get(cpk, 0), cy = pk_get(cpk, 1), cz = pk_get(cpk, 2);
+        const uint4 br = OCLR_LDG(S.bricks + ((cx >> 2) + S.nb * ((cy >> 2) + S.nb * (cz >> 2))));
+        PackedWalk b;
+        b.maskLo = br.x;
+        b.maskHi = br.y;
+        b.rankBase = br.z;
+        const int bit = pwalk_bit(cpk);
+        if (COUNT) cnt->cells++;
+        if (!pwalk_occupied(b, bit)) return;
+        const uint32_t rank = pwalk_rank(b, bit);
+        const uint2 range = OCLR_LDG(S.cellRange + rank);
+        const uint32_t fm = face != kFaceNone ? OCLR_LDG(S.faceMask + 6 * (size_t)rank + face) : 0xFFFFFFFFu;
+        if (COUNT) cnt->cellsNonEmpty++;
+        outT = maxD;
+        for (uint32_t k = pwalk_next_entry(range.x, range.y, fm, range.x); k < range.y; k = pwalk_next_entry(range.x, range.y, fm, k + 1)) {
+            const uint32_t tri = OCLR_LDG(S.cellList + k);
+            if (tri == excl) continue;
+            float t, ab, ac;
+            if (COUNT) cnt->gridCandidates++;
+            if (tri_test(S.triGeo + 4 * (size_t)tri, o, r, minD, outT, t, ab, ac)) {
+                closest = tri;
+                outT = t;
+                outAB = ab;
+                outAC = ac;
+            }
+        }
+    };
+    uint32_t closest = kNoTriangle;
+    test_cell(w.cpk, kFaceNone, closest);   // the start cell
+    if (closest != kNoTriangle) return closest;
+    if (w.cpk == w.epk) {
+        outT = maxD;
+        return kNoTriangle;
+    }
+    CoopRay ray;
+    ray.o = o;
+    ray.r = r;
+    ray.c0[0] = pk_get(w.cpk, 0);
+    ray.c0[1] = pk_get(w.cpk, 1);
+    ray.c0[2] = pk_get(w.cpk, 2);
+    ray.epk = w.epk;
+    for (;;) {
+        uint32_t cells[kCoopLanes];
+        int faces[kCoopLanes];
+        bool finished;
+        const int count = coop_burst_serial(ray, n, planes, cells, faces, finished);
+        for (int q = 0; q < count; ++q) {
+            test_cell(cells[q], faces[q], closest);
+            if (closest != kNoTriangle) return closest;
+        }
+        if (finished) break;
+    }
+    outT = maxD;
+    return kNoTriangle;
+}
+
 }  // namespace oclr

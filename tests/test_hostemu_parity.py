@@ -97,3 +97,21 @@ def test_split_walk_is_exact(name, part_cells, hostemu, monkeypatch):
         assert np.array_equal(flat[0][c], split[0][c])
     assert np.array_equal(flat[1], split[1]) and np.array_equal(flat[2], split[2])
     assert split[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_cooperative_walk_is_exact(name, hostemu, monkeypatch):
+    """rt_walk.h coop_*: the walk of one ray taken 32 plane crossings at a time, every crossing placed by the merge-order rule
+    instead of by stepping (the trace kernel's tail mode) -- identical planes / ids / flags, and exactly the cells (empty and
+    non-empty) the reference's cell walk visits."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "1000")
+    coop = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], coop[0][c])
+    assert np.array_equal(flat[1], coop[1]) and np.array_equal(flat[2], coop[2])
+    assert coop[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
+    if name != "coarse_grid":      # rays with a zero direction component fall back to the packed (two-level) walk, which skips empty cells
+        assert coop[3]["cells"] <= flat[3]["cells"]
