@@ -11,7 +11,8 @@
 
 namespace oclr {
 
-enum PackError { kPackOk = 0, kPackBadVertexIndex = 1, kPackBadMaterial = 2, kPackBadCsr = 4, kPackBadListEntry = 8 };
+enum PackError { kPackOk = 0, kPackBadVertexIndex = 1, kPackBadMaterial = 2, kPackBadCsr = 4, kPackBadListEntry = 8, kPackListTooLong = 16 };
+enum { kMaxCellListLength = 1 << 17 };   // wf_pipe_kernel orders the pairs of one drain (<= 127 cells) with a 24-bit index
 
 // One thread per triangle: gathers the 3 vertices (16 B loads), precomputes the plane/Gram terms, writes 4 + 8 float4.
 __global__ void __launch_bounds__(256) pack_triangles_kernel(uint32_t triangleCount, uint32_t vertexCount, uint32_t materialCount,
@@ -68,6 +69,7 @@ __device__ __forceinline__ uint64_t brick_mask(const uint32_t* __restrict__ star
             for (int x = 0; x < side; ++x) {
                 const uint32_t e = __ldg(start + row + x + 1);
                 if (e < s || e > total) atomicOr(error, (uint32_t)kPackBadCsr);
+                else if (e - s >= (uint32_t)kMaxCellListLength) atomicOr(error, (uint32_t)kPackListTooLong);
                 if (s < e) {
                     mask |= 1ull << (x | (y << 2) | (z << 4));
                     if (ranges) ranges[k] = make_uint2(s, e);

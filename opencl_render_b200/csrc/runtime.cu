@@ -379,7 +379,8 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
         err = std::string("scene arrays are inconsistent:") + ((flag & kPackBadVertexIndex) ? " triangleVertexIndex out of range;" : "") +
               ((flag & kPackBadMaterial) ? " triangleMaterialId out of range;" : "") +
               ((flag & kPackBadCsr) ? " scenePixelTriangleListStart is not a monotone CSR;" : "") +
-              ((flag & kPackBadListEntry) ? " scenePixelTriangleList entry out of range;" : "");
+              ((flag & kPackBadListEntry) ? " scenePixelTriangleList entry out of range;" : "") +
+              ((flag & kPackListTooLong) ? " a grid cell lists 131072 triangles or more (unsupported);" : "");
         return false;
     }
     SceneView& v = s->view;
