@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <thread>
+#include <utility>
+#include <vector>
 
 #include "cam_builder.cuh"
 #include "grid_builder.cuh"
@@ -69,21 +71,35 @@ struct Scene {
     int smCount = 148;
 };
 
+// Wavefront path state of one slice of a launch domain (launch_wavefront): its own buffers, queue counters and stream, so
+// the rounds of different slices overlap on the GPU.
+enum { kMaxSlices = 8 };
+struct WfSlice {
+    DeviceBuffer ctl, rng, colour, ring, carry, rayO, rayD, rayExcl, hit, queue;
+    DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
+    DeviceBuffer workCounter;                          // {count, cursor, class counts} x 2, alternating between rounds
+    uint32_t capacity = 0;
+    uint32_t lastRounds = 4;          // rounds the previous sample needed (first chunk of the next one)
+    cudaStream_t stream = nullptr;    // internal stream (slice 0 runs on the caller's stream)
+    cudaEvent_t done = nullptr;
+    std::vector<cudaEvent_t> traceEvents;   // pairs around the trace launches of the last timed render
+    uint32_t traceEventsUsed = 0;
+    DeviceBuffer* buffers(int i) {
+        DeviceBuffer* all[] = {&ctl, &rng, &colour, &ring, &carry, &rayO, &rayD, &rayExcl, &hit, &queue, &recO, &recD, &recS0, &recS1,
+                               &recOrder, &workCounter};
+        return i < 16 ? all[i] : nullptr;
+    }
+};
+
 struct Frame {
     Scene* scene = nullptr;
     Camera cam = {};
-    DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters, workCounter;
-    // wavefront path state (allocated on first use, sized for the largest launch domain seen)
-    DeviceBuffer wfCtl, wfRng, wfColour, wfRing, wfCarry, wfRayO, wfRayD, wfRayExcl, wfHit, wfQueue;
-    DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
-    uint32_t wfCapacity = 0;
-    uint32_t* hostCount = nullptr;   // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters;
+    WfSlice slices[kMaxSlices];      // wavefront path state (allocated on first use, sized for the largest slice seen)
+    uint32_t* hostCount = nullptr;   // pinned, one per slice
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr;
     uint32_t lastLaunches = 0;
     size_t camListSize = 0;
-    uint32_t lastRounds = 4;         // rounds the previous sample needed (first chunk of the next one)
-    std::vector<cudaEvent_t> traceEvents;   // pairs around the trace launches of the last timed render
-    uint32_t traceEventsUsed = 0;
 };
 
 int device_count() {
@@ -448,10 +464,10 @@ static bool frame_setup_common(Frame* f, std::string& err) {
     if (!f->flags.alloc(sizeof(uint8_t) * P, err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->flags.p, 0, f->flags.bytes, 0));
     if (!f->counters.alloc(sizeof(Counters), err)) return false;
-    if (!f->workCounter.alloc(sizeof(uint32_t) * 2 * (2 + kLengthClasses), err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
+    OCLR_CUDA(cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     OCLR_CUDA(cudaStreamSynchronize(0));
     return true;
 }
@@ -623,14 +639,18 @@ bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t*
 void frame_destroy(Frame* f) {
     if (!f) return;
     cudaSetDevice(f->scene->device);
-    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->workCounter,
-                           &f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl, &f->wfHit,
-                           &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1, &f->recOrder};
+    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters};
     for (DeviceBuffer* b : all) b->release();
+    for (WfSlice& sl : f->slices) {
+        for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release();
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+        if (sl.done) cudaEventDestroy(sl.done);
+        for (cudaEvent_t e : sl.traceEvents) cudaEventDestroy(e);
+    }
     if (f->hostCount) cudaFreeHost(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
-    for (cudaEvent_t e : f->traceEvents) cudaEventDestroy(e);
+    if (f->evFork) cudaEventDestroy(f->evFork);
     delete f;
 }
 
@@ -641,57 +661,115 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
     return owned;
 }
 
+// Slices of a launch domain.  The trace kernel is a persistent grid that owns every SM; the end of each launch is a tail in which
+// a few long walks keep a few warps busy (profiles/README.md), and the logic kernel between two trace launches is latency-bound.
+// The domain is therefore cut into slices -- sub-band sets of the rows -- with their own path state, queue counters and stream:
+// the rounds of one slice are still strictly ordered, but the CTAs of another slice's kernels move into the SMs a draining
+// launch gives up.  Pixels are independent, so the cut is invisible in the output.
+// Measured (B200, gpurun_out/slices*.log): config 3 (8.3 M paths) 24.4 -> 23.7 ms with 2 slices, flat to 4, worse at 8; config 2
+// (2.1 M paths) 4.51 ms with 1 or 2 slices and slower beyond -- every slice's launches end in their own partly filled warps, which
+// costs what the overlap wins.  Default: one slice per 4 M paths, at most 4 (OCLR_SLICES=k forces k).
+static int slice_count_for(uint32_t rows, uint32_t width) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* v = getenv("OCLR_SLICES");
+        forced = v && atoi(v) > 0 ? std::min(atoi(v), (int)kMaxSlices) : 0;
+    }
+    if (forced) return forced;
+    const uint64_t paths = (uint64_t)rows * width;
+    return (int)std::min<uint64_t>(4, std::max<uint64_t>(1, paths / (4ull << 20)));
+}
+
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
-static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, int smCount, Counters* dcnt, cudaStream_t st,
+static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall, int smCount, Counters* dcnt, cudaStream_t st,
                              uint32_t& launches, bool timeTrace, std::string& err) {
-    f->traceEventsUsed = 0;
-    const uint32_t rows = launch_rows(F), W = F.cam.width;
-    const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
-    if (Q64 > 0xFFFFFFF0ull) {
-        err = "launch domain too large";
-        return false;
-    }
-    const uint32_t Q = (uint32_t)Q64;
-    if (Q > f->wfCapacity) {
-        DeviceBuffer* all[] = {&f->wfCtl, &f->wfRng, &f->wfColour, &f->wfRing, &f->wfCarry, &f->wfRayO, &f->wfRayD, &f->wfRayExcl,
-                               &f->wfHit, &f->wfQueue, &f->recO, &f->recD, &f->recS0, &f->recS1, &f->recOrder};
-        for (DeviceBuffer* b : all) b->release(st);
-        if (!f->wfCtl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) || !f->wfRng.alloc(sizeof(uint64_t) * (size_t)Q, err, st) ||
-            !f->wfColour.alloc(sizeof(float4) * (size_t)Q, err, st) ||
-            !f->wfRing.alloc(sizeof(float4) * (size_t)Q * kRingSize * kRingParts, err, st) ||
-            !f->wfCarry.alloc(sizeof(float4) * (size_t)Q * kCarryParts, err, st) || !f->wfRayO.alloc(sizeof(float4) * (size_t)Q, err, st) ||
-            !f->wfRayD.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfRayExcl.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
-            !f->wfHit.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->wfQueue.alloc(sizeof(uint32_t) * (size_t)Q, err, st) ||
-            !f->recO.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recD.alloc(sizeof(float4) * (size_t)Q, err, st) ||
-            !f->recS0.alloc(sizeof(float4) * (size_t)Q, err, st) || !f->recS1.alloc(sizeof(uint4) * (size_t)Q, err, st) ||
-            !f->recOrder.alloc(sizeof(uint32_t) * (size_t)Q * kLengthClasses, err, st))
-            return false;
-        f->wfCapacity = Q;
-    }
-    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * 2, cudaHostAllocDefault));
-    WfState w;
-    w.Q = Q;
-    w.ctl = (uint32_t*)f->wfCtl.p;
-    w.rng = (uint64_t*)f->wfRng.p;
-    w.colour = (float4*)f->wfColour.p;
-    w.ring = (float4*)f->wfRing.p;
-    w.carry = (float4*)f->wfCarry.p;
-    w.rayO = (float4*)f->wfRayO.p;
-    w.rayD = (float4*)f->wfRayD.p;
-    w.rayExcl = (uint32_t*)f->wfRayExcl.p;
-    w.hit = (float4*)f->wfHit.p;
-    w.queue = (uint32_t*)f->wfQueue.p;
-    WalkRecords rec;
-    rec.o = (float4*)f->recO.p;
-    rec.d = (float4*)f->recD.p;
-    rec.s0 = (float4*)f->recS0.p;
-    rec.s1 = (uint4*)f->recS1.p;
-    rec.order = (uint32_t*)f->recOrder.p;
-    rec.Q = Q;
+    const uint32_t W = Fall.cam.width;
     if (S.n > 1024) {
         err = "axesDivCount > 1024 is not supported by the packed walk";
         return false;
     }
+    // ---- cut the launch domain into slices -------------------------------------------------------------------------------------------
+    const uint32_t rowsAll = launch_rows(Fall);
+    int K = slice_count_for(rowsAll, W);
+    FrameView FV[kMaxSlices];
+    if (Fall.bandWorld <= 1) {   // contiguous row ranges, multiples of 8 rows (the logic kernel's tile height)
+        const uint32_t per = ((rowsAll + (uint32_t)K - 1) / (uint32_t)K + 7u) / 8u * 8u;
+        int used = 0;
+        for (uint32_t r0 = 0; r0 < rowsAll; r0 += per, ++used) {
+            FV[used] = Fall;
+            FV[used].rowBegin = Fall.rowBegin + r0;
+            FV[used].rowEnd = Fall.rowBegin + std::min(rowsAll, r0 + per);
+            FV[used].ownedRows = FV[used].rowEnd - FV[used].rowBegin;
+        }
+        K = used;
+    } else {   // band set of rank r in world N -> sub-band sets r + N*k in world N*K (b % (N*K) == r + N*k implies b % N == r)
+        int used = 0;
+        for (int k = 0; k < K; ++k) {
+            FrameView v = Fall;
+            v.bandWorld = Fall.bandWorld * (uint32_t)K;
+            v.bandRank = Fall.bandRank + Fall.bandWorld * (uint32_t)k;
+            v.ownedRows = band_owned_rows(Fall.cam.height, v.bandRows, v.bandRank, v.bandWorld);
+            if (v.ownedRows) FV[used++] = v;
+        }
+        K = used;
+    }
+    if (K == 0) return true;
+
+    WfState w[kMaxSlices];
+    WalkRecords rec[kMaxSlices];
+    dim3 logicGrid[kMaxSlices];
+    unsigned setupGrid[kMaxSlices];
+    cudaStream_t stream[kMaxSlices];
+    for (int k = 0; k < K; ++k) {
+        WfSlice& sl = f->slices[k];
+        const uint32_t rows = launch_rows(FV[k]);
+        const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
+        if (Q64 > 0xFFFFFFF0ull) {
+            err = "launch domain too large";
+            return false;
+        }
+        const uint32_t Q = (uint32_t)Q64;
+        if (Q > sl.capacity) {
+            for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release(st);
+            const size_t q = Q;
+            if (!sl.ctl.alloc(sizeof(uint32_t) * q, err, st) || !sl.rng.alloc(sizeof(uint64_t) * q, err, st) ||
+                !sl.colour.alloc(sizeof(float4) * q, err, st) || !sl.ring.alloc(sizeof(float4) * q * kRingSize * kRingParts, err, st) ||
+                !sl.carry.alloc(sizeof(float4) * q * kCarryParts, err, st) || !sl.rayO.alloc(sizeof(float4) * q, err, st) ||
+                !sl.rayD.alloc(sizeof(float4) * q, err, st) || !sl.rayExcl.alloc(sizeof(uint32_t) * q, err, st) ||
+                !sl.hit.alloc(sizeof(float4) * q, err, st) || !sl.queue.alloc(sizeof(uint32_t) * q, err, st) ||
+                !sl.recO.alloc(sizeof(float4) * q, err, st) || !sl.recD.alloc(sizeof(float4) * q, err, st) ||
+                !sl.recS0.alloc(sizeof(float4) * q, err, st) || !sl.recS1.alloc(sizeof(uint4) * q, err, st) ||
+                !sl.recOrder.alloc(sizeof(uint32_t) * q * kLengthClasses, err, st) ||
+                !sl.workCounter.alloc(sizeof(uint32_t) * 2 * (2 + kLengthClasses), err, st))
+                return false;
+            sl.capacity = Q;
+        }
+        if (k > 0 && !sl.stream) OCLR_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.done) OCLR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        stream[k] = k == 0 ? st : sl.stream;
+        sl.traceEventsUsed = 0;
+        w[k].Q = Q;
+        w[k].ctl = (uint32_t*)sl.ctl.p;
+        w[k].rng = (uint64_t*)sl.rng.p;
+        w[k].colour = (float4*)sl.colour.p;
+        w[k].ring = (float4*)sl.ring.p;
+        w[k].carry = (float4*)sl.carry.p;
+        w[k].rayO = (float4*)sl.rayO.p;
+        w[k].rayD = (float4*)sl.rayD.p;
+        w[k].rayExcl = (uint32_t*)sl.rayExcl.p;
+        w[k].hit = (float4*)sl.hit.p;
+        w[k].queue = (uint32_t*)sl.queue.p;
+        rec[k].o = (float4*)sl.recO.p;
+        rec[k].d = (float4*)sl.recD.p;
+        rec[k].s0 = (float4*)sl.recS0.p;
+        rec[k].s1 = (uint4*)sl.recS1.p;
+        rec[k].order = (uint32_t*)sl.recOrder.p;
+        rec[k].Q = Q;
+        logicGrid[k] = dim3((W + 15) / 16, (rows + 7) / 8);
+        setupGrid[k] = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)Q + 255) / 256);
+    }
+    for (int k = K; k < kMaxSlices; ++k) f->slices[k].traceEventsUsed = 0;
+    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * kMaxSlices, cudaHostAllocDefault));
 
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
@@ -710,59 +788,91 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& F, i
         tune.switchMin = env("OCLR_SWITCH_MIN", 6);
         tune.tailDrain = env("OCLR_TAIL_DRAIN", 8);
     }
-    const dim3 logicGrid((W + 15) / 16, (rows + 7) / 8);
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
     const unsigned traceGrid = (unsigned)(smCount * perSm);
-    if (F.flagOut) OCLR_CUDA(cudaMemsetAsync(F.flagOut, 0, (size_t)F.cam.width * F.cam.height, st));
+    if (Fall.flagOut) OCLR_CUDA(cudaMemsetAsync(Fall.flagOut, 0, (size_t)Fall.cam.width * Fall.cam.height, st));
+    // fork: the internal streams start after everything already enqueued on the caller's stream
+    if (K > 1) {
+        OCLR_CUDA(cudaEventRecord(f->evFork, st));
+        for (int k = 1; k < K; ++k) OCLR_CUDA(cudaStreamWaitEvent(stream[k], f->evFork, 0));
+    }
     // Rounds (logic -> setup -> trace) are enqueued ahead in chunks without a host round trip: every kernel reads the ray count
     // of its round from device memory and returns at once when there is nothing to do.  The host looks at the count of the last
-    // enqueued round once per chunk; the first chunk is as long as the previous sample / frame needed.
-    uint32_t* counters = (uint32_t*)f->workCounter.p;   // {count, cursor, class counts} x 2, alternating between rounds
-    const unsigned setupGrid = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)Q + 255) / 256);
-    for (uint32_t s = 0; s < F.sampleCount; ++s) {
-        uint32_t round = 0;
+    // enqueued round once per chunk; the first chunk is as long as the previous sample / frame needed.  Slices are enqueued round
+    // by round, alternating, so that their launches interleave on the device.
+    const uint32_t cstride = 2 + kLengthClasses;
+    for (uint32_t s = 0; s < Fall.sampleCount; ++s) {
+        uint32_t round[kMaxSlices] = {0};
+        bool live[kMaxSlices];
+        for (int k = 0; k < K; ++k) live[k] = true;
         for (;;) {
-            const uint32_t chunk = round == 0 ? std::max<uint32_t>(f->lastRounds, 2) : 2;
-            for (uint32_t k = 0; k < chunk; ++k, ++round) {
-                w.queueCount = counters + (2 + kLengthClasses) * (round & 1u);
-                w.queueCursor = w.queueCount + 1;
-                rec.classCount = w.queueCount + 2;
-                const uint32_t* prev = round ? counters + (2 + kLengthClasses) * ((round - 1) & 1u) : nullptr;
-                OCLR_CUDA(cudaMemsetAsync(w.queueCount, 0, sizeof(uint32_t) * (2 + kLengthClasses), st));
-                if (dcnt)
-                    wf_logic_kernel<true><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, prev, dcnt);
-                else
-                    wf_logic_kernel<false><<<logicGrid, 128, 0, st>>>(S, F, w, s, round == 0 ? 1u : 0u, prev, dcnt);
-                ++launches;
-                if (timeTrace) {
-                    while (f->traceEvents.size() < (size_t)f->traceEventsUsed + 2) {
-                        cudaEvent_t e;
-                        OCLR_CUDA(cudaEventCreate(&e));
-                        f->traceEvents.push_back(e);
-                    }
-                    OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed], st));
-                }
-                wf_setup_kernel<<<setupGrid, 256, shBytes, st>>>(S, w, rec);
-                ++launches;
-                if (dcnt)
-                    wf_pipe_kernel<true><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
-                else
-                    wf_pipe_kernel<false><<<traceGrid, 128, shBytes, st>>>(S, w, rec, tune, dcnt);
-                if (timeTrace) {
-                    OCLR_CUDA(cudaEventRecord(f->traceEvents[f->traceEventsUsed + 1], st));
-                    f->traceEventsUsed += 2;
-                }
-                ++launches;
+            uint32_t chunk[kMaxSlices], maxChunk = 0;
+            for (int k = 0; k < K; ++k) {
+                chunk[k] = !live[k] ? 0u : (round[k] == 0 ? std::max<uint32_t>(f->slices[k].lastRounds, 2) : 2u);
+                maxChunk = std::max(maxChunk, chunk[k]);
             }
-            OCLR_CUDA(cudaMemcpyAsync(f->hostCount, counters + (2 + kLengthClasses) * ((round - 1) & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            OCLR_CUDA(cudaStreamSynchronize(st));
-            if (f->hostCount[0] == 0) break;   // the last enqueued round found no path waiting for a ray: the sample is complete
-            if (round > 100000) {
-                err = "wavefront did not converge";
-                return false;
+            if (maxChunk == 0) break;
+            for (uint32_t c = 0; c < maxChunk; ++c) {
+                for (int k = 0; k < K; ++k) {
+                    if (c >= chunk[k]) continue;
+                    WfSlice& sl = f->slices[k];
+                    cudaStream_t ks = stream[k];
+                    uint32_t* counters = (uint32_t*)sl.workCounter.p;
+                    const uint32_t r = round[k];
+                    w[k].queueCount = counters + cstride * (r & 1u);
+                    w[k].queueCursor = w[k].queueCount + 1;
+                    rec[k].classCount = w[k].queueCount + 2;
+                    const uint32_t* prev = r ? counters + cstride * ((r - 1) & 1u) : nullptr;
+                    OCLR_CUDA(cudaMemsetAsync(w[k].queueCount, 0, sizeof(uint32_t) * cstride, ks));
+                    if (dcnt)
+                        wf_logic_kernel<true><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt);
+                    else
+                        wf_logic_kernel<false><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt);
+                    ++launches;
+                    if (timeTrace) {
+                        while (sl.traceEvents.size() < (size_t)sl.traceEventsUsed + 2) {
+                            cudaEvent_t e;
+                            OCLR_CUDA(cudaEventCreate(&e));
+                            sl.traceEvents.push_back(e);
+                        }
+                        OCLR_CUDA(cudaEventRecord(sl.traceEvents[sl.traceEventsUsed], ks));
+                    }
+                    wf_setup_kernel<<<setupGrid[k], 256, shBytes, ks>>>(S, w[k], rec[k]);
+                    ++launches;
+                    if (dcnt)
+                        wf_pipe_kernel<true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                    else
+                        wf_pipe_kernel<false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                    if (timeTrace) {
+                        OCLR_CUDA(cudaEventRecord(sl.traceEvents[sl.traceEventsUsed + 1], ks));
+                        sl.traceEventsUsed += 2;
+                    }
+                    ++launches;
+                    ++round[k];
+                }
+            }
+            for (int k = 0; k < K; ++k)
+                if (chunk[k])
+                    OCLR_CUDA(cudaMemcpyAsync(f->hostCount + k, (uint32_t*)f->slices[k].workCounter.p + cstride * ((round[k] - 1) & 1u),
+                                              sizeof(uint32_t), cudaMemcpyDeviceToHost, stream[k]));
+            for (int k = 0; k < K; ++k)
+                if (chunk[k]) OCLR_CUDA(cudaStreamSynchronize(stream[k]));
+            for (int k = 0; k < K; ++k) {
+                if (!chunk[k]) continue;
+                if (f->hostCount[k] == 0) {   // the last enqueued round found no path waiting for a ray: the slice's sample is complete
+                    live[k] = false;
+                    f->slices[k].lastRounds = round[k];
+                } else if (round[k] > 100000) {
+                    err = "wavefront did not converge";
+                    return false;
+                }
             }
         }
-        f->lastRounds = round;
+    }
+    // join: later work on the caller's stream (plane reads, gathers) follows every slice
+    for (int k = 1; k < K; ++k) {
+        OCLR_CUDA(cudaEventRecord(f->slices[k].done, stream[k]));
+        OCLR_CUDA(cudaStreamWaitEvent(st, f->slices[k].done, 0));
     }
     return true;
 }
@@ -807,11 +917,26 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         stats->launches = launches;
         stats->traceMs = 0.f;
         stats->traceLaunches = 0;
-        for (uint32_t k = 0; variant != kKernelSimple && k + 1 < f->traceEventsUsed; k += 2) {
-            float ms = 0.f;
-            OCLR_CUDA(cudaEventElapsedTime(&ms, f->traceEvents[k], f->traceEvents[k + 1]));
-            stats->traceMs += ms;
-            if (ms > 0.015f) ++stats->traceLaunches;   // rounds enqueued ahead that found no ray return at once (~6 us): not counted
+        // Trace-stage time = length of the union of the [setup start, trace end] intervals of all slices (their launches overlap),
+        // measured against ev0 on the device clock.
+        std::vector<std::pair<float, float>> spans;
+        for (WfSlice& sl : f->slices) {
+            for (uint32_t k = 0; variant != kKernelSimple && k + 1 < sl.traceEventsUsed; k += 2) {
+                float t0 = 0.f, ms = 0.f;
+                OCLR_CUDA(cudaEventElapsedTime(&t0, f->ev0, sl.traceEvents[k]));
+                OCLR_CUDA(cudaEventElapsedTime(&ms, sl.traceEvents[k], sl.traceEvents[k + 1]));
+                if (ms > 0.015f) {   // rounds enqueued ahead that found no ray return at once (~6 us): not counted
+                    ++stats->traceLaunches;
+                    spans.emplace_back(t0, t0 + ms);
+                }
+            }
+        }
+        std::sort(spans.begin(), spans.end());
+        float covered = -1.f;
+        for (const auto& sp : spans) {
+            const float from = std::max(sp.first, covered);
+            if (sp.second > from) stats->traceMs += sp.second - from;
+            covered = std::max(covered, sp.second);
         }
         if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
     }
