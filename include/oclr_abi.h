@@ -271,6 +271,42 @@ int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, 
 /* Same for the interleaved band set of one rank: the rows y with (y / bandRows) % worldSize == rank, in ONE launch. */
 int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint bandRows, int rank, int worldSize, int kernelVariant,
                             int countEvents, void* cudaStream, oclr_render_stats* stats);
+/* Progressive rendering (source/opencl/raytrace_opencl.c:726-741: every sample is truncated to an integer and ADDED to the 16-bit
+ * planes -- the planes are the job's only partial state).  Samples [sampleBegin,sampleEnd) of a sampleCount-sample job: sample 0
+ * overwrites the planes, later samples add, so a job of up to 16 384 samples (render.cpp:182) can be rendered over several calls,
+ * looked at in between (oclr_frame_read), checkpointed and resumed on another frame or process (oclr_frame_write + sampleBegin). */
+int oclr_frame_render_samples(oclr_frame* frame, cl_uint sampleCount, cl_uint sampleBegin, cl_uint sampleEnd, cl_uint rowBegin,
+                              cl_uint rowEnd, int kernelVariant, int countEvents, void* cudaStream, oclr_render_stats* stats);
+int oclr_frame_render_bands_samples(oclr_frame* frame, cl_uint sampleCount, cl_uint sampleBegin, cl_uint sampleEnd, cl_uint bandRows,
+                                    int rank, int worldSize, int kernelVariant, int countEvents, void* cudaStream,
+                                    oclr_render_stats* stats);
+/* Host -> device copy of rows [rowBegin,rowEnd) of full-frame planes (restores a checkpoint). */
+int oclr_frame_write(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, const cl_ushort* red, const cl_ushort* green,
+                     const cl_ushort* blue, void* cudaStream);
+/* Accumulation mode of a frame.  0 (default): the reference's rule above.  1: fp32 sums per pixel without per-sample truncation
+ * (the reference loses up to one 16-bit step per sample: at 16 384 samples a quarter of the range); after every render call the
+ * planes hold (int)(sum * 65535 / samples so far), i.e. the running mean converted by the reference's own rule.  With one sample
+ * both modes give identical planes.  The accumulator is W*H x (sum r, sum g, sum b, samples) floats. */
+enum { OCLR_ACCUMULATE_REFERENCE_16BIT = 0, OCLR_ACCUMULATE_FLOAT = 1 };
+int oclr_frame_set_accumulation(oclr_frame* frame, int mode);
+int oclr_frame_read_accum(oclr_frame* frame, cl_float* rgbn);
+int oclr_frame_write_accum(oclr_frame* frame, const cl_float* rgbn);
+/* Pixel-samples finished / requested by the render call in flight on this frame (callable from another thread). */
+int oclr_frame_progress(oclr_frame* frame, unsigned long long* done, unsigned long long* total);
+/* The "Estimated Time Left" of the plugin dialog (render.cpp:334-343) for the RaytraceAll in flight, on the wall clock; -1 while
+ * unknown.  GetProgress() itself is live during RaytraceAll: it reads the device counter of every GPU taking part. */
+double oclr_estimated_seconds_left(void);
+
+/* Image output of finished planes (source/render.cpp:1372-1386, source/util/writebmp.cpp:124-177).  BMP mode 0: byte = value/256
+ * (what the plugin displays); mode 1: the low byte, exactly what the reference's writebmp3s writes.  Return 1 on success. */
+int oclr_write_bmp(const char* path, cl_uint width, cl_uint height, const cl_ushort* red, const cl_ushort* green, const cl_ushort* blue,
+                   int mode);
+int oclr_write_ppm16(const char* path, cl_uint width, cl_uint height, const cl_ushort* red, const cl_ushort* green, const cl_ushort* blue);
+int oclr_write_png16(const char* path, cl_uint width, cl_uint height, const cl_ushort* red, const cl_ushort* green, const cl_ushort* blue);
+
+/* Run-time options (developer knobs).  "slices": how many slices a launch domain is cut into (0 = automatic). Returns 1 if known. */
+int oclr_set_option(const char* name, int value);
+
 /* Copy rows [rowBegin,rowEnd) of the planes to full-frame host arrays. */
 int oclr_frame_read(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, cl_ushort* outputRed, cl_ushort* outputGreen,
                     cl_ushort* outputBlue, void* cudaStream);

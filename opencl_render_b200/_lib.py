@@ -73,6 +73,10 @@ EXPORTS = [
     "oclr_frame_read_camera_lists", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
     "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_last_launches", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
     "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_build_scene_grid_device", "oclr_free_camera_lists", "oclr_free_scene_grid",
+    # progressive rendering, progress, image output
+    "oclr_frame_render_samples", "oclr_frame_render_bands_samples", "oclr_frame_write", "oclr_frame_set_accumulation", "oclr_frame_read_accum",
+    "oclr_frame_write_accum", "oclr_frame_progress", "oclr_estimated_seconds_left", "oclr_write_bmp", "oclr_write_ppm16", "oclr_write_png16",
+    "oclr_set_option",
 ]
 
 _lib = None
@@ -149,6 +153,30 @@ def load() -> C.CDLL:
     lib.oclr_free_camera_lists.restype = None
     lib.oclr_free_scene_grid.argtypes = [C.POINTER(SceneGrid)]
     lib.oclr_free_scene_grid.restype = None
+    lib.oclr_frame_render_samples.restype = C.c_int
+    lib.oclr_frame_render_samples.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                              C.c_void_p, C.POINTER(RenderStats)]
+    lib.oclr_frame_render_bands_samples.restype = C.c_int
+    lib.oclr_frame_render_bands_samples.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                                    C.c_int, C.c_void_p, C.POINTER(RenderStats)]
+    lib.oclr_frame_write.restype = C.c_int
+    lib.oclr_frame_write.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oclr_frame_set_accumulation.restype = C.c_int
+    lib.oclr_frame_set_accumulation.argtypes = [C.c_void_p, C.c_int]
+    lib.oclr_frame_read_accum.restype = C.c_int
+    lib.oclr_frame_read_accum.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oclr_frame_write_accum.restype = C.c_int
+    lib.oclr_frame_write_accum.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oclr_frame_progress.restype = C.c_int
+    lib.oclr_frame_progress.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.oclr_estimated_seconds_left.restype = C.c_double
+    for name in ("oclr_write_ppm16", "oclr_write_png16"):
+        getattr(lib, name).restype = C.c_int
+        getattr(lib, name).argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oclr_write_bmp.restype = C.c_int
+    lib.oclr_write_bmp.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.oclr_set_option.restype = C.c_int
+    lib.oclr_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.InitOpenCL.restype = None
     lib.ResetComputationType.restype = None
     lib.GetIsComputationTypeUpdated.restype = C.c_uint32

@@ -22,6 +22,7 @@ CH_COLOR, CH_REFLECTION, CH_TRANSPARENCY, CH_BUMP, CH_LUMINANCE = range(5)
 LIGHT_OMNI, LIGHT_SPOT, LIGHT_SPOTRECT, LIGHT_DISTANT, LIGHT_PARALLEL, LIGHT_PARSPOT, LIGHT_PARSPOTRECT, LIGHT_TUBE, \
     LIGHT_AREA, LIGHT_PHOTOMETRIC = range(10)
 KERNEL_SIMPLE, KERNEL_PIPE, KERNEL_DEFAULT = 0, 2, -1
+ACCUMULATE_REFERENCE_16BIT, ACCUMULATE_FLOAT = 0, 1
 NO_TRIANGLE = 0xFFFFFFFF
 
 
@@ -319,23 +320,28 @@ class DeviceFrame:
         return CameraLists(start, end, lst[:n])
 
     def render(self, sample_count: int = 1, rows=None, variant: int = KERNEL_DEFAULT, count: bool = False, stream: int = 0,
-               sync: bool = True):
-        """Trace rows [rows[0], rows[1]) (default: all).  Returns (device_ms, launches, counters dict | None)."""
+               sync: bool = True, samples=None):
+        """Trace rows [rows[0], rows[1]) (default: all).  `samples` = (begin, end): only that range of the sample_count-sample
+        job (progressive rendering: sample 0 overwrites the planes, later samples add).  Returns (device_ms, launches,
+        counters dict | None)."""
         r0, r1 = rows if rows is not None else (0, self.camera.height)
+        s0, s1 = samples if samples is not None else (0, sample_count)
         stats = _lib.RenderStats()
-        ok = self._lib.oclr_frame_render(self.handle, sample_count, r0, r1, variant, 1 if count else 0, C.c_void_p(stream),
-                                         C.byref(stats) if (sync or count) else None)
+        ok = self._lib.oclr_frame_render_samples(self.handle, sample_count, s0, s1, r0, r1, variant, 1 if count else 0,
+                                                 C.c_void_p(stream), C.byref(stats) if (sync or count) else None)
         if not ok:
             raise OclrError(_lib.last_error())
         self.last_trace_ms, self.last_trace_launches = float(stats.traceMs), int(stats.traceLaunches)
         return float(stats.deviceMs), int(stats.launches), (stats.counters.as_dict() if count else None)
 
     def render_bands(self, sample_count: int, band_rows: int, rank: int, world: int, variant: int = KERNEL_DEFAULT,
-                     count: bool = False, stream: int = 0, sync: bool = True):
+                     count: bool = False, stream: int = 0, sync: bool = True, samples=None):
         """Trace the rows y with (y // band_rows) % world == rank in one launch."""
+        s0, s1 = samples if samples is not None else (0, sample_count)
         stats = _lib.RenderStats()
-        ok = self._lib.oclr_frame_render_bands(self.handle, sample_count, band_rows, rank, world, variant, 1 if count else 0,
-                                               C.c_void_p(stream), C.byref(stats) if (sync or count) else None)
+        ok = self._lib.oclr_frame_render_bands_samples(self.handle, sample_count, s0, s1, band_rows, rank, world, variant,
+                                                       1 if count else 0, C.c_void_p(stream),
+                                                       C.byref(stats) if (sync or count) else None)
         if not ok:
             raise OclrError(_lib.last_error())
         self.last_trace_ms, self.last_trace_launches = float(stats.traceMs), int(stats.traceLaunches)
@@ -349,6 +355,37 @@ class DeviceFrame:
         if not self._lib.oclr_frame_read(self.handle, r0, r1, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), C.c_void_p(stream)):
             raise OclrError(_lib.last_error())
         return out
+
+    def write(self, planes, rows=None, stream: int = 0):
+        """Uploads full-frame uint16 planes (rows [rows[0], rows[1]) of them): restores a checkpoint taken with read()."""
+        r0, r1 = rows if rows is not None else (0, self.camera.height)
+        p = [_c(a, np.uint16) for a in planes]
+        if not self._lib.oclr_frame_write(self.handle, r0, r1, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), C.c_void_p(stream)):
+            raise OclrError(_lib.last_error())
+
+    def set_accumulation(self, mode: int):
+        """ACCUMULATE_REFERENCE_16BIT (default, raytrace_opencl.c:726-741) or ACCUMULATE_FLOAT (fp32 sums, no per-sample truncation)."""
+        if not self._lib.oclr_frame_set_accumulation(self.handle, mode):
+            raise OclrError(_lib.last_error())
+
+    def read_accum(self) -> np.ndarray:
+        """float32 [H,W,4]: (sum r, sum g, sum b, samples) of the float accumulator."""
+        out = np.empty((self.camera.height, self.camera.width, 4), np.float32)
+        if not self._lib.oclr_frame_read_accum(self.handle, _ptr(out)):
+            raise OclrError(_lib.last_error())
+        return out
+
+    def write_accum(self, acc: np.ndarray):
+        a = _c(acc, np.float32)
+        if not self._lib.oclr_frame_write_accum(self.handle, _ptr(a)):
+            raise OclrError(_lib.last_error())
+
+    def progress(self):
+        """(done, total) pixel-samples of the render call in flight (thread-safe)."""
+        d, t = C.c_ulonglong(), C.c_ulonglong()
+        if not self._lib.oclr_frame_progress(self.handle, C.byref(d), C.byref(t)):
+            raise OclrError(_lib.last_error())
+        return int(d.value), int(t.value)
 
     def primary_ids(self) -> np.ndarray:
         ids = np.empty((self.camera.height, self.camera.width), dtype=np.uint32)
@@ -379,6 +416,31 @@ class DeviceFrame:
 
     def __del__(self):
         self.close()
+
+
+def write_image(path: str, planes, fmt: str | None = None, bmp_reference_cast: bool = False):
+    """Writes uint16 [H,W] planes (r, g, b): .bmp (24 bit, value/256 -- or the reference's low-byte cast, writebmp.cpp:136-141),
+    .ppm (16 bit) or .png (16 bit)."""
+    lib = _lib.load()
+    r, g, b = (_c(a, np.uint16) for a in planes)
+    h, w = r.shape
+    fmt = (fmt or str(path).rsplit(".", 1)[-1]).lower()
+    p = str(path).encode()
+    if fmt == "bmp":
+        ok = lib.oclr_write_bmp(p, w, h, _ptr(r), _ptr(g), _ptr(b), 1 if bmp_reference_cast else 0)
+    elif fmt == "ppm":
+        ok = lib.oclr_write_ppm16(p, w, h, _ptr(r), _ptr(g), _ptr(b))
+    elif fmt == "png":
+        ok = lib.oclr_write_png16(p, w, h, _ptr(r), _ptr(g), _ptr(b))
+    else:
+        raise ValueError(f"unknown image format {fmt!r}")
+    if not ok:
+        raise OclrError(f"could not write {path}")
+
+
+def set_option(name: str, value: int):
+    if not _lib.load().oclr_set_option(name.encode(), int(value)):
+        raise OclrError(_lib.last_error())
 
 
 def band_partition(height: int, rank: int, world: int, band_rows: int = 128) -> list[tuple[int, int]]:

@@ -24,7 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-unused-function", f"-I{CUDA / 'include'}", "-pthread"]
 C_FLAGS = ["-O2", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-Wall"]
 
-SOURCES = [("runtime.cu", "nvcc"), ("abi.cpp", "g++"), ("scene_pack.cpp", "g++"), ("builders.cpp", "g++"), ("abi_helpers.c", "gcc")]
+SOURCES = [("runtime.cu", "nvcc"), ("abi.cpp", "g++"), ("scene_pack.cpp", "g++"), ("builders.cpp", "g++"), ("image_io.cpp", "g++"),
+           ("abi_helpers.c", "gcc")]
 
 
 def _digest() -> str:
@@ -66,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and r.stderr:
             print(r.stderr, file=sys.stderr)
         objs.append(str(obj))
-    cmd = [str(CUDA / "bin" / "nvcc"), "-shared", "-o", str(LIB), *objs, "-cudart", "static", "-Xlinker", "-Bsymbolic", "-lpthread"]
+    cmd = [str(CUDA / "bin" / "nvcc"), "-shared", "-o", str(LIB), *objs, "-cudart", "static", "-Xlinker", "-Bsymbolic", "-lpthread", "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")

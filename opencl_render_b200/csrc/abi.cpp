@@ -92,8 +92,53 @@ cl_bool GetComputationTypeName(size_t id, size_t strLen, cl_char* str) {
 // ---- progress / timing cells: raytrace.c:155-173 --------------------------------------------------------------------------
 static std::atomic<float> g_progress(0.f);
 static std::atomic<clock_t> g_startTime(0), g_endTime(0);
-cl_float GetProgress(void) { return g_progress.load(); }
-void SetProgress(cl_float p) { g_progress.store(p); }
+// Frames RaytraceAll is rendering right now: while there are any, GetProgress() is live -- pixel-samples finished (a device
+// counter the logic kernel bumps, read through the frame's own stream) over pixel-samples requested -- instead of the
+// reference's once-per-second event poll (raytrace.c:566-587).  Capped at 0.999 like the reference (:580); 1.0 is the caller's
+// (render.cpp:1397).
+static std::mutex g_liveMutex;
+static std::vector<Frame*> g_liveFrames;
+static std::atomic<double> g_wallStart(0.0), g_wallLastChange(0.0);
+static double wall_now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+cl_float GetProgress(void) {
+    std::lock_guard<std::mutex> lock(g_liveMutex);
+    if (!g_liveFrames.empty()) {
+        unsigned long long done = 0, total = 0;
+        for (Frame* f : g_liveFrames) {
+            unsigned long long d = 0, t = 0;
+            if (frame_progress(f, &d, &t)) {
+                done += d;
+                total += t;
+            }
+        }
+        if (total) {
+            const float p = 0.999f * (float)((double)done / (double)total);
+            if (p > g_progress.load()) {
+                g_progress.store(p);
+                g_wallLastChange.store(wall_now());
+            }
+        }
+    }
+    return g_progress.load();
+}
+void SetProgress(cl_float p) {
+    g_progress.store(p);
+    g_wallLastChange.store(wall_now());
+}
+// Estimated seconds left, the dialog's rule (render.cpp:334-343): (start - now) + (last progress change - start) / progress,
+// on the wall clock; negative values are clamped to 0 and "unknown" (no progress yet) is reported as -1.
+double oclr_estimated_seconds_left(void) {
+    const float p = GetProgress();
+    const double start = g_wallStart.load(), last = g_wallLastChange.load(), now = wall_now();
+    if (!(p > 0.f) || start == 0.0) return -1.0;
+    const double t = (start - now) + (last - start) / (double)p;
+    return t < 0.0 ? 0.0 : t;
+}
+int oclr_frame_progress(oclr_frame* frame, unsigned long long* done, unsigned long long* total);
 clock_t GetStartTime(void) { return g_startTime.load(); }
 clock_t GetEndTime(void) { return g_endTime.load(); }
 void ResetTime(void) {
@@ -105,6 +150,14 @@ void ResetTime(void) {
 const char* oclr_last_error(void) { return g_err.c_str(); }
 int oclr_device_count(void) { return device_count(); }
 const char* oclr_version(void) { return "opencl_render_b200 0.1 (sm_100a)"; }
+int oclr_set_option(const char* name, int value) {
+    if (name && strcmp(name, "slices") == 0) {
+        set_slice_count(value);
+        return 1;
+    }
+    fail(std::string("oclr_set_option: unknown option ") + (name ? name : "(null)"));
+    return 0;
+}
 
 static HostScene to_host(const oclr_scene_desc* d) {
     HostScene h;
@@ -231,49 +284,98 @@ static int default_variant() {
 }
 static int pick_variant(int v) { return v == OCLR_KERNEL_DEFAULT ? default_variant() : v; }
 
-int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, cl_uint rowEnd, int kernelVariant, int countEvents,
-                      void* cudaStream, oclr_render_stats* stats) {
+static void copy_stats(oclr_render_stats* stats, const RenderStats& rs) {
+    stats->deviceMs = rs.deviceMs;
+    stats->launches = rs.launches;
+    stats->traceMs = rs.traceMs;
+    stats->traceLaunches = rs.traceLaunches;
+    memcpy(&stats->counters, &rs.counters, sizeof(Counters));
+}
+
+int oclr_frame_render_samples(oclr_frame* frame, cl_uint sampleCount, cl_uint sampleBegin, cl_uint sampleEnd, cl_uint rowBegin, cl_uint rowEnd,
+                              int kernelVariant, int countEvents, void* cudaStream, oclr_render_stats* stats) {
     if (!frame) {
         fail("oclr_frame_render: null frame");
         return 0;
     }
     std::string err;
     RenderStats rs;
-    if (!frame_render(frame->impl, sampleCount, rowBegin, rowEnd, pick_variant(kernelVariant), countEvents != 0, cudaStream,
-                      stats ? &rs : nullptr, err)) {
+    if (!frame_render(frame->impl, sampleCount, sampleBegin, sampleEnd, rowBegin, rowEnd, pick_variant(kernelVariant), countEvents != 0,
+                      cudaStream, stats ? &rs : nullptr, err)) {
         fail("oclr_frame_render: " + err);
         return 0;
     }
-    if (stats) {
-        stats->deviceMs = rs.deviceMs;
-        stats->launches = rs.launches;
-        stats->traceMs = rs.traceMs;
-        stats->traceLaunches = rs.traceLaunches;
-        memcpy(&stats->counters, &rs.counters, sizeof(Counters));
-    }
+    if (stats) copy_stats(stats, rs);
     return 1;
 }
+int oclr_frame_render(oclr_frame* frame, cl_uint sampleCount, cl_uint rowBegin, cl_uint rowEnd, int kernelVariant, int countEvents,
+                      void* cudaStream, oclr_render_stats* stats) {
+    return oclr_frame_render_samples(frame, sampleCount, 0, sampleCount, rowBegin, rowEnd, kernelVariant, countEvents, cudaStream, stats);
+}
 
-int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint bandRows, int rank, int worldSize, int kernelVariant,
-                            int countEvents, void* cudaStream, oclr_render_stats* stats) {
+int oclr_frame_render_bands_samples(oclr_frame* frame, cl_uint sampleCount, cl_uint sampleBegin, cl_uint sampleEnd, cl_uint bandRows, int rank,
+                                    int worldSize, int kernelVariant, int countEvents, void* cudaStream, oclr_render_stats* stats) {
     if (!frame || rank < 0 || worldSize < 1) {
         fail("oclr_frame_render_bands: bad argument");
         return 0;
     }
     std::string err;
     RenderStats rs;
-    if (!frame_render_bands(frame->impl, sampleCount, bandRows, (uint32_t)rank, (uint32_t)worldSize, pick_variant(kernelVariant),
-                            countEvents != 0, cudaStream, stats ? &rs : nullptr, err)) {
+    if (!frame_render_bands(frame->impl, sampleCount, sampleBegin, sampleEnd, bandRows, (uint32_t)rank, (uint32_t)worldSize,
+                            pick_variant(kernelVariant), countEvents != 0, cudaStream, stats ? &rs : nullptr, err)) {
         fail("oclr_frame_render_bands: " + err);
         return 0;
     }
-    if (stats) {
-        stats->deviceMs = rs.deviceMs;
-        stats->launches = rs.launches;
-        stats->traceMs = rs.traceMs;
-        stats->traceLaunches = rs.traceLaunches;
-        memcpy(&stats->counters, &rs.counters, sizeof(Counters));
+    if (stats) copy_stats(stats, rs);
+    return 1;
+}
+int oclr_frame_render_bands(oclr_frame* frame, cl_uint sampleCount, cl_uint bandRows, int rank, int worldSize, int kernelVariant,
+                            int countEvents, void* cudaStream, oclr_render_stats* stats) {
+    return oclr_frame_render_bands_samples(frame, sampleCount, 0, sampleCount, bandRows, rank, worldSize, kernelVariant, countEvents, cudaStream,
+                                           stats);
+}
+
+int oclr_frame_write(oclr_frame* frame, cl_uint rowBegin, cl_uint rowEnd, const cl_ushort* r, const cl_ushort* g, const cl_ushort* b,
+                     void* cudaStream) {
+    std::string err;
+    if (!frame || !r || !g || !b || !frame_write(frame->impl, rowBegin, rowEnd, r, g, b, cudaStream, err)) {
+        fail("oclr_frame_write: " + (err.empty() ? std::string("null argument") : err));
+        return 0;
     }
+    return 1;
+}
+int oclr_frame_set_accumulation(oclr_frame* frame, int mode) {
+    std::string err;
+    if (!frame || !frame_set_accumulation(frame->impl, mode, err)) {
+        fail("oclr_frame_set_accumulation: " + (err.empty() ? std::string("null frame") : err));
+        return 0;
+    }
+    return 1;
+}
+int oclr_frame_read_accum(oclr_frame* frame, cl_float* rgbn) {
+    std::string err;
+    if (!frame || !frame_accum_copy(frame->impl, rgbn, true, err)) {
+        fail("oclr_frame_read_accum: " + (err.empty() ? std::string("null frame") : err));
+        return 0;
+    }
+    return 1;
+}
+int oclr_frame_write_accum(oclr_frame* frame, const cl_float* rgbn) {
+    std::string err;
+    if (!frame || !frame_accum_copy(frame->impl, const_cast<cl_float*>(rgbn), false, err)) {
+        fail("oclr_frame_write_accum: " + (err.empty() ? std::string("null frame") : err));
+        return 0;
+    }
+    return 1;
+}
+int oclr_frame_progress(oclr_frame* frame, unsigned long long* done, unsigned long long* total) {
+    unsigned long long d = 0, t = 0;
+    if (!frame || !frame_progress(frame->impl, &d, &t)) {
+        fail("oclr_frame_progress: query failed");
+        return 0;
+    }
+    if (done) *done = d;
+    if (total) *total = t;
     return 1;
 }
 
@@ -356,6 +458,10 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
     double tRender = 0, tRead = 0;
     bool ok = f != nullptr;
     if (ok) {
+        {
+            std::lock_guard<std::mutex> lock(g_liveMutex);
+            g_liveFrames.push_back(f);
+        }
         const int maxBands = (int)((cam.height + 127) / 128) + 1;
         std::vector<cl_uint> rows(2 * (size_t)maxBands);
         const int owned = world > 1 ? oclr_band_partition(cam.height, 128, rank, world, rows.data(), maxBands) : 1;
@@ -363,16 +469,22 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
             rows[0] = 0;
             rows[1] = cam.height;
         }
-        for (int k = 0; ok && k < owned; ++k) {
-            RenderStats rs;
-            const double a = now_ms();
-            ok = frame_render(f, sampleCount, rows[2 * k], rows[2 * k + 1], default_variant(), false, nullptr, &rs, err);
-            const double c = now_ms();
-            if (ok) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
-            tRender += c - a;
-            tRead += now_ms() - c;
-            if (world <= 1) g_progress.store(0.999f * (float)(k + 1) / (float)owned);
-        }
+        RenderStats rs;
+        const double a = now_ms();
+        // all bands of this device in one launch sequence (tile height 128 = the reference's, raytrace.c:507)
+        ok = frame_render_bands(f, sampleCount, 0, sampleCount, 128, (uint32_t)rank, (uint32_t)(world > 1 ? world : 1), default_variant(), false,
+                                nullptr, &rs, err);
+        const double c = now_ms();
+        for (int k = 0; ok && k < owned; ++k) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
+        tRender += c - a;
+        tRead += now_ms() - c;
+        GetProgress();   // latch the last value of the device counter before the frame goes away
+        std::lock_guard<std::mutex> lock(g_liveMutex);
+        for (size_t i = 0; i < g_liveFrames.size(); ++i)
+            if (g_liveFrames[i] == f) {
+                g_liveFrames.erase(g_liveFrames.begin() + (long)i);
+                break;
+            }
     }
     const double t3 = now_ms();
     if (f) frame_destroy(f);
@@ -407,6 +519,8 @@ static cl_bool raytrace_all_impl(cl_uint computationType, const Camera& cam, con
         return CL_FALSE;
     }
     g_progress.store(0.f);
+    g_wallStart.store(wall_now());
+    g_wallLastChange.store(g_wallStart.load());
     g_startTime = clock();
     g_endTime = g_startTime.load();
     bool ok = true;

@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(128) raytrace_simple_kernel(SceneView S, Frame
 
     Counters cnt = {};
     const float scale = 65535.f / (float)F.sampleCount;
-    uint16_t r = 0, g = 0, b = 0;  // planes start from zero (raytrace.c:476-486)
+    // planes start from zero (raytrace.c:476-486); a later sample range of the same job adds to what is there
+    uint16_t r = F.sampleBegin ? F.outR[pixel] : (uint16_t)0, g = F.sampleBegin ? F.outG[pixel] : (uint16_t)0,
+             b = F.sampleBegin ? F.outB[pixel] : (uint16_t)0;
     bool undef = false;
-    for (uint32_t s = 0; s < F.sampleCount; ++s) {
+    for (uint32_t s = F.sampleBegin; s < F.sampleEnd; ++s) {
         uint32_t pid;
         const f3 c = trace_sample<COUNT>(S, F, px, py, pz, pixel, s, &pid, undef, &cnt);
         if (s == 0 && F.idOut) F.idOut[pixel] = pid;

@@ -88,7 +88,8 @@ struct FrameView {
     const uint32_t* camStart;
     const uint32_t* camEnd;
     const uint32_t* camList;
-    uint32_t sampleCount;
+    uint32_t sampleCount;        // S of the whole job: seeds are pixel*S + s+1 and every sample is scaled by 65535/S
+    uint32_t sampleBegin, sampleEnd;   // samples rendered by this call (progressive rendering: 0 <= begin < end <= S)
     uint32_t rowBegin, rowEnd;   // rows rendered by this launch when bandWorld <= 1
     // Screen-band partition across GPUs: when bandWorld > 1 the launch covers the rows y with
     // (y / bandRows) % bandWorld == bandRank; `ownedRows` of them exist.  Launch-domain row k maps to frame row map_row(k).
@@ -98,6 +99,12 @@ struct FrameView {
     uint16_t* outB;
     uint32_t* idOut;             // optional: primary-hit triangle id per pixel (sample 0), or nullptr
     uint8_t* flagOut;            // optional: per pixel, bit 0 = the reference's result is undefined here (rt_core.h triangle_normal)
+    // Progressive accumulation.  Default (accum == nullptr): the reference's rule, every sample is
+    // truncated to an integer and added to the 16-bit planes (raytrace_opencl.c:726-741); sample 0 overwrites, later samples add,
+    // so a job can be rendered in several calls over sample ranges.  accum != nullptr: (sum r, sum g, sum b, samples) per pixel
+    // in fp32, no per-sample truncation; the planes are resolved from it after the call (resolve_accum_kernel).
+    float4* accum;
+    unsigned long long* doneCount;   // optional: pixel-samples finished so far by the current render call (progress, raytrace.c:580)
 };
 
 // Launch-domain row k -> frame row (>= height when k is past the owned rows).

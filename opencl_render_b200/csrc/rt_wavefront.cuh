@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
     const uint32_t pixel = valid ? y * F.cam.width + x : 0;
     uint32_t ctl = valid ? (startSample ? (uint32_t)kWfNew : w.ctl[q]) : (uint32_t)kWfDone;
     int stage = (int)(ctl & 7u);
-    bool want = false;
+    bool want = false, finished = false;
     if (stage != kWfDone) {
         Counters cnt = {};
         const Camera& cam = F.cam;
@@ -345,13 +345,23 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
             } else {  // GO_POP
                 begin = (begin + 1) % kRingSize;
                 if (begin == end) {
-                    const float scale = 65535.f / (float)F.sampleCount;
-                    const uint16_t pr = sampleIdx ? F.outR[pixel] : (uint16_t)0;
-                    const uint16_t pg = sampleIdx ? F.outG[pixel] : (uint16_t)0;
-                    const uint16_t pb = sampleIdx ? F.outB[pixel] : (uint16_t)0;
-                    F.outR[pixel] = accumulate16(pr, colour.x, scale);
-                    F.outG[pixel] = accumulate16(pg, colour.y, scale);
-                    F.outB[pixel] = accumulate16(pb, colour.z, scale);
+                    if (F.accum) {   // float accumulation: no per-sample truncation (resolved by resolve_accum_kernel)
+                        float4 a = sampleIdx ? F.accum[pixel] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a.x += colour.x;
+                        a.y += colour.y;
+                        a.z += colour.z;
+                        a.w += 1.f;
+                        F.accum[pixel] = a;
+                    } else {
+                        const float scale = 65535.f / (float)F.sampleCount;
+                        const uint16_t pr = sampleIdx ? F.outR[pixel] : (uint16_t)0;
+                        const uint16_t pg = sampleIdx ? F.outG[pixel] : (uint16_t)0;
+                        const uint16_t pb = sampleIdx ? F.outB[pixel] : (uint16_t)0;
+                        F.outR[pixel] = accumulate16(pr, colour.x, scale);
+                        F.outG[pixel] = accumulate16(pg, colour.y, scale);
+                        F.outB[pixel] = accumulate16(pb, colour.z, scale);
+                    }
+                    finished = true;
                     stage = kWfDone;
                     go = GO_EXIT;
                 } else {
@@ -369,7 +379,25 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
         w.ctl[q] = (uint32_t)stage | ((uint32_t)begin << 4) | ((uint32_t)end << 8) | (j << 12);
         if (COUNT) flush_counters(cnt, gcnt);
     }
+    if (F.doneCount) {   // progress: pixel-samples finished, one atomic per warp
+        const unsigned fm = __ballot_sync(0xFFFFFFFFu, finished);
+        if (fm != 0u && (threadIdx.x & 31) == 0) atomicAdd(F.doneCount, (unsigned long long)__popc(fm));
+    }
     enqueue(w, q, want);
+}
+
+// Planes from the float accumulator: out = (int)(sum * 65535 / samples so far), the reference's conversion (:726-741) applied once
+// to the mean instead of once per sample.  One thread per pixel of the launch domain.
+__global__ void resolve_accum_kernel(FrameView F) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = map_row(F, blockIdx.y);
+    if (x >= F.cam.width || y >= F.cam.height) return;
+    const uint32_t pixel = y * F.cam.width + x;
+    const float4 a = F.accum[pixel];
+    const float scale = 65535.f / (a.w > 0.f ? a.w : 1.f);
+    F.outR[pixel] = accumulate16(0, a.x, scale);
+    F.outG[pixel] = accumulate16(0, a.y, scale);
+    F.outB[pixel] = accumulate16(0, a.z, scale);
 }
 
 }  // namespace oclr

@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -100,6 +102,13 @@ struct Frame {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr;
     uint32_t lastLaunches = 0;
     size_t camListSize = 0;
+    // progressive accumulation + progress
+    DeviceBuffer accum;              // float4 per pixel when float accumulation is on (frame_set_accumulation)
+    DeviceBuffer doneCount;          // pixel-samples finished by the render call in flight
+    cudaStream_t progStream = nullptr;
+    unsigned long long* hostDone = nullptr;   // pinned
+    std::atomic<unsigned long long> jobPaths{0};   // pixel-samples of the render call in flight (0: none)
+    std::mutex progMutex;
 };
 
 int device_count() {
@@ -464,6 +473,10 @@ static bool frame_setup_common(Frame* f, std::string& err) {
     if (!f->flags.alloc(sizeof(uint8_t) * P, err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->flags.p, 0, f->flags.bytes, 0));
     if (!f->counters.alloc(sizeof(Counters), err)) return false;
+    if (!f->doneCount.alloc(sizeof(unsigned long long), err)) return false;
+    OCLR_CUDA(cudaMemsetAsync(f->doneCount.p, 0, sizeof(unsigned long long), 0));
+    OCLR_CUDA(cudaStreamCreateWithFlags(&f->progStream, cudaStreamNonBlocking));
+    OCLR_CUDA(cudaHostAlloc((void**)&f->hostDone, sizeof(unsigned long long), cudaHostAllocDefault));
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
@@ -639,8 +652,10 @@ bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t*
 void frame_destroy(Frame* f) {
     if (!f) return;
     cudaSetDevice(f->scene->device);
-    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters};
+    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount};
     for (DeviceBuffer* b : all) b->release();
+    if (f->progStream) cudaStreamDestroy(f->progStream);
+    if (f->hostDone) cudaFreeHost(f->hostDone);
     for (WfSlice& sl : f->slices) {
         for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release();
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -669,12 +684,14 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 // Measured (B200, gpurun_out/slices*.log): config 3 (8.3 M paths) 24.4 -> 23.7 ms with 2 slices, flat to 4, worse at 8; config 2
 // (2.1 M paths) 4.51 ms with 1 or 2 slices and slower beyond -- every slice's launches end in their own partly filled warps, which
 // costs what the overlap wins.  Default: one slice per 4 M paths, at most 4 (OCLR_SLICES=k forces k).
+static std::atomic<int> g_sliceCount(-1);   // -1: not yet read from OCLR_SLICES; 0: automatic
+void set_slice_count(int k) { g_sliceCount.store(std::max(0, std::min(k, (int)kMaxSlices))); }
 static int slice_count_for(uint32_t rows, uint32_t width) {
-    static int forced = -1;
-    if (forced < 0) {
+    if (g_sliceCount.load() < 0) {
         const char* v = getenv("OCLR_SLICES");
-        forced = v && atoi(v) > 0 ? std::min(atoi(v), (int)kMaxSlices) : 0;
+        set_slice_count(v ? atoi(v) : 0);
     }
+    const int forced = g_sliceCount.load();
     if (forced) return forced;
     const uint64_t paths = (uint64_t)rows * width;
     return (int)std::min<uint64_t>(4, std::max<uint64_t>(1, paths / (4ull << 20)));
@@ -801,7 +818,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // enqueued round once per chunk; the first chunk is as long as the previous sample / frame needed.  Slices are enqueued round
     // by round, alternating, so that their launches interleave on the device.
     const uint32_t cstride = 2 + kLengthClasses;
-    for (uint32_t s = 0; s < Fall.sampleCount; ++s) {
+    for (uint32_t s = Fall.sampleBegin; s < Fall.sampleEnd; ++s) {
         uint32_t round[kMaxSlices] = {0};
         bool live[kMaxSlices];
         for (int k = 0; k < K; ++k) live[k] = true;
@@ -890,6 +907,14 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
     F.outB = F.outG + P;
     F.idOut = (uint32_t*)f->ids.p;
     F.flagOut = (uint8_t*)f->flags.p;
+    F.accum = (float4*)f->accum.p;   // nullptr unless float accumulation is on
+    F.doneCount = (unsigned long long*)f->doneCount.p;
+    if (F.accum && variant == kKernelSimple) {
+        err = "float accumulation is implemented by the wavefront pipeline only";
+        return false;
+    }
+    OCLR_CUDA(cudaMemsetAsync(F.doneCount, 0, sizeof(unsigned long long), st));
+    f->jobPaths.store((unsigned long long)launch_rows(F) * f->cam.width * (F.sampleEnd - F.sampleBegin));
     Counters* dcnt = (Counters*)f->counters.p;
     if (count) OCLR_CUDA(cudaMemsetAsync(dcnt, 0, sizeof(Counters), st));
     const size_t shBytes = sizeof(float) * 3 * (s->view.n + 1);
@@ -907,6 +932,10 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
     } else {
         err = "unknown kernel variant";
         return false;
+    }
+    if (F.accum) {
+        resolve_accum_kernel<<<dim3((f->cam.width + 255) / 256, launch_rows(F)), 256, 0, st>>>(F);
+        ++launches;
     }
     OCLR_CUDA(cudaGetLastError());
     f->lastLaunches = launches;
@@ -943,20 +972,22 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
     return true;
 }
 
-bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
-                  RenderStats* stats, std::string& err) {
+bool frame_render(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t rowBegin, uint32_t rowEnd, int variant,
+                  bool count, void* stream, RenderStats* stats, std::string& err) {
     if (!f) {
         err = "null frame";
         return false;
     }
     OCLR_CUDA(cudaSetDevice(f->scene->device));
     if (rowEnd > f->cam.height) rowEnd = f->cam.height;
-    if (sampleCount == 0 || rowBegin >= rowEnd) {
+    if (sampleCount == 0 || rowBegin >= rowEnd || sampleBegin >= sampleEnd || sampleEnd > sampleCount) {
         err = "empty render request";
         return false;
     }
     FrameView F = {};
     F.sampleCount = sampleCount;
+    F.sampleBegin = sampleBegin;
+    F.sampleEnd = sampleEnd;
     F.rowBegin = rowBegin;
     F.rowEnd = rowEnd;
     F.bandRows = 0;
@@ -966,20 +997,22 @@ bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t ro
     return frame_launch(f, F, variant, count, stream, stats, err);
 }
 
-bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, int variant, bool count,
-                        void* stream, RenderStats* stats, std::string& err) {
+bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t bandRows, uint32_t rank, uint32_t world,
+                        int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
     if (!f) {
         err = "null frame";
         return false;
     }
     OCLR_CUDA(cudaSetDevice(f->scene->device));
-    if (sampleCount == 0 || bandRows == 0 || world == 0 || rank >= world) {
+    if (sampleCount == 0 || bandRows == 0 || world == 0 || rank >= world || sampleBegin >= sampleEnd || sampleEnd > sampleCount) {
         err = "bad band request";
         return false;
     }
-    if (world == 1) return frame_render(f, sampleCount, 0, f->cam.height, variant, count, stream, stats, err);
+    if (world == 1) return frame_render(f, sampleCount, sampleBegin, sampleEnd, 0, f->cam.height, variant, count, stream, stats, err);
     FrameView F = {};
     F.sampleCount = sampleCount;
+    F.sampleBegin = sampleBegin;
+    F.sampleEnd = sampleEnd;
     F.rowBegin = 0;
     F.rowEnd = f->cam.height;
     F.bandRows = bandRows;
@@ -1010,6 +1043,82 @@ bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, ui
     OCLR_CUDA(cudaMemcpyAsync(outG + off, d + P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
     OCLR_CUDA(cudaMemcpyAsync(outB + off, d + 2 * P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
     OCLR_CUDA(cudaStreamSynchronize(st));
+    return true;
+}
+
+// Host -> device copy of rows [rowBegin,rowEnd) of the three planes: restores a checkpoint taken with frame_read after k samples;
+// the job then continues with frame_render(sampleBegin = k).
+bool frame_write(Frame* f, uint32_t rowBegin, uint32_t rowEnd, const uint16_t* inR, const uint16_t* inG, const uint16_t* inB, void* stream,
+                 std::string& err) {
+    if (!f) {
+        err = "null frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rowEnd > f->cam.height) rowEnd = f->cam.height;
+    if (rowBegin >= rowEnd) return true;
+    const size_t P = (size_t)f->cam.width * f->cam.height;
+    const size_t off = (size_t)rowBegin * f->cam.width, cnt = (size_t)(rowEnd - rowBegin) * f->cam.width;
+    uint16_t* d = (uint16_t*)f->planesRGB.p;
+    OCLR_CUDA(cudaMemcpyAsync(d + off, inR + off, cnt * 2, cudaMemcpyHostToDevice, st));
+    OCLR_CUDA(cudaMemcpyAsync(d + P + off, inG + off, cnt * 2, cudaMemcpyHostToDevice, st));
+    OCLR_CUDA(cudaMemcpyAsync(d + 2 * P + off, inB + off, cnt * 2, cudaMemcpyHostToDevice, st));
+    OCLR_CUDA(cudaStreamSynchronize(st));
+    return true;
+}
+
+// Accumulation mode: 0 = the reference's 16-bit planes with per-sample truncation, 1 = fp32 sums (allocates 16 B per pixel).
+bool frame_set_accumulation(Frame* f, int mode, std::string& err) {
+    if (!f || (mode != 0 && mode != 1)) {
+        err = "bad accumulation mode";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    if (mode == 0) {
+        f->accum.release();
+        f->accum.bytes = 0;
+        return true;
+    }
+    if (!f->accum.p) {
+        const size_t P = (size_t)f->cam.width * f->cam.height;
+        if (!f->accum.alloc(sizeof(float4) * P, err)) return false;
+        OCLR_CUDA(cudaMemsetAsync(f->accum.p, 0, sizeof(float4) * P, 0));
+        OCLR_CUDA(cudaStreamSynchronize(0));
+    }
+    return true;
+}
+
+// The fp32 accumulator, (sum r, sum g, sum b, samples) per pixel: read (checkpoint / float output) or write (resume).
+bool frame_accum_copy(Frame* f, float* host, bool toHost, std::string& err) {
+    if (!f || !f->accum.p || !host) {
+        err = "float accumulation is not enabled on this frame";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const size_t bytes = sizeof(float4) * (size_t)f->cam.width * f->cam.height;
+    if (toHost)
+        OCLR_CUDA(cudaMemcpy(host, f->accum.p, bytes, cudaMemcpyDeviceToHost));
+    else
+        OCLR_CUDA(cudaMemcpy(f->accum.p, host, bytes, cudaMemcpyHostToDevice));
+    return true;
+}
+
+// Progress of the render call in flight on this frame: pixel-samples finished / pixel-samples requested.  Safe to call from another
+// thread while frame_render runs (raytrace.c:156-173 polls from the UI thread); reads a device counter through its own stream.
+bool frame_progress(Frame* f, unsigned long long* done, unsigned long long* total) {
+    if (!f) return false;
+    std::lock_guard<std::mutex> lock(f->progMutex);
+    *total = f->jobPaths.load();
+    *done = 0;
+    if (*total == 0 || !f->progStream) return true;
+    if (cudaSetDevice(f->scene->device) != cudaSuccess) return false;
+    if (cudaMemcpyAsync(f->hostDone, f->doneCount.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, f->progStream) != cudaSuccess ||
+        cudaStreamSynchronize(f->progStream) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    *done = std::min(*f->hostDone, *total);
     return true;
 }
 

@@ -91,11 +91,21 @@ struct RenderStats {
 // Renders rows [rowBegin,rowEnd) with `sampleCount` samples into the frame's device planes (zeroed first, like the
 // OpenCL branch raytrace.c:476-486).  `stream` is a cudaStream_t (0 = default stream).  Synchronous w.r.t. the host
 // only when `stats` is non-null (it needs the event time).
-bool frame_render(Frame* f, uint32_t sampleCount, uint32_t rowBegin, uint32_t rowEnd, int variant, bool count, void* stream,
-                  RenderStats* stats, std::string& err);
+// Samples [sampleBegin,sampleEnd) of a sampleCount-sample job: sample 0 overwrites the planes, later samples add to them
+// (raytrace_opencl.c:726-741), so a job can be rendered progressively over several calls.
+bool frame_render(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t rowBegin, uint32_t rowEnd, int variant,
+                  bool count, void* stream, RenderStats* stats, std::string& err);
 // Same, for the rows y with (y / bandRows) % world == rank (one launch covers all bands the rank owns).
-bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, int variant, bool count,
-                        void* stream, RenderStats* stats, std::string& err);
+bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t bandRows, uint32_t rank, uint32_t world,
+                        int variant, bool count, void* stream, RenderStats* stats, std::string& err);
+// Progressive accumulation / checkpoint-resume / progress; see runtime.cu.
+bool frame_write(Frame* f, uint32_t rowBegin, uint32_t rowEnd, const uint16_t* inR, const uint16_t* inG, const uint16_t* inB, void* stream,
+                 std::string& err);
+bool frame_set_accumulation(Frame* f, int mode, std::string& err);
+bool frame_accum_copy(Frame* f, float* host, bool toHost, std::string& err);
+bool frame_progress(Frame* f, unsigned long long* done, unsigned long long* total);
+// Slices a launch domain is cut into (runtime.cu launch_wavefront): 0 = automatic, k = always k.
+void set_slice_count(int k);
 uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint32_t world);
 // Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,

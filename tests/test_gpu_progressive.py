@@ -1,0 +1,177 @@
+"""GPU suite for the rows SURVEY.md section 8f-3 / 8f-4 add around the trace path: progressive accumulation over sample ranges
+(raytrace_opencl.c:726-741), checkpoint / resume through the 16-bit planes, the fp32 accumulation option, the live progress
+counter (raytrace.c:156-173, 566-587) and the slice cut of a launch domain.  Everything goes through the C-ABI; expected
+values are the golden vectors generated from the reference build."""
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from opencl_render_b200 import _lib, api
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _gold(name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    return g["r"], g["g"], g["b"]
+
+
+def _equal(img, want):
+    return all(np.array_equal(img[c], want[c]) for c in range(3))
+
+
+@pytest.mark.parametrize("variant", [api.KERNEL_SIMPLE, api.KERNEL_PIPE])
+@pytest.mark.parametrize("name,cuts", [("soup_s4", [0, 1, 3, 4]), ("soup_mirror_glass", [0, 2, 3]), ("spheres_mirror", [0, 1, 2])])
+def test_sample_ranges_accumulate_to_the_whole_job(name, cuts, variant):
+    sc, cam, lists, samples = helpers.make_case(name)
+    assert cuts[-1] == samples
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        fr.render(samples, variant=variant, samples=(a, b))
+    assert _equal(fr.read(), _gold(name))
+    with pytest.raises(api.OclrError):
+        fr.render(samples, samples=(2, samples + 1))
+
+
+def test_checkpoint_and_resume_on_another_frame():
+    sc, cam, lists, samples = helpers.make_case("soup_s4")
+    ds = api.DeviceScene(sc, 0)
+    a = api.DeviceFrame(ds, cam, lists)
+    a.render(samples, samples=(0, 2))
+    saved = a.read()
+    a.close()
+    b = api.DeviceFrame(ds, cam, lists)
+    b.write(saved)
+    assert _equal(b.read(), saved)
+    b.render(samples, samples=(2, samples))
+    assert _equal(b.read(), _gold("soup_s4"))
+
+
+def test_float_accumulation_one_sample_equals_reference_planes():
+    sc, cam, lists, samples = helpers.make_case("spheres")
+    assert samples == 1
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.set_accumulation(api.ACCUMULATE_FLOAT)
+    fr.render(1)
+    assert _equal(fr.read(), _gold("spheres"))
+    acc = fr.read_accum()
+    assert np.all(acc[..., 3] == 1.0)
+
+
+@pytest.mark.parametrize("name", ["soup_s4", "soup_mirror_glass"])
+def test_float_accumulation_bounds_the_truncation_loss(name):
+    """Reference: sum_i trunc(c_i * 65535/S); float mode: trunc(sum_i c_i * 65535/S).  Each truncation loses [0, 1) of a 16-bit
+    step, so float - reference lies in [0, S) up to one step of fp32 rounding -- and the progressive float job resumes exactly."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.set_accumulation(api.ACCUMULATE_FLOAT)
+    fr.render(samples)
+    img = fr.read()
+    want = _gold(name)
+    for c in range(3):
+        d = img[c].astype(np.int64) - want[c].astype(np.int64)
+        sat = want[c] == 65535
+        assert d[~sat].min() >= -1 and d[~sat].max() <= samples, (d.min(), d.max())
+    acc = fr.read_accum()
+    assert np.all(acc[..., 3] == float(samples))
+    # resume the float job on a second frame from the accumulator after the first sample
+    one = api.DeviceFrame(ds, cam, lists)
+    one.set_accumulation(api.ACCUMULATE_FLOAT)
+    one.render(samples, samples=(0, 1))
+    part = one.read_accum()
+    two = api.DeviceFrame(ds, cam, lists)
+    two.set_accumulation(api.ACCUMULATE_FLOAT)
+    two.write_accum(part)
+    two.render(samples, samples=(1, samples))
+    assert _equal(two.read(), img) and np.array_equal(two.read_accum(), acc)
+    with pytest.raises(api.OclrError):
+        two.render(samples, variant=api.KERNEL_SIMPLE)          # float mode is a wavefront-pipeline feature
+    two.set_accumulation(api.ACCUMULATE_REFERENCE_16BIT)
+    two.render(samples)
+    assert _equal(two.read(), want)
+
+
+@pytest.mark.parametrize("slices", [2, 3, 5])
+def test_sliced_launch_domain_is_invisible(slices):
+    try:
+        for name in ("spheres", "soup_s4", "terrain_textured"):
+            sc, cam, lists, samples = helpers.make_case(name)
+            ds = api.DeviceScene(sc, 0)
+            fr = api.DeviceFrame(ds, cam, lists)
+            api.set_option("slices", 1)
+            fr.render(samples)
+            whole, ids, flags = fr.read(), fr.primary_ids(), fr.undefined_flags()
+            api.set_option("slices", slices)
+            _, launches, cnt = fr.render(samples, count=True)
+            assert _equal(fr.read(), whole) and np.array_equal(fr.primary_ids(), ids) and np.array_equal(fr.undefined_flags(), flags)
+            assert launches >= 3 * slices and cnt["segments"] > 0
+            # the band set of one rank is cut into sub-band sets
+            out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
+            for rank in range(2):
+                fr.render_bands(samples, 16, rank, 2)
+                for rows in api.band_partition(cam.height, rank, 2, band_rows=16):
+                    fr.read(rows=rows, out=out)
+            assert _equal(out, whole)
+    finally:
+        api.set_option("slices", 0)
+    with pytest.raises(api.OclrError):
+        api.set_option("no_such_option", 1)
+
+
+def test_progress_counter_counts_pixel_samples():
+    sc, cam, lists, _ = helpers.make_case("spheres")
+    samples = 24
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    total = cam.width * cam.height * samples
+    seen = []
+    stop = threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            seen.append(fr.progress())
+
+    t = threading.Thread(target=poll)
+    t.start()
+    try:
+        fr.render(samples)
+    finally:
+        stop.set()
+        t.join()
+    assert fr.progress() == (total, total)
+    done = [d for d, tot in seen if tot == total]
+    assert done == sorted(done) and all(0 <= d <= total for d in done)
+    fr.render(samples, rows=(8, 24), samples=(3, 5))
+    assert fr.progress() == (16 * cam.width * 2, 16 * cam.width * 2)
+
+
+def test_raytrace_all_reports_live_progress():
+    lib = _lib.load()
+    sc, cam, lists, _ = helpers.make_case("spheres")
+    seen = []
+    stop = threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            seen.append((float(lib.GetProgress()), float(lib.oclr_estimated_seconds_left())))
+
+    lib.SetProgress(0.0)
+    t = threading.Thread(target=poll)
+    t.start()
+    try:
+        api.raytrace_all(1, cam, lists, 48, sc)
+    finally:
+        stop.set()
+        t.join()
+    p = [a for a, _ in seen]
+    assert all(0.0 <= a <= 0.9991 for a in p)
+    assert abs(lib.GetProgress() - 0.999) < 1e-4            # raytrace.c:580: the call itself never reports 1.0 (render.cpp:1397 does)
+    assert any(0.0 < a < 0.999 for a in p), "no intermediate progress value was observed"
+    assert all(e >= -1.0 for _, e in seen)
