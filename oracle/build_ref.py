@@ -59,7 +59,9 @@ def reference_available() -> bool:
 def build(force: bool = False, verbose: bool = True) -> Path | None:
     """Build oracle/_ref/libref_raytrace.so.  Returns its path, or None when /root/reference is absent
     (the GPU box: it only uses the prebuilt file that travelled with the snapshot)."""
-    if LIB.is_file() and not force:
+    shim = Path(__file__).resolve().parent / "ref_shim.cpp"
+    stale = LIB.is_file() and reference_available() and shim.stat().st_mtime > LIB.stat().st_mtime   # our shim changed
+    if LIB.is_file() and not force and not stale:
         return LIB
     if not reference_available():
         return LIB if LIB.is_file() else None

@@ -51,6 +51,8 @@ def load() -> C.CDLL:
         assert _lib.port_job_size() == C.sizeof(Job), "port_job layout mismatch"
         _lib.port_render_rows.restype = None
         _lib.port_render_rows.argtypes = [C.POINTER(Job), C.c_uint32, C.c_uint32, C.c_int]
+        _lib.port_render_rows_step.restype = None
+        _lib.port_render_rows_step.argtypes = [C.POINTER(Job), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         _lib.port_kat_rand.restype = C.c_float
         _lib.port_kat_rand.argtypes = [C.POINTER(C.c_uint64), C.c_float, C.c_float]
         _lib.port_kat_hit.restype = C.c_int
@@ -64,8 +66,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-def render(camera, lists, scene, samples: int = 1, threads: int | None = None, rows=None, want_ids: bool = False):
-    """CPU render of rows [rows[0], rows[1]) with the C port.  Returns (r, g, b) uint16 [H,W] (+ ids uint32 [H,W])."""
+def render(camera, lists, scene, samples: int = 1, threads: int | None = None, rows=None, want_ids: bool = False, row_step: int = 1):
+    """CPU render of rows [rows[0], rows[1]) -- every row_step-th of them -- with the C port.  Returns (r, g, b) uint16 [H,W]
+    (+ ids uint32 [H,W])."""
     lib = load()
     h, w = camera.height, camera.width
     r0, r1 = rows if rows is not None else (0, h)
@@ -92,7 +95,7 @@ def render(camera, lists, scene, samples: int = 1, threads: int | None = None, r
     j.light_colour, j.light_radius, j.light_half = _p(scene.light_colour), _p(scene.light_radius), _p(scene.light_half)
     j.out_r, j.out_g, j.out_b = _p(out[0]), _p(out[1]), _p(out[2])
     j.primary_id = _p(ids) if want_ids else None
-    lib.port_render_rows(C.byref(j), r0, r1, threads or (os.cpu_count() or 1))
+    lib.port_render_rows_step(C.byref(j), r0, r1, row_step, threads or (os.cpu_count() or 1))
     return (out[0], out[1], out[2], ids) if want_ids else tuple(out)
 
 

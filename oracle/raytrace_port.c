@@ -423,14 +423,14 @@ void port_pixel_sample(const port_job* j, uint32_t pixel, uint32_t sample_id) {
 /* ---- flat entry points for ctypes --------------------------------------------------------------------------------- */
 typedef struct {
     const port_job* job;
-    uint32_t row_begin, row_end;
+    uint32_t row_begin, row_end, row_step;
     volatile uint32_t* next_row;
 } port_worker;
 
 static void* port_worker_main(void* arg) {
     port_worker* w = (port_worker*)arg;
     for (;;) {
-        const uint32_t row = __sync_fetch_and_add(w->next_row, 1u);
+        const uint32_t row = __sync_fetch_and_add(w->next_row, w->row_step);
         uint32_t x, s;
         if (row >= w->row_end) break;
         for (x = 0; x < w->job->width; ++x)
@@ -439,18 +439,22 @@ static void* port_worker_main(void* arg) {
     return 0;
 }
 
-/* Renders rows [row_begin,row_end) into planes that the caller zeroed; `threads` host threads. */
-void port_render_rows(const port_job* job, uint32_t row_begin, uint32_t row_end, int threads) {
+/* Renders rows row_begin, row_begin + row_step, ... below row_end into planes that the caller zeroed; `threads` host threads. */
+void port_render_rows_step(const port_job* job, uint32_t row_begin, uint32_t row_end, uint32_t row_step, int threads) {
     volatile uint32_t next = row_begin;
     port_worker w;
     pthread_t tid[256];
     int i;
     if (row_end > job->height) row_end = job->height;
-    w.job = job; w.row_begin = row_begin; w.row_end = row_end; w.next_row = &next;
+    w.job = job; w.row_begin = row_begin; w.row_end = row_end; w.row_step = row_step ? row_step : 1u; w.next_row = &next;
     if (threads > 256) threads = 256;
     if (threads <= 1) { port_worker_main(&w); return; }
     for (i = 0; i < threads; ++i) pthread_create(&tid[i], 0, port_worker_main, &w);
     for (i = 0; i < threads; ++i) pthread_join(tid[i], 0);
+}
+
+void port_render_rows(const port_job* job, uint32_t row_begin, uint32_t row_end, int threads) {
+    port_render_rows_step(job, row_begin, row_end, 1u, threads);
 }
 
 size_t port_job_size(void) { return sizeof(port_job); }

@@ -58,6 +58,8 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ref_raytrace_all.restype = C.c_uint32
     lib.ref_raytrace_all.argtypes = [C.c_uint32] + lib.ref_raytrace_threads.argtypes[3:]
+    lib.ref_raytrace_threads_step.restype = None
+    lib.ref_raytrace_threads_step.argtypes = lib.ref_raytrace_threads.argtypes[:3] + [C.c_uint32] + lib.ref_raytrace_threads.argtypes[3:]
     _lib = lib
     return lib
 
@@ -121,15 +123,16 @@ def _scene_args(camera, lists, scene, samples):
     return args, keep
 
 
-def render(camera, lists, scene, samples: int = 1, threads: int | None = None, rows=None):
-    """The reference kernel (compiled as C) over rows [rows[0], rows[1]) on `threads` host threads (default: all cores).
+def render(camera, lists, scene, samples: int = 1, threads: int | None = None, rows=None, row_step: int = 1):
+    """The reference kernel (compiled as C) over rows [rows[0], rows[1]) -- every row_step-th of them -- on `threads` host threads
+    (default: all cores).
     Bit-identical to RaytraceAll(0, ...) for any thread count (the C-path seed depends only on pixel and sample)."""
     lib = load()
     h, w = camera.height, camera.width
     r0, r1 = rows if rows is not None else (0, h)
     out = [np.zeros((h, w), np.uint16) for _ in range(3)]
     args, keep = _scene_args(camera, lists, scene, samples)
-    lib.ref_raytrace_threads(threads or (os.cpu_count() or 1), r0, r1, *args, _p(out[0]), _p(out[1]), _p(out[2]))
+    lib.ref_raytrace_threads_step(threads or (os.cpu_count() or 1), r0, r1, row_step, *args, _p(out[0]), _p(out[1]), _p(out[2]))
     return tuple(out)
 
 

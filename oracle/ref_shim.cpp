@@ -87,7 +87,8 @@ void ref_scene_list_free(void* p) { delete (SceneTriangleList*)p; }
 // ---- the reference kernel on N host threads --------------------------------------------------------
 // Rows [rowBegin, rowEnd) only (so a bounded sample of a big frame can be timed); rows are dealt to
 // threads dynamically.  Output planes are full-frame sized; untouched rows keep their contents.
-void ref_raytrace_threads(int nThreads, cl_uint rowBegin, cl_uint rowEnd,
+// rowStep > 1: only rows rowBegin, rowBegin + rowStep, ... (a sample spread evenly over the frame).
+void ref_raytrace_threads_step(int nThreads, cl_uint rowBegin, cl_uint rowEnd, cl_uint rowStep,
                           cl_uint w, cl_uint h, const float* eye, const float* eyeToTopLeft,
                           const float* leftToRight, const float* topToBottom, float pixelSizeInv,
                           cl_uint* camStart, cl_uint* camEnd, cl_uint* camList, cl_uint sampleCount,
@@ -107,7 +108,7 @@ void ref_raytrace_threads(int nThreads, cl_uint rowBegin, cl_uint rowEnd,
         cl_uint2 d = dim; cl_float3 le = e, ltl = tl, llr = lr, ltb = tb; cl_float psi = pixelSizeInv;
         cl_uint sc = sampleCount, tc = triangleCount, lc = lightCount; cl_int adc = axesDivCount;
         for (;;) {
-            cl_uint row = nextRow.fetch_add(1);
+            cl_uint row = nextRow.fetch_add(rowStep ? rowStep : 1);
             if (row >= rowEnd) break;
             for (cl_uint x = 0; x < w; ++x) {
                 cl_uint pixel = row * w + x;
@@ -125,6 +126,22 @@ void ref_raytrace_threads(int nThreads, cl_uint rowBegin, cl_uint rowEnd,
     std::vector<std::thread> pool;
     for (int t = 0; t < nThreads; ++t) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
+}
+
+void ref_raytrace_threads(int nThreads, cl_uint rowBegin, cl_uint rowEnd,
+                          cl_uint w, cl_uint h, const float* eye, const float* eyeToTopLeft,
+                          const float* leftToRight, const float* topToBottom, float pixelSizeInv,
+                          cl_uint* camStart, cl_uint* camEnd, cl_uint* camList, cl_uint sampleCount,
+                          cl_float3* vertex, cl_uint triangleCount, cl_int3* triIdx, cl_int* triMat,
+                          cl_float2* triUv, cl_float3* triNormal, cl_int axesDivCount, cl_float3* boxMin,
+                          cl_uint* gridStart, cl_uint* gridList, cl_uint2* matSize, cl_int* matStart,
+                          cl_uchar3* textures, cl_uint lightCount, cl_int* lightType, cl_float3* lightPos,
+                          cl_float3* lightDir, cl_float3* lightColour, cl_float* lightRadius,
+                          cl_float* lightHalf, cl_ushort* outR, cl_ushort* outG, cl_ushort* outB) {
+    ref_raytrace_threads_step(nThreads, rowBegin, rowEnd, 1, w, h, eye, eyeToTopLeft, leftToRight, topToBottom, pixelSizeInv, camStart, camEnd,
+                              camList, sampleCount, vertex, triangleCount, triIdx, triMat, triUv, triNormal, axesDivCount, boxMin, gridStart,
+                              gridList, matSize, matStart, textures, lightCount, lightType, lightPos, lightDir, lightColour, lightRadius,
+                              lightHalf, outR, outG, outB);
 }
 
 // ---- the reference's own RaytraceAll through a pointer-only door (ctypes cannot pass the vector unions by value) ------
