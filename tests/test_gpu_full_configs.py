@@ -1,0 +1,121 @@
+"""BASELINE.json configs 3, 4 and 5 at FULL size on the GPU (config 1 = the `soup` family, config 2 = test_gpu_parity.py).
+At these sizes the reference needs minutes per frame on the host, so each test compares a band of rows bit for bit with the
+reference build (oracle/_ref, or the C port when that did not travel) and checks size-independent properties on the whole frame:
+the id-material decode equals the id plane, a frame assembled from 8 ranks' bands equals the single-GPU frame, device-built
+lists equal the host builder's."""
+import numpy as np
+import pytest
+
+from opencl_render_b200 import api, scenes
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(port):
+    try:
+        import ref
+        if ref.available():
+            ref.load()
+            return ref
+    except Exception:
+        pass
+    return port
+
+
+def _setup(cfg_id):
+    cfg = scenes.CONFIGS[cfg_id]
+    sc = cfg["make"]()
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+    lists = api.camera_triangle_list(cam, sc)
+    api.scene_triangle_list(sc, 256)
+    return cfg, sc, cam, lists
+
+
+def _band_equals_oracle(oracle, cam, lists, sc, samples, img, flags, rows):
+    want = oracle.render(cam, lists, sc, samples, rows=rows)
+    sl = slice(*rows)
+    bad = sum(int(((img[c][sl] != want[c][sl]) & (flags[sl] == 0)).sum()) for c in range(3))
+    res = helpers.compare_rgb(tuple(p[sl] for p in img), tuple(p[sl] for p in want))
+    return bad, res
+
+
+def test_config3_terrain_1m_4k(port):
+    cfg, sc, cam, lists = _setup(3)
+    assert sc.triangle_count == 1002528 and (cam.width, cam.height) == (3840, 2160)
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(1)
+    img, ids, flags = fr.read(), fr.primary_ids(), fr.undefined_flags()
+    assert flags.sum() == 0
+    bad, res = _band_equals_oracle(_oracle(port), cam, lists, sc, 1, img, flags, (1000, 1064))
+    assert bad == 0 and res["diff_pixels"] == 0, res
+    # screen-band partition at 8 ranks reproduces the frame
+    out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
+    for rank in range(8):
+        fr.render_bands(1, 128, rank, 8)
+        for rows in api.band_partition(cam.height, rank, 8):
+            fr.read(rows=rows, out=out)
+    assert all(np.array_equal(out[c], img[c]) for c in range(3))
+    # lists built on the device are the host builder's
+    dev = api.DeviceFrame(ds, cam)
+    got = dev.camera_lists()
+    assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
+    dev.close()
+    fr.close()
+    ds.close()
+    idsc = scenes.id_material_variant(sc)
+    ds = api.DeviceScene(idsc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(1)
+    assert np.array_equal(scenes.decode_id_planes(*fr.read()), ids)
+
+
+def test_config4_terrain_10m_textured_8k(port):
+    cfg, sc, cam, lists = _setup(4)
+    assert sc.triangle_count == 10008338 and (cam.width, cam.height) == (7680, 4320) and sc.material_count == 11
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(1)
+    img, flags = fr.read(), fr.undefined_flags()
+    rows = (1000, 1032)
+    bad, res = _band_equals_oracle(_oracle(port), cam, lists, sc, 1, img, flags, rows)
+    # bit-exact wherever the reference's own result is defined; the flagged pixels (uninitialised read in the reference's bump
+    # path, include/oclr_abi.h) are few and still inside the stated tolerance as an image
+    assert bad == 0, res
+    assert res["diff_pixels"] <= int(flags[rows[0]:rows[1]].sum()) and flags.mean() < 1e-3
+    assert res["psnr"] >= helpers.PSNR_MIN, res
+    # one rank's band share of an 8-GPU render (the configuration config 4 is quoted on) equals those rows of the frame
+    fr.render_bands(1, 128, 3, 8)
+    part = fr.read()
+    for rows in api.band_partition(cam.height, 3, 8):
+        assert all(np.array_equal(part[c][rows[0]:rows[1]], img[c][rows[0]:rows[1]]) for c in range(3))
+
+
+def test_config5_camera_sweep_upload_once(port):
+    cfg = scenes.CONFIGS[5]
+    sc = cfg["make"]()
+    api.scene_triangle_list(sc, 256)
+    ds = api.DeviceScene(sc, 0)                        # uploaded once for all 64 frames
+    cams = scenes.sweep_cameras(sc, cfg["frames"])
+    assert len(cams) == 64
+    oracle = _oracle(port)
+    lit = []
+    for k, m in enumerate(cams):
+        if k not in (0, 21, 42, 63):
+            continue
+        cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+        fr = api.DeviceFrame(ds, cam)                  # per-frame camera lists built on the device
+        _, launches, cnt = fr.render(cfg["samples"], count=True)
+        img, flags = fr.read(), fr.undefined_flags()
+        lists = api.camera_triangle_list(cam, sc)
+        got = fr.camera_lists()
+        assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
+        bad, res = _band_equals_oracle(oracle, cam, lists, sc, cfg["samples"], img, flags, (500, 532))
+        assert bad == 0, (k, res)
+        # mirror chains run to the reference's maximum bounce depth (12): far more rounds than the 4 of a diffuse scene
+        assert launches >= 3 * 13 and cnt["segments"] > cam.width * cam.height
+        lit.append(int((img[0] > 0).sum()))
+        fr.close()
+    assert min(lit) > 0.5 * cfg["width"] * cfg["height"]
