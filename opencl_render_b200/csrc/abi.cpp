@@ -155,6 +155,10 @@ int oclr_set_option(const char* name, int value) {
         set_slice_count(value);
         return 1;
     }
+    if (name && strcmp(name, "ahead") == 0) {
+        set_ahead_mode(value);
+        return 1;
+    }
     fail(std::string("oclr_set_option: unknown option ") + (name ? name : "(null)"));
     return 0;
 }

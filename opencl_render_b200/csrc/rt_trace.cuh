@@ -33,7 +33,7 @@ struct TraceTuning {
 };
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
-enum { kLengthClasses = 4 };
+enum { kLengthClasses = 4, kRoundLogSize = 64 };
 struct WalkRecords {
     float4* o;    // (o.xyz, minD)
     float4* d;    // (r.xyz, maxD)
@@ -71,6 +71,7 @@ __device__ __forceinline__ int walk_length_estimate(const PackedWalk& g, int n, 
 __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, WalkRecords rec) {
     extern __shared__ float shPlanes[];
     const uint32_t count = *w.queueCount;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && w.roundIndex < kRoundLogSize) w.roundLog[w.roundIndex] = count;
     if (blockIdx.x * blockDim.x >= count) return;
     load_planes(shPlanes, S);
     const int n = S.n;

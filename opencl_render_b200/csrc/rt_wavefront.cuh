@@ -15,6 +15,17 @@
 //
 // The host enqueues rounds of (logic, setup, trace) ahead until a round finds no path waiting; the arithmetic is rt_core.h /
 // rt_walk.h, identical to the simple kernel, so results are bit-identical by construction (tests assert it).
+//
+// Running one trace ahead.  In the reference a ring segment is finished (:639-722: colour, then the spawn of the diffuse / mirror /
+// glass segments) only after the shadow rays of all its lights have returned, and only then is the next segment popped and traced.
+// But the spawn depends on nothing the shadow rays return (weights = segment multiplier x texture x reflectance/transparency; the
+// bounce direction = the next RNG draws, and the shadow loop :608-627 draws none), and the next segment's closest-hit query depends
+// only on the ring.  So when a path suspends for the shadow ray of its LAST light it performs the spawn at once (same RNG position
+// as the reference: right after that light's sample draws) and, if the ring then holds a next non-camera segment, queues that
+// segment's closest-hit ray in the same round through a second ray slot.  When the shadow result arrives the segment's colour is
+// accumulated (the only thing that needed it) and the next segment continues with its hit already there.  A diffuse frame needs
+// 2 trace rounds instead of 3 (shadow + bounce | bounce's shadow), a mirror chain of depth d about d instead of 2d; fewer, fuller
+// trace launches and one pass less of the logic kernel over the path state.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,6 +36,7 @@
 namespace oclr {
 
 enum WfStage { kWfDone = 0, kWfNew = 1, kWfWaitClosest = 2, kWfWaitShadow = 3 };
+enum : uint32_t { kCtlSpawned = 1u << 28, kCtlAhead = 1u << 29 };   // ctl = stage | begin << 4 | end << 8 | light << 12 | flags
 enum { kCarryParts = 7, kRingParts = 3 };
 
 // Path state (device pointers; Q = paths in the launch domain).  All float4 planes are [part][Q].
@@ -35,13 +47,17 @@ struct WfState {
     float4* colour;
     float4* ring;        // [slot * 3 + part][Q]
     float4* carry;       // [part][Q], part < 7
+    // two ray slots per path, slot-major [slot * Q + path]: slot 0 = the query the path is suspended on, slot 1 = the closest-hit
+    // query of the NEXT ring segment traced one round ahead.  Queue entries are these flat indices (the trace stage knows no paths).
     float4* rayO;        // (o.xyz, minD)
     float4* rayD;        // (d.xyz, maxD)
     uint32_t* rayExcl;
     float4* hit;         // (as_float(tri), t, abL, acL)
-    uint32_t* queue;     // path indices waiting for a trace
+    uint32_t* queue;     // ray indices waiting for a trace (up to 2 Q)
     uint32_t* queueCount;
     uint32_t* queueCursor;
+    uint32_t* roundLog;  // rays queued per round of the current sample (written by the setup kernel): tells the host how many rounds
+    uint32_t roundIndex; // the sample really needed, so that the next one enqueues exactly that many ahead
 };
 
 struct Segment {
@@ -74,16 +90,17 @@ __device__ __forceinline__ Segment ring_load(const WfState& w, uint32_t q, int s
     return s;
 }
 
-// Appends path q to the ray queue: one atomic per warp (ballot + popc + shuffle).
-__device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want) {
-    const unsigned m = __ballot_sync(__activemask(), want);
-    if (!want) return;
+// Appends ray index q (slot 0) and / or Q + q (slot 1) to the ray queue: one atomic per warp (ballot + popc + shuffle).
+__device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want0, bool want1) {
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
+    if ((m0 | m1) == 0u) return;
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(w.queueCount, (uint32_t)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    w.queue[base + __popc(m & ((1u << lane) - 1u))] = q;
+    if (lane == 0) base = atomicAdd(w.queueCount, (uint32_t)(__popc(m0) + __popc(m1)));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (want0) w.queue[base + __popc(m0 & lt)] = q;
+    if (want1) w.queue[base + __popc(m0) + __popc(m1 & lt)] = w.Q + q;
 }
 
 // ---- logic kernel -----------------------------------------------------------------------------------------------------
@@ -93,7 +110,7 @@ __device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(SceneView S, FrameView F, WfState w, uint32_t sampleIdx, uint32_t startSample,
-                                                       const uint32_t* prevCount, Counters* gcnt) {
+                                                       const uint32_t* prevCount, Counters* gcnt, int aheadMode) {
     // Rounds are enqueued ahead without a host round trip; a round whose predecessor traced no ray has nothing to resume.
     if (prevCount != nullptr && *prevCount == 0u) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,12 +122,14 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
     const uint32_t pixel = valid ? y * F.cam.width + x : 0;
     uint32_t ctl = valid ? (startSample ? (uint32_t)kWfNew : w.ctl[q]) : (uint32_t)kWfDone;
     int stage = (int)(ctl & 7u);
-    bool want = false, finished = false;
+    bool want = false, wantAhead = false, finished = false;
     if (stage != kWfDone) {
         Counters cnt = {};
         const Camera& cam = F.cam;
         int begin = (int)((ctl >> 4) & 15u), end = (int)((ctl >> 8) & 15u);
         uint32_t j = (ctl >> 12) & 0xFFFFu;
+        bool spawned = (ctl & kCtlSpawned) != 0u;   // the current segment's spawn (:656-722) was done ahead of its shadow result
+        bool ahead = (ctl & kCtlAhead) != 0u;       // slot 1 holds (or is about to receive) the next segment's closest hit
         uint64_t rng;
         f3 colour;
         Segment seg;
@@ -122,7 +141,8 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
         LightRay lr;
         bool undef = false;
         bool first = (stage == kWfNew);
-        enum { GO_SEGMENT, GO_SHADE, GO_LIGHTS, GO_FINISH, GO_POP, GO_EXIT } go;
+        enum { GO_SEGMENT, GO_SHADE, GO_LIGHTS, GO_FINISH, GO_SPAWN, GO_POP, GO_EXIT } go;
+        bool suspendAfterSpawn = false;
 
         if (stage == kWfNew) {
             rng = (uint64_t)pixel * (uint64_t)F.sampleCount + (uint64_t)(sampleIdx + 1u);
@@ -277,6 +297,13 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                         cp[6 * (size_t)w.Q] = make_float4(face[1].x, face[1].y, face[1].z, 0.f);
                         stage = kWfWaitShadow;
                         want = true;
+                        // last light: spawn now and trace the next segment one round ahead (aheadMode 2: every segment; 1: all but
+                        // camera segments -- on a large diffuse frame the primary hits gain nothing from it, see runtime.cu)
+                        if (!spawned && j + 1u == S.lightCount && (aheadMode == 2 || (aheadMode == 1 && !seg.cam))) {
+                            suspendAfterSpawn = true;
+                            go = GO_SPAWN;
+                            break;
+                        }
                         go = GO_EXIT;
                         break;
                     }
@@ -293,8 +320,15 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                 colour.x += (1.f - colour.x) * rm.x * (1.f - transp.x) * tex.x * light.x;
                 colour.y += (1.f - colour.y) * rm.y * (1.f - transp.y) * tex.y * light.y;
                 colour.z += (1.f - colour.z) * rm.z * (1.f - transp.z) * tex.z * light.z;
-                go = GO_POP;
+                go = spawned ? GO_POP : GO_SPAWN;
+                spawned = false;
+            } else if (go == GO_SPAWN) {
+                // :656-722 -- the segments the current hit spawns.  Reads nothing a shadow ray returns, so it may run before the
+                // segment's colour is accumulated ("running one trace ahead" at the top of this file); reached either from GO_FINISH
+                // (the reference's order) or from GO_LIGHTS right before the path suspends on its last light's shadow ray.
                 if (seg.maxB > 0) {
+                    const f3 rm = seg.mul, rv = seg.v;
+                    const int front = (int)(dot3(nrm, rv) <= 0.f);
                     float total = (refl.x + transp.x) > (refl.y + transp.y) ? (refl.x + transp.x) : (refl.y + transp.y);
                     total = total > (refl.z + transp.z) ? total : (refl.z + transp.z);
                     f3 diffuse = mk3(0.f, 0.f, 0.f);
@@ -342,6 +376,24 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                         }
                     }
                 }
+                if (!suspendAfterSpawn) {
+                    spawned = false;
+                    go = GO_POP;
+                } else {
+                    spawned = true;
+                    const int nb = (begin + 1) % kRingSize;
+                    if (nb != end) {
+                        const Segment nx = ring_load(w, q, nb);
+                        if (!nx.cam) {   // (a camera segment is resolved from the pixel's list by this kernel: nothing to trace)
+                            w.rayO[w.Q + q] = make_float4(nx.o.x, nx.o.y, nx.o.z, nx.minD);
+                            w.rayD[w.Q + q] = make_float4(nx.v.x, nx.v.y, nx.v.z, OCLR_INF);
+                            w.rayExcl[w.Q + q] = nx.excl;
+                            ahead = true;
+                            wantAhead = true;
+                        }
+                    }
+                    go = GO_EXIT;
+                }
             } else {  // GO_POP
                 begin = (begin + 1) % kRingSize;
                 if (begin == end) {
@@ -366,8 +418,19 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                     go = GO_EXIT;
                 } else {
                     seg = ring_load(w, q, begin);
-                    stage = kWfWaitClosest;  // provisional; GO_SEGMENT decides
-                    go = GO_SEGMENT;
+                    if (ahead) {   // this segment's closest hit was traced one round ahead (slot 1)
+                        ahead = false;
+                        const float4 h2 = w.hit[w.Q + q];
+                        hit = __float_as_uint(h2.x);
+                        hitT = h2.y;
+                        hitAB = h2.z;
+                        hitAC = h2.w;
+                        if (COUNT) cnt.segments++;
+                        go = (hit == kNoTriangle) ? GO_POP : GO_SHADE;
+                    } else {
+                        stage = kWfWaitClosest;  // provisional; GO_SEGMENT decides
+                        go = GO_SEGMENT;
+                    }
                 }
             }
         }
@@ -376,14 +439,15 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
             w.rng[q] = rng;
             w.colour[q] = make_float4(colour.x, colour.y, colour.z, 0.f);
         }
-        w.ctl[q] = (uint32_t)stage | ((uint32_t)begin << 4) | ((uint32_t)end << 8) | (j << 12);
+        w.ctl[q] = (uint32_t)stage | ((uint32_t)begin << 4) | ((uint32_t)end << 8) | (j << 12) | (spawned ? kCtlSpawned : 0u) |
+                   (ahead ? kCtlAhead : 0u);
         if (COUNT) flush_counters(cnt, gcnt);
     }
     if (F.doneCount) {   // progress: pixel-samples finished, one atomic per warp
         const unsigned fm = __ballot_sync(0xFFFFFFFFu, finished);
         if (fm != 0u && (threadIdx.x & 31) == 0) atomicAdd(F.doneCount, (unsigned long long)__popc(fm));
     }
-    enqueue(w, q, want);
+    enqueue(w, q, want, wantAhead);
 }
 
 // Planes from the float accumulator: out = (int)(sum * 65535 / samples so far), the reference's conversion (:726-741) applied once

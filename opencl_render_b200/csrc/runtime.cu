@@ -79,7 +79,7 @@ enum { kMaxSlices = 8 };
 struct WfSlice {
     DeviceBuffer ctl, rng, colour, ring, carry, rayO, rayD, rayExcl, hit, queue;
     DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
-    DeviceBuffer workCounter;                          // {count, cursor, class counts} x 2, alternating between rounds
+    DeviceBuffer workCounter;                          // {count, cursor, class counts} x 2, alternating between rounds; then the round log
     uint32_t capacity = 0;
     uint32_t lastRounds = 4;          // rounds the previous sample needed (first chunk of the next one)
     cudaStream_t stream = nullptr;    // internal stream (slice 0 runs on the caller's stream)
@@ -684,6 +684,23 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 // Measured (B200, gpurun_out/slices*.log): config 3 (8.3 M paths) 24.4 -> 23.7 ms with 2 slices, flat to 4, worse at 8; config 2
 // (2.1 M paths) 4.51 ms with 1 or 2 slices and slower beyond -- every slice's launches end in their own partly filled warps, which
 // costs what the overlap wins.  Default: one slice per 4 M paths, at most 4 (OCLR_SLICES=k forces k).
+// Tracing one round ahead (rt_wavefront.cuh): 0 never, 1 for every segment but the camera's, 2 for all.  -1 = automatic.
+static std::atomic<int> g_aheadMode(-2);
+void set_ahead_mode(int m) { g_aheadMode.store(m < -1 || m > 2 ? -1 : m); }
+static int ahead_mode_for(uint32_t paths) {
+    if (g_aheadMode.load() == -2) {
+        const char* v = getenv("OCLR_AHEAD");
+        set_ahead_mode(v ? atoi(v) : -1);
+    }
+    const int m = g_aheadMode.load();
+    if (m >= 0) return m;
+    // Measured on a B200 (scripts/ahead_probe.py, gpurun_out/ahead_probe*.log): config 2, 2.07 M paths: 4.54 / 4.54 / 4.52 ms for
+    // modes 0 / 1 / 2; its 1/8 band share 1.28 / 1.26 / 0.97 ms (two latency floors instead of three); config 3, 8.3 M paths:
+    // 24.7 / 24.7 / 25.4 ms (shadow and bounce rays of 8 M paths in one launch thrash the L2-resident working set); the mirror
+    // chains of config 5 need 48 launches per frame instead of 90 with mode 1 or 2 (27 -> 12 ms per frame).
+    return paths < 3000000u ? 2 : 1;
+}
+
 static std::atomic<int> g_sliceCount(-1);   // -1: not yet read from OCLR_SLICES; 0: automatic
 void set_slice_count(int k) { g_sliceCount.store(std::max(0, std::min(k, (int)kMaxSlices))); }
 static int slice_count_for(uint32_t rows, uint32_t width) {
@@ -736,12 +753,13 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     WalkRecords rec[kMaxSlices];
     dim3 logicGrid[kMaxSlices];
     unsigned setupGrid[kMaxSlices];
+    int aheadMode[kMaxSlices];
     cudaStream_t stream[kMaxSlices];
     for (int k = 0; k < K; ++k) {
         WfSlice& sl = f->slices[k];
         const uint32_t rows = launch_rows(FV[k]);
         const uint64_t Q64 = (uint64_t)((rows + 7) / 8 * 8) * W;
-        if (Q64 > 0xFFFFFFF0ull) {
+        if (Q64 > 0x7FFFFFF0ull) {   // ray indices are slot * Q + path
             err = "launch domain too large";
             return false;
         }
@@ -751,13 +769,14 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
             const size_t q = Q;
             if (!sl.ctl.alloc(sizeof(uint32_t) * q, err, st) || !sl.rng.alloc(sizeof(uint64_t) * q, err, st) ||
                 !sl.colour.alloc(sizeof(float4) * q, err, st) || !sl.ring.alloc(sizeof(float4) * q * kRingSize * kRingParts, err, st) ||
-                !sl.carry.alloc(sizeof(float4) * q * kCarryParts, err, st) || !sl.rayO.alloc(sizeof(float4) * q, err, st) ||
-                !sl.rayD.alloc(sizeof(float4) * q, err, st) || !sl.rayExcl.alloc(sizeof(uint32_t) * q, err, st) ||
-                !sl.hit.alloc(sizeof(float4) * q, err, st) || !sl.queue.alloc(sizeof(uint32_t) * q, err, st) ||
-                !sl.recO.alloc(sizeof(float4) * q, err, st) || !sl.recD.alloc(sizeof(float4) * q, err, st) ||
-                !sl.recS0.alloc(sizeof(float4) * q, err, st) || !sl.recS1.alloc(sizeof(uint4) * q, err, st) ||
-                !sl.recOrder.alloc(sizeof(uint32_t) * q * kLengthClasses, err, st) ||
-                !sl.workCounter.alloc(sizeof(uint32_t) * 2 * (2 + kLengthClasses), err, st))
+                !sl.carry.alloc(sizeof(float4) * q * kCarryParts, err, st) ||
+                // two ray slots per path (rt_wavefront.cuh: the next segment's closest hit is traced one round ahead)
+                !sl.rayO.alloc(sizeof(float4) * 2 * q, err, st) || !sl.rayD.alloc(sizeof(float4) * 2 * q, err, st) ||
+                !sl.rayExcl.alloc(sizeof(uint32_t) * 2 * q, err, st) || !sl.hit.alloc(sizeof(float4) * 2 * q, err, st) ||
+                !sl.queue.alloc(sizeof(uint32_t) * 2 * q, err, st) || !sl.recO.alloc(sizeof(float4) * 2 * q, err, st) ||
+                !sl.recD.alloc(sizeof(float4) * 2 * q, err, st) || !sl.recS0.alloc(sizeof(float4) * 2 * q, err, st) ||
+                !sl.recS1.alloc(sizeof(uint4) * 2 * q, err, st) || !sl.recOrder.alloc(sizeof(uint32_t) * 2 * q * kLengthClasses, err, st) ||
+                !sl.workCounter.alloc(sizeof(uint32_t) * (2 * (2 + kLengthClasses) + kRoundLogSize), err, st))
                 return false;
             sl.capacity = Q;
         }
@@ -781,12 +800,13 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         rec[k].s0 = (float4*)sl.recS0.p;
         rec[k].s1 = (uint4*)sl.recS1.p;
         rec[k].order = (uint32_t*)sl.recOrder.p;
-        rec[k].Q = Q;
+        rec[k].Q = 2 * Q;   // queue slots (two rays per path at most)
+        aheadMode[k] = ahead_mode_for(Q);
         logicGrid[k] = dim3((W + 15) / 16, (rows + 7) / 8);
-        setupGrid[k] = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, ((uint64_t)Q + 255) / 256);
+        setupGrid[k] = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, (2 * (uint64_t)Q + 255) / 256);
     }
     for (int k = K; k < kMaxSlices; ++k) f->slices[k].traceEventsUsed = 0;
-    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * kMaxSlices, cudaHostAllocDefault));
+    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * kMaxSlices * kRoundLogSize, cudaHostAllocDefault));
 
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
@@ -839,12 +859,14 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     w[k].queueCount = counters + cstride * (r & 1u);
                     w[k].queueCursor = w[k].queueCount + 1;
                     rec[k].classCount = w[k].queueCount + 2;
+                    w[k].roundLog = counters + 2 * cstride;
+                    w[k].roundIndex = r;
                     const uint32_t* prev = r ? counters + cstride * ((r - 1) & 1u) : nullptr;
                     OCLR_CUDA(cudaMemsetAsync(w[k].queueCount, 0, sizeof(uint32_t) * cstride, ks));
                     if (dcnt)
-                        wf_logic_kernel<true><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt);
+                        wf_logic_kernel<true><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
                     else
-                        wf_logic_kernel<false><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt);
+                        wf_logic_kernel<false><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
                     ++launches;
                     if (timeTrace) {
                         while (sl.traceEvents.size() < (size_t)sl.traceEventsUsed + 2) {
@@ -868,17 +890,34 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     ++round[k];
                 }
             }
+            // one read per chunk: the round log (rays queued by every round so far; the last enqueued round decides)
             for (int k = 0; k < K; ++k)
                 if (chunk[k])
-                    OCLR_CUDA(cudaMemcpyAsync(f->hostCount + k, (uint32_t*)f->slices[k].workCounter.p + cstride * ((round[k] - 1) & 1u),
-                                              sizeof(uint32_t), cudaMemcpyDeviceToHost, stream[k]));
+                    OCLR_CUDA(cudaMemcpyAsync(f->hostCount + k * kRoundLogSize, (uint32_t*)f->slices[k].workCounter.p + 2 * cstride,
+                                              sizeof(uint32_t) * std::min<uint32_t>(round[k], kRoundLogSize), cudaMemcpyDeviceToHost, stream[k]));
             for (int k = 0; k < K; ++k)
                 if (chunk[k]) OCLR_CUDA(cudaStreamSynchronize(stream[k]));
             for (int k = 0; k < K; ++k) {
                 if (!chunk[k]) continue;
-                if (f->hostCount[k] == 0) {   // the last enqueued round found no path waiting for a ray: the slice's sample is complete
+                const uint32_t* log = f->hostCount + k * kRoundLogSize;
+                bool finished = false;
+                uint32_t needed = round[k];
+                if (round[k] <= kRoundLogSize) {
+                    finished = log[round[k] - 1] == 0;
+                    for (uint32_t r = 0; r < round[k]; ++r)
+                        if (log[r] == 0) {   // the first round that queued no ray is the last one that had anything to do
+                            needed = r + 1;
+                            break;
+                        }
+                } else {   // beyond the log: fall back to the live counter of the last enqueued round
+                    uint32_t last = 1;
+                    OCLR_CUDA(cudaMemcpy(&last, (uint32_t*)f->slices[k].workCounter.p + cstride * ((round[k] - 1) & 1u), sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost));
+                    finished = last == 0;
+                }
+                if (finished) {
                     live[k] = false;
-                    f->slices[k].lastRounds = round[k];
+                    f->slices[k].lastRounds = needed;
                 } else if (round[k] > 100000) {
                     err = "wavefront did not converge";
                     return false;

@@ -106,6 +106,8 @@ bool frame_accum_copy(Frame* f, float* host, bool toHost, std::string& err);
 bool frame_progress(Frame* f, unsigned long long* done, unsigned long long* total);
 // Slices a launch domain is cut into (runtime.cu launch_wavefront): 0 = automatic, k = always k.
 void set_slice_count(int k);
+// Tracing one round ahead (rt_wavefront.cuh): 0 never, 1 all segments but the camera's, 2 all, -1 automatic.
+void set_ahead_mode(int m);
 uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint32_t world);
 // Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,

@@ -9,9 +9,28 @@ RGB_TOL = 1e-3      # north_star: max-abs 1e-3 per channel (of full scale 65535)
 PSNR_MIN = 60.0     # north_star: PSNR >= 60 dB
 
 
+def _with_lights(sc, entries):
+    """Replaces the scene's lights (several lights per scene: the light loop raytrace_opencl.c:563-637 runs one shadow query per
+    light in order; the omni type contributes nothing, :585-588)."""
+    lt, pos, dr, col, rad, half = scenes._lights(entries)
+    sc.light_type, sc.light_pos, sc.light_dir, sc.light_colour, sc.light_radius, sc.light_half = lt, pos, dr, col, rad, half
+    return sc.normalise()
+
+
+_SPOT = dict(type=api.LIGHT_SPOT, pos=(3.0, 8.0, -5.0), colour=(0.9, 0.8, 0.7), radius=0.25)
+_SUN = dict(type=api.LIGHT_DISTANT, dir=(-0.4, -0.8, 0.3), colour=(0.5, 0.55, 0.7), radius=0.52)
+_OMNI = dict(type=api.LIGHT_OMNI, pos=(0.0, 6.0, 0.0), colour=(1, 1, 1), radius=0.1)
+_AREA = dict(type=api.LIGHT_AREA, pos=(-4.0, 5.0, -3.0), colour=(0.6, 0.6, 0.6), radius=0.6, half=9.0)
+
+
 def make_case(name):
     """Small seeded instances of the five config families (+ edge cases).  Returns (scene, camera, lists, samples)."""
     cases = {
+        # several lights: shadow queries of one hit in sequence; the last light that casts one / an omni light in last place
+        "soup_lights_sun_last": (lambda: _with_lights(scenes.soup(260, seed=21, reflective=True, transparent=True), [_OMNI, _SPOT, _AREA, _SUN]),
+                                 144, 112, 2, 256),
+        "soup_lights_omni_last": (lambda: _with_lights(scenes.soup(260, seed=22, reflective=True, transparent=True), [_SPOT, _SUN, _OMNI]),
+                                  144, 112, 2, 256),
         "soup": (lambda: scenes.soup(400, seed=11), 192, 160, 1, 256),
         "soup_s4": (lambda: scenes.soup(200, seed=12, light_radius=0.3), 96, 80, 4, 64),
         "soup_mirror_glass": (lambda: scenes.soup(300, seed=5, light_radius=0.4, reflective=True, transparent=True), 160, 120, 3, 256),
@@ -30,7 +49,8 @@ def make_case(name):
     return sc, cam, lists, samples
 
 
-CASE_NAMES = ["soup", "soup_s4", "soup_mirror_glass", "spheres", "spheres_mirror", "terrain", "terrain_textured", "coarse_grid"]
+CASE_NAMES = ["soup", "soup_s4", "soup_mirror_glass", "spheres", "spheres_mirror", "terrain", "terrain_textured", "coarse_grid",
+              "soup_lights_sun_last", "soup_lights_omni_last"]
 
 
 def compare_rgb(a, b, mask=None):

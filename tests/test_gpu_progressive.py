@@ -166,7 +166,7 @@ def test_raytrace_all_reports_live_progress():
     t = threading.Thread(target=poll)
     t.start()
     try:
-        api.raytrace_all(1, cam, lists, 48, sc)
+        api.raytrace_all(1, cam, lists, 320, sc)          # long enough (a few hundred ms) for the poller to catch it in flight
     finally:
         stop.set()
         t.join()
