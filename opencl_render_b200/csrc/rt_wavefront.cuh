@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
         uint64_t rng;
         f3 colour;
         Segment seg;
-        uint32_t hit = kNoTriangle;
+        uint32_t hit = kNoTriangle, tri2 = 0;
         float hitT = 0.f, hitAB = 0.f, hitAC = 0.f;
         // shading state
         f3 loc, nrm, tex, transp, refl, lum, att;
@@ -239,9 +239,15 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                     hit = kNoTriangle;
                     hitT = OCLR_INF;
                     hitAB = hitAC = 0.f;
+                    // The scan is a chain of dependent loads (list entry -> triangle record) and a warp waits for its longest list:
+                    // entries are fetched two iterations ahead and the next triangle's record is pulled into L1 meanwhile.
                     const uint32_t e = __ldg(F.camEnd + pixel);
-                    for (uint32_t i = __ldg(F.camStart + pixel); i < e; ++i) {
-                        const uint32_t tri = __ldg(F.camList + i);
+                    uint32_t i = __ldg(F.camStart + pixel);
+                    uint32_t tri = i < e ? __ldg(F.camList + i) : 0u;
+                    uint32_t tri1 = i + 1u < e ? __ldg(F.camList + i + 1u) : 0u;
+                    for (; i < e; ++i, tri = tri1, tri1 = tri2) {
+                        tri2 = i + 2u < e ? __ldg(F.camList + i + 2u) : 0u;
+                        if (i + 1u < e) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.triGeo + 4 * (size_t)tri1));
                         if (seg.excl != tri) {
                             float t, ab, ac;
                             if (COUNT) cnt.primCandidates++;

@@ -125,6 +125,36 @@ def test_sliced_launch_domain_is_invisible(slices):
         api.set_option("no_such_option", 1)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tracing_one_round_ahead_is_invisible(mode):
+    """rt_wavefront.cuh: the spawn of a segment and the next segment's closest-hit query may run before the segment's last shadow
+    ray has returned.  Every mode must reproduce the golden planes, ids and flags; modes 1 / 2 need fewer rounds on mirror chains."""
+    launches = {}
+    try:
+        for name in ("soup_mirror_glass", "spheres_mirror", "terrain_textured", "soup_lights_sun_last", "soup_lights_omni_last", "soup_s4"):
+            sc, cam, lists, samples = helpers.make_case(name)
+            gold = np.load(GOLDEN / f"{name}.npz")
+            ds = api.DeviceScene(sc, 0)
+            fr = api.DeviceFrame(ds, cam, lists)
+            api.set_option("ahead", mode)
+            _, n, _ = fr.render(samples)
+            fr.render(samples)                      # second render: enqueues exactly the rounds the first one needed
+            launches[name] = fr.last_launches
+            img, flags = fr.read(), fr.undefined_flags()
+            assert helpers.compare_rgb(img, (gold["r"], gold["g"], gold["b"]), mask=(flags == 0))["diff_pixels"] == 0, name
+            if samples == 1:
+                assert np.array_equal(fr.primary_ids(), gold["ids"])
+        api.set_option("ahead", 0)
+        sc, cam, lists, samples = helpers.make_case("spheres_mirror")
+        fr = api.DeviceFrame(api.DeviceScene(sc, 0), cam, lists)
+        fr.render(samples)
+        fr.render(samples)
+        if mode:
+            assert launches["spheres_mirror"] < fr.last_launches, (launches, fr.last_launches)
+    finally:
+        api.set_option("ahead", -1)
+
+
 def test_progress_counter_counts_pixel_samples():
     sc, cam, lists, _ = helpers.make_case("spheres")
     samples = 24
