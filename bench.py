@@ -161,7 +161,10 @@ def run_reference(args):
 
 
 def run_b200(args):
-    os.environ["NCCL_DEBUG"] = os.environ.get("OCLR_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
+    # stdout carries ONE JSON line: everything libraries print there (NCCL's version banner, ...) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from opencl_render_b200 import api, dist as odist
@@ -181,7 +184,7 @@ def run_b200(args):
     ds = api.DeviceScene(sc, local)
     fr = api.DeviceFrame(ds, cam, lists)
     part = odist.BandPartition(h, w, rank, world, args.band_rows)
-    gather = odist.PlaneGather(fr, part, torch.device("cuda", local)) if world > 1 else None
+    gather, gather_kind = odist.plane_exchange(fr, part, torch.device("cuda", local)) if world > 1 else (None, None)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -289,7 +292,7 @@ def run_b200(args):
             "config": {"workload": cfg["name"], "triangles": sc.triangle_count, "width": w, "height": h, "samples": S,
                        "ray_unit": "pixel-sample (raytrace.c:545)", "l2": "flushed before every timed step (256 MiB memset)",
                        "partition": f"row bands of {args.band_rows} dealt round-robin over {world} GPU(s), scene replicated, "
-                                    f"NCCL all-gather of the planes" if world > 1 else "single GPU, whole frame",
+                                    f"frame assembled by {gather_kind}" if world > 1 else "single GPU, whole frame",
                        "kernel_variant": args.variant},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": e2e.h2d_bytes, "d2h_bytes_per_step": e2e.d2h_bytes,
                     "steps": e2e_steps, "call": "RaytraceAll (C-ABI, host buffers)" if world == 1 else "oclr scene/frame API, rank-local rows"},
@@ -299,7 +302,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

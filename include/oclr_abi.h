@@ -321,6 +321,12 @@ cl_uint oclr_frame_last_launches(const oclr_frame* frame);
 /* Device addresses of the three planes (W*H cl_ushort each) -- for NCCL gathers issued by the host layer. */
 void oclr_frame_device_planes(oclr_frame* frame, void** red, void** green, void** blue);
 
+/* Frame assembly over NVLink peer memory: stores the rows `rank` owns (bands of bandRows rows dealt round-robin over worldSize)
+ * from the frame's planes into the full-frame planes ([3][H][W] cl_ushort: red, green, blue) of EVERY GPU listed in peerPlanes --
+ * worldSize device pointers valid in this process (the rank's own buffer and its peers', e.g. from CUDA IPC / symmetric memory).
+ * One kernel on cudaStream; the caller orders a cross-GPU barrier behind it.  The reference has no counterpart (one device). */
+int oclr_frame_push_rows(oclr_frame* frame, cl_uint bandRows, int rank, int worldSize, void* const* peerPlanes, void* cudaStream);
+
 /* Rows of a W x H image owned by `rank` of `worldSize` when the image is cut into bands of `bandRows` rows dealt
  * round-robin (band height 128 = the reference's tile height, raytrace.c:507).  Writes up to
  * `maxBands` [begin,end) pairs to `rows` and returns the number of bands owned. */

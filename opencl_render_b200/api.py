@@ -404,6 +404,12 @@ class DeviceFrame:
     def last_launches(self) -> int:
         return int(self._lib.oclr_frame_last_launches(self.handle))
 
+    def push_rows(self, band_rows: int, rank: int, world: int, peer_planes, stream: int = 0):
+        """Stores this rank's rows into the full-frame planes of every GPU in `peer_planes` (device addresses, one per rank)."""
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_planes])
+        if not self._lib.oclr_frame_push_rows(self.handle, band_rows, rank, world, arr, C.c_void_p(stream)):
+            raise OclrError(_lib.last_error())
+
     def device_planes(self):
         r, g, b = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._lib.oclr_frame_device_planes(self.handle, C.byref(r), C.byref(g), C.byref(b))

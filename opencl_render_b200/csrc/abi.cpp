@@ -424,6 +424,16 @@ int oclr_frame_read_flags(oclr_frame* frame, cl_uchar* flags) {
 
 cl_uint oclr_frame_last_launches(const oclr_frame* frame) { return frame ? frame_last_launches(frame->impl) : 0; }
 
+int oclr_frame_push_rows(oclr_frame* frame, cl_uint bandRows, int rank, int worldSize, void* const* peerPlanes, void* cudaStream) {
+    std::string err;
+    if (!frame || rank < 0 || worldSize < 1 ||
+        !frame_push_rows(frame->impl, bandRows, (uint32_t)rank, (uint32_t)worldSize, peerPlanes, cudaStream, err)) {
+        fail("oclr_frame_push_rows: " + (err.empty() ? std::string("bad argument") : err));
+        return 0;
+    }
+    return 1;
+}
+
 void oclr_frame_device_planes(oclr_frame* frame, void** red, void** green, void** blue) {
     if (frame) frame_device_planes(frame->impl, red, green, blue);
 }

@@ -1175,6 +1175,64 @@ bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err) {
 
 uint32_t frame_last_launches(const Frame* f) { return f ? f->lastLaunches : 0; }
 
+// ---- frame assembly over NVLink peer memory (the path's only exchange step) -------------------------------------
+// Every rank owns the rows y with (y / bandRows) % world == rank.  Instead of packing them, calling an all-gather and unpacking,
+// one kernel STORES the rank's finished rows straight into the full-frame planes of every GPU of the box -- its own and its
+// peers', whose buffers are mapped into this process (NVLink 5 / NVSwitch peer access) -- at the place they belong.  16-byte
+// stores, one row segment of 8 pixels per thread and destination; the caller puts a cross-GPU barrier behind it.
+enum { kMaxPeers = 16 };
+struct PeerPlanes {
+    uint16_t* p[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) push_rows_kernel(const uint16_t* __restrict__ src, PeerPlanes dst, int world, uint32_t W, uint32_t H,
+                                                        uint32_t bandRows, uint32_t rank, uint32_t ownedRows) {
+    const uint32_t vecPerRow = (W + 7u) / 8u;   // 8 pixels = 16 bytes
+    const uint64_t total = (uint64_t)ownedRows * vecPerRow * 3u;
+    const size_t P = (size_t)W * H;
+    const bool aligned = (W % 8u) == 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = (uint32_t)(i % vecPerRow);
+        const uint64_t rowPlane = i / vecPerRow;
+        const uint32_t k = (uint32_t)(rowPlane % ownedRows), plane = (uint32_t)(rowPlane / ownedRows);
+        const uint32_t y = (k / bandRows) * (bandRows * (uint32_t)world) + rank * bandRows + (k % bandRows);   // map_row()
+        const size_t off = plane * P + (size_t)y * W + (size_t)v * 8u;
+        if (aligned) {
+            const uint4 val = *reinterpret_cast<const uint4*>(src + off);
+            for (int d = 0; d < world; ++d) *reinterpret_cast<uint4*>(dst.p[d] + off) = val;
+        } else {
+            const uint32_t n = min(8u, W - v * 8u);
+            for (uint32_t e = 0; e < n; ++e) {
+                const uint16_t val = src[off + e];
+                for (int d = 0; d < world; ++d) dst.p[d][off + e] = val;
+            }
+        }
+    }
+}
+
+bool frame_push_rows(Frame* f, uint32_t bandRows, uint32_t rank, uint32_t world, void* const* peerPlanes, void* stream, std::string& err) {
+    if (!f || !peerPlanes || bandRows == 0 || world == 0 || world > kMaxPeers || rank >= world) {
+        err = "bad push request";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const uint32_t owned = band_owned_rows(f->cam.height, bandRows, rank, world);
+    if (owned == 0) return true;
+    PeerPlanes dst = {};
+    for (uint32_t d = 0; d < world; ++d) {
+        if (!peerPlanes[d]) {
+            err = "null peer plane pointer";
+            return false;
+        }
+        dst.p[d] = (uint16_t*)peerPlanes[d];
+    }
+    const uint64_t total = (uint64_t)owned * ((f->cam.width + 7u) / 8u) * 3u;
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)f->scene->smCount * 8);
+    push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)f->planesRGB.p, dst, (int)world, f->cam.width, f->cam.height, bandRows,
+                                                             rank, owned);
+    OCLR_CUDA(cudaGetLastError());
+    return true;
+}
+
 void frame_device_planes(Frame* f, void** r, void** g, void** b) {
     const size_t P = (size_t)f->cam.width * f->cam.height;
     uint16_t* d = (uint16_t*)f->planesRGB.p;

@@ -118,6 +118,9 @@ bool build_scene_grid_device(int device, int32_t n, uint32_t vertexCount, const 
 uint32_t frame_last_launches(const Frame* f);
 bool frame_read_ids(Frame* f, uint32_t* ids, std::string& err);
 bool frame_read_flags(Frame* f, uint8_t* flags, std::string& err);
+// Stores the rows rank owns (bands of bandRows dealt round-robin over world) into the full-frame planes [3][H][W] of every GPU
+// listed in peerPlanes (device pointers valid in this process: the rank's own buffer and its NVLink peers').
+bool frame_push_rows(Frame* f, uint32_t bandRows, uint32_t rank, uint32_t world, void* const* peerPlanes, void* stream, std::string& err);
 // Device pointers of the planes (for NCCL gathers done by the host layer) and of the id plane.
 void frame_device_planes(Frame* f, void** r, void** g, void** b);
 

@@ -84,6 +84,52 @@ class PlaneGather:
         return self.full
 
 
+class PlanePush:
+    """Assembles the full frame on every rank WITHOUT a collective call: each rank stores its finished rows straight into the
+    full-frame planes of all GPUs of the box over NVLink peer memory (one kernel, oclr_frame_push_rows) and one cross-GPU barrier
+    on the stream orders the readers behind the writers.  The destination planes live in torch symmetric memory (peer-mapped on
+    every rank), double-buffered: while a rank still reads frame k from one buffer, its peers may already push frame k + 1 into the
+    other; the barrier of frame k + 1 is behind every read of frame k that was enqueued on the same stream."""
+
+    def __init__(self, frame, part: BandPartition, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.frame, self.part = torch, frame, part
+        h, w = part.height, part.width
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty((3, h, w), dtype=torch.int16, device=device)
+            self.handles.append(symm_mem.rendezvous(t, dist.group.WORLD))
+            self.bufs.append(t)
+        for hdl in self.handles:
+            if len(hdl.buffer_ptrs) != part.world:
+                raise RuntimeError("symmetric memory rendezvous returned the wrong number of peers")
+        self.step = 0
+        self.launches = 2       # push kernel + barrier kernel
+
+    def run(self):
+        i = self.step & 1
+        self.step += 1
+        hdl = self.handles[i]
+        self.frame.push_rows(self.part.band_rows, self.part.rank, self.part.world, hdl.buffer_ptrs,
+                             stream=self.torch.cuda.current_stream().cuda_stream)
+        hdl.barrier(channel=0)
+        return self.bufs[i]
+
+
+def plane_exchange(frame, part: BandPartition, device):
+    """The frame-assembly step for world > 1: peer stores over NVLink (PlanePush); the NCCL all-gather (PlaneGather) only where
+    peer-mapped memory cannot be set up (said on stderr).  Returns (object with .run() / .launches, name)."""
+    import sys
+    try:
+        return PlanePush(frame, part, device), "peer stores over NVLink (oclr_frame_push_rows) + symmetric-memory barrier"
+    except Exception as e:      # no P2P mapping between these devices / symmetric memory unavailable in this torch build
+        print(f"[opencl_render_b200] peer-memory frame assembly unavailable ({type(e).__name__}: {e}); using the NCCL all-gather",
+              file=sys.stderr, flush=True)
+        return PlaneGather(frame, part, device), "NCCL all-gather of compact rows + scatter"
+
+
 class EndToEnd:
     """The drop-in call with HOST buffers: at world == 1 it is RaytraceAll itself (upload + repack + trace + read back);
     at world > 1 each rank uploads the scene, traces its bands and reads its rows back through the scene/frame API."""

@@ -119,3 +119,20 @@ def test_config5_camera_sweep_upload_once(port):
         lit.append(int((img[0] > 0).sum()))
         fr.close()
     assert min(lit) > 0.5 * cfg["width"] * cfg["height"]
+
+
+def test_frame_assembly_over_peer_memory_two_gpus():
+    """SURVEY 8e at world size 2 on real GPUs (skipped on a one-GPU box; the gloo tests cover the host logic on CPU): bands rendered
+    by two ranks and assembled by peer stores (oclr_frame_push_rows) and by the NCCL all-gather both equal the one-GPU frame."""
+    import os
+    import subprocess
+    import sys
+    from opencl_render_b200 import _lib
+    if _lib.load().oclr_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "push_probe.py"), "1", "16"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "equals single-GPU frame: True" in r.stdout and "equals single-GPU frame: False" not in r.stdout
