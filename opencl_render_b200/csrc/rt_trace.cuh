@@ -70,6 +70,7 @@ __device__ __forceinline__ int walk_length_estimate(const PackedWalk& g, int n, 
 
 __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, WalkRecords rec) {
     extern __shared__ float shPlanes[];
+    __shared__ uint32_t shCount[kLengthClasses], shBase[kLengthClasses];
     const uint32_t count = *w.queueCount;
     if (blockIdx.x == 0 && threadIdx.x == 0 && w.roundIndex < kRoundLogSize) w.roundLog[w.roundIndex] = count;
     if (blockIdx.x * blockDim.x >= count) return;
@@ -96,16 +97,23 @@ __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, W
             // classes by quarters of n, longest first (a walk can be up to 3n cells long; 8 classes measured no better than 4)
             cls = kLengthClasses - 1 - min(kLengthClasses - 1, (len * kLengthClasses) / (n > 0 ? n : 1));
         }
+        // one global atomic per CTA, class and iteration (the warps' counts are first summed in shared memory)
+        if (threadIdx.x < kLengthClasses) shCount[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t within = 0;
 #pragma unroll
-        for (int c = 0; c < kLengthClasses; ++c) {  // one atomic per warp and class
+        for (int c = 0; c < kLengthClasses; ++c) {
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
             if (m == 0u) continue;
-            const int leader = __ffs(m) - 1;
             uint32_t pos = 0;
-            if (lane == leader) pos = atomicAdd(rec.classCount + c, (uint32_t)__popc(m));
-            pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-            if (cls == c) rec.order[(size_t)c * rec.Q + pos + (uint32_t)__popc(m & ((1u << lane) - 1u))] = idx;
+            if (lane == 0) pos = atomicAdd(&shCount[c], (uint32_t)__popc(m));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            if (cls == c) within = pos + (uint32_t)__popc(m & ((1u << lane) - 1u));
         }
+        __syncthreads();
+        if (threadIdx.x < kLengthClasses) shBase[threadIdx.x] = shCount[threadIdx.x] ? atomicAdd(rec.classCount + threadIdx.x, shCount[threadIdx.x]) : 0u;
+        __syncthreads();
+        if (cls >= 0) rec.order[(size_t)cls * rec.Q + shBase[cls] + within] = idx;
     }
 }
 

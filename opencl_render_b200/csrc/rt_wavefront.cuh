@@ -90,14 +90,29 @@ __device__ __forceinline__ Segment ring_load(const WfState& w, uint32_t q, int s
     return s;
 }
 
-// Appends ray index q (slot 0) and / or Q + q (slot 1) to the ray queue: one atomic per warp (ballot + popc + shuffle).
-__device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want0, bool want1) {
+// Appends ray index q (slot 0) and / or Q + q (slot 1) to the ray queue.  One atomic per CTA: the 16 k CTAs of a pass all bump the
+// same counter, and with one returning atomic per WARP the logic kernel spent 9 % of its stall samples waiting for them (ncu,
+// profiles/README.md).  Must be reached by every thread of the CTA (two barriers).
+// `finished` / doneCount: the progress counter (pixel-samples finished) rides on the same CTA-level sums.
+__device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want0, bool want1, bool finished, unsigned long long* doneCount) {
+    __shared__ uint32_t warpCount[4], warpDone[4], ctaBase;
     const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
-    if ((m0 | m1) == 0u) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(w.queueCount, (uint32_t)(__popc(m0) + __popc(m1)));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const unsigned md = __ballot_sync(0xFFFFFFFFu, finished);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        warpCount[warp] = (uint32_t)(__popc(m0) + __popc(m1));
+        warpDone[warp] = (uint32_t)__popc(md);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = warpCount[0] + warpCount[1] + warpCount[2] + warpCount[3];
+        ctaBase = total ? atomicAdd(w.queueCount, total) : 0u;
+        const uint32_t done = warpDone[0] + warpDone[1] + warpDone[2] + warpDone[3];
+        if (doneCount && done) atomicAdd(doneCount, (unsigned long long)done);
+    }
+    __syncthreads();
+    uint32_t base = ctaBase;
+    for (int k = 0; k < warp; ++k) base += warpCount[k];
     const unsigned lt = (1u << lane) - 1u;
     if (want0) w.queue[base + __popc(m0 & lt)] = q;
     if (want1) w.queue[base + __popc(m0) + __popc(m1 & lt)] = w.Q + q;
@@ -449,11 +464,7 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                    (ahead ? kCtlAhead : 0u);
         if (COUNT) flush_counters(cnt, gcnt);
     }
-    if (F.doneCount) {   // progress: pixel-samples finished, one atomic per warp
-        const unsigned fm = __ballot_sync(0xFFFFFFFFu, finished);
-        if (fm != 0u && (threadIdx.x & 31) == 0) atomicAdd(F.doneCount, (unsigned long long)__popc(fm));
-    }
-    enqueue(w, q, want, wantAhead);
+    enqueue(w, q, want, wantAhead, finished, F.doneCount);
 }
 
 // Planes from the float accumulator: out = (int)(sum * 65535 / samples so far), the reference's conversion (:726-741) applied once
