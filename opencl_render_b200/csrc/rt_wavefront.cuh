@@ -95,27 +95,34 @@ __device__ __forceinline__ Segment ring_load(const WfState& w, uint32_t q, int s
 // profiles/README.md).  Must be reached by every thread of the CTA (two barriers).
 // `finished` / doneCount: the progress counter (pixel-samples finished) rides on the same CTA-level sums.
 __device__ __forceinline__ void enqueue(const WfState& w, uint32_t q, bool want0, bool want1, bool finished, unsigned long long* doneCount) {
-    __shared__ uint32_t warpCount[4], warpDone[4], ctaBase;
+    __shared__ uint32_t warpCount0[4], warpCount1[4], warpDone[4], ctaBase;
     const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
     const unsigned md = __ballot_sync(0xFFFFFFFFu, finished);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-        warpCount[warp] = (uint32_t)(__popc(m0) + __popc(m1));
+        warpCount0[warp] = (uint32_t)__popc(m0);
+        warpCount1[warp] = (uint32_t)__popc(m1);
         warpDone[warp] = (uint32_t)__popc(md);
     }
     __syncthreads();
+    const uint32_t total0 = warpCount0[0] + warpCount0[1] + warpCount0[2] + warpCount0[3];
     if (threadIdx.x == 0) {
-        const uint32_t total = warpCount[0] + warpCount[1] + warpCount[2] + warpCount[3];
+        const uint32_t total = total0 + warpCount1[0] + warpCount1[1] + warpCount1[2] + warpCount1[3];
         ctaBase = total ? atomicAdd(w.queueCount, total) : 0u;
         const uint32_t done = warpDone[0] + warpDone[1] + warpDone[2] + warpDone[3];
         if (doneCount && done) atomicAdd(doneCount, (unsigned long long)done);
     }
     __syncthreads();
-    uint32_t base = ctaBase;
-    for (int k = 0; k < warp; ++k) base += warpCount[k];
+    // the CTA's slot-0 rays (shadow / closest of a 16x8 pixel tile) first, then its slot-1 rays (bounce rays traced ahead): the trace
+    // kernel takes consecutive queue entries into one warp, and rays of one kind from one tile walk the grid together
+    uint32_t base0 = ctaBase, base1 = ctaBase + total0;
+    for (int k = 0; k < warp; ++k) {
+        base0 += warpCount0[k];
+        base1 += warpCount1[k];
+    }
     const unsigned lt = (1u << lane) - 1u;
-    if (want0) w.queue[base + __popc(m0 & lt)] = q;
-    if (want1) w.queue[base + __popc(m0) + __popc(m1 & lt)] = w.Q + q;
+    if (want0) w.queue[base0 + __popc(m0 & lt)] = q;
+    if (want1) w.queue[base1 + __popc(m1 & lt)] = w.Q + q;
 }
 
 // ---- logic kernel -----------------------------------------------------------------------------------------------------
