@@ -141,36 +141,35 @@ OCLR_HD void pwalk_enter_coarse(PackedWalk& w, int n, const float* planes) {
     w.level = 1;
 }
 
+// One axis of the refinement, select-only form of refine_axis() / the entry-axis case of walk_refine() (rt_core.h): every lane of a
+// warp runs the same instructions whatever axis its ray entered the brick along (the branchy form ran with 2.2 of 32 lanes active,
+// profiles/r01d_wf_pipe_cfg2_phases.txt).  For the entry axis the answer is "first cell in travel direction, next crossing = the
+// plane that cell is left through" -- exactly what the probe sequence yields when both probes are forced to "not before E" (the
+// second probe then reads crossing 0, the very plane the entry case divides by), so forcing the predicates is all it takes.
+OCLR_HD void prefine_axis(bool entry, int b, float tExit, float o, float r, const float* p, float E, bool strict, int& cell, float& tNext) {
+    const int up = (0 <= r) ? 1 : 0;
+    const int base = b << 2;
+    const float t1 = (p[base + 2] - o) / r;
+    const bool pre1 = (!entry) & (strict ? (t1 < E) : (t1 <= E));
+    const int p2 = (pre1 == (up != 0)) ? base + 3 : base + 1;   // pre1: crossing 2 (up: base+3, down: base+1); else crossing 0 (up: base+1, down: base+3)
+    const float t2 = (p[p2] - o) / r;
+    const bool pre2 = (!entry) & (strict ? (t2 < E) : (t2 <= E));
+    const int j = (pre1 ? 2 : 0) + (pre2 ? 1 : 0);
+    tNext = pre1 ? (pre2 ? tExit : t2) : (pre2 ? t1 : t2);
+    cell = up ? base + j : base + 3 - j;
+}
+
 // Level 1 -> level 0 after the brick-level step along `axis` (crossing value E) entered a brick that has to be walked cell
 // by cell: the exact cell state the cell-level walk would have on entering this brick (rt_core.h: walk_refine).
 OCLR_HD void pwalk_refine(PackedWalk& w, int n, const float* planes, int axis, float E) {
     const float* px = planes;
     const float* py = planes + (n + 1);
     const float* pz = planes + 2 * (n + 1);
-    const int bx = pk_get(w.cpk, 0), by = pk_get(w.cpk, 1), bz = pk_get(w.cpk, 2);
     int cx, cy, cz;
     float tx, ty, tz;
-    if (axis == 0) {
-        const int up = (0 <= w.r.x);
-        cx = up ? (bx << 2) : (bx << 2) + 3;
-        tx = (px[cx + up] - w.o.x) / w.r.x;
-    } else {
-        refine_axis(bx, w.tx, w.o.x, w.r.x, px, E, true, cx, tx);
-    }
-    if (axis == 1) {
-        const int up = (0 <= w.r.y);
-        cy = up ? (by << 2) : (by << 2) + 3;
-        ty = (py[cy + up] - w.o.y) / w.r.y;
-    } else {
-        refine_axis(by, w.ty, w.o.y, w.r.y, py, E, axis == 2, cy, ty);
-    }
-    if (axis == 2) {
-        const int up = (0 <= w.r.z);
-        cz = up ? (bz << 2) : (bz << 2) + 3;
-        tz = (pz[cz + up] - w.o.z) / w.r.z;
-    } else {
-        refine_axis(bz, w.tz, w.o.z, w.r.z, pz, E, false, cz, tz);
-    }
+    prefine_axis(axis == 0, pk_get(w.cpk, 0), w.tx, w.o.x, w.r.x, px, E, true, cx, tx);       // x precedes y / z crossings only when strictly smaller
+    prefine_axis(axis == 1, pk_get(w.cpk, 1), w.ty, w.o.y, w.r.y, py, E, axis == 2, cy, ty);  // y: "<= E" against x, "< E" against z
+    prefine_axis(axis == 2, pk_get(w.cpk, 2), w.tz, w.o.z, w.r.z, pz, E, false, cz, tz);      // z wins ties against x and y
     w.cpk = pk_make(cx, cy, cz);
     w.tx = tx;
     w.ty = ty;
