@@ -29,6 +29,13 @@ def make_case(name):
         # several lights: shadow queries of one hit in sequence; the last light that casts one / an omni light in last place
         "soup_lights_sun_last": (lambda: _with_lights(scenes.soup(260, seed=21, reflective=True, transparent=True), [_OMNI, _SPOT, _AREA, _SUN]),
                                  144, 112, 2, 256),
+        # axis-parallel shadow rays (a distant light straight overhead with zero angular size: two direction components are exactly
+        # 0, so two of the three crossing values are +-inf or NaN in every cell -- the tie rule of raytrace_opencl.c:387-398 and the
+        # "no brick-level walk" path are what is tested) plus a spot light exactly above the look-at point
+        "soup_axis_light": (lambda: _with_lights(scenes.soup(320, seed=31, reflective=True),
+                                                 [dict(type=api.LIGHT_DISTANT, dir=(0.0, -1.0, 0.0), colour=(0.8, 0.8, 0.8), radius=0.0),
+                                                  dict(type=api.LIGHT_SPOT, pos=(0.0, 9.0, 0.0), colour=(0.5, 0.4, 0.3), radius=0.0)]),
+                            160, 120, 1, 256),
         "soup_lights_omni_last": (lambda: _with_lights(scenes.soup(260, seed=22, reflective=True, transparent=True), [_SPOT, _SUN, _OMNI]),
                                   144, 112, 2, 256),
         "soup": (lambda: scenes.soup(400, seed=11), 192, 160, 1, 256),
@@ -50,7 +57,7 @@ def make_case(name):
 
 
 CASE_NAMES = ["soup", "soup_s4", "soup_mirror_glass", "spheres", "spheres_mirror", "terrain", "terrain_textured", "coarse_grid",
-              "soup_lights_sun_last", "soup_lights_omni_last"]
+              "soup_lights_sun_last", "soup_lights_omni_last", "soup_axis_light"]
 
 
 def compare_rgb(a, b, mask=None):
