@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <utility>
@@ -46,6 +47,122 @@ static void prepare_pool(int device) {
     done[device] = true;
 }
 
+// Host -> device copies from PAGEABLE memory.  The plugin hands RaytraceAll plain new[] arrays (render.cpp:1086-1134) -- 133 MB for
+// config 2 -- and cudaMemcpyAsync moves pageable memory through the driver's own staging buffer at ~10 GB/s on one thread (the
+// call then spends 14 ms of its 20 ms uploading, scripts/e2e_trace.py).  StagePool does the staging itself with several host
+// threads: each copies its chunks into its own two pinned slots and enqueues the H2D copy of a chunk as soon as it is staged, so
+// the copies of all threads overlap with each other and with the PCIe transfers.  Pinned / registered sources skip it.
+// OPT-IN (OCLR_STAGING=1): measured on the B200 box (scripts/pageable_probe.py, config 2) the call drops from 19.8 ms to 14.2 ms
+// with 4 threads, but individual calls took 27 ms, and with 8-16 threads single phases stalled for 10-340 ms (driver lock
+// contention between the staging threads is the suspect) -- not dependable enough to be the default this round.
+class StagePool {
+public:
+    static StagePool* get(int device) {
+        static std::mutex m;
+        static StagePool* pools[64] = {nullptr};
+        std::lock_guard<std::mutex> lock(m);
+        if (device < 0 || device >= 64) return nullptr;
+        if (!pools[device]) pools[device] = new StagePool(device);   // lives until the process ends (its threads are detached)
+        return pools[device]->ok_ ? pools[device] : nullptr;
+    }
+    // Enqueues dst[0, n) = src[0, n) on `st`; returns after the last chunk has been ENQUEUED (the caller may then enqueue consumers).
+    bool copy(void* dst, const void* src, size_t n, cudaStream_t st) {
+        std::unique_lock<std::mutex> lock(m_);
+        while (busy_) cvDone_.wait(lock);   // one job at a time per device
+        busy_ = true;
+        dst_ = (char*)dst;
+        src_ = (const char*)src;
+        n_ = n;
+        st_ = st;
+        failed_ = false;
+        remaining_ = kThreads;
+        ++generation_;
+        cvJob_.notify_all();
+        while (remaining_ != 0) cvDone_.wait(lock);
+        busy_ = false;
+        cvDone_.notify_all();
+        return !failed_;
+    }
+
+private:
+    enum { kMaxThreads = 32 };
+    static constexpr size_t kChunk = 2u << 20;
+    int kThreads = 4;
+    explicit StagePool(int device) : device_(device) {
+        if (const char* v = getenv("OCLR_STAGING_THREADS")) kThreads = std::max(1, std::min(atoi(v), (int)kMaxThreads));
+        kThreads = std::min<int>(kThreads, std::max(1u, std::thread::hardware_concurrency()));
+        cudaSetDevice(device);
+        for (int t = 0; t < kThreads && ok_; ++t)
+            for (int k = 0; k < 2 && ok_; ++k)
+                ok_ = cudaHostAlloc(&slot_[t][k], kChunk, cudaHostAllocDefault) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&event_[t][k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok_) {
+            cudaGetLastError();
+            return;
+        }
+        for (int t = 0; t < kThreads; ++t) std::thread([this, t]() { worker(t); }).detach();
+    }
+    void worker(int t) {
+        cudaSetDevice(device_);
+        unsigned long long seen = 0;
+        bool used[2] = {false, false};
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                while (generation_ == seen) cvJob_.wait(lock);
+                seen = generation_;
+            }
+            bool bad = false;
+            int k = 0;
+            for (size_t off = (size_t)t * kChunk; off < n_ && !bad; off += (size_t)kThreads * kChunk, k ^= 1) {
+                const size_t len = std::min(kChunk, n_ - off);
+                if (used[k]) bad = cudaEventSynchronize(event_[t][k]) != cudaSuccess;   // the slot's previous H2D copy has left it
+                memcpy(slot_[t][k], src_ + off, len);
+                bad = bad || cudaMemcpyAsync(dst_ + off, slot_[t][k], len, cudaMemcpyHostToDevice, st_) != cudaSuccess ||
+                      cudaEventRecord(event_[t][k], st_) != cudaSuccess;
+                used[k] = true;
+            }
+            std::lock_guard<std::mutex> lock(m_);
+            if (bad) failed_ = true;
+            if (--remaining_ == 0) cvDone_.notify_all();
+        }
+    }
+    int device_;
+    bool ok_ = true;
+    void* slot_[kMaxThreads][2] = {};
+    cudaEvent_t event_[kMaxThreads][2] = {};
+    std::mutex m_;
+    std::condition_variable cvJob_, cvDone_;
+    unsigned long long generation_ = 0;
+    int remaining_ = 0;
+    bool busy_ = false, failed_ = false;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t n_ = 0;
+    cudaStream_t st_ = nullptr;
+};
+
+static bool host_to_device(void* dst, const void* src, size_t n, cudaStream_t st, std::string& err) {
+    static const bool staging = [] { const char* v = getenv("OCLR_STAGING"); return v && atoi(v) != 0; }();
+    if (staging && n >= (4u << 20)) {
+        cudaPointerAttributes attr;
+        const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        int device = 0;
+        if (pageable && cudaGetDevice(&device) == cudaSuccess) {
+            StagePool* pool = StagePool::get(device);
+            if (pool) {
+                if (pool->copy(dst, src, n, st)) return true;
+                err = "staged host-to-device copy failed";
+                cudaGetLastError();
+                return false;
+            }
+        }
+    }
+    OCLR_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st));
+    return true;
+}
+
 struct DeviceBuffer {
     void* p = nullptr;
     size_t bytes = 0;
@@ -56,7 +173,7 @@ struct DeviceBuffer {
     }
     bool upload(const void* src, size_t n, std::string& err, cudaStream_t st = 0) {
         if (!alloc(n, err, st)) return false;
-        if (n) OCLR_CUDA(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st));
+        if (n) return host_to_device(p, src, n, st, err);
         return true;
     }
     void release(cudaStream_t st = 0) {
