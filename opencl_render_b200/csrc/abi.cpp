@@ -7,6 +7,7 @@
 #include <time.h>
 
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -463,12 +464,37 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
                                   const cl_uint* camList, size_t camListSize, cl_uint sampleCount, int rank, int world,
                                   cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
     const bool trace = getenv("OCLR_TRACE") != nullptr;
+    static const bool overlap = [] { const char* v = getenv("OCLR_OVERLAP_UPLOAD"); return !v || atoi(v) != 0; }();
     const double t0 = now_ms();
-    Scene* s = scene_create(device, h, err);
-    if (!s) return false;
-    const double t1 = now_ms();
-    Frame* f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err);
-    const double t2 = now_ms();
+    // The camera lists go up and the primary-ray round starts as soon as the triangles are on the device, under the upload of the
+    // grid (scene_create's `early` hook + frame_prelaunch); the render call below continues from that round.
+    Frame* f = nullptr;
+    std::string frameErr;
+    double tFrame = 0;
+    const std::function<void(Scene*)> early = [&](Scene* partial) {
+        const double a = now_ms();
+        f = frame_create(partial, cam, camStart, camEnd, camList, camListSize, frameErr, false);
+        std::string ignored;
+        if (f && default_variant() == (int)kKernelPipe) frame_prelaunch(f, sampleCount, 128, (uint32_t)rank, (uint32_t)(world > 1 ? world : 1), ignored);
+        tFrame = now_ms() - a;
+    };
+    Scene* s = scene_create(device, h, err, overlap && camStart && camEnd ? &early : nullptr);
+    if (!s) {
+        if (f) frame_destroy(f);
+        return false;
+    }
+    const double t1 = now_ms() - tFrame;
+    if (!f) {
+        if (!frameErr.empty()) {   // the hook ran and the frame could not be created
+            err = frameErr;
+            scene_destroy(s);
+            return false;
+        }
+        const double a = now_ms();
+        f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err);
+        tFrame = now_ms() - a;
+    }
+    const double t2 = t1 + tFrame;
     double tRender = 0, tRead = 0;
     bool ok = f != nullptr;
     if (ok) {

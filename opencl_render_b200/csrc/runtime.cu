@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <utility>
@@ -212,6 +213,7 @@ struct WfSlice {
 
 struct Frame {
     Scene* scene = nullptr;
+    int device = 0;
     Camera cam = {};
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters;
     WfSlice slices[kMaxSlices];      // wavefront path state (allocated on first use, sized for the largest slice seen)
@@ -226,6 +228,11 @@ struct Frame {
     unsigned long long* hostDone = nullptr;   // pinned
     std::atomic<unsigned long long> jobPaths{0};   // pixel-samples of the render call in flight (0: none)
     std::mutex progMutex;
+    // first logic round started ahead of the render call (frame_prelaunch): it runs on preStream while the scene's grid is uploaded
+    cudaStream_t preStream = nullptr;
+    cudaEvent_t preReady = nullptr, preDone = nullptr;
+    bool prelaunched = false;
+    FrameView preView = {};
 };
 
 int device_count() {
@@ -404,7 +411,7 @@ bool build_scene_grid_device(int device, int32_t n, uint32_t V, const float4* ve
     return done(true);
 }
 
-static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
+static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early) {
     OCLR_CUDA(cudaSetDevice(s->device));
     int major = 0, minor = 0, sms = 0;   // attribute queries: cudaGetDeviceProperties costs milliseconds per call
     OCLR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, s->device));
@@ -430,22 +437,47 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     std::vector<Light> lights;
     pack_lights(h, lights);
 
-    // 1. raw reference arrays -> HBM, straight from the caller's memory (async on the default stream)
+    // 1a. everything the primary-ray round needs -- triangles, materials, lights -- goes first: raw reference arrays -> HBM straight
+    //     from the caller's memory (async on the default stream), repacked by pack_triangles_kernel
     DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag, cellIds;
     bool ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
               triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
               triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) &&
-              (buildGrid || (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
-                             gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
-                             s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err))) &&
               s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
               s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
               s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
               s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&
               s->triGeo.alloc(sizeof(float4) * 4 * N, err) && s->triShade.alloc(sizeof(float4) * 8 * N, err) &&
-              s->bricks.alloc(sizeof(uint4) * nBricks, err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
-              counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err) &&
               errFlag.alloc(sizeof(uint32_t) * 2, err);
+    if (ok) {
+        cudaMemsetAsync(errFlag.p, 0, sizeof(uint32_t) * 2, 0);
+        if (N)
+            pack_triangles_kernel<<<(unsigned)((N + 255) / 256), 256>>>((uint32_t)N, h.vertexCount, h.materialCount, (const float4*)vertex.p,
+                                                                      (const int4*)triIdx.p, (const int32_t*)triMat.p, (const float2*)triUv.p,
+                                                                      (const float4*)triNormal.p, (float4*)s->triGeo.p,
+                                                                      (float4*)s->triShade.p, (uint32_t*)errFlag.p);
+        SceneView& v = s->view;   // the part of the view the logic kernel reads (the grid part follows below)
+        v.triGeo = (const float4*)s->triGeo.p;
+        v.triShade = (const float4*)s->triShade.p;
+        v.matSize = (const uint2*)s->matSize.p;
+        v.matStart = (const int32_t*)s->matStart.p;
+        v.textures = (const uchar4*)s->textures.p;
+        v.lights = (const Light*)s->lights.p;
+        v.triangleCount = h.triangleCount;
+        v.materialCount = h.materialCount;
+        v.lightCount = h.lightCount;
+        v.n = n;
+        v.nb = nb;
+        // RaytraceAll uploads its camera lists and starts the primary-ray round HERE, on a stream of its own, so that round runs
+        // under the upload of the grid (94 of config 2's 133 MB) instead of after it
+        if (early && *early) (*early)(s);
+    }
+    // 1b. the grid
+    ok = ok && (buildGrid || (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
+                              gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
+                              s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err))) &&
+         s->bricks.alloc(sizeof(uint4) * nBricks, err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
+         counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err);
     uint32_t nonEmpty = 0, flag = 0;
     if (ok && buildGrid) {
         for (size_t i = 0; ok && i < N; ++i) {  // the builder gathers vertices by index before the packers have validated them
@@ -466,13 +498,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     }
     if (ok) {
         // 2. repack on the device
-        cudaMemsetAsync(errFlag.p, 0, sizeof(uint32_t) * 2, 0);
         cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (nBricks + 1), 0);
-        if (N)
-            pack_triangles_kernel<<<(unsigned)((N + 255) / 256), 256>>>((uint32_t)N, h.vertexCount, h.materialCount, (const float4*)vertex.p,
-                                                                      (const int4*)triIdx.p, (const int32_t*)triMat.p, (const float2*)triUv.p,
-                                                                      (const float4*)triNormal.p, (float4*)s->triGeo.p,
-                                                                      (float4*)s->triShade.p, (uint32_t*)errFlag.p);
         split_planes_kernel<<<(n + 1 + 127) / 128, 128>>>((const float4*)boxMin.p, n, (float*)s->planes.p);
         brick_count_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (uint32_t*)counts.p,
                                                                       (uint32_t*)errFlag.p);
@@ -547,14 +573,15 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err) {
     return true;
 }
 
-Scene* scene_create(int device, const HostScene& h, std::string& err) {
+Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early) {
     if (device < 0 || device >= device_count()) {
         err = "no such CUDA device: " + std::to_string(device) + " (the library has no CPU fallback)";
         return nullptr;
     }
     Scene* s = new Scene();
     s->device = device;
-    if (!scene_upload(s, h, err)) {
+    if (!scene_upload(s, h, err, early)) {
+        cudaDeviceSynchronize();   // the `early` hook may have started work on another stream that still reads this scene
         scene_destroy(s);
         return nullptr;
     }
@@ -583,7 +610,7 @@ size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap) {
 }
 int scene_device(const Scene* s) { return s->device; }
 
-static bool frame_setup_common(Frame* f, std::string& err) {
+static bool frame_setup_common(Frame* f, std::string& err, bool sync = true) {
     const size_t P = (size_t)f->cam.width * f->cam.height;
     if (!f->planesRGB.alloc(sizeof(uint16_t) * 3 * P, err)) return false;
     if (!f->ids.alloc(sizeof(uint32_t) * P, err)) return false;
@@ -598,12 +625,12 @@ static bool frame_setup_common(Frame* f, std::string& err) {
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
-    OCLR_CUDA(cudaStreamSynchronize(0));
+    if (sync) OCLR_CUDA(cudaStreamSynchronize(0));
     return true;
 }
 
 static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
-                        std::string& err) {
+                        std::string& err, bool sync) {
     OCLR_CUDA(cudaSetDevice(f->scene->device));
     const size_t P = (size_t)f->cam.width * f->cam.height;
     if (!camStart || !camEnd || (listSize && !camList)) {
@@ -614,7 +641,7 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
     if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
     if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
     f->camListSize = listSize;
-    return frame_setup_common(f, err);
+    return frame_setup_common(f, err, sync);
 }
 
 // CameraTriangleList::New on the device (cam_builder.cuh): the frame's camera lists are built from the resident scene.
@@ -730,7 +757,7 @@ static bool frame_build_camera_lists(Frame* f, std::string& err) {
 }
 
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
-                    size_t camListSize, std::string& err) {
+                    size_t camListSize, std::string& err, bool sync) {
     if (!s) {
         err = "null scene";
         return nullptr;
@@ -741,8 +768,9 @@ Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const
     }
     Frame* f = new Frame();
     f->scene = s;
+    f->device = s->device;
     f->cam = cam;
-    const bool ok = camStart ? frame_setup(f, camStart, camEnd, camList, camListSize, err)
+    const bool ok = camStart ? frame_setup(f, camStart, camEnd, camList, camListSize, err, sync)
                              : (frame_build_camera_lists(f, err) && frame_setup_common(f, err));   // no lists given: build them on the device
     if (!ok) {
         frame_destroy(f);
@@ -768,11 +796,14 @@ bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t*
 
 void frame_destroy(Frame* f) {
     if (!f) return;
-    cudaSetDevice(f->scene->device);
+    cudaSetDevice(f->device);
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount};
     for (DeviceBuffer* b : all) b->release();
     if (f->progStream) cudaStreamDestroy(f->progStream);
     if (f->hostDone) cudaFreeHost(f->hostDone);
+    if (f->preStream) cudaStreamDestroy(f->preStream);
+    if (f->preReady) cudaEventDestroy(f->preReady);
+    if (f->preDone) cudaEventDestroy(f->preDone);
     for (WfSlice& sl : f->slices) {
         for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release();
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -832,8 +863,11 @@ static int slice_count_for(uint32_t rows, uint32_t width) {
 }
 
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
+// `prelaunchOnly`: allocate the path state and enqueue nothing but the first logic round of the first sample, on the frame's own
+// stream behind everything already enqueued on `st` (frame_prelaunch).  A later normal call with the same view finds
+// f->prelaunched set, skips that round's logic launch and orders its first setup kernel behind it.
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall, int smCount, Counters* dcnt, cudaStream_t st,
-                             uint32_t& launches, bool timeTrace, std::string& err) {
+                             uint32_t& launches, bool timeTrace, std::string& err, bool prelaunchOnly = false) {
     const uint32_t W = Fall.cam.width;
     if (S.n > 1024) {
         err = "axesDivCount > 1024 is not supported by the packed walk";
@@ -865,6 +899,12 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         K = used;
     }
     if (K == 0) return true;
+    const bool resumePre = !prelaunchOnly && f->prelaunched && K == 1 && memcmp(&f->preView, &Fall, sizeof(FrameView)) == 0;
+    if (!prelaunchOnly && f->prelaunched && !resumePre) {   // a prelaunched round nobody can use: wait it out and start over
+        OCLR_CUDA(cudaStreamWaitEvent(st, f->preDone, 0));
+        f->prelaunched = false;
+    }
+    if (prelaunchOnly && K != 1) return true;   // (only the one-slice case is started ahead)
 
     WfState w[kMaxSlices];
     WalkRecords rec[kMaxSlices];
@@ -944,7 +984,30 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     }
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
     const unsigned traceGrid = (unsigned)(smCount * perSm);
-    if (Fall.flagOut) OCLR_CUDA(cudaMemsetAsync(Fall.flagOut, 0, (size_t)Fall.cam.width * Fall.cam.height, st));
+    if (Fall.flagOut && !resumePre) OCLR_CUDA(cudaMemsetAsync(Fall.flagOut, 0, (size_t)Fall.cam.width * Fall.cam.height, st));
+    if (prelaunchOnly) {
+        if (!f->preStream) {
+            OCLR_CUDA(cudaStreamCreateWithFlags(&f->preStream, cudaStreamNonBlocking));
+            OCLR_CUDA(cudaEventCreateWithFlags(&f->preReady, cudaEventDisableTiming));
+            OCLR_CUDA(cudaEventCreateWithFlags(&f->preDone, cudaEventDisableTiming));
+        }
+        WfSlice& sl = f->slices[0];
+        uint32_t* counters = (uint32_t*)sl.workCounter.p;
+        w[0].queueCount = counters;
+        w[0].queueCursor = counters + 1;
+        w[0].roundLog = counters + 2 * (2 + kLengthClasses);
+        w[0].roundIndex = 0;
+        OCLR_CUDA(cudaEventRecord(f->preReady, st));
+        OCLR_CUDA(cudaStreamWaitEvent(f->preStream, f->preReady, 0));
+        OCLR_CUDA(cudaMemsetAsync(w[0].queueCount, 0, sizeof(uint32_t) * (2 + kLengthClasses), f->preStream));
+        wf_logic_kernel<false><<<logicGrid[0], 128, 0, f->preStream>>>(S, FV[0], w[0], Fall.sampleBegin, 1u, nullptr, nullptr, aheadMode[0]);
+        OCLR_CUDA(cudaGetLastError());
+        OCLR_CUDA(cudaEventRecord(f->preDone, f->preStream));
+        f->prelaunched = true;
+        f->preView = Fall;
+        ++launches;
+        return true;
+    }
     // fork: the internal streams start after everything already enqueued on the caller's stream
     if (K > 1) {
         OCLR_CUDA(cudaEventRecord(f->evFork, st));
@@ -979,12 +1042,18 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     w[k].roundLog = counters + 2 * cstride;
                     w[k].roundIndex = r;
                     const uint32_t* prev = r ? counters + cstride * ((r - 1) & 1u) : nullptr;
-                    OCLR_CUDA(cudaMemsetAsync(w[k].queueCount, 0, sizeof(uint32_t) * cstride, ks));
-                    if (dcnt)
-                        wf_logic_kernel<true><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
-                    else
-                        wf_logic_kernel<false><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
-                    ++launches;
+                    if (resumePre && f->prelaunched && s == Fall.sampleBegin && r == 0) {
+                        // this round's logic kernel is already running (or done) on the frame's own stream: frame_prelaunch
+                        OCLR_CUDA(cudaStreamWaitEvent(ks, f->preDone, 0));
+                        f->prelaunched = false;
+                    } else {
+                        OCLR_CUDA(cudaMemsetAsync(w[k].queueCount, 0, sizeof(uint32_t) * cstride, ks));
+                        if (dcnt)
+                            wf_logic_kernel<true><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
+                        else
+                            wf_logic_kernel<false><<<logicGrid[k], 128, 0, ks>>>(S, FV[k], w[k], s, r == 0 ? 1u : 0u, prev, dcnt, aheadMode[k]);
+                        ++launches;
+                    }
                     if (timeTrace) {
                         while (sl.traceEvents.size() < (size_t)sl.traceEventsUsed + 2) {
                             cudaEvent_t e;
@@ -1050,9 +1119,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     return true;
 }
 
-static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
-    Scene* s = f->scene;
-    cudaStream_t st = (cudaStream_t)stream;
+static void fill_view(Frame* f, FrameView& F) {
     const size_t P = (size_t)f->cam.width * f->cam.height;
     F.cam = f->cam;
     F.camStart = (const uint32_t*)f->camStart.p;
@@ -1065,11 +1132,23 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
     F.flagOut = (uint8_t*)f->flags.p;
     F.accum = (float4*)f->accum.p;   // nullptr unless float accumulation is on
     F.doneCount = (unsigned long long*)f->doneCount.p;
+}
+
+static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
+    Scene* s = f->scene;
+    cudaStream_t st = (cudaStream_t)stream;
+    fill_view(f, F);
     if (F.accum && variant == kKernelSimple) {
         err = "float accumulation is implemented by the wavefront pipeline only";
         return false;
     }
-    OCLR_CUDA(cudaMemsetAsync(F.doneCount, 0, sizeof(unsigned long long), st));
+    // (a first round started ahead by frame_prelaunch for exactly this request has already counted its finished paths)
+    const bool continuesPre = f->prelaunched && variant == kKernelPipe && !count && memcmp(&f->preView, &F, sizeof(FrameView)) == 0;
+    if (f->prelaunched && !continuesPre) {
+        OCLR_CUDA(cudaStreamWaitEvent(st, f->preDone, 0));
+        f->prelaunched = false;
+    }
+    if (!continuesPre) OCLR_CUDA(cudaMemsetAsync(F.doneCount, 0, sizeof(unsigned long long), st));
     f->jobPaths.store((unsigned long long)launch_rows(F) * f->cam.width * (F.sampleEnd - F.sampleBegin));
     Counters* dcnt = (Counters*)f->counters.p;
     if (count) OCLR_CUDA(cudaMemsetAsync(dcnt, 0, sizeof(Counters), st));
@@ -1180,6 +1259,43 @@ bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, ui
         return true;
     }
     return frame_launch(f, F, variant, count, stream, stats, err);
+}
+
+// Starts the first logic round (ray generation, camera-list scan, shading of the primary hits) of the request
+// frame_render_bands(f, sampleCount, 0, sampleCount, bandRows, rank, world, kKernelPipe, ...) would make, on a stream of the frame's own
+// behind everything enqueued on the default stream so far.  Needs only the triangle / material / light part of the scene (see
+// scene_create's `early` hook).  The matching render call continues from there; any other request waits the round out and starts over.
+bool frame_prelaunch(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, std::string& err) {
+    if (!f || sampleCount == 0 || world == 0 || rank >= world || bandRows == 0) {
+        err = "bad prelaunch request";
+        return false;
+    }
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    FrameView F = {};
+    F.sampleCount = sampleCount;
+    F.sampleBegin = 0;
+    F.sampleEnd = sampleCount;
+    if (world == 1) {
+        F.rowBegin = 0;
+        F.rowEnd = f->cam.height;
+        F.bandRows = 0;
+        F.bandRank = 0;
+        F.bandWorld = 1;
+        F.ownedRows = f->cam.height;
+    } else {
+        F.rowBegin = 0;
+        F.rowEnd = f->cam.height;
+        F.bandRows = bandRows;
+        F.bandRank = rank;
+        F.bandWorld = world;
+        F.ownedRows = band_owned_rows(f->cam.height, bandRows, rank, world);
+        if (F.ownedRows == 0) return true;
+    }
+    fill_view(f, F);
+    if (F.accum) return true;
+    OCLR_CUDA(cudaMemsetAsync(F.doneCount, 0, sizeof(unsigned long long), 0));
+    uint32_t launches = 0;
+    return launch_wavefront(f, f->scene->view, F, f->scene->smCount, nullptr, 0, launches, false, err, true);
 }
 
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,

@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -62,7 +63,9 @@ struct Frame;
 int device_count();
 bool device_name(int dev, char* buf, size_t len);
 
-Scene* scene_create(int device, const HostScene& h, std::string& err);
+// `early` (optional) is called once the triangles, materials and lights are on their way to the device and BEFORE the grid is
+// uploaded, with the partly built scene: RaytraceAll uses it to start the primary-ray round under the grid upload (frame_prelaunch).
+Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early = nullptr);
 void scene_destroy(Scene* s);
 size_t scene_device_bytes(const Scene* s);
 int scene_device(const Scene* s);
@@ -71,7 +74,7 @@ size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap);
 // Camera lists are per-frame inputs (CameraTriangleList::New output, trianglelist.cpp:520-626).  `camStart`/`camEnd`
 // hold width*height entries; only rows [rowBegin,rowEnd) need to be valid (band-partitioned multi-GPU rendering).
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
-                    size_t camListSize, std::string& err);
+                    size_t camListSize, std::string& err, bool sync = true);   // sync = false: the host arrays outlive the copies
 void frame_destroy(Frame* f);
 // camStart == nullptr: CameraTriangleList::New runs on the device from the resident scene (cam_builder.cuh).  The lists a frame
 // holds (uploaded or device-built) can be copied back: `list` needs frame_camera_list_size() entries.
@@ -98,6 +101,9 @@ bool frame_render(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t
 // Same, for the rows y with (y / bandRows) % world == rank (one launch covers all bands the rank owns).
 bool frame_render_bands(Frame* f, uint32_t sampleCount, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t bandRows, uint32_t rank, uint32_t world,
                         int variant, bool count, void* stream, RenderStats* stats, std::string& err);
+// Starts the first logic round of frame_render_bands(f, sampleCount, 0, sampleCount, bandRows, rank, world, kKernelPipe, ...) ahead, on the
+// frame's own stream (runtime.cu); the matching render call on the default stream continues from it.
+bool frame_prelaunch(Frame* f, uint32_t sampleCount, uint32_t bandRows, uint32_t rank, uint32_t world, std::string& err);
 // Progressive accumulation / checkpoint-resume / progress; see runtime.cu.
 bool frame_write(Frame* f, uint32_t rowBegin, uint32_t rowEnd, const uint16_t* inR, const uint16_t* inG, const uint16_t* inB, void* stream,
                  std::string& err);
