@@ -164,6 +164,32 @@ static bool host_to_device(void* dst, const void* src, size_t n, cudaStream_t st
     return true;
 }
 
+// Small pinned blocks (the frames' read-back words) are recycled: cudaHostAlloc / cudaFreeHost cost ~50-100 us each, which a
+// RaytraceAll call that creates and destroys its frame would pay every time.  Blocks are 4 KB, portable, never returned to the driver.
+static std::mutex g_pinMutex;
+static std::vector<void*> g_pinFree;
+static void* pinned_block() {
+    {
+        std::lock_guard<std::mutex> lock(g_pinMutex);
+        if (!g_pinFree.empty()) {
+            void* p = g_pinFree.back();
+            g_pinFree.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 4096, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+static void pinned_release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pinMutex);
+    g_pinFree.push_back(p);
+}
+
 struct DeviceBuffer {
     void* p = nullptr;
     size_t bytes = 0;
@@ -619,8 +645,11 @@ static bool frame_setup_common(Frame* f, std::string& err, bool sync = true) {
     if (!f->counters.alloc(sizeof(Counters), err)) return false;
     if (!f->doneCount.alloc(sizeof(unsigned long long), err)) return false;
     OCLR_CUDA(cudaMemsetAsync(f->doneCount.p, 0, sizeof(unsigned long long), 0));
-    OCLR_CUDA(cudaStreamCreateWithFlags(&f->progStream, cudaStreamNonBlocking));
-    OCLR_CUDA(cudaHostAlloc((void**)&f->hostDone, sizeof(unsigned long long), cudaHostAllocDefault));
+    f->hostDone = (unsigned long long*)pinned_block();
+    if (!f->hostDone) {
+        err = "out of pinned host memory";
+        return false;
+    }
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
     OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
@@ -800,7 +829,7 @@ void frame_destroy(Frame* f) {
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount};
     for (DeviceBuffer* b : all) b->release();
     if (f->progStream) cudaStreamDestroy(f->progStream);
-    if (f->hostDone) cudaFreeHost(f->hostDone);
+    pinned_release(f->hostDone);
     if (f->preStream) cudaStreamDestroy(f->preStream);
     if (f->preReady) cudaEventDestroy(f->preReady);
     if (f->preDone) cudaEventDestroy(f->preDone);
@@ -810,7 +839,7 @@ void frame_destroy(Frame* f) {
         if (sl.done) cudaEventDestroy(sl.done);
         for (cudaEvent_t e : sl.traceEvents) cudaEventDestroy(e);
     }
-    if (f->hostCount) cudaFreeHost(f->hostCount);
+    pinned_release(f->hostCount);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     if (f->evFork) cudaEventDestroy(f->evFork);
@@ -963,7 +992,12 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         setupGrid[k] = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, (2 * (uint64_t)Q + 255) / 256);
     }
     for (int k = K; k < kMaxSlices; ++k) f->slices[k].traceEventsUsed = 0;
-    if (!f->hostCount) OCLR_CUDA(cudaHostAlloc((void**)&f->hostCount, sizeof(uint32_t) * kMaxSlices * kRoundLogSize, cudaHostAllocDefault));
+    static_assert(sizeof(uint32_t) * kMaxSlices * kRoundLogSize <= 4096, "round logs fit one pinned block");
+    if (!f->hostCount) f->hostCount = (uint32_t*)pinned_block();
+    if (!f->hostCount) {
+        err = "out of pinned host memory";
+        return false;
+    }
 
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
@@ -1383,8 +1417,13 @@ bool frame_progress(Frame* f, unsigned long long* done, unsigned long long* tota
     std::lock_guard<std::mutex> lock(f->progMutex);
     *total = f->jobPaths.load();
     *done = 0;
-    if (*total == 0 || !f->progStream) return true;
-    if (cudaSetDevice(f->scene->device) != cudaSuccess) return false;
+    if (*total == 0) return true;
+    if (cudaSetDevice(f->device) != cudaSuccess) return false;
+    if (!f->progStream && cudaStreamCreateWithFlags(&f->progStream, cudaStreamNonBlocking) != cudaSuccess) {   // first poll of this frame
+        cudaGetLastError();
+        f->progStream = nullptr;
+        return false;
+    }
     if (cudaMemcpyAsync(f->hostDone, f->doneCount.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, f->progStream) != cudaSuccess ||
         cudaStreamSynchronize(f->progStream) != cudaSuccess) {
         cudaGetLastError();
