@@ -86,7 +86,7 @@ enum KernelVariant { kKernelSimple = 0, kKernelPipe = 2 };   // (1 was the lane-
 struct RenderStats {
     float deviceMs = 0.f;        // CUDA-event time of the trace kernel(s) on the launch stream
     uint32_t launches = 0;       // kernels launched
-    float traceMs = 0.f;         // CUDA-event time of the wf_trace_kernel launches alone (the dominant kernel)
+    float traceMs = 0.f;         // device time during which a trace-stage launch (wf_setup_kernel + wf_pipe_kernel, the dominant kernel) was in flight
     uint32_t traceLaunches = 0;
     Counters counters = {};      // filled when `count` was requested
 };

@@ -1,6 +1,6 @@
 """Instruction shares of the trace kernel by phase (source-line ranges are looked up from marker comments in rt_trace.cuh)."""
 import csv, io, subprocess, sys, re
-rep = sys.argv[1]; kernel = sys.argv[2] if len(sys.argv) > 2 else "wf_trace3_kernel"
+rep = sys.argv[1]; kernel = sys.argv[2] if len(sys.argv) > 2 else "wf_pipe_kernel"
 src = open("opencl_render_b200/csrc/rt_trace.cuh").read().split("\n")
 # find line ranges inside the kernel by markers
 start = next(i for i, l in enumerate(src) if kernel + "(" in l and "__global__" in "".join(src[max(0,i-1):i+1])) + 1
