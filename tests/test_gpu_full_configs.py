@@ -136,3 +136,24 @@ def test_frame_assembly_over_peer_memory_two_gpus():
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "equals single-GPU frame: True" in r.stdout and "equals single-GPU frame: False" not in r.stdout
+
+
+def test_raytrace_all_on_all_devices_of_the_box(port):
+    """computationType = deviceCount + 1: rows dealt in bands of 128 (the reference's tile height, raytrace.c:507) over every GPU of
+    the box from ONE process, each GPU copying its rows straight into the caller's planes.  Skipped on a one-GPU box."""
+    from opencl_render_b200 import _lib
+    n = _lib.load().oclr_device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    names = api.computation_types()
+    assert len(names) == n + 2 and "all" in names[n + 1]
+    sc = scenes.sphere_grid(3, 12, 24, reflection=64)
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], 400, 600)       # 600 rows = 5 bands: both GPUs get some
+    lists = api.camera_triangle_list(cam, sc)
+    api.scene_triangle_list(sc, 256)
+    one = api.raytrace_all(1, cam, lists, 2, sc)
+    every = api.raytrace_all(n + 1, cam, lists, 2, sc)
+    want = port.render(cam, lists, sc, 2)
+    for c in range(3):
+        assert np.array_equal(one[c], want[c]) and np.array_equal(every[c], want[c])
