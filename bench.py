@@ -84,10 +84,13 @@ class ClockSampler:
     def __init__(self, index=0):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.index = index
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -104,6 +107,39 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
+    def _run_nvml(self) -> bool:
+        """The same counters nvidia-smi prints, read through NVML directly: a query takes well under a millisecond, so a timed region
+        of ~100 ms yields dozens of samples instead of one.  False when NVML is not usable (then nvidia-smi is polled)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            index = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:      # CUDA's device index -> NVML's
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    index = int(ids[index])
+            dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(dev)
+        except Exception:
+            return False
+        bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        self.source = "nvml"
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM)))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(dev))
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+        return True
+
     def __enter__(self):
         self._t.start()
         return self
@@ -114,7 +150,7 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def run_reference(args):
