@@ -1,4 +1,4 @@
-"""Scene loader: Wavefront OBJ/MTL (+ bitmaps) -> the scene arrays RaytraceAll takes.
+"""Scene loader: Wavefront OBJ/MTL (+ bitmaps) and PLY -> the scene arrays RaytraceAll takes.
 
 Stands in for the Cinema4D scene extraction of the plugin (source/render.cpp:707-1308), which needs the C4D SDK, so that real
 assets can be rendered through the same boundary.  It follows the plugin's conventions wherever they are observable:
@@ -165,6 +165,12 @@ def load_obj(path, eye=(0.0, 0.0, 0.0), lights=None, reference_fallbacks: bool =
             for k in range(1, len(poly) - 1):              # (a,b,c), (a,c,d), ...   render.cpp:733-736, 778-781
                 corners.append((poly[0], poly[k], poly[k + 1]))
                 tri_mat_name.append(cur_mat)
+    return _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name)
+
+
+def _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name) -> HostScene:
+    """Parsed geometry (positions, UVs, normals, per-triangle corner index triples (vertex, uv, normal; -1 = absent) and material names)
+    -> HostScene with the plugin's conventions (module docstring)."""
     if not corners:
         raise ValueError(f"{path}: no faces")
     V = np.zeros((len(v), 4), np.float32)
@@ -231,6 +237,106 @@ def load_obj(path, eye=(0.0, 0.0, 0.0), lights=None, reference_fallbacks: bool =
     return HostScene(vertex=V, tri_idx=idx, tri_mat=tri_mat, tri_uv=uv, tri_normal=nrm, mat_size=size, mat_start=start, textures=tex,
                      light_type=lt, light_pos=pos, light_dir=dr, light_colour=col, light_radius=rad, light_half=half,
                      name=name or path.stem, meta=dict(materials=[m or "(default)" for m in order])).normalise()
+
+
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2",
+              "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def load_ply(path, eye=(0.0, 0.0, 0.0), lights=None, material: dict | None = None, reference_fallbacks: bool = True,
+             normalise_normals: bool = True, name: str | None = None) -> HostScene:
+    """Reads a PLY file (ascii, binary_little_endian or binary_big_endian) into a HostScene with the same conventions as load_obj.
+    Used per vertex: x y z, nx ny nz (optional), s t or u v (optional); per face: vertex_indices / vertex_index (triangles, quads and
+    larger polygons are fanned as render.cpp:733-781 does).  PLY has no materials: the one material of the scene is `material`
+    ({channel id: (r, g, b) bytes | uint8 [h,w,3] image}, default: the plugin's white)."""
+    path = Path(path)
+    data = path.read_bytes()
+    end = data.find(b"end_header")
+    if not data.startswith(b"ply") or end < 0:
+        raise ValueError(f"{path}: not a PLY file")
+    body = data[data.index(b"\n", end) + 1:]
+    fmt = None
+    elements = []          # (name, count, [(kind, ...)])
+    for line in data[:end].decode("ascii", "replace").splitlines():
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "format":
+            fmt = t[1]
+        elif t[0] == "element":
+            elements.append((t[1], int(t[2]), []))
+        elif t[0] == "property" and elements:
+            if t[1] == "list":
+                elements[-1][2].append(("list", _PLY_TYPES[t[2]], _PLY_TYPES[t[3]], t[4]))
+            else:
+                elements[-1][2].append(("scalar", _PLY_TYPES[t[1]], t[2]))
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+        raise ValueError(f"{path}: unknown PLY format {fmt!r}")
+    order = "<" if fmt == "binary_little_endian" else ">"
+    vertex_cols: dict = {}
+    faces: list = []
+    tokens = body.split() if fmt == "ascii" else None
+    tpos = 0
+    off = 0
+    for ename, count, props in elements:
+        scalar_only = all(p[0] == "scalar" for p in props)
+        if fmt != "ascii" and scalar_only:
+            dt = np.dtype([(p[2], order + p[1]) for p in props])
+            arr = np.frombuffer(body, dt, count, off)
+            off += dt.itemsize * count
+            cols = {p[2]: arr[p[2]] for p in props}
+            rows = None
+        else:
+            cols, rows = {p[-1]: [] for p in props}, None
+            for _ in range(count):
+                for pr in props:
+                    if pr[0] == "scalar":
+                        if fmt == "ascii":
+                            val = float(tokens[tpos]); tpos += 1
+                        else:
+                            dt = np.dtype(order + pr[1]); val = np.frombuffer(body, dt, 1, off)[0]; off += dt.itemsize
+                        cols[pr[2]].append(val)
+                    else:
+                        if fmt == "ascii":
+                            n = int(tokens[tpos]); tpos += 1
+                            vals = [int(float(x)) for x in tokens[tpos:tpos + n]]; tpos += n
+                        else:
+                            dc, di = np.dtype(order + pr[1]), np.dtype(order + pr[2])
+                            n = int(np.frombuffer(body, dc, 1, off)[0]); off += dc.itemsize
+                            vals = np.frombuffer(body, di, n, off).astype(np.int64).tolist(); off += di.itemsize * n
+                        cols[pr[3]].append(vals)
+        if ename == "vertex":
+            vertex_cols = {k: np.asarray(val, np.float64) for k, val in cols.items()}
+        elif ename == "face":
+            key = "vertex_indices" if "vertex_indices" in cols else ("vertex_index" if "vertex_index" in cols else None)
+            if key is None:
+                raise ValueError(f"{path}: face element without vertex_indices")
+            faces = cols[key]
+    if not {"x", "y", "z"} <= set(vertex_cols):
+        raise ValueError(f"{path}: vertex element without x y z")
+    nv = len(vertex_cols["x"])
+    v = np.stack([vertex_cols["x"], vertex_cols["y"], vertex_cols["z"]], axis=1).tolist()
+    has_n = {"nx", "ny", "nz"} <= set(vertex_cols)
+    vn = np.stack([vertex_cols["nx"], vertex_cols["ny"], vertex_cols["nz"]], axis=1).tolist() if has_n else []
+    ukey = ("s", "t") if {"s", "t"} <= set(vertex_cols) else (("u", "v") if {"u", "v"} <= set(vertex_cols) else None)
+    vt = np.stack([vertex_cols[ukey[0]], vertex_cols[ukey[1]]], axis=1).tolist() if ukey else []
+    corners, names = [], []
+    for poly in faces:
+        if len(poly) < 3:
+            raise ValueError(f"{path}: face with fewer than 3 corners")
+        if min(poly) < 0 or max(poly) >= nv:
+            raise ValueError(f"{path}: vertex index out of range in a face")
+        pc = [(int(i), int(i) if ukey else -1, int(i) if has_n else -1) for i in poly]
+        for k in range(1, len(pc) - 1):
+            corners.append((pc[0], pc[k], pc[k + 1]))
+            names.append("ply")
+    mtl = {"ply": dict(material or {})}
+    return _assemble(path, v, vt, vn, corners, names, mtl, eye, lights, reference_fallbacks, normalise_normals, name)
+
+
+def load_scene(path, **kw) -> HostScene:
+    """OBJ or PLY by file extension."""
+    return load_ply(path, **kw) if str(path).lower().endswith(".ply") else load_obj(path, **kw)
 
 
 def save_obj(scene: HostScene, path, bitmap_format: str = "png") -> Path:

@@ -3,7 +3,7 @@
 
     python -m opencl_render_b200.render SCENE --out img.png [--size 1024x768] [--samples 100] [--device 1] ...
 
-SCENE is a Wavefront OBJ file (loader.py) or the name of a built-in synthetic scene (`config1` .. `config4`, scenes.py).
+SCENE is a Wavefront OBJ or a PLY file (loader.py) or the name of a built-in synthetic scene (`config1` .. `config4`, scenes.py).
 Defaults are the dialog's: 1024x768, 100 samples per pixel (render.cpp:176-182); `--device` is the dialog's processor combo index
 (`--list-devices` prints it; index 0 is the reference's CPU entry and is refused -- this library has no CPU path).
 
@@ -59,7 +59,7 @@ def _time_str(seconds: float) -> str:
 
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="python -m opencl_render_b200.render", description=__doc__.split("\n\n")[0])
-    ap.add_argument("scene", nargs="?", help="OBJ file or config1..config4")
+    ap.add_argument("scene", nargs="?", help="OBJ / PLY file or config1..config4")
     ap.add_argument("--out", default="img.png", help=".png / .ppm (16 bit) or .bmp (8 bit); the reference writes img.bmp")
     ap.add_argument("--size", default="1024x768")
     ap.add_argument("--samples", type=int, default=100)
@@ -100,7 +100,7 @@ def main(argv=None) -> int:
     else:
         from . import loader
         eye = a.eye or [0.0, 1.0, -5.0]
-        sc = loader.load_obj(a.scene, eye=eye, lights=a.light)
+        sc = loader.load_scene(a.scene, eye=eye, lights=a.light)
         cm = dict(eye=eye, look_at=[0.0, 0.0, 0.0], up=a.up, fov=0.9)
     if a.eye:
         cm["eye"] = a.eye

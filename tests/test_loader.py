@@ -135,3 +135,62 @@ def test_render_harness_cli(tmp_path):
     assert all(np.array_equal(px[..., c], want[c]) for c in range(3))
     # the finished checkpoint resumes to the same picture without rendering anything
     assert int(np.load(ck)["done"]) == 6 and render.main(args) == 0 and out.read_bytes() == first
+
+
+def _ply_text(verts, faces, normals=None, uvs=None):
+    props = ["property float x", "property float y", "property float z"]
+    if normals is not None:
+        props += ["property float nx", "property float ny", "property float nz"]
+    if uvs is not None:
+        props += ["property float s", "property float t"]
+    head = ["ply", "format ascii 1.0", "comment test", f"element vertex {len(verts)}", *props, f"element face {len(faces)}",
+            "property list uchar int vertex_indices", "end_header"]
+    rows = []
+    for i, p in enumerate(verts):
+        r = list(p) + (list(normals[i]) if normals is not None else []) + (list(uvs[i]) if uvs is not None else [])
+        rows.append(" ".join(f"{float(x):.9g}" for x in r))
+    for f in faces:
+        rows.append(" ".join(str(x) for x in [len(f), *f]))
+    return "\n".join(head + rows) + "\n"
+
+
+def test_ply_ascii_and_binary_agree_with_the_obj_loader(tmp_path):
+    import struct
+    verts = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0.5, 0.5, 1.5)]
+    faces = [[0, 1, 2, 3], [0, 1, 4], [1, 2, 4]]
+    (tmp_path / "a.ply").write_text(_ply_text(verts, faces))
+    ply = loader.load_scene(tmp_path / "a.ply", eye=(0.3, 0.2, -4.0))
+    (tmp_path / "a.obj").write_text("".join(f"v {x} {y} {z}\n" for x, y, z in verts) + "".join("f " + " ".join(str(i + 1) for i in f) + "\n" for f in faces))
+    obj = loader.load_scene(tmp_path / "a.obj", eye=(0.3, 0.2, -4.0))
+    assert ply.triangle_count == 4 and ply.tri_idx[:, :3].tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 4], [1, 2, 4]]      # quad split as render.cpp:733-781
+    for f in ("vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type", "light_dir"):
+        assert np.array_equal(getattr(ply, f), getattr(obj, f)), f
+    # the same file as binary_little_endian / binary_big_endian with normals and uvs per vertex
+    normals = [(0, 0, -2), (0, 0, -1), (0, 0, -1), (0, 0, -1), (0, 3, 0)]
+    uvs = [(0, 0), (1, 0), (1, 1), (0, 1), (0.5, 0.25)]
+    ascii_scene = None
+    for fmt, order in (("ascii", None), ("binary_little_endian", "<"), ("binary_big_endian", ">")):
+        p = tmp_path / f"{fmt}.ply"
+        if order is None:
+            p.write_text(_ply_text(verts, faces, normals, uvs))
+        else:
+            head = "\n".join(["ply", f"format {fmt} 1.0", f"element vertex {len(verts)}", "property float x", "property float y",
+                              "property float z", "property float nx", "property float ny", "property float nz", "property float s",
+                              "property float t", f"element face {len(faces)}", "property list uchar uint vertex_indices", "end_header"]) + "\n"
+            blob = b"".join(struct.pack(order + "8f", *verts[i], *normals[i], *uvs[i]) for i in range(len(verts)))
+            blob += b"".join(struct.pack(order + "B" + str(len(f)) + "I", len(f), *f) for f in faces)
+            p.write_bytes(head.encode() + blob)
+        sc = loader.load_ply(p, eye=(0, 0, -4), material={api.CH_COLOR: (10, 20, 30), api.CH_REFLECTION: (128, 128, 128)})
+        if ascii_scene is None:
+            ascii_scene = sc
+            assert np.array_equal(sc.tri_normal[0, 0, :3], np.array([0, 0, -1], np.float32))           # normalised (render.cpp:744-749)
+            assert np.array_equal(sc.tri_uv[2], np.array([[0, 0], [1, 0], [0.5, 0.25]], np.float32))
+            assert sc.textures[:2, :3].tolist() == [[10, 20, 30], [128, 128, 128]] and sc.material_count == 1
+        for f in ("vertex", "tri_idx", "tri_uv", "tri_normal", "textures", "mat_size"):
+            assert np.array_equal(getattr(sc, f), getattr(ascii_scene, f)), (fmt, f)
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.ply").write_text(_ply_text(verts, [[0, 1, 9]]))
+        loader.load_ply(tmp_path / "bad.ply")
+    with pytest.raises(ValueError):
+        (tmp_path / "nope.ply").write_text("solid\n")
+        loader.load_ply(tmp_path / "nope.ply")
