@@ -93,3 +93,15 @@ def test_empty_scene_builders():
     assert lists.list.size == 0 and (lists.start == 0).all() and (lists.end == 0).all()
     api.scene_triangle_list(sc, 16)
     assert sc.grid_list.size == 0 and (sc.grid_start == 0).all()
+
+
+def test_sub_band_sets_partition_a_ranks_band_set():
+    """launch_wavefront cuts the band set of rank r in world N into slices = the band sets of ranks r + N*k in world N*K
+    (b % (N*K) == r + N*k implies b % N == r): together they are exactly the rows rank r owns, without overlap."""
+    from opencl_render_b200 import api
+    for height, band, world, slices in ((1080, 16, 8, 4), (2160, 128, 2, 3), (75, 8, 3, 2), (600, 128, 2, 5)):
+        for rank in range(world):
+            own = {y for a, b in api.band_partition(height, rank, world, band_rows=band) for y in range(a, b)}
+            parts = [{y for a, b in api.band_partition(height, rank + world * k, world * slices, band_rows=band) for y in range(a, b)}
+                     for k in range(slices)]
+            assert set().union(*parts) == own and sum(len(p) for p in parts) == len(own)

@@ -194,3 +194,17 @@ def test_ply_ascii_and_binary_agree_with_the_obj_loader(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "nope.ply").write_text("solid\n")
         loader.load_ply(tmp_path / "nope.ply")
+
+
+def test_render_harness_arguments_without_a_gpu(capsys):
+    """The harness's device list is the dialog's combo (index 0 = the reference's CPU entry, a label only); picking it is refused."""
+    from opencl_render_b200 import _lib, render
+    assert render.main(["--list-devices"]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "0: Local CPU single thread"
+    for bad in (["config1", "--device", "0"], []):
+        with pytest.raises(SystemExit):
+            render.main(bad)
+    if _lib.load().oclr_device_count() == 0:
+        with pytest.raises(SystemExit):
+            render.main(["config1", "--device", "1"])      # no CUDA device enumerated: there is nothing to pick
