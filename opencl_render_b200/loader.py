@@ -8,7 +8,9 @@ assets can be rendered through the same boundary.  It follows the plugin's conve
 * normals: per-corner normals when the file has them, normalised in double and rounded to float (render.cpp:744-755); otherwise
   one flat normal per triangle, cross(b - a, c - a) scaled by +-1/length so that it FACES THE CAMERA (render.cpp:757-772) -- which
   is why the eye position is an input of the loader;
-* UVs: the file's `vt` per corner, else (0,0), (0,1), (1,1) (render.cpp:946-951);
+* UVs: the file's `vt` per corner; else, on request, one of the plugin's texture-tag projections (spherical, cylindrical, flat, cubic,
+  shrink wrap; `project_uv` = ShdProjectPoint, render.cpp:495-673, applied as at render.cpp:920-944); else (0,0), (0,1), (1,1)
+  (render.cpp:946-951);
 * materials: five channel images per material in one 4-byte-per-texel atlas, channel order COLOR, REFLECTION, TRANSPARENCY, BUMP,
   LUMINANCE (raytrace_opencl.h:14-22), a bitmap copied row by row from the top (render.cpp:1165-1186), a plain colour stored as a
   1x1 image `floor(0.5 + 255 c)` (render.cpp:1256-1275), an enabled reflection channel without bitmap = 0.2 (render.cpp:1219-1227),
@@ -33,6 +35,64 @@ from .scenes import MaterialAtlas, _lights
 
 SUN_ANGLE_DEGREES = 0.52      # render.cpp:961
 _CHANNEL_NAMES = {CH_COLOR: "color", CH_REFLECTION: "reflection", CH_TRANSPARENCY: "transparency", CH_BUMP: "bump", CH_LUMINANCE: "luminance"}
+
+
+PROJECTIONS = ("spherical", "cylindrical", "flat", "cubic", "shrinkwrap", "volume")
+
+
+def project_uv(p, n, projection: str = "spherical", ox: float = 0.0, oy: float = 0.0, lenx: float = 1.0, leny: float = 1.0):
+    """The texture-tag projections the plugin falls back to for polygons without UVW data (ShdProjectPoint, render.cpp:495-673, used at
+    render.cpp:920-944): point p (object space, double), polygon normal n -> (u, v).  `ox, oy, lenx, leny` = the tag's offset / length."""
+    x, y, z = (float(c) for c in p[:3])
+    lxi = 1.0 / lenx if lenx != 0.0 else 0.0
+    lyi = 1.0 / leny if leny != 0.0 else 0.0
+    pi, pi2 = math.pi, 2.0 * math.pi
+    sq = math.sqrt(x * x + z * z)
+
+    def around():     # angle of (x, z) about the y axis as a fraction of a turn  (:528-529, :552-553, :566-567)
+        u = math.acos(max(-1.0, min(1.0, x / sq))) / pi2
+        return 1.0 - u if z < 0.0 else u
+
+    def wrap(u):      # :530-535
+        u -= ox
+        if lenx > 0.0 and u < 0.0:
+            u += 1.0
+        elif lenx < 0.0 and u > 0.0:
+            u -= 1.0
+        return u * lxi
+
+    if projection == "volume":                                   # P_VOLUMESHADER :514-518
+        return x, y
+    if projection == "spherical":                                # :519-541
+        if sq == 0.0:
+            u, v = 0.0, (0.5 if y > 0.0 else -0.5)
+        else:
+            u, v = wrap(around()), 0.5 + math.atan(y / sq) / pi
+        return u, -(v - oy) * lyi
+    if projection == "shrinkwrap":                               # :542-561
+        if sq == 0.0:
+            u, v = 0.0, (0.0 if y > 0.0 else 1.0)
+        else:
+            u, v = around(), 0.5 - math.atan(y / sq) / pi
+        sn, cs = math.sin(u * pi2), math.cos(u * pi2)
+        return (0.5 + 0.5 * cs * v - ox) * lxi, (0.5 + 0.5 * sn * v - oy) * lyi
+    if projection == "cylindrical":                              # :562-580
+        u = 0.0 if sq == 0.0 else wrap(around())
+        return u, -(y * 0.5 + oy) * lyi
+    if projection == "flat":                                     # P_FLAT / P_SPATIAL :581-587
+        return (x * 0.5 - ox) * lxi, -(y * 0.5 + oy) * lyi
+    if projection == "cubic":                                    # :588-639
+        nx, ny, nz = (float(c) for c in n[:3])
+        if abs(nx) > abs(ny):
+            axis = 0 if abs(nx) > abs(nz) else 2
+        else:
+            axis = 1 if abs(ny) > abs(nz) else 2
+        if axis == 0:
+            return ((-z if nx < 0.0 else z) * 0.5 - ox) * lxi, -(y * 0.5 + oy) * lyi
+        if axis == 1:
+            return (x * 0.5 - ox) * lxi, ((z if ny < 0.0 else -z) * 0.5 - oy) * lyi
+        return ((x if nz < 0.0 else -x) * 0.5 - ox) * lxi, -(y * 0.5 + oy) * lyi
+    raise ValueError(f"unknown projection {projection!r} (one of {PROJECTIONS})")
 
 
 def _byte(c: float) -> int:
@@ -120,9 +180,11 @@ def _atlas_from(materials: list[dict], reference_fallbacks: bool) -> MaterialAtl
 
 
 def load_obj(path, eye=(0.0, 0.0, 0.0), lights=None, reference_fallbacks: bool = True, normalise_normals: bool = True,
-             name: str | None = None) -> HostScene:
+             name: str | None = None, uv_projection=None) -> HostScene:
     """Reads `path` (and the MTL files it names) into a HostScene.  `eye`: camera position (flat normals face it).
-    `lights`: list of dict(type, pos, dir, colour, radius, half) -- see scenes._lights; default one distant sun."""
+    `lights`: list of dict(type, pos, dir, colour, radius, half) -- see scenes._lights; default one distant sun.
+    `uv_projection`: for faces without `vt`, a projection name (PROJECTIONS) or (name, dict(ox, oy, lenx, leny)) -- the plugin's
+    texture-tag fallback (project_uv); None keeps the default triangle (0,0), (0,1), (1,1) it uses without a texture tag."""
     path = Path(path)
     v, vt, vn = [], [], []
     corners = []           # per triangle: 3 x (vi, ti, ni) with -1 = absent
@@ -165,10 +227,11 @@ def load_obj(path, eye=(0.0, 0.0, 0.0), lights=None, reference_fallbacks: bool =
             for k in range(1, len(poly) - 1):              # (a,b,c), (a,c,d), ...   render.cpp:733-736, 778-781
                 corners.append((poly[0], poly[k], poly[k + 1]))
                 tri_mat_name.append(cur_mat)
-    return _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name)
+    return _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name, uv_projection)
 
 
-def _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name) -> HostScene:
+def _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, reference_fallbacks, normalise_normals, name,
+              uv_projection=None) -> HostScene:
     """Parsed geometry (positions, UVs, normals, per-triangle corner index triples (vertex, uv, normal; -1 = absent) and material names)
     -> HostScene with the plugin's conventions (module docstring)."""
     if not corners:
@@ -186,6 +249,14 @@ def _assemble(path, v, vt, vn, corners, tri_mat_name, mtl, eye, lights, referenc
     if has_uv.any():
         vt_a = np.asarray(vt, np.float64).astype(np.float32)
         uv[has_uv] = vt_a[c[has_uv][:, :, 1]]
+    if uv_projection is not None and (~has_uv).any():      # render.cpp:920-944: project the (untransformed) corners, n = (p1-p0) x (p2-p0)
+        kind, kw = (uv_projection, {}) if isinstance(uv_projection, str) else (uv_projection[0], dict(uv_projection[1]))
+        vd = np.asarray(v, np.float64)
+        for t in np.nonzero(~has_uv)[0]:
+            p0, p1, p2 = (vd[c[t, k, 0]] for k in range(3))
+            nn = np.cross(p1 - p0, p2 - p0)
+            for k, pk in enumerate((p0, p1, p2)):
+                uv[t, k] = project_uv(pk, nn, kind, **kw)
 
     # normals
     nrm = np.zeros((n_tri, 3, 4), np.float32)
@@ -244,7 +315,7 @@ _PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short":
 
 
 def load_ply(path, eye=(0.0, 0.0, 0.0), lights=None, material: dict | None = None, reference_fallbacks: bool = True,
-             normalise_normals: bool = True, name: str | None = None) -> HostScene:
+             normalise_normals: bool = True, name: str | None = None, uv_projection=None) -> HostScene:
     """Reads a PLY file (ascii, binary_little_endian or binary_big_endian) into a HostScene with the same conventions as load_obj.
     Used per vertex: x y z, nx ny nz (optional), s t or u v (optional); per face: vertex_indices / vertex_index (triangles, quads and
     larger polygons are fanned as render.cpp:733-781 does).  PLY has no materials: the one material of the scene is `material`
@@ -331,7 +402,7 @@ def load_ply(path, eye=(0.0, 0.0, 0.0), lights=None, material: dict | None = Non
             corners.append((pc[0], pc[k], pc[k + 1]))
             names.append("ply")
     mtl = {"ply": dict(material or {})}
-    return _assemble(path, v, vt, vn, corners, names, mtl, eye, lights, reference_fallbacks, normalise_normals, name)
+    return _assemble(path, v, vt, vn, corners, names, mtl, eye, lights, reference_fallbacks, normalise_normals, name, uv_projection)
 
 
 def load_scene(path, **kw) -> HostScene:

@@ -208,3 +208,37 @@ def test_render_harness_arguments_without_a_gpu(capsys):
     if _lib.load().oclr_device_count() == 0:
         with pytest.raises(SystemExit):
             render.main(["config1", "--device", "1"])      # no CUDA device enumerated: there is nothing to pick
+
+
+def test_texture_tag_projections():
+    """project_uv restates ShdProjectPoint (render.cpp:495-673): spot values per projection, derived from the reference's formulas."""
+    P = loader.project_uv
+    n = (0.0, 0.0, 1.0)
+    # spherical: u = angle about y / 2pi (mirrored for z < 0), v = -(0.5 + atan(y / sqrt(x^2+z^2)) / pi)
+    assert P((1, 0, 0), n, "spherical") == pytest.approx((0.0, -0.5))
+    assert P((0, 0, 1), n, "spherical") == pytest.approx((0.25, -0.5))
+    assert P((0, 0, -1), n, "spherical") == pytest.approx((0.75, -0.5))
+    assert P((1, 1, 0), n, "spherical") == pytest.approx((0.0, -0.75))
+    assert P((0, 2, 0), n, "spherical") == pytest.approx((0.0, -0.5)) and P((0, -2, 0), n, "spherical") == pytest.approx((0.0, 0.5))
+    assert P((0, 0, 1), n, "spherical", ox=0.5, lenx=0.5) == pytest.approx((1.5, -0.5))        # (0.25 - 0.5 + 1) / 0.5
+    # cylindrical / flat: v = -(y/2 + oy) / leny
+    assert P((0, 3, 1), n, "cylindrical", oy=0.5, leny=2.0) == pytest.approx((0.25, -1.0))
+    assert P((0, 3, 0), n, "cylindrical") == pytest.approx((0.0, -1.5))
+    assert P((2, 3, 9), n, "flat", ox=0.25) == pytest.approx((0.75, -1.5))
+    # cubic: dominant normal axis picks the plane, sign picks the mirror
+    assert P((2, 4, 6), (1, 0, 0), "cubic") == pytest.approx((3.0, -2.0)) and P((2, 4, 6), (-1, 0, 0), "cubic") == pytest.approx((-3.0, -2.0))
+    assert P((2, 4, 6), (0, 1, 0), "cubic") == pytest.approx((1.0, -3.0)) and P((2, 4, 6), (0, -1, 0), "cubic") == pytest.approx((1.0, 3.0))
+    assert P((2, 4, 6), (0, 0, 1), "cubic") == pytest.approx((-1.0, -2.0)) and P((2, 4, 6), (0, 0, -1), "cubic") == pytest.approx((1.0, -2.0))
+    assert P((2, 4, 6), (1, 1, 1), "cubic") == pytest.approx((-1.0, -2.0))        # ties fall through to z (render.cpp:594-606)
+    # shrink wrap: the pole maps to the centre, the equator to a circle of radius 1/4
+    assert P((0, 5, 0), n, "shrinkwrap") == pytest.approx((0.5, 0.5)) and P((1, 0, 0), n, "shrinkwrap") == pytest.approx((0.75, 0.5))
+    assert P((1, 2, 3), n, "volume") == (1.0, 2.0)
+    with pytest.raises(ValueError):
+        P((0, 0, 0), n, "frontal")
+
+
+def test_loader_applies_the_projection_to_faces_without_uvs(tmp_path):
+    p = _write(tmp_path, "v 0 0 0\nv 2 0 0\nv 2 2 0\nvt 0.1 0.2\nf 1 2 3\nf 1/1 2/1 3/1\n")
+    sc = loader.load_obj(p, eye=(0, 0, -5), uv_projection=("flat", dict(ox=0.0, oy=0.0, lenx=2.0, leny=1.0)))
+    assert np.allclose(sc.tri_uv[0], [[0, 0], [0.5, 0], [0.5, -1.0]])          # u = x/2/lenx, v = -y/2
+    assert np.allclose(sc.tri_uv[1], [[0.1, 0.2]] * 3)                          # faces with vt keep their own
