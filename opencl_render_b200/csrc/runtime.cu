@@ -826,6 +826,7 @@ bool frame_read_camera_lists(Frame* f, uint32_t* start, uint32_t* end, uint32_t*
 void frame_destroy(Frame* f) {
     if (!f) return;
     cudaSetDevice(f->device);
+    if (f->prelaunched && f->preDone) cudaEventSynchronize(f->preDone);   // a round started ahead that no render call picked up
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount};
     for (DeviceBuffer* b : all) b->release();
     if (f->progStream) cudaStreamDestroy(f->progStream);
