@@ -63,3 +63,22 @@ def test_host_helpers_equal_reference_build(ref):
         fa, fb = a.view(np.float32)[differ], b.view(np.float32)[differ]
         assert np.isnan(fa).all() and np.isnan(fb).all(), int(differ.sum())
     assert (a.view(np.float32)[np.isfinite(a.view(np.float32))] != 0).sum() > 100000
+
+
+def test_plain_c_example_builds_against_the_header_and_links():
+    """examples/raytrace_all_min.c: the whole boundary from C -- helpers, builders, device list, RaytraceAll by value, image writer --
+    compiles against include/oclr_abi.h and links against the library.  Without a GPU it must stop at the device list with exit code
+    3 (no CPU path); with one it renders."""
+    from opencl_render_b200 import _lib
+    lib = _lib.load()
+    out = ROOT / "tests" / "_build"
+    out.mkdir(exist_ok=True)
+    exe = out / "raytrace_all_min"
+    subprocess.run(["gcc", "-O1", "-std=gnu11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "raytrace_all_min.c"),
+                    f"-L{_lib.LIB_PATH.parent}", "-lopencl_render_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}", "-lm", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), str(out / "example.bmp")], capture_output=True, text=True, timeout=300)
+    if lib.oclr_device_count() == 0:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
+        assert (out / "example.bmp").stat().st_size == 54 + 320 * 240 * 3
