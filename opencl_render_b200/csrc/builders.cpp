@@ -76,7 +76,9 @@ void set_camera(oclr_camera* out, const float position[3], const float object[3]
     const f3 camV = mk3(object[0] - position[0], object[1] - position[1], object[2] - position[2]);
     const f3 up = mk3(up3);
     const f3 r2l = cross3(up, camV);
-    const float midToLeft = sqrt_c(dot3(camV, camV)) * (float)tan((double)(fov / 2.f));
+    // render.cpp is C++: `tan(fov / 2.f)` and `sqrt(dot(...))` on float arguments resolve to the float overloads (tanf / sqrtf), not to
+    // the double functions the C kernel path uses -- pinned against the reference's own lines compiled by g++ (oracle/_ref, ref_set_camera)
+    const float midToLeft = sqrt_c(dot3(camV, camV)) * tanf(fov / 2.f);
     const float midToTop = midToLeft * (float)h / (float)w;
     const float r2lLen = sqrt_c(dot3(r2l, r2l));
     const float upLen = sqrt_c(dot3(up, up));

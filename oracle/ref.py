@@ -15,7 +15,10 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "_ref" / "libref_raytrace.so"
+LIB_COUNTED = HERE / "_ref" / "libref_raytrace_counted.so"
+COUNTER_NAMES = ["tests", "gridRays", "cells", "emptyCells", "segments", "primCandidates", "shadedHits", "gridCandidates", "occluderLookups"]
 _lib = None
+_counted = None
 
 
 def available() -> bool:
@@ -26,9 +29,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB.is_file():
-        sys.path.insert(0, str(HERE))
-        import build_ref
+    sys.path.insert(0, str(HERE))
+    import build_ref
+    if not LIB.is_file() or build_ref.reference_available():     # (re)build when the recipe changed; the GPU box uses what travelled
         if build_ref.build(verbose=False) is None:
             raise RuntimeError("oracle/_ref/libref_raytrace.so missing and /root/reference not present to build it")
     lib = C.CDLL(str(LIB))
@@ -60,8 +63,51 @@ def load() -> C.CDLL:
     lib.ref_raytrace_all.argtypes = [C.c_uint32] + lib.ref_raytrace_threads.argtypes[3:]
     lib.ref_raytrace_threads_step.restype = None
     lib.ref_raytrace_threads_step.argtypes = lib.ref_raytrace_threads.argtypes[:3] + [C.c_uint32] + lib.ref_raytrace_threads.argtypes[3:]
+    if hasattr(lib, "ref_set_camera"):
+        lib.ref_set_camera.restype = None
+        lib.ref_set_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
+
+
+def set_camera(eye, look_at, up, fov: float, width: int, height: int):
+    """The reference's SetCamera (render.cpp:461-491).  Returns (eye_to_top_left[3], left_to_right[3], top_to_bottom[3], pixel_size_inv)."""
+    lib = load()
+    e, o, u = _f4(eye), _f4(look_at), _f4(up)
+    tl, lr, tb, psi = np.zeros(4, np.float32), np.zeros(4, np.float32), np.zeros(4, np.float32), np.zeros(1, np.float32)
+    lib.ref_set_camera(_p(e), _p(o), _p(u), C.c_float(fov), width, height, _p(tl), _p(lr), _p(tb), _p(psi))
+    return tl[:3].copy(), lr[:3].copy(), tb[:3].copy(), float(psi[0])
+
+
+def counted_available() -> bool:
+    return LIB_COUNTED.is_file()
+
+
+def render_counted(camera, lists, scene, samples: int = 1, threads: int | None = None, rows=None, row_step: int = 1):
+    """The INSTRUMENTED copy of the reference kernel (build_ref.py): same planes as render() plus the event
+    counts of the rendered rows as a dict keyed by COUNTER_NAMES."""
+    global _counted
+    if _counted is None:
+        if not LIB_COUNTED.is_file():
+            load()          # builds both libraries when /root/reference is present
+        lib = C.CDLL(str(LIB_COUNTED))
+        lib.ref_raytrace_threads_step.restype = None
+        lib.ref_raytrace_threads_step.argtypes = load().ref_raytrace_threads_step.argtypes
+        lib.ref_counters_reset.restype = None
+        lib.ref_counters_read.restype = None
+        lib.ref_counters_read.argtypes = [C.c_void_p]
+        _counted = lib
+    lib = _counted
+    h, w = camera.height, camera.width
+    r0, r1 = rows if rows is not None else (0, h)
+    out = [np.zeros((h, w), np.uint16) for _ in range(3)]
+    args, keep = _scene_args(camera, lists, scene, samples)
+    lib.ref_counters_reset()
+    lib.ref_raytrace_threads_step(threads or (os.cpu_count() or 1), r0, r1, row_step, *args, _p(out[0]), _p(out[1]), _p(out[2]))
+    raw = np.zeros(16, np.uint64)
+    lib.ref_counters_read(_p(raw))
+    return tuple(out), {k: int(raw[i]) for i, k in enumerate(COUNTER_NAMES)}
 
 
 def _p(a):

@@ -44,6 +44,30 @@ extern "C" void Raytrace(cl_uint* nextPixelId, cl_uint2* dim, cl_float3* eye, cl
                          cl_float* lightRadius, cl_float* lightHalf, cl_ushort* outR, cl_ushort* outG,
                          cl_ushort* outB);
 
+// ---- event counters of the instrumented build (oracle/build_ref.py, libref_raytrace_counted.so) -------------
+// The instrumented kernel copy bumps thread-local cells; every worker adds its cells to the totals when it is done.
+#ifdef REF_COUNTED
+#include <mutex>
+extern "C" { __thread unsigned long long ref_cnt[16]; }
+static unsigned long long g_refTotals[16];
+static std::mutex g_refMutex;
+static void ref_counters_flush() {
+    std::lock_guard<std::mutex> lock(g_refMutex);
+    for (int i = 0; i < 16; ++i) { g_refTotals[i] += ref_cnt[i]; ref_cnt[i] = 0; }
+}
+extern "C" void ref_counters_reset() {
+    std::lock_guard<std::mutex> lock(g_refMutex);
+    for (int i = 0; i < 16; ++i) g_refTotals[i] = 0;
+}
+extern "C" void ref_counters_read(unsigned long long* out) {
+    ref_counters_flush();   // (the calling thread's own cells: RaytraceAll(0) runs in the caller)
+    std::lock_guard<std::mutex> lock(g_refMutex);
+    for (int i = 0; i < 16; ++i) out[i] = g_refTotals[i];
+}
+#else
+static void ref_counters_flush() {}
+#endif
+
 extern "C" {
 
 // ---- camera list ---------------------------------------------------------------------------------
@@ -121,6 +145,7 @@ void ref_raytrace_threads_step(int nThreads, cl_uint rowBegin, cl_uint rowEnd, c
                 }
             }
         }
+        ref_counters_flush();
     };
     if (nThreads <= 1) { worker(); return; }
     std::vector<std::thread> pool;

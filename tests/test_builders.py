@@ -105,3 +105,24 @@ def test_sub_band_sets_partition_a_ranks_band_set():
             parts = [{y for a, b in api.band_partition(height, rank + world * k, world * slices, band_rows=band) for y in range(a, b)}
                      for k in range(slices)]
             assert set().union(*parts) == own and sum(len(p) for p in parts) == len(own)
+
+
+def test_set_camera_equals_reference(ref):
+    """oclr_set_camera against the reference's own SetCamera (render.cpp:461-491, cut out of render.cpp into oracle/_ref by
+    oracle/build_ref.py): bit for bit on 1 000 random cameras, including the image shapes of the five configs."""
+    rng = np.random.default_rng(20261018)
+    shapes = [(512, 512), (1920, 1080), (3840, 2160), (7680, 4320), (1024, 768), (1, 1), (333, 7)]
+    for k in range(1000):
+        eye = rng.uniform(-50, 50, 3).astype(np.float32)
+        look = (eye + rng.uniform(-20, 20, 3)).astype(np.float32)
+        up = rng.uniform(-1, 1, 3).astype(np.float32)
+        if k % 4 == 0:
+            up = np.array([0, 1, 0], np.float32)
+        fov = float(np.float32(rng.uniform(0.05, 3.0)))
+        w, h = shapes[k % len(shapes)]
+        cam = api.set_camera(eye, look, up, fov, w, h)
+        tl, lr, tb, psi = ref.set_camera(eye, look, up, fov, w, h)
+        got = np.concatenate([np.asarray(cam.eye_to_top_left, np.float32)[:3], np.asarray(cam.left_to_right, np.float32)[:3],
+                              np.asarray(cam.top_to_bottom, np.float32)[:3], [np.float32(cam.pixel_size_inv)]]).astype(np.float32)
+        want = np.concatenate([tl, lr, tb, [np.float32(psi)]]).astype(np.float32)
+        assert got.tobytes() == want.tobytes(), (k, got, want)       # NaNs included: byte comparison

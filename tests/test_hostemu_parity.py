@@ -115,3 +115,26 @@ def test_cooperative_walk_is_exact(name, hostemu, monkeypatch):
     assert coop[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
     if name != "coarse_grid":      # rays with a zero direction component fall back to the packed (two-level) walk, which skips empty cells
         assert coop[3]["cells"] <= flat[3]["cells"]
+
+
+@pytest.mark.parametrize("name", ["spheres", "soup_mirror_glass", "terrain_textured", "soup_lights_sun_last", "coarse_grid"])
+def test_counters_equal_instrumented_reference(name, hostemu, ref, monkeypatch):
+    """the event counts behind `roofline.achieved` (the counting build of the product's own
+    arithmetic, here compiled for the host; the CUDA counting kernel is compared with the same numbers in test_gpu_parity.py)
+    equal the counts of an INSTRUMENTED COPY OF THE REFERENCE KERNEL (oracle/build_ref.py puts counters at
+    raytrace_opencl.c:126, 347, 365, 369, 510, 517, 532, 619), event class by event class."""
+    if not ref.counted_available():
+        pytest.skip("oracle/_ref/libref_raytrace_counted.so not built")
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)      # the reference's own cell walk
+    img, _, flags, cnt = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    want_img, want = ref.render_counted(cam, lists, sc, samples)
+    ok = flags == 0
+    assert helpers.compare_rgb(img, want_img, mask=ok)["diff_pixels"] == 0
+    for k in ("segments", "primCandidates", "gridRays", "cells", "gridCandidates", "shadedHits", "occluderLookups"):
+        assert cnt[k] == want[k], (k, cnt[k], want[k])
+    assert cnt["cells"] - cnt["cellsNonEmpty"] == want["emptyCells"]
+    # every RayIntersectsTriangle call of the reference is a primary candidate, a grid candidate or one of the two helper rays
+    # of a bump-mapped hit (raytrace_opencl.c:244-247)
+    extra = want["tests"] - want["primCandidates"] - want["gridCandidates"]
+    assert 0 <= extra <= 2 * want["shadedHits"] and (extra == 0 or name == "terrain_textured")
