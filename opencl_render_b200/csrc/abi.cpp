@@ -83,8 +83,10 @@ cl_bool GetComputationTypeName(size_t id, size_t strLen, cl_char* str) {
     else if (id - 1 < (size_t)g_devCount + (g_devCount > 1 ? 1 : 0))
         name = g_devName[id - 1];
     if (!name || !str) return CL_FALSE;
-    if (strlen(name) <= strLen) {  // the reference's (off-by-one tolerant) length rule, raytrace.c:139,146
-        memcpy(str, name, strlen(name) + (strlen(name) < strLen ? 1 : 0));
+    // The reference accepts strlen(name) <= strLen and then strcpy's strlen + 1 bytes (raytrace.c:139-141: one past the caller's
+    // buffer when the lengths are equal).  Here the name is returned only when it fits WITH its terminator.
+    if (strlen(name) < strLen) {
+        memcpy(str, name, strlen(name) + 1);
         return CL_TRUE;
     }
     return CL_FALSE;

@@ -58,14 +58,15 @@ int oclr_write_bmp(const char* path, cl_uint width, cl_uint height, const cl_ush
     FILE* f = fopen(path, "wb");
     if (!f) return 0;
     unsigned char header[54] = {'B', 'M'};
-    put32le(header + 2, (uint32_t)fileSize);
+    // mode 1 is writebmp3s byte for byte (writebmp.cpp:124-177): its bfSize ignores the row padding and biSizeImage stays 0
+    put32le(header + 2, mode == 1 ? (uint32_t)(54ull + 3ull * width * height) : (uint32_t)fileSize);
     put32le(header + 10, 54);
     put32le(header + 14, 40);
     put32le(header + 18, width);
     put32le(header + 22, height);
     header[26] = 1;    // planes
     header[28] = 24;   // bits per pixel
-    put32le(header + 34, (uint32_t)(rowBytes * height));
+    if (mode == 0) put32le(header + 34, (uint32_t)(rowBytes * height));
     bool ok = fwrite(header, 1, 54, f) == 54;
     std::vector<unsigned char> row(rowBytes, 0);
     for (cl_uint j = 0; ok && j < height; ++j) {

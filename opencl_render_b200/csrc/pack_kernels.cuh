@@ -136,6 +136,24 @@ __global__ void __launch_bounds__(256) check_list_kernel(const uint32_t* __restr
     if (i < total && __ldg(list + i) >= triangleCount) atomicOr(error, (uint32_t)kPackBadListEntry);
 }
 
+// Caller-supplied camera lists (cameraPixelTriangleListStart / End / list, raytrace.h:58-106): Start <= End <= list size for every
+// pixel, every entry a triangle id.  The reference trusts them; a bad entry here would be an illegal address -- a sticky fault for the
+// whole process.  Runs on the upload stream in front of the first logic launch (also the one started ahead); no host round trip.
+enum { kCamBadRange = 1, kCamBadEntry = 2 };
+__global__ void __launch_bounds__(256) check_camera_lists_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                                 const uint32_t* __restrict__ list, uint32_t pixels, uint32_t listSize,
+                                                                 uint32_t triangleCount, uint32_t* __restrict__ flag) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
+        const uint32_t s = __ldg(start + i), e = __ldg(end + i);
+        if (s > e || e > listSize) bad |= kCamBadRange;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < listSize; i += stride)
+        if (__ldg(list + i) >= triangleCount) bad |= kCamBadEntry;
+    if (bad) atomicOr(flag, bad);
+}
+
 // sceneBoxMin (cl_float3 per plane index) -> three contiguous float arrays
 __global__ void split_planes_kernel(const float4* __restrict__ boxMin, int n, float* __restrict__ planes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -48,6 +48,7 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
 template <bool COUNT>
 __global__ void __launch_bounds__(128) raytrace_simple_kernel(SceneView S, FrameView F, Counters* gcnt) {
     extern __shared__ float shPlanes[];
+    if (F.camBad != nullptr && *F.camBad != 0u) return;   // caller's camera lists failed the range check
     load_planes(shPlanes, S);
     const float* px = shPlanes;
     const float* py = shPlanes + (S.n + 1);

@@ -105,6 +105,9 @@ struct FrameView {
     // in fp32, no per-sample truncation; the planes are resolved from it after the call (resolve_accum_kernel).
     float4* accum;
     unsigned long long* doneCount;   // optional: pixel-samples finished so far by the current render call (progress, raytrace.c:580)
+    // optional: non-zero when the caller's camera lists failed the range check (check_camera_lists_kernel, pack_kernels.cuh): the
+    // kernels then return without touching the lists and the host reports the error at its next synchronisation
+    const uint32_t* camBad;
 };
 
 // Launch-domain row k -> frame row (>= height when k is past the owned rows).

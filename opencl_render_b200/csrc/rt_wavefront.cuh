@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                                                        const uint32_t* prevCount, Counters* gcnt, int aheadMode) {
     // Rounds are enqueued ahead without a host round trip; a round whose predecessor traced no ray has nothing to resume.
     if (prevCount != nullptr && *prevCount == 0u) return;
+    if (F.camBad != nullptr && *F.camBad != 0u) return;   // caller's camera lists failed the range check: nothing is read from them
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t k = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);

@@ -242,6 +242,7 @@ struct Frame {
     int device = 0;
     Camera cam = {};
     DeviceBuffer camStart, camEnd, camList, planesRGB, ids, flags, counters;
+    DeviceBuffer camCheck;           // range-check flag of caller-supplied camera lists (check_camera_lists_kernel); unset for device-built lists
     WfSlice slices[kMaxSlices];      // wavefront path state (allocated on first use, sized for the largest slice seen)
     uint32_t* hostCount = nullptr;   // pinned, one per slice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr;
@@ -443,7 +444,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     OCLR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, s->device));
     OCLR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, s->device));
     OCLR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    if (major < 10) {
+    if (major != 10) {   // the library holds sm_100a SASS only (arch-specific: no PTX fallback for sm_12x either)
         err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(major) + std::to_string(minor);
         return false;
     }
@@ -670,6 +671,17 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
     if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
     if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
     f->camListSize = listSize;
+    if (listSize > 0xFFFFFFFFull) {
+        err = "camera triangle list too long";
+        return false;
+    }
+    // range check on the device, stream-ordered in front of every kernel that reads the lists (no host round trip: the kernels look
+    // at the flag themselves, the host reports it at its next synchronisation -- launch_wavefront / frame_launch)
+    if (!f->camCheck.alloc(sizeof(uint32_t), err)) return false;
+    OCLR_CUDA(cudaMemsetAsync(f->camCheck.p, 0, sizeof(uint32_t), 0));
+    check_camera_lists_kernel<<<(unsigned)std::min<size_t>((std::max(P, listSize) + 255) / 256, (size_t)f->scene->smCount * 8), 256>>>(
+        (const uint32_t*)f->camStart.p, (const uint32_t*)f->camEnd.p, (const uint32_t*)f->camList.p, (uint32_t)P, (uint32_t)listSize,
+        f->scene->view.triangleCount, (uint32_t*)f->camCheck.p);
     return frame_setup_common(f, err, sync);
 }
 
@@ -827,7 +839,8 @@ void frame_destroy(Frame* f) {
     if (!f) return;
     cudaSetDevice(f->device);
     if (f->prelaunched && f->preDone) cudaEventSynchronize(f->preDone);   // a round started ahead that no render call picked up
-    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount};
+    DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount,
+                           &f->camCheck};
     for (DeviceBuffer* b : all) b->release();
     if (f->progStream) cudaStreamDestroy(f->progStream);
     pinned_release(f->hostDone);
@@ -892,6 +905,13 @@ static int slice_count_for(uint32_t rows, uint32_t width) {
     return (int)std::min<uint64_t>(4, std::max<uint64_t>(1, paths / (4ull << 20)));
 }
 
+static bool same_request(const FrameView& a, const FrameView& b);
+static std::string cam_check_message(uint32_t flag);
+// A round started ahead by frame_prelaunch is continued only by the identical request rendered as ONE slice (the only case started
+// ahead).  frame_launch and launch_wavefront both decide with this, so the progress counter and the round agree.
+static int slice_count_for(uint32_t rows, uint32_t width);
+static bool resumes_prelaunch(const Frame* f, const FrameView& F);
+
 // Wavefront driver: alternate the logic and trace kernels until no path is waiting for a ray (rt_wavefront.cuh).
 // `prelaunchOnly`: allocate the path state and enqueue nothing but the first logic round of the first sample, on the frame's own
 // stream behind everything already enqueued on `st` (frame_prelaunch).  A later normal call with the same view finds
@@ -929,7 +949,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         K = used;
     }
     if (K == 0) return true;
-    const bool resumePre = !prelaunchOnly && f->prelaunched && K == 1 && memcmp(&f->preView, &Fall, sizeof(FrameView)) == 0;
+    const bool resumePre = !prelaunchOnly && K == 1 && resumes_prelaunch(f, Fall);
     if (!prelaunchOnly && f->prelaunched && !resumePre) {   // a prelaunched round nobody can use: wait it out and start over
         OCLR_CUDA(cudaStreamWaitEvent(st, f->preDone, 0));
         f->prelaunched = false;
@@ -993,7 +1013,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         setupGrid[k] = (unsigned)std::min<uint64_t>((uint64_t)smCount * 8, (2 * (uint64_t)Q + 255) / 256);
     }
     for (int k = K; k < kMaxSlices; ++k) f->slices[k].traceEventsUsed = 0;
-    static_assert(sizeof(uint32_t) * kMaxSlices * kRoundLogSize <= 4096, "round logs fit one pinned block");
+    static_assert(sizeof(uint32_t) * (kMaxSlices * kRoundLogSize + 1) <= 4096, "round logs + camera-check word fit one pinned block");
     if (!f->hostCount) f->hostCount = (uint32_t*)pinned_block();
     if (!f->hostCount) {
         err = "out of pinned host memory";
@@ -1007,16 +1027,19 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     else
         OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
-    static TraceTuning tune = {0, 1, 0, 0, 0, 0};
-    if (tune.refillMin == 0) {
+    // (function-local static built by a lambda: initialised once, thread-safe -- RaytraceAll's all-devices mode launches from one
+    // host thread per GPU)
+    static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        tune.refillMin = env("OCLR_REFILL_MIN", 4);
-        tune.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
-        tune.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
-        tune.walkMin3 = env("OCLR_WALK_MIN3", 8);
-        tune.switchMin = env("OCLR_SWITCH_MIN", 6);
-        tune.tailDrain = env("OCLR_TAIL_DRAIN", 8);
-    }
+        TraceTuning t = {0, 1, 0, 0, 0, 0};
+        t.refillMin = env("OCLR_REFILL_MIN", 4);
+        t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
+        t.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
+        t.walkMin3 = env("OCLR_WALK_MIN3", 8);
+        t.switchMin = env("OCLR_SWITCH_MIN", 6);
+        t.tailDrain = env("OCLR_TAIL_DRAIN", 8);
+        return t;
+    }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
     const unsigned traceGrid = (unsigned)(smCount * perSm);
     if (Fall.flagOut && !resumePre) OCLR_CUDA(cudaMemsetAsync(Fall.flagOut, 0, (size_t)Fall.cam.width * Fall.cam.height, st));
@@ -1116,8 +1139,15 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                 if (chunk[k])
                     OCLR_CUDA(cudaMemcpyAsync(f->hostCount + k * kRoundLogSize, (uint32_t*)f->slices[k].workCounter.p + 2 * cstride,
                                               sizeof(uint32_t) * std::min<uint32_t>(round[k], kRoundLogSize), cudaMemcpyDeviceToHost, stream[k]));
+            uint32_t* camFlag = f->hostCount + kMaxSlices * kRoundLogSize;   // (same pinned block, behind the round logs)
+            *camFlag = 0;
+            if (Fall.camBad) OCLR_CUDA(cudaMemcpyAsync(camFlag, Fall.camBad, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream[0]));
             for (int k = 0; k < K; ++k)
                 if (chunk[k]) OCLR_CUDA(cudaStreamSynchronize(stream[k]));
+            if (*camFlag) {
+                err = cam_check_message(*camFlag);
+                return false;
+            }
             for (int k = 0; k < K; ++k) {
                 if (!chunk[k]) continue;
                 const uint32_t* log = f->hostCount + k * kRoundLogSize;
@@ -1154,6 +1184,10 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     return true;
 }
 
+static bool resumes_prelaunch(const Frame* f, const FrameView& F) {
+    return f->prelaunched && same_request(f->preView, F) && slice_count_for(launch_rows(F), F.cam.width) == 1;
+}
+
 static void fill_view(Frame* f, FrameView& F) {
     const size_t P = (size_t)f->cam.width * f->cam.height;
     F.cam = f->cam;
@@ -1167,6 +1201,22 @@ static void fill_view(Frame* f, FrameView& F) {
     F.flagOut = (uint8_t*)f->flags.p;
     F.accum = (float4*)f->accum.p;   // nullptr unless float accumulation is on
     F.doneCount = (unsigned long long*)f->doneCount.p;
+    F.camBad = (const uint32_t*)f->camCheck.p;
+}
+
+static std::string cam_check_message(uint32_t flag) {
+    return std::string("camera triangle lists are inconsistent:") + ((flag & kCamBadRange) ? " Start <= End <= list size violated;" : "") +
+           ((flag & kCamBadEntry) ? " list entry >= triangleCount;" : "");
+}
+
+// Two render requests are the same job (a round started ahead by frame_prelaunch may be continued): field by field -- the structs
+// carry padding, memcmp would compare it.
+static bool same_request(const FrameView& a, const FrameView& b) {
+    return memcmp(&a.cam, &b.cam, sizeof(Camera)) == 0 && a.camStart == b.camStart && a.camEnd == b.camEnd && a.camList == b.camList &&
+           a.sampleCount == b.sampleCount && a.sampleBegin == b.sampleBegin && a.sampleEnd == b.sampleEnd && a.rowBegin == b.rowBegin &&
+           a.rowEnd == b.rowEnd && a.bandRows == b.bandRows && a.bandRank == b.bandRank && a.bandWorld == b.bandWorld &&
+           a.ownedRows == b.ownedRows && a.outR == b.outR && a.outG == b.outG && a.outB == b.outB && a.idOut == b.idOut &&
+           a.flagOut == b.flagOut && a.accum == b.accum && a.doneCount == b.doneCount && a.camBad == b.camBad;
 }
 
 static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* stream, RenderStats* stats, std::string& err) {
@@ -1178,8 +1228,14 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
         return false;
     }
     // (a first round started ahead by frame_prelaunch for exactly this request has already counted its finished paths)
-    const bool continuesPre = f->prelaunched && variant == kKernelPipe && !count && memcmp(&f->preView, &F, sizeof(FrameView)) == 0;
+    const bool continuesPre = variant == kKernelPipe && !count && resumes_prelaunch(f, F);
     if (f->prelaunched && !continuesPre) {
+        // The round started ahead belongs to another request: wait it out and start over.  It rendered sample 0 of ITS job into the
+        // planes (sample 0 overwrites), so a request that continues an earlier job (sampleBegin > 0) has lost those samples.
+        if (F.sampleBegin > 0) {
+            err = "a first round started ahead (frame_prelaunch) for another request has overwritten the planes this request continues";
+            return false;
+        }
         OCLR_CUDA(cudaStreamWaitEvent(st, f->preDone, 0));
         f->prelaunched = false;
     }
@@ -1238,6 +1294,14 @@ static bool frame_launch(Frame* f, FrameView& F, int variant, bool count, void* 
             covered = std::max(covered, sp.second);
         }
         if (count) OCLR_CUDA(cudaMemcpy(&stats->counters, dcnt, sizeof(Counters), cudaMemcpyDeviceToHost));
+        if (variant == kKernelSimple && F.camBad) {
+            uint32_t flag = 0;
+            OCLR_CUDA(cudaMemcpy(&flag, F.camBad, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (flag) {
+                err = cam_check_message(flag);
+                return false;
+            }
+        }
     }
     return true;
 }

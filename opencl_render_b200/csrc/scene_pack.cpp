@@ -40,11 +40,21 @@ bool validate_scene(const HostScene& h, std::string& err, bool gridMayBeMissing)
         return false;
     }
     for (uint32_t m = 0; m < h.materialCount * kMaterialChannels; ++m) {
+        // a channel is present when size.x > 0 (raytrace_opencl.h:14-22, channel_present()); a present channel with size.y == 0 would
+        // index the atlas with (float)(size.y - 1u) = 4.29e9 (Get2dTableValue3, :103-122) -- rejected instead of read out of bounds
+        if (h.matSize[m].x && !h.matSize[m].y) {
+            err = "material image with width > 0 and height 0";
+            return false;
+        }
         const uint64_t texels = (uint64_t)h.matSize[m].x * h.matSize[m].y;
-        if (texels && (h.matStart[m] < 0 || (uint64_t)h.matStart[m] + texels > h.texturesSize)) {
+        if (texels && (!h.textures || h.matStart[m] < 0 || (uint64_t)h.matStart[m] + texels > h.texturesSize)) {
             err = "material image outside the texture atlas";
             return false;
         }
+    }
+    if (h.lightCount && (!h.lightType || !h.lightPos || !h.lightDir || !h.lightColour || !h.lightRadius || !h.lightHalf)) {
+        err = "light arrays missing (lightCount > 0)";
+        return false;
     }
     return true;
 }

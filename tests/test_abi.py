@@ -57,6 +57,11 @@ def test_computation_type_list_and_cpu_label():
     assert lib.GetComputationTypeCount() == len(names)
     buf = C.create_string_buffer(4)
     assert lib.GetComputationTypeName(0, 3, buf) == 0     # too short -> CL_FALSE
+    n = len(names[0])
+    buf = C.create_string_buffer(b"\xAA" * (n + 2), n + 2)
+    assert lib.GetComputationTypeName(0, n, buf) == 0      # fits only WITHOUT its terminator: refused, nothing written past the buffer
+    assert buf.raw == b"\xAA" * (n + 2)
+    assert lib.GetComputationTypeName(0, n + 1, buf) == 1 and buf.raw[:n + 1] == names[0].encode() + b"\0" and buf.raw[n + 1] == 0xAA
     lib.ResetComputationType()
     assert lib.GetIsComputationTypeUpdated() == 0
 

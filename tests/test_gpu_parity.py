@@ -154,6 +154,40 @@ def test_inconsistent_scene_is_refused():
         api.DeviceScene(sc, 0)
 
 
+def test_bad_caller_arrays_are_refused_not_faulted():
+    """Caller-supplied arrays the reference trusts blindly: a present material channel of height 0, a NULL light array with
+    lightCount > 0, camera lists that point outside the list or name a triangle that does not exist.  Each is an error return
+    (CL_FALSE + message), never an illegal address -- and the device stays usable afterwards."""
+    import copy
+    sc, cam, lists, samples = helpers.make_case("soup")
+    want = api.raytrace_all(1, cam, lists, samples, sc)
+    bad = copy.copy(sc)
+    bad.mat_size = sc.mat_size.copy()
+    bad.mat_size.reshape(-1, 2)[0] = (3, 0)
+    with pytest.raises(api.OclrError, match="height 0"):
+        api.DeviceScene(bad, 0)
+    for make, msg in [(lambda l: api.CameraLists(l.start, l.end + np.uint32(lists.list.size + 5), l.list), "Start <= End"),
+                      (lambda l: api.CameraLists(l.end.copy(), l.start.copy(), l.list), "Start <= End"),
+                      (lambda l: api.CameraLists(l.start, l.end, np.where(np.arange(l.list.size) == 3, np.uint32(sc.triangle_count), l.list).astype(np.uint32)),
+                       "triangleCount")]:
+        bl = make(lists)
+        if np.array_equal(bl.start, lists.start) and np.array_equal(bl.end, lists.end) and np.array_equal(bl.list, lists.list):
+            continue
+        with pytest.raises(api.OclrError, match=msg):
+            api.raytrace_all(1, cam, bl, samples, sc)
+        ds = api.DeviceScene(sc, 0)
+        fr = api.DeviceFrame(ds, cam, bl)
+        with pytest.raises(api.OclrError, match=msg):
+            fr.render(samples)
+        with pytest.raises(api.OclrError, match=msg):
+            fr.render(samples, variant=api.KERNEL_SIMPLE)
+        fr.close()
+        ds.close()
+    got = api.raytrace_all(1, cam, lists, samples, sc)          # the device took no fault
+    for c in range(3):
+        assert np.array_equal(got[c], want[c])
+
+
 def test_edge_cases(port):
     # empty scene, no lights, all-miss camera, single triangle, 1x1 image
     cam = api.set_camera((0, 4.4, -8), (0, 0, 0), (0, 1, 0), 0.9, 40, 30)

@@ -25,7 +25,20 @@ def test_bmp_layout_and_conversion(tmp_path, w, h, cast):
     assert data[:2] == b"BM" and len(data) == 54 + row * h
     size, off = struct.unpack_from("<I4xI", data, 2)
     hdr, bw, bh, planes, bpp = struct.unpack_from("<IiiHH", data, 14)
-    assert (size, off, hdr, bw, bh, planes, bpp) == (len(data), 54, 40, w, h, 1, 24)
+    # writebmp3s writes bfSize = 54 + 3*w*h (row padding not counted) and leaves biSizeImage 0 (writebmp.cpp:129, 146-152); the cast
+    # mode reproduces that header byte for byte, the corrected mode writes the true sizes
+    want_size = 54 + 3 * w * h if cast else len(data)
+    assert (size, off, hdr, bw, bh, planes, bpp) == (want_size, 54, 40, w, h, 1, 24)
+    assert struct.unpack_from("<I", data, 34)[0] == (0 if cast else row * h)
+    if cast:
+        head = bytearray(54)
+        head[0:2] = b"BM"
+        struct.pack_into("<I", head, 2, 54 + 3 * w * h)
+        head[10] = 54
+        head[14] = 40
+        struct.pack_into("<ii", head, 18, w, h)
+        head[26], head[28] = 1, 24
+        assert data[:54] == bytes(head)
     conv = (lambda a: (a & 0xFF).astype(np.uint8)) if cast else (lambda a: (a // 256).astype(np.uint8))
     for j in range(h):          # file rows are bottom-up, pixels BGR (writebmp.cpp:136-141, 167-170)
         line = np.frombuffer(data, np.uint8, 3 * w, 54 + row * j).reshape(w, 3)
