@@ -304,7 +304,10 @@ int oclr_write_bmp(const char* path, cl_uint width, cl_uint height, const cl_ush
 int oclr_write_ppm16(const char* path, cl_uint width, cl_uint height, const cl_ushort* red, const cl_ushort* green, const cl_ushort* blue);
 int oclr_write_png16(const char* path, cl_uint width, cl_uint height, const cl_ushort* red, const cl_ushort* green, const cl_ushort* blue);
 
-/* Run-time options (developer knobs).  "slices": how many slices a launch domain is cut into (0 = automatic). Returns 1 if known. */
+/* Run-time options.  "slices": how many slices a launch domain is cut into (0 = automatic).  "ahead": tracing one round ahead
+ * (0 never, 1 all segments but the camera's, 2 all, -1 automatic).  "devices": the "all devices" computation type
+ * (RaytraceAll(deviceCount + 1, ...), the analogue of the reference's multi-device tile loop raytrace.c:507-556) renders on the first
+ * `value` GPUs of the box (0 = all of them).  Returns 1 if the option is known. */
 int oclr_set_option(const char* name, int value);
 
 /* Copy rows [rowBegin,rowEnd) of the planes to full-frame host arrays. */

@@ -60,7 +60,7 @@ void InitOpenCL(void) {
     for (int i = 0; i < n; ++i)
         if (!device_name(i, g_devName[i], sizeof(g_devName[i]))) snprintf(g_devName[i], sizeof(g_devName[i]), "CUDA device #%d", i);
     g_devCount = n;
-    if (n > 1) snprintf(g_devName[n], sizeof(g_devName[n]), "CUDA all %d devices (row bands of 128)", n);
+    if (n > 1) snprintf(g_devName[n], sizeof(g_devName[n]), "CUDA all %d devices (row bands, shared upload over NVLink)", n);
     g_devUpdated = CL_TRUE;
 }
 void ResetComputationType(void) {
@@ -153,6 +153,9 @@ void ResetTime(void) {
 const char* oclr_last_error(void) { return g_err.c_str(); }
 int oclr_device_count(void) { return device_count(); }
 const char* oclr_version(void) { return "opencl_render_b200 0.1 (sm_100a)"; }
+// Devices the "all devices" computation type renders on: all of them, or the first k (oclr_set_option("devices", k)).
+static std::atomic<int> g_allDevicesLimit(0);
+
 int oclr_set_option(const char* name, int value) {
     if (name && strcmp(name, "slices") == 0) {
         set_slice_count(value);
@@ -160,6 +163,10 @@ int oclr_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "ahead") == 0) {
         set_ahead_mode(value);
+        return 1;
+    }
+    if (name && strcmp(name, "devices") == 0) {   // the "all devices" computation type uses the first `value` GPUs (0 = all)
+        g_allDevicesLimit.store(value < 0 ? 0 : value);
         return 1;
     }
     fail(std::string("oclr_set_option: unknown option ") + (name ? name : "(null)"));
@@ -462,40 +469,54 @@ static double now_ms() {
 }
 
 // ---- one frame on one device: upload, trace, read back ---------------------------------------------------------------------
+// world > 1: this is one of `world` threads (one per GPU) rendering the rows y with (y / bandRows) % world == rank; `shareCtx` (when
+// peer access is available) makes the N uploads ONE upload: every GPU pulls 1/N of each large array and fans it out over NVLink.
 static bool render_rows_on_device(int device, const HostScene& h, const Camera& cam, const cl_uint* camStart, const cl_uint* camEnd,
-                                  const cl_uint* camList, size_t camListSize, cl_uint sampleCount, int rank, int world,
-                                  cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
+                                  const cl_uint* camList, size_t camListSize, cl_uint sampleCount, int rank, int world, cl_uint bandRows,
+                                  ShardCtx* shareCtx, cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
     const bool trace = getenv("OCLR_TRACE") != nullptr;
     static const bool overlap = [] { const char* v = getenv("OCLR_OVERLAP_UPLOAD"); return !v || atoi(v) != 0; }();
     const double t0 = now_ms();
+    const uint32_t bandWorld = (uint32_t)(world > 1 ? world : 1);
     // The camera lists go up and the primary-ray round starts as soon as the triangles are on the device, under the upload of the
     // grid (scene_create's `early` hook + frame_prelaunch); the render call below continues from that round.
     Frame* f = nullptr;
     std::string frameErr;
     double tFrame = 0;
+    UploadShare share;
+    share.ctx = shareCtx;
+    share.rank = rank;
+    share.camStart = camStart;
+    share.camEnd = camEnd;
+    share.camList = camList;
+    share.camListSize = camListSize;
+    share.pixels = (size_t)cam.width * cam.height;
     const std::function<void(Scene*)> early = [&](Scene* partial) {
         const double a = now_ms();
-        f = frame_create(partial, cam, camStart, camEnd, camList, camListSize, frameErr, false);
+        f = frame_create(partial, cam, camStart, camEnd, camList, camListSize, frameErr, false, shareCtx ? &share.staged : nullptr);
         std::string ignored;
-        if (f && default_variant() == (int)kKernelPipe) frame_prelaunch(f, sampleCount, 128, (uint32_t)rank, (uint32_t)(world > 1 ? world : 1), ignored);
+        if (f && default_variant() == (int)kKernelPipe) frame_prelaunch(f, sampleCount, bandRows, (uint32_t)rank, bandWorld, ignored);
         tFrame = now_ms() - a;
     };
-    Scene* s = scene_create(device, h, err, overlap && camStart && camEnd ? &early : nullptr);
+    Scene* s = scene_create(device, h, err, overlap && camStart && camEnd ? &early : nullptr, shareCtx ? &share : nullptr);
     if (!s) {
         if (f) frame_destroy(f);
+        staged_release(share.staged);
         return false;
     }
     const double t1 = now_ms() - tFrame;
     if (!f) {
         if (!frameErr.empty()) {   // the hook ran and the frame could not be created
             err = frameErr;
+            staged_release(share.staged);
             scene_destroy(s);
             return false;
         }
         const double a = now_ms();
-        f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err);
+        f = frame_create(s, cam, camStart, camEnd, camList, camListSize, err, true, shareCtx ? &share.staged : nullptr);
         tFrame = now_ms() - a;
     }
+    staged_release(share.staged);   // (no-op once a frame has adopted the lists)
     const double t2 = t1 + tFrame;
     double tRender = 0, tRead = 0;
     bool ok = f != nullptr;
@@ -504,20 +525,12 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
             std::lock_guard<std::mutex> lock(g_liveMutex);
             g_liveFrames.push_back(f);
         }
-        const int maxBands = (int)((cam.height + 127) / 128) + 1;
-        std::vector<cl_uint> rows(2 * (size_t)maxBands);
-        const int owned = world > 1 ? oclr_band_partition(cam.height, 128, rank, world, rows.data(), maxBands) : 1;
-        if (world <= 1) {
-            rows[0] = 0;
-            rows[1] = cam.height;
-        }
         RenderStats rs;
         const double a = now_ms();
-        // all bands of this device in one launch sequence (tile height 128 = the reference's, raytrace.c:507)
-        ok = frame_render_bands(f, sampleCount, 0, sampleCount, 128, (uint32_t)rank, (uint32_t)(world > 1 ? world : 1), default_variant(), false,
-                                nullptr, &rs, err);
+        // all bands of this device in one launch sequence
+        ok = frame_render_bands(f, sampleCount, 0, sampleCount, bandRows, (uint32_t)rank, bandWorld, default_variant(), false, nullptr, &rs, err);
         const double c = now_ms();
-        for (int k = 0; ok && k < owned; ++k) ok = frame_read(f, rows[2 * k], rows[2 * k + 1], r, g, b, nullptr, err);
+        ok = ok && frame_read_bands(f, bandRows, (uint32_t)rank, bandWorld, r, g, b, err);
         tRender += c - a;
         tRead += now_ms() - c;
         GetProgress();   // latch the last value of the device counter before the frame goes away
@@ -535,6 +548,20 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
         fprintf(stderr, "[opencl_render_b200] RaytraceAll dev %d: scene upload+repack %.2f ms, camera lists %.2f ms, trace %.2f ms, read back %.2f ms, "
                         "release %.2f ms\n", device, t1 - t0, t2 - t1, tRender, tRead, now_ms() - t3);
     return ok;
+}
+
+static int all_devices_world(int devices) {
+    const int k = g_allDevicesLimit.load();
+    return k > 0 && k < devices ? k : devices;
+}
+// Band height of the all-devices mode: about eight bands per GPU (sky and geometry rows cost very different amounts), multiple of 8
+// rows (the logic kernel's tile height), at most 128 = the reference's tile height (raytrace.c:507).
+static cl_uint all_devices_band_rows(cl_uint height, int world) {
+    static const int forced = [] { const char* v = getenv("OCLR_BAND_ROWS"); return v ? atoi(v) : 0; }();
+    if (forced > 0) return (cl_uint)forced;
+    cl_uint rows = height / (cl_uint)(world * 8);
+    rows = rows / 8 * 8;
+    return rows < 8 ? 8 : (rows > 128 ? 128 : rows);
 }
 
 static cl_bool raytrace_all_impl(cl_uint computationType, const Camera& cam, const HostScene& h, const cl_uint* camStart,
@@ -567,24 +594,26 @@ static cl_bool raytrace_all_impl(cl_uint computationType, const Camera& cam, con
     g_endTime = g_startTime.load();
     bool ok = true;
     std::string err;
-    if (!allDevices) {
-        ok = render_rows_on_device(type, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, 0, 1, r, g, b, err);
+    const int world = allDevices ? all_devices_world(devices) : 1;
+    if (world <= 1) {
+        ok = render_rows_on_device(allDevices ? 0 : type, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, 0, 1, 128, nullptr, r, g,
+                                   b, err);
     } else {
-        // Scene replicated per GPU, rows dealt in bands of 128; every GPU copies its own rows straight to the
-        // caller's planes (disjoint), so no gather step is needed inside one process.
-        std::vector<std::thread> pool;
-        std::vector<std::string> errs(devices);
-        std::vector<char> oks(devices, 1);
-        for (int d = 0; d < devices; ++d)
-            pool.emplace_back([&, d]() {
-                oks[d] = render_rows_on_device(d, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, d, devices, r, g,
-                                               b, errs[d]);
-            });
-        for (auto& t : pool) t.join();
-        for (int d = 0; d < devices; ++d)
+        // Rows dealt in bands over the GPUs, ONE upload shared by all of them (each pulls 1/N over PCIe, NVLink fan-out), every GPU
+        // copies its own rows back to the caller's planes (disjoint), so no gather step is needed inside one process.
+        static const bool shareUpload = [] { const char* v = getenv("OCLR_SHARE_UPLOAD"); return !v || atoi(v) != 0; }();
+        const cl_uint bandRows = all_devices_band_rows(cam.height, world);
+        std::vector<std::string> errs(world);
+        std::vector<char> oks(world, 1);
+        ok = run_on_devices(world, shareUpload, [&](int d, ShardCtx* share) {
+            oks[d] = render_rows_on_device(d, h, cam, camStart, camEnd, camList, (size_t)camListSize, sampleCount, d, world, bandRows, share, r, g, b,
+                                           errs[d]);
+        }, err);
+        for (int d = 0; ok && d < world; ++d)
             if (!oks[d]) {
                 ok = false;
                 err = errs[d];
+                break;
             }
     }
     g_endTime = clock();

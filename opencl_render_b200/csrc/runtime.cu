@@ -209,6 +209,200 @@ struct DeviceBuffer {
     }
 };
 
+// ---- one scene, N GPUs of one box: sharded upload + NVLink fan-out ---------------------------------------------------------------------
+// RaytraceAll(all devices) used to let every GPU pull the WHOLE scene (133 MB for config 2) over its own PCIe link.  Now GPU k
+// uploads the k-th 1/N of every large array into its own buffer and one kernel stores that slice into the same place of every
+// peer's buffer over NVLink peer memory (16-byte stores, like push_rows_kernel); events order the consumers behind all N slices.
+// PCIe moves every byte once in total instead of once per GPU.  Arrays travel in two groups so that the triangle repack and the
+// primary-ray round start while the grid (the larger group) is still in flight.
+enum { kMaxPeers = 16, kShardArrays = 12, kShardGroups = 2 };
+
+struct FanoutItem {
+    const uint4* src;              // this GPU's slice inside its own buffer
+    unsigned long long vecs;       // 16-byte vectors in the slice
+    uint4* dst[kMaxPeers];         // the same place inside every peer's buffer
+};
+struct FanoutTable {
+    int items, peers;
+    FanoutItem it[kShardArrays];
+};
+__global__ void __launch_bounds__(256) fanout_kernel(const __grid_constant__ FanoutTable t) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (int a = 0; a < t.items; ++a) {
+        const FanoutItem& it = t.it[a];
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.vecs; i += stride) {
+            const uint4 v = it.src[i];
+            for (int d = 0; d < t.peers; ++d) it.dst[d][i] = v;
+        }
+    }
+}
+
+struct ShardCtx {
+    int world = 0;
+    int devices[kMaxPeers] = {0};
+    cudaEvent_t allocReady[kMaxPeers] = {}, pushed[kShardGroups][kMaxPeers] = {};
+    void* ptr[kShardArrays][kMaxPeers] = {};
+    // spin barrier with a verdict: every thread arrives with its own status, all leave with the AND (a thread that failed keeps
+    // arriving at the remaining barriers so that nobody waits for it forever)
+    std::atomic<int> arrived{0};
+    std::atomic<unsigned> generation{0};
+    std::atomic<int> bad{0};
+    bool arrive(bool ok) {
+        if (!ok) bad.store(1);
+        const unsigned gen = generation.load();
+        if (arrived.fetch_add(1) + 1 == world) {
+            arrived.store(0);
+            generation.fetch_add(1);
+        } else {
+            while (generation.load() == gen) std::this_thread::yield();
+        }
+        return bad.load() == 0;
+    }
+};
+
+// Slice k of n bytes cut N ways on 256-byte boundaries.
+static inline void shard_range(size_t n, int k, int world, size_t& begin, size_t& end) {
+    const size_t per = ((n + (size_t)world - 1) / (size_t)world + 255) & ~(size_t)255;
+    begin = std::min(n, per * (size_t)k);
+    end = std::min(n, begin + per);
+}
+
+// Peer access between the first `world` devices, for direct stores and for memory from the stream-ordered pools.  Once per process.
+static bool ensure_peer_access(int world, std::string& err) {
+    static std::mutex m;
+    static int enabledFor = 0;
+    static bool usable = false;
+    std::lock_guard<std::mutex> lock(m);
+    if (enabledFor >= world) return usable;
+    usable = true;
+    for (int i = 0; i < world && usable; ++i) {
+        if (cudaSetDevice(i) != cudaSuccess) usable = false;
+        prepare_pool(i);
+        cudaMemPool_t pool;
+        if (usable && cudaDeviceGetDefaultMemPool(&pool, i) != cudaSuccess) usable = false;
+        for (int j = 0; j < world && usable; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, i, j) != cudaSuccess || !can) {
+                usable = false;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) usable = false;
+            cudaGetLastError();
+            // device j may read and write what device i's pool hands out
+            cudaMemAccessDesc desc = {};
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = j;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (usable && cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) usable = false;
+        }
+    }
+    cudaGetLastError();
+    if (!usable) err = "peer access between the GPUs is not available";
+    enabledFor = world;
+    return usable;
+}
+
+// One worker thread per GPU, alive for the life of the process: RaytraceAll(all devices) hands each its share of the frame.
+// (Creating N threads per call costs ~30 us each, serially, in front of a 2 ms call.)
+class DevicePool {
+public:
+    static DevicePool& get() {
+        static DevicePool* p = new DevicePool();   // never destroyed: its threads are detached
+        return *p;
+    }
+    // Runs fn(rank) for rank in [0, world) on the worker bound to device rank; returns when all have finished.  One job at a time.
+    void run(int world, const std::function<void(int)>& fn) {
+        std::lock_guard<std::mutex> job(jobMutex_);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            while ((int)workers_ < world) {
+                const int d = (int)workers_++;
+                std::thread([this, d]() { worker(d); }).detach();
+            }
+            fn_ = &fn;
+            world_ = world;
+            pending_ = world;
+            ++generation_;
+        }
+        cvJob_.notify_all();
+        std::unique_lock<std::mutex> lock(m_);
+        cvDone_.wait(lock, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ShardCtx ctx;   // (guarded by the one-job-at-a-time rule)
+
+private:
+    void worker(int d) {
+        cudaSetDevice(d);
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cvJob_.wait(lock, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (d < world_) fn = fn_;
+            }
+            if (!fn) continue;
+            (*fn)(d);
+            std::lock_guard<std::mutex> lock(m_);
+            if (--pending_ == 0) cvDone_.notify_all();
+        }
+    }
+    std::mutex jobMutex_, m_;
+    std::condition_variable cvJob_, cvDone_;
+    const std::function<void(int)>* fn_ = nullptr;
+    unsigned workers_ = 0;
+    int world_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+bool run_on_devices(int world, bool shareUpload, const std::function<void(int rank, ShardCtx* share)>& fn, std::string& err) {
+    if (world < 1 || world > kMaxPeers || world > device_count()) {
+        err = "bad device count";
+        return false;
+    }
+    DevicePool& pool = DevicePool::get();
+    std::string peerErr;
+    const bool share = shareUpload && world > 1 && ensure_peer_access(world, peerErr);
+    if (shareUpload && world > 1 && !share) {
+        static bool said = false;
+        if (!said) fprintf(stderr, "[opencl_render_b200] %s: every GPU uploads the whole scene over its own PCIe link\n", peerErr.c_str());
+        said = true;
+    }
+    ShardCtx* ctx = nullptr;
+    std::function<void(int)> job = [&](int rank) { fn(rank, ctx); };
+    if (!share) {
+        pool.run(world, job);
+        return true;
+    }
+    // (the pool's ShardCtx is touched only between its run() calls and by the job itself; run() admits one job at a time, and this
+    // function is the only user of ctx, serialised by a mutex of its own)
+    static std::mutex shareMutex;
+    std::lock_guard<std::mutex> lock(shareMutex);
+    ctx = &pool.ctx;
+    ctx->world = world;
+    ctx->arrived.store(0);
+    ctx->bad.store(0);
+    for (int d = 0; d < world; ++d) {
+        ctx->devices[d] = d;
+        if (!ctx->allocReady[d]) {
+            cudaSetDevice(d);
+            bool ok = cudaEventCreateWithFlags(&ctx->allocReady[d], cudaEventDisableTiming) == cudaSuccess;
+            for (int g = 0; g < kShardGroups; ++g) ok = ok && cudaEventCreateWithFlags(&ctx->pushed[g][d], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) {
+                err = "cannot create the upload events";
+                cudaGetLastError();
+                return false;
+            }
+        }
+    }
+    pool.run(world, job);
+    return true;
+}
+
 struct Scene {
     int device = 0;
     DeviceBuffer triGeo, triShade, bricks, cellRange, cellList, faceMask, planes, matSize, matStart, textures, lights;
@@ -438,7 +632,89 @@ bool build_scene_grid_device(int device, int32_t n, uint32_t V, const float4* ve
     return done(true);
 }
 
-static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early) {
+// Sharded upload (see ShardCtx): the calling thread is `rank` of ctx->world threads that run this same function for the same host
+// arrays, one per GPU.  `arrays` lists the large arrays in two groups; buffers are allocated here, slice `rank` goes up over PCIe and
+// is fanned out to the peers.  On return (true) the copies are ENQUEUED and the `pushed` events of this rank recorded; the caller
+// makes its stream wait for a group with shard_wait_group().  Every rank passes both barriers whatever happens to it.
+struct ShardBarriers {   // the two barriers of shard_upload, passed with `false` on scope exit by a rank that never got there
+    ShardCtx* ctx;
+    int left;
+    explicit ShardBarriers(ShardCtx* c) : ctx(c), left(c ? 2 : 0) {}
+    ~ShardBarriers() {
+        while (left-- > 0) ctx->arrive(false);
+    }
+    bool arrive(bool ok) {
+        --left;
+        return ctx->arrive(ok);
+    }
+};
+struct ShardArray {
+    DeviceBuffer* buf;
+    const void* host;
+    size_t bytes;
+    int group;
+};
+static bool shard_upload(ShardCtx* ctx, ShardBarriers& barriers, int rank, ShardArray* arrays, int count, std::string& err) {
+    const int world = ctx->world;
+    bool ok = count <= kShardArrays;
+    // 1. allocate (16-byte padded: the fan-out moves whole vectors), publish the addresses
+    for (int a = 0; ok && a < count; ++a) {
+        ok = arrays[a].buf->alloc((arrays[a].bytes + 15) & ~(size_t)15, err);
+        arrays[a].buf->bytes = arrays[a].bytes;
+        ctx->ptr[a][rank] = arrays[a].buf->p;
+    }
+    if (ok && cudaEventRecord(ctx->allocReady[rank], 0) != cudaSuccess) {
+        err = "cudaEventRecord failed";
+        ok = false;
+    }
+    ok = barriers.arrive(ok);
+    // 2. own slices up, then out to the peers -- peers' buffers are written only after their allocation point in THEIR stream
+    if (ok)
+        for (int d = 0; d < world && ok; ++d)
+            if (d != rank) ok = cudaStreamWaitEvent(0, ctx->allocReady[d], 0) == cudaSuccess;
+    for (int g = 0; g < kShardGroups; ++g) {
+        FanoutTable t = {};
+        t.peers = world - 1;
+        for (int a = 0; ok && a < count; ++a) {
+            if (arrays[a].group != g || arrays[a].bytes == 0) continue;
+            size_t b0, b1;
+            shard_range(arrays[a].bytes, rank, world, b0, b1);
+            if (b0 >= b1) continue;
+            ok = host_to_device((char*)arrays[a].buf->p + b0, (const char*)arrays[a].host + b0, b1 - b0, 0, err);
+            FanoutItem& it = t.it[t.items++];
+            it.src = (const uint4*)((const char*)arrays[a].buf->p + b0);
+            it.vecs = (b1 - b0 + 15) / 16;
+            int k = 0;
+            for (int d = 0; d < world; ++d)
+                if (d != rank) it.dst[k++] = (uint4*)((char*)ctx->ptr[a][d] + b0);
+        }
+        if (ok && t.items) {
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->devices[rank]);
+            fanout_kernel<<<sms * 4, 256>>>(t);
+            if (cudaGetLastError() != cudaSuccess) {
+                err = "fan-out launch failed";
+                ok = false;
+            }
+        }
+        if (ok && cudaEventRecord(ctx->pushed[g][rank], 0) != cudaSuccess) {
+            err = "cudaEventRecord failed";
+            ok = false;
+        }
+    }
+    // 3. every rank's events are recorded before anybody waits on them (waiting on an unrecorded event is a no-op)
+    ok = barriers.arrive(ok);
+    if (!ok && err.empty()) err = "the upload failed on another GPU";
+    return ok;
+}
+static bool shard_wait_group(ShardCtx* ctx, int group, std::string& err) {
+    for (int d = 0; d < ctx->world; ++d) OCLR_CUDA(cudaStreamWaitEvent(0, ctx->pushed[group][d], 0));
+    return true;
+}
+
+static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early, UploadShare* share) {
+    ShardCtx* ctx = share ? share->ctx : nullptr;
+    ShardBarriers barriers(ctx);   // (any early return below still passes the barriers the other GPUs' threads wait at)
     OCLR_CUDA(cudaSetDevice(s->device));
     int major = 0, minor = 0, sms = 0;   // attribute queries: cudaGetDeviceProperties costs milliseconds per call
     OCLR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, s->device));
@@ -467,15 +743,45 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     // 1a. everything the primary-ray round needs -- triangles, materials, lights -- goes first: raw reference arrays -> HBM straight
     //     from the caller's memory (async on the default stream), repacked by pack_triangles_kernel
     DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag, cellIds;
-    bool ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
-              triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
-              triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) &&
-              s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
-              s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
-              s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
-              s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&
-              s->triGeo.alloc(sizeof(float4) * 4 * N, err) && s->triShade.alloc(sizeof(float4) * 8 * N, err) &&
-              errFlag.alloc(sizeof(uint32_t) * 2, err);
+    bool ok;
+    if (ctx) {
+        // one of N GPUs uploading the same arrays: slice + fan-out for the large ones (group 0 = what the triangle repack and the
+        // primary-ray round need, the camera lists included; group 1 = the grid), the small tables go up whole
+        DeviceBuffer camStart, camEnd, camList;
+        const size_t P = share->pixels;
+        ShardArray arrays[] = {
+            {&vertex, h.vertex, sizeof(float4) * h.vertexCount, 0},
+            {&triIdx, h.triIdx, sizeof(int4) * N, 0},
+            {&triMat, h.triMat, sizeof(int32_t) * N, 0},
+            {&triUv, h.triUv, sizeof(float2) * 3 * N, 0},
+            {&triNormal, h.triNormal, sizeof(float4) * 3 * N, 0},
+            {&s->textures, h.textures, sizeof(uchar4) * h.texturesSize, 0},
+            {&camStart, share->camStart, share->camStart ? sizeof(uint32_t) * P : 0, 0},
+            {&camEnd, share->camEnd, share->camStart ? sizeof(uint32_t) * P : 0, 0},
+            {&camList, share->camList, share->camStart ? sizeof(uint32_t) * share->camListSize : 0, 0},
+            {&gridStart, h.gridStart, buildGrid ? 0 : sizeof(uint32_t) * (cells + 1), 1},
+            {&s->cellList, h.gridList, buildGrid ? 0 : sizeof(uint32_t) * total, 1},
+        };
+        ok = shard_upload(ctx, barriers, share->rank, arrays, (int)(sizeof(arrays) / sizeof(arrays[0])), err);
+        share->staged.start = camStart.p;   // handed to the frame (frame_create adopts them) or freed by staged_release()
+        share->staged.end = camEnd.p;
+        share->staged.list = camList.p;
+        share->staged.listSize = share->camListSize;
+        ok = ok && s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
+             s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
+             s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&
+             (buildGrid || boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err)) && shard_wait_group(ctx, 0, err);
+    } else {
+        ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
+             triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
+             triNormal.upload(h.triNormal, sizeof(float4) * 3 * N, err) &&
+             s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
+             s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
+             s->textures.upload(h.textures, sizeof(uchar4) * h.texturesSize, err) &&
+             s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err);
+    }
+    ok = ok && s->triGeo.alloc(sizeof(float4) * 4 * N, err) && s->triShade.alloc(sizeof(float4) * 8 * N, err) &&
+         errFlag.alloc(sizeof(uint32_t) * 2, err);
     if (ok) {
         cudaMemsetAsync(errFlag.p, 0, sizeof(uint32_t) * 2, 0);
         if (N)
@@ -500,9 +806,10 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
         if (early && *early) (*early)(s);
     }
     // 1b. the grid
-    ok = ok && (buildGrid || (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
-                              gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
-                              s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err))) &&
+    ok = ok && (buildGrid || (ctx ? shard_wait_group(ctx, 1, err)
+                                  : (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
+                                     gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
+                                     s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err)))) &&
          s->bricks.alloc(sizeof(uint4) * nBricks, err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
          counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err);
     uint32_t nonEmpty = 0, flag = 0;
@@ -600,14 +907,15 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     return true;
 }
 
-Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early) {
+Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early, UploadShare* share) {
     if (device < 0 || device >= device_count()) {
         err = "no such CUDA device: " + std::to_string(device) + " (the library has no CPU fallback)";
+        ShardBarriers barriers(share ? share->ctx : nullptr);
         return nullptr;
     }
     Scene* s = new Scene();
     s->device = device;
-    if (!scene_upload(s, h, err, early)) {
+    if (!scene_upload(s, h, err, early, share)) {
         cudaDeviceSynchronize();   // the `early` hook may have started work on another stream that still reads this scene
         scene_destroy(s);
         return nullptr;
@@ -660,16 +968,27 @@ static bool frame_setup_common(Frame* f, std::string& err, bool sync = true) {
 }
 
 static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList, size_t listSize,
-                        std::string& err, bool sync) {
+                        std::string& err, bool sync, StagedCamLists* staged) {
     OCLR_CUDA(cudaSetDevice(f->scene->device));
     const size_t P = (size_t)f->cam.width * f->cam.height;
-    if (!camStart || !camEnd || (listSize && !camList)) {
-        err = "camera triangle lists missing";
-        return false;
+    if (staged && staged->start && !staged->adopted) {   // already in HBM (uploaded together with the scene, shard_upload)
+        staged->adopted = true;
+        f->camStart.p = staged->start;
+        f->camStart.bytes = sizeof(uint32_t) * P;
+        f->camEnd.p = staged->end;
+        f->camEnd.bytes = sizeof(uint32_t) * P;
+        f->camList.p = staged->list;
+        f->camList.bytes = sizeof(uint32_t) * staged->listSize;
+        listSize = staged->listSize;
+    } else {
+        if (!camStart || !camEnd || (listSize && !camList)) {
+            err = "camera triangle lists missing";
+            return false;
+        }
+        if (!f->camStart.upload(camStart, sizeof(uint32_t) * P, err)) return false;
+        if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
+        if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
     }
-    if (!f->camStart.upload(camStart, sizeof(uint32_t) * P, err)) return false;
-    if (!f->camEnd.upload(camEnd, sizeof(uint32_t) * P, err)) return false;
-    if (!f->camList.upload(camList, sizeof(uint32_t) * listSize, err)) return false;
     f->camListSize = listSize;
     if (listSize > 0xFFFFFFFFull) {
         err = "camera triangle list too long";
@@ -797,8 +1116,16 @@ static bool frame_build_camera_lists(Frame* f, std::string& err) {
     return done(true);
 }
 
+void staged_release(StagedCamLists& st) {
+    if (st.adopted) return;
+    if (st.start) cudaFreeAsync(st.start, 0);
+    if (st.end) cudaFreeAsync(st.end, 0);
+    if (st.list) cudaFreeAsync(st.list, 0);
+    st = StagedCamLists();
+}
+
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
-                    size_t camListSize, std::string& err, bool sync) {
+                    size_t camListSize, std::string& err, bool sync, StagedCamLists* staged) {
     if (!s) {
         err = "null scene";
         return nullptr;
@@ -811,7 +1138,7 @@ Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const
     f->scene = s;
     f->device = s->device;
     f->cam = cam;
-    const bool ok = camStart ? frame_setup(f, camStart, camEnd, camList, camListSize, err, sync)
+    const bool ok = (camStart || (staged && staged->start)) ? frame_setup(f, camStart, camEnd, camList, camListSize, err, sync, staged)
                              : (frame_build_camera_lists(f, err) && frame_setup_common(f, err));   // no lists given: build them on the device
     if (!ok) {
         frame_destroy(f);
@@ -1417,6 +1744,82 @@ bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, ui
     return true;
 }
 
+// ---- read-back of a band set (RaytraceAll on all devices) --------------------------------------------------------------------------
+// A rank's rows are bands scattered over the frame.  Copying them band by band into the caller's pageable planes is 3 blocking
+// copies per band; instead the rows are compacted on the device ([plane][owned row][W]), cross PCIe in ONE transfer into a pinned
+// block that lives as long as the process, and the calling thread scatters them (N threads do that side by side).
+__global__ void __launch_bounds__(256) compact_rows_kernel(const uint16_t* __restrict__ planes, uint16_t* __restrict__ out, uint32_t W, uint32_t H,
+                                                           uint32_t bandRows, uint32_t rank, uint32_t world, uint32_t ownedRows) {
+    const size_t P = (size_t)W * H;
+    const uint64_t total = (uint64_t)ownedRows * W * 3u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(i % W);
+        const uint64_t rowPlane = i / W;
+        const uint32_t k = (uint32_t)(rowPlane % ownedRows), plane = (uint32_t)(rowPlane / ownedRows);
+        const uint32_t y = (k / bandRows) * (bandRows * world) + rank * bandRows + (k % bandRows);   // map_row()
+        out[i] = planes[plane * P + (size_t)y * W + x];
+    }
+}
+
+struct PinnedStage {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+static PinnedStage& read_stage(int device, size_t need) {
+    static PinnedStage stages[64];
+    PinnedStage& st = stages[device & 63];
+    if (st.bytes < need) {   // (one render at a time per device: RaytraceAll's worker thread)
+        if (st.p) cudaFreeHost(st.p);
+        st.p = nullptr;
+        st.bytes = 0;
+        if (cudaHostAlloc(&st.p, need, cudaHostAllocPortable) == cudaSuccess)
+            st.bytes = need;
+        else
+            cudaGetLastError();
+    }
+    return st;
+}
+
+bool frame_read_bands(Frame* f, uint32_t bandRows, uint32_t rank, uint32_t world, uint16_t* outR, uint16_t* outG, uint16_t* outB,
+                      std::string& err) {
+    if (!f || bandRows == 0 || world == 0 || rank >= world) {
+        err = "bad read request";
+        return false;
+    }
+    const uint32_t W = f->cam.width, H = f->cam.height;
+    if (world == 1) return frame_read(f, 0, H, outR, outG, outB, nullptr, err);
+    OCLR_CUDA(cudaSetDevice(f->scene->device));
+    const uint32_t owned = band_owned_rows(H, bandRows, rank, world);
+    if (owned == 0) return true;
+    const size_t bytes = sizeof(uint16_t) * 3 * (size_t)owned * W;
+    PinnedStage& st = read_stage(f->scene->device, bytes);
+    if (!st.p) {
+        err = "out of pinned host memory";
+        return false;
+    }
+    DeviceBuffer pack;
+    if (!pack.alloc(bytes, err)) return false;
+    const uint64_t total = (uint64_t)owned * W * 3u;
+    compact_rows_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)f->scene->smCount * 8), 256>>>(
+        (const uint16_t*)f->planesRGB.p, (uint16_t*)pack.p, W, H, bandRows, rank, world, owned);
+    cudaError_t e = cudaMemcpyAsync(st.p, pack.p, bytes, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    pack.release();
+    if (e != cudaSuccess) {
+        err = std::string("frame_read_bands: ") + cudaGetErrorString(e);
+        return false;
+    }
+    const uint16_t* src = (const uint16_t*)st.p;
+    uint16_t* dst[3] = {outR, outG, outB};
+    for (int plane = 0; plane < 3; ++plane)
+        for (uint32_t k = 0; k < owned; k += bandRows) {   // one band = consecutive frame rows
+            const uint32_t y = (k / bandRows) * (bandRows * world) + rank * bandRows;
+            const uint32_t rows = std::min(bandRows, owned - k);
+            memcpy(dst[plane] + (size_t)y * W, src + ((size_t)plane * owned + k) * W, sizeof(uint16_t) * (size_t)rows * W);
+        }
+    return true;
+}
+
 // Host -> device copy of rows [rowBegin,rowEnd) of the three planes: restores a checkpoint taken with frame_read after k samples;
 // the job then continues with frame_render(sampleBegin = k).
 bool frame_write(Frame* f, uint32_t rowBegin, uint32_t rowEnd, const uint16_t* inR, const uint16_t* inG, const uint16_t* inB, void* stream,
@@ -1517,7 +1920,6 @@ uint32_t frame_last_launches(const Frame* f) { return f ? f->lastLaunches : 0; }
 // one kernel STORES the rank's finished rows straight into the full-frame planes of every GPU of the box -- its own and its
 // peers', whose buffers are mapped into this process (NVLink 5 / NVSwitch peer access) -- at the place they belong.  16-byte
 // stores, one row segment of 8 pixels per thread and destination; the caller puts a cross-GPU barrier behind it.
-enum { kMaxPeers = 16 };
 struct PeerPlanes {
     uint16_t* p[kMaxPeers];
 };

@@ -63,9 +63,33 @@ struct Frame;
 int device_count();
 bool device_name(int dev, char* buf, size_t len);
 
+// RaytraceAll(all devices): the N per-GPU scene_create calls of one frame share the upload -- each GPU pulls 1/N of every large array over
+// PCIe and stores it into its peers over NVLink (runtime.cu, ShardCtx).  run_on_devices() runs fn(rank, share) on a persistent worker
+// thread per GPU; `share` is null when peer access is unavailable (every GPU then uploads everything itself).
+struct ShardCtx;
+struct StagedCamLists {   // camera lists that went up with the scene; frame_create adopts them
+    void* start = nullptr;
+    void* end = nullptr;
+    void* list = nullptr;
+    size_t listSize = 0;
+    bool adopted = false;
+};
+struct UploadShare {
+    ShardCtx* ctx = nullptr;
+    int rank = 0;
+    const uint32_t* camStart = nullptr;
+    const uint32_t* camEnd = nullptr;
+    const uint32_t* camList = nullptr;
+    size_t camListSize = 0, pixels = 0;
+    StagedCamLists staged;
+};
+bool run_on_devices(int world, bool shareUpload, const std::function<void(int rank, ShardCtx* share)>& fn, std::string& err);
+void staged_release(StagedCamLists& st);
+
 // `early` (optional) is called once the triangles, materials and lights are on their way to the device and BEFORE the grid is
 // uploaded, with the partly built scene: RaytraceAll uses it to start the primary-ray round under the grid upload (frame_prelaunch).
-Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early = nullptr);
+Scene* scene_create(int device, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early = nullptr,
+                    UploadShare* share = nullptr);
 void scene_destroy(Scene* s);
 size_t scene_device_bytes(const Scene* s);
 int scene_device(const Scene* s);
@@ -74,7 +98,8 @@ size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap);
 // Camera lists are per-frame inputs (CameraTriangleList::New output, trianglelist.cpp:520-626).  `camStart`/`camEnd`
 // hold width*height entries; only rows [rowBegin,rowEnd) need to be valid (band-partitioned multi-GPU rendering).
 Frame* frame_create(Scene* s, const Camera& cam, const uint32_t* camStart, const uint32_t* camEnd, const uint32_t* camList,
-                    size_t camListSize, std::string& err, bool sync = true);   // sync = false: the host arrays outlive the copies
+                    size_t camListSize, std::string& err, bool sync = true,   // sync = false: the host arrays outlive the copies
+                    StagedCamLists* staged = nullptr);
 void frame_destroy(Frame* f);
 // camStart == nullptr: CameraTriangleList::New runs on the device from the resident scene (cam_builder.cuh).  The lists a frame
 // holds (uploaded or device-built) can be copied back: `list` needs frame_camera_list_size() entries.
@@ -115,6 +140,10 @@ void set_slice_count(int k);
 // Tracing one round ahead (rt_wavefront.cuh): 0 never, 1 all segments but the camera's, 2 all, -1 automatic.
 void set_ahead_mode(int m);
 uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint32_t world);
+// Device -> host copy of ALL rows `rank` owns (bands of bandRows dealt round-robin over world): compacted on the device, one transfer
+// into a pinned staging block, scattered to the caller's (pageable) planes by the calling thread.
+bool frame_read_bands(Frame* f, uint32_t bandRows, uint32_t rank, uint32_t world, uint16_t* outR, uint16_t* outG, uint16_t* outB,
+                      std::string& err);
 // Device -> host copy of rows [rowBegin,rowEnd) of the three planes (full-frame sized host arrays).
 bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, uint16_t* outG, uint16_t* outB, void* stream,
                 std::string& err);

@@ -130,47 +130,52 @@ def plane_exchange(frame, part: BandPartition, device):
         return PlaneGather(frame, part, device), "NCCL all-gather of compact rows + scatter"
 
 
+_SCENE_ARRAYS = ("vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type", "light_pos",
+                 "light_dir", "light_colour", "light_radius", "light_half", "box_min", "grid_start", "grid_list")
+
+
 class EndToEnd:
-    """The drop-in call with HOST buffers: at world == 1 it is RaytraceAll itself (upload + repack + trace + read back);
-    at world > 1 each rank uploads the scene, traces its bands and reads its rows back through the scene/frame API."""
+    """The drop-in call with HOST buffers, made by ONE process: RaytraceAll on one GPU (world == 1) or on the first `world` GPUs of
+    the box (computation type deviceCount + 1 with the "devices" option: every GPU pulls 1/N of the scene over PCIe, fans it out over
+    NVLink, traces its row bands and copies them back).  Upload + repack + trace + read back are all inside the call."""
 
-    def __init__(self, scene: api.HostScene, cam: api.CameraSetup, lists: api.CameraLists, part: BandPartition, device: int):
-        import torch
-        self.scene, self.cam, self.part, self.device = scene, cam, part, device
-
-        def pin(a):
-            a = np.ascontiguousarray(a)
-            if a.size == 0:
-                return a
-            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
-            v = t.numpy().view(a.dtype).reshape(a.shape)
-            v[...] = a
-            self._keep.append(t)
-            return v
-
+    def __init__(self, scene: api.HostScene, cam: api.CameraSetup, lists: api.CameraLists, world: int, device: int, n_devices: int = 1,
+                 pinned: bool = True):
+        import copy
+        self.cam, self.world, self.device, self.n_devices = cam, world, device, n_devices
         self._keep = []
-        for name in ("vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type",
-                     "light_pos", "light_dir", "light_colour", "light_radius", "light_half", "box_min", "grid_start", "grid_list"):
-            setattr(scene, name, pin(getattr(scene, name)))
-        self.lists = api.CameraLists(pin(lists.start), pin(lists.end), pin(lists.list))
-        self.out = tuple(pin(np.zeros((cam.height, cam.width), np.uint16)) for _ in range(3))
-        self.h2d_bytes = int(sum(getattr(scene, n).nbytes for n in (
-            "vertex", "tri_idx", "tri_mat", "tri_uv", "tri_normal", "mat_size", "mat_start", "textures", "light_type", "light_pos",
-            "light_dir", "light_colour", "light_radius", "light_half", "box_min", "grid_start", "grid_list")) +
-            self.lists.start.nbytes + self.lists.end.nbytes + self.lists.list.nbytes)
-        self.d2h_bytes = int(6 * part.owned_rows * cam.width)
+        self.scene = copy.copy(scene)
+        conv = self._pin if pinned else (lambda a: np.array(a, copy=True))
+        for name in _SCENE_ARRAYS:
+            setattr(self.scene, name, conv(getattr(scene, name)))
+        self.lists = api.CameraLists(conv(lists.start), conv(lists.end), conv(lists.list))
+        self.out = tuple(conv(np.zeros((cam.height, cam.width), np.uint16)) for _ in range(3))
+        self.h2d_bytes = int(sum(getattr(self.scene, n).nbytes for n in _SCENE_ARRAYS) + self.lists.start.nbytes + self.lists.end.nbytes +
+                             self.lists.list.nbytes)
+        self.d2h_bytes = int(6 * cam.height * cam.width)
+        if world > 1:
+            api.set_option("devices", world)
+            self.computation_type = n_devices + 1
+            self.call = f"RaytraceAll(all devices) on {world} GPUs from one process (C-ABI, host buffers; shared upload over NVLink)"
+        else:
+            self.computation_type = 1 + device
+            self.call = "RaytraceAll (C-ABI, host buffers)"
+        self._source = (scene, lists)
+
+    def _pin(self, a):
+        import torch
+        a = np.ascontiguousarray(a)
+        if a.size == 0:
+            return a
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        self._keep.append(t)
+        return v
+
+    def pageable_copy(self) -> "EndToEnd":
+        """The same call fed from plain (pageable) arrays, as the plugin allocates them (render.cpp:1086-1134)."""
+        return EndToEnd(self._source[0], self.cam, self._source[1], self.world, self.device, self.n_devices, pinned=False)
 
     def step(self, samples: int):
-        if self.part.world == 1:
-            api.raytrace_all(1 + self.device, self.cam, self.lists, samples, self.scene, out=self.out)
-            return
-        ds = api.DeviceScene(self.scene, self.device)
-        fr = api.DeviceFrame(ds, self.cam, self.lists)
-        fr.render_bands(samples, self.part.band_rows, self.part.rank, self.part.world)
-        rows = self.part.rows
-        if rows.size:      # contiguous runs of owned rows
-            cuts = np.nonzero(np.diff(rows) != 1)[0] + 1
-            for seg in np.split(rows, cuts):
-                fr.read(rows=(int(seg[0]), int(seg[-1]) + 1), out=self.out)
-        fr.close()
-        ds.close()
+        api.raytrace_all(self.computation_type, self.cam, self.lists, samples, self.scene, out=self.out)

@@ -23,6 +23,19 @@ _OMNI = dict(type=api.LIGHT_OMNI, pos=(0.0, 6.0, 0.0), colour=(1, 1, 1), radius=
 _AREA = dict(type=api.LIGHT_AREA, pos=(-4.0, 5.0, -3.0), colour=(0.6, 0.6, 0.6), radius=0.6, half=9.0)
 
 
+# every light type the reference's switch (raytrace_opencl.c:566-607) knows but the config scenes never use -- SPOTRECT (2), PARALLEL (4),
+# PARSPOT (5), PARSPOTRECT (6), TUBE (7), PHOTOMETRIC (9) -- plus a type outside the switch (contributes nothing, like OMNI)
+_ALL_TYPES = [
+    dict(type=api.LIGHT_SPOTRECT, pos=(2.5, 7.0, -4.0), colour=(0.5, 0.45, 0.4), radius=0.2, half=14.0),
+    dict(type=api.LIGHT_PARALLEL, dir=(0.3, -0.9, 0.2), colour=(0.25, 0.3, 0.35), radius=0.4),
+    dict(type=api.LIGHT_PARSPOT, dir=(-0.5, -0.7, -0.1), colour=(0.3, 0.2, 0.2), radius=1.5, half=40.0),
+    dict(type=api.LIGHT_PARSPOTRECT, dir=(0.1, -1.0, -0.4), colour=(0.15, 0.25, 0.15), radius=0.0),
+    dict(type=api.LIGHT_TUBE, pos=(-3.5, 4.0, 2.0), colour=(0.4, 0.4, 0.2), radius=0.5),
+    dict(type=11, pos=(0.0, 5.0, 0.0), colour=(1, 1, 1), radius=0.3),
+    dict(type=api.LIGHT_PHOTOMETRIC, pos=(0.5, 9.0, 1.0), colour=(0.3, 0.3, 0.45), radius=0.05, half=6.0),
+]
+
+
 def make_case(name):
     """Small seeded instances of the five config families (+ edge cases).  Returns (scene, camera, lists, samples)."""
     cases = {
@@ -38,6 +51,7 @@ def make_case(name):
                             160, 120, 1, 256),
         "soup_lights_omni_last": (lambda: _with_lights(scenes.soup(260, seed=22, reflective=True, transparent=True), [_SPOT, _SUN, _OMNI]),
                                   144, 112, 2, 256),
+        "soup_all_light_types": (lambda: _with_lights(scenes.soup(220, seed=41, reflective=True, transparent=True), _ALL_TYPES), 128, 96, 2, 256),
         "soup": (lambda: scenes.soup(400, seed=11), 192, 160, 1, 256),
         "soup_s4": (lambda: scenes.soup(200, seed=12, light_radius=0.3), 96, 80, 4, 64),
         "soup_mirror_glass": (lambda: scenes.soup(300, seed=5, light_radius=0.4, reflective=True, transparent=True), 160, 120, 3, 256),
@@ -57,7 +71,7 @@ def make_case(name):
 
 
 CASE_NAMES = ["soup", "soup_s4", "soup_mirror_glass", "spheres", "spheres_mirror", "terrain", "terrain_textured", "coarse_grid",
-              "soup_lights_sun_last", "soup_lights_omni_last", "soup_axis_light"]
+              "soup_lights_sun_last", "soup_lights_omni_last", "soup_axis_light", "soup_all_light_types"]
 
 
 def compare_rgb(a, b, mask=None):

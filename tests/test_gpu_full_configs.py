@@ -1,8 +1,9 @@
 """BASELINE.json configs 3, 4 and 5 at FULL size on the GPU (config 1 = the `soup` family, config 2 = test_gpu_parity.py).
-At these sizes the reference needs minutes per frame on the host, so each test compares a band of rows bit for bit with the
-reference build (oracle/_ref, or the C port when that did not travel) and checks size-independent properties on the whole frame:
-the id-material decode equals the id plane, a frame assembled from 8 ranks' bands equals the single-GPU frame, device-built
-lists equal the host builder's."""
+The reference's own kernel on all host cores (oracle/_ref; the C port when that build did not travel) does 3-6 Mrays/s, so:
+config 3 is compared on EVERY pixel of the 3840x2160 frame, config 4 on every 8th row of the 7680x4320 frame (540 rows spread
+over sky and terrain alike), config 5 on every 8th frame of the sweep with every 8th row of each (135 rows) -- all bit for bit --
+plus size-independent properties on the whole frame: the id-material decode equals the id plane, a frame assembled from 8 ranks'
+bands equals the single-GPU frame, device-built lists equal the host builder's."""
 import numpy as np
 import pytest
 
@@ -33,11 +34,13 @@ def _setup(cfg_id):
     return cfg, sc, cam, lists
 
 
-def _band_equals_oracle(oracle, cam, lists, sc, samples, img, flags, rows):
-    want = oracle.render(cam, lists, sc, samples, rows=rows)
-    sl = slice(*rows)
+def _rows_equal_oracle(oracle, cam, lists, sc, samples, img, flags, row_step):
+    """Every row_step-th row of the whole frame against the oracle.  Returns (unflagged differing samples, compare_rgb over the rows)."""
+    want = oracle.render(cam, lists, sc, samples, row_step=row_step)
+    sl = slice(0, cam.height, row_step)
     bad = sum(int(((img[c][sl] != want[c][sl]) & (flags[sl] == 0)).sum()) for c in range(3))
     res = helpers.compare_rgb(tuple(p[sl] for p in img), tuple(p[sl] for p in want))
+    res["rows"] = len(range(0, cam.height, row_step))
     return bad, res
 
 
@@ -49,8 +52,8 @@ def test_config3_terrain_1m_4k(port):
     fr.render(1)
     img, ids, flags = fr.read(), fr.primary_ids(), fr.undefined_flags()
     assert flags.sum() == 0
-    bad, res = _band_equals_oracle(_oracle(port), cam, lists, sc, 1, img, flags, (1000, 1064))
-    assert bad == 0 and res["diff_pixels"] == 0, res
+    bad, res = _rows_equal_oracle(_oracle(port), cam, lists, sc, 1, img, flags, 1)        # the WHOLE frame, 8.3 M pixel-samples
+    assert bad == 0 and res["diff_pixels"] == 0 and res["rows"] == 2160, res
     # screen-band partition at 8 ranks reproduces the frame
     out = tuple(np.zeros((cam.height, cam.width), np.uint16) for _ in range(3))
     for rank in range(8):
@@ -79,13 +82,12 @@ def test_config4_terrain_10m_textured_8k(port):
     fr = api.DeviceFrame(ds, cam, lists)
     fr.render(1)
     img, flags = fr.read(), fr.undefined_flags()
-    rows = (1000, 1032)
-    bad, res = _band_equals_oracle(_oracle(port), cam, lists, sc, 1, img, flags, rows)
+    bad, res = _rows_equal_oracle(_oracle(port), cam, lists, sc, 1, img, flags, 8)        # 540 rows spread over the frame
     # bit-exact wherever the reference's own result is defined; the flagged pixels (uninitialised read in the reference's bump
     # path, include/oclr_abi.h) are few and still inside the stated tolerance as an image
-    assert bad == 0, res
-    assert res["diff_pixels"] <= int(flags[rows[0]:rows[1]].sum()) and flags.mean() < 1e-3
-    assert res["psnr"] >= helpers.PSNR_MIN, res
+    assert bad == 0 and res["rows"] == 540, res
+    assert res["diff_pixels"] <= int(flags[::8].sum()) and flags.mean() < 1e-3
+    assert res["psnr"] >= helpers.PSNR_MIN and res["max_abs"] <= 1.0, res
     # one rank's band share of an 8-GPU render (the configuration config 4 is quoted on) equals those rows of the frame
     fr.render_bands(1, 128, 3, 8)
     part = fr.read()
@@ -103,7 +105,7 @@ def test_config5_camera_sweep_upload_once(port):
     oracle = _oracle(port)
     lit = []
     for k, m in enumerate(cams):
-        if k not in (0, 21, 42, 63):
+        if k % 8 != 5 and k not in (0, 63):           # every 8th frame of the sweep + its two ends
             continue
         cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
         fr = api.DeviceFrame(ds, cam)                  # per-frame camera lists built on the device
@@ -112,8 +114,8 @@ def test_config5_camera_sweep_upload_once(port):
         lists = api.camera_triangle_list(cam, sc)
         got = fr.camera_lists()
         assert np.array_equal(got.start, lists.start) and np.array_equal(got.end, lists.end) and np.array_equal(got.list, lists.list)
-        bad, res = _band_equals_oracle(oracle, cam, lists, sc, cfg["samples"], img, flags, (500, 532))
-        assert bad == 0, (k, res)
+        bad, res = _rows_equal_oracle(oracle, cam, lists, sc, cfg["samples"], img, flags, 8)     # 135 rows spread over the frame
+        assert bad == 0 and res["rows"] == 135, (k, res)
         # mirror chains run to the reference's maximum bounce depth (12): far more rounds than the 4 of a diffuse scene
         assert launches >= 3 * 13 and cnt["segments"] > cam.width * cam.height
         lit.append(int((img[0] > 0).sum()))
