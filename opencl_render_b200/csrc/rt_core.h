@@ -608,6 +608,9 @@ OCLR_HD void light_accumulate(const Light& L, f3 nrm, const LightRay& lr, f3 att
 template <bool COUNT>
 OCLR_HD uint32_t grid_trace_packed(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl,
                                    float& outT, float& outAB, float& outAC, Counters* cnt);
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_split_mid(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                      float& outAB, float& outAC, Counters* cnt, int walkFirst, int maxParts, int minPartCells);
 
 template <bool COUNT>
 OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
@@ -621,6 +624,8 @@ template <bool COUNT>
 OCLR_HD uint32_t grid_trace_mode(int walkMode, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
                                  float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC, Counters* cnt) {
     if (walkMode == 2) return grid_trace_packed<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);  // px = base of all planes
+    if (walkMode >= 2000)   // walkMode = 2000 + 100 * (cells walked before the cut) + parts: the trace kernel's run-time split (rt_walk.h)
+        return grid_trace_split_mid<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, (walkMode - 2000) / 100, (walkMode - 2000) % 100, 3);
     if (walkMode == 1000) return grid_trace_coop<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);   // walked by cooperative bursts
     if (walkMode >= 3) return grid_trace_split<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode);  // parts of `walkMode` cells
     return grid_trace<COUNT>(S, px, py, pz, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode == 1);

@@ -30,6 +30,8 @@ struct TraceTuning {
     int drainMin;      // drain the warp's cell queue at this size
     int walkMin3;      // end a walk burst below this many walking lanes
     int switchMin;     // run parked level switches once this many lanes wait for one
+    int splitMin;      // queue dry: a walk with at least this many cells to go is cut into parts for the warp's idle lanes (0 = never)
+    int splitPart;     // ... of at least this many cells each
 };
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, W
     }
 }
 
-enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4 };
+enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4, kWsHeld = 5, kWsPartDone = 6 };
 
 // ---- wf_pipe_kernel: warp-level pipeline ----------------------------------------------------------------------------------
 // ncu on the lane-owned trace kernels: 37 % of all instructions are the
@@ -137,6 +139,15 @@ enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4 };
 //   RESOLVE after a drain every owner looks at its key: hit -> write (tri, t, abL, acL) and free the lane; walk finished and
 //           nothing found -> miss.  Rays keep walking between drains (bounded speculation: a batch is ~one cell per lane).
 //
+//   SPLIT   (tail of the launch: the ray queue is dry and lanes sit idle) a launch cannot end before its longest walk does, and one
+//           lane stepping through several hundred cells alone is ~0.3 ms that nothing hides -- the floor that capped strong scaling
+//           at 0.50 on 8 GPUs.  The warp therefore cuts the longest walk it still holds into parts along its dominant axis
+//           (pwalk_split_plan): the owner keeps the first part, idle lanes start the others from the exact state pwalk_jump computes
+//           at each stop plane (binary search over the crossing values, no walking; exactness: tests/test_hostemu_parity.py
+//           test_run_time_split_is_exact).  Parts are ordinary lane-owned walks with their own best-hit keys; a group record per
+//           head lane (hit / miss bit per part) gives the ray's result by the reference's rule -- the first part in walk order with
+//           a hit wins once every part before it has finished without one; a hit cancels the parts behind it.
+//
 // No mailbox here: pairs of one ray are tested concurrently, and face masks already remove the repeats between adjacent cells
 // (a per-lane mailbox removed 6 % more in the lane-owned kernel).
 #ifndef OCLR_CELLQ_CAP
@@ -152,6 +163,12 @@ struct WarpPipe {
     float bestAB[32], bestAC[32];
     uint32_t cellQ[2][kCellQCap];   // [0] rank | face << 29, [1] owner | seq << 8
     uint32_t pairQ[2][kPairQCap];   // [0] triangle, [1] owner | seq << 8
+    // run-time split of long walks (SPLIT above)
+    uint32_t grp[32];               // per lane: 0 = a whole ray; else 1 << 31 | head lane | part index << 8
+    uint32_t gHit[32], gMiss[32];   // per group, indexed by head lane: bit j = part j holds a hit / finished without one (bit 31 of gMiss: result written)
+    uint32_t gParts[32];            // parts of the group
+    uint32_t groups;                // live groups of this warp
+    int sParts, sAxis, sCut[kMaxWalkParts];   // plan of the split in progress
 };
 
 // Next list entry at or after k that this ray still has to test: entries whose face-mask bit is clear were in the cell the walk
@@ -190,6 +207,13 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     const int nbShift = 31 - __clz(S.nb);
     const unsigned long long kEmptyKey = ~0ull;
 
+
+    P.grp[lane] = 0u;
+    if (lane == 0) P.groups = 0u;
+    int splitWait = 0;   // warp-uniform: outer iterations until the next split attempt
+    const float* px = shPlanes;
+    const float* py = shPlanes + (n + 1);
+    const float* pz = shPlanes + 2 * (n + 1);
 
     Counters cnt = {};
     PackedWalk g;
@@ -261,6 +285,92 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         if (__ballot_sync(0xFFFFFFFFu, ws != kWsNone) == 0u) break;
         __syncwarp();
 
+        // ---- SPLIT: queue dry, idle lanes -> they take parts of the longest whole walk this warp still holds ---------------------------
+        if (tune.splitMin > 0 && exhausted && --splitWait < 0) {
+            const unsigned idleNow = __ballot_sync(0xFFFFFFFFu, ws == kWsNone);
+            int best = 0, who = lane;
+            if (idleNow != 0u) {
+                if (ws == kWsRun && g.level == 0 && g.coarseOk && P.grp[lane] == 0u) best = walk_length_estimate(g, n, px, py, pz);
+#pragma unroll
+                for (int off = 16; off; off >>= 1) {
+                    const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off), ow = __shfl_xor_sync(0xFFFFFFFFu, who, off);
+                    if (ob > best || (ob == best && ow < who)) {
+                        best = ob;
+                        who = ow;
+                    }
+                }
+            }
+            if (best < tune.splitMin) {
+                splitWait = 4;   // nothing worth cutting (or nobody to take a part): look again a few drains later
+            } else {
+                const int cand = who;
+                if (lane == cand) {
+                    int axis = 0, cut[kMaxWalkParts];
+                    const int parts = pwalk_split_plan(g, n, px, py, pz, __popc(idleNow) + 1, tune.splitPart, axis, cut);
+                    P.sParts = parts;
+                    P.sAxis = axis;
+#pragma unroll
+                    for (int j = 0; j < kMaxWalkParts; ++j) P.sCut[j] = cut[j];
+                    if (parts >= 2) {
+                        P.gHit[cand] = 0u;
+                        P.gMiss[cand] = 0u;
+                        P.gParts[cand] = (uint32_t)parts;
+                        P.groups += 1u;
+                    }
+                }
+                __syncwarp();
+                const int parts = P.sParts;
+                if (parts >= 2) {
+                    const int axis = P.sAxis;
+                    int cut[kMaxWalkParts];
+#pragma unroll
+                    for (int j = 0; j < kMaxWalkParts; ++j) cut[j] = P.sCut[j];
+                    PackedWalk head;   // what pwalk_split_part needs of the interrupted walk
+                    head.o = mk3(P.ray[0][cand], P.ray[1][cand], P.ray[2][cand]);
+                    head.r = mk3(P.ray[3][cand], P.ray[4][cand], P.ray[5][cand]);
+                    head.cpk = __shfl_sync(0xFFFFFFFFu, g.cpk, cand);
+                    head.epk = __shfl_sync(0xFFFFFFFFu, g.epk, cand);
+                    head.endBrick = __shfl_sync(0xFFFFFFFFu, g.endBrick, cand);
+                    const uint32_t headPath = __shfl_sync(0xFFFFFFFFu, path, cand);
+                    const int myPart = __popc(idleNow & ltMask) + 1;
+                    if (ws == kWsNone && myPart < parts) {
+                        PackedWalk part;
+                        if (pwalk_split_part(part, head, n, S.nb, px, py, pz, axis, cut, parts, myPart)) {
+                            g = part;
+                            pwalk_load_brick(g, S.bricks);
+                            const float minD = P.ray[6][cand];
+                            maxD = P.ray[7][cand];
+                            P.ray[0][lane] = head.o.x;
+                            P.ray[1][lane] = head.o.y;
+                            P.ray[2][lane] = head.o.z;
+                            P.ray[3][lane] = head.r.x;
+                            P.ray[4][lane] = head.r.y;
+                            P.ray[5][lane] = head.r.z;
+                            P.ray[6][lane] = minD;
+                            P.ray[7][lane] = maxD;
+                            P.excl[lane] = P.excl[cand];
+                            P.bestKey[lane] = kEmptyKey;
+                            P.grp[lane] = 0x80000000u | (uint32_t)cand | ((uint32_t)myPart << 8);
+                            path = headPath;
+                            ws = kWsRun;
+                            face = kFaceNone;
+                            seqNext = 0;
+                            if (COUNT) cnt.bricksLoaded++;
+                        } else {
+                            atomicOr(&P.gMiss[cand], 1u << myPart);   // the walk leaves the grid before this part begins
+                        }
+                    }
+                    if (lane == cand) {
+                        pwalk_split_head(g, axis, cut);
+                        P.grp[lane] = 0x80000000u | (uint32_t)cand;
+                    }
+                    __syncwarp();
+                } else {
+                    splitWait = 4;
+                }
+            }
+        }
+
         // ---- WALK burst: step every walking lane until the cell queue is worth draining or too few lanes still walk ----------------
         for (;;) {
             const bool walking = ws == kWsRun;
@@ -312,6 +422,8 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     if (COUNT && coarse) cnt.coarseSteps++;
                     if (!pwalk_step(g, n, nbShift, shPlanes, lastAxis, up, lastE, crossed)) {
                         ws = kWsFinished;
+                    } else if (pk_is_stop(g.epk) && pwalk_stopped(g, lastAxis, up)) {
+                        ws = kWsFinished;   // this part of a cut walk ends here; the cell just entered belongs to the next part
                     } else {
                         face = coarse ? (int)kFaceNone : lastAxis * 2 + up;
                         if (crossed) {
@@ -321,8 +433,10 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     }
                 }
                 if ((ws == kWsFinished) & (seqNext == 0u)) {  // walk over and nothing of this ray awaits a test: miss
-                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
-                    ws = kWsNone;
+                    if (P.grp[lane] == 0u) {                  // (a part of a cut walk reports to its group in RESOLVE instead)
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                        ws = kWsNone;
+                    }
                 }
             }
             const int nSwitch = __popc(__ballot_sync(0xFFFFFFFFu, (ws == kWsRefine) | (ws == kWsEnter)));
@@ -430,16 +544,69 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
 
         // ---- RESOLVE ----------------------------------------------------------------------------------------------------------------
-        if (ws != kWsNone) {
-            const unsigned long long key = P.bestKey[lane];
-            if (key != kEmptyKey) {  // first cell with any hit wins (:380); whatever the walker found beyond it is dropped
-                w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
-                ws = kWsNone;
-            } else if (ws == kWsFinished) {
-                w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
-                ws = kWsNone;
+        if (P.groups == 0u) {   // (warp-uniform; the only case outside the tail of a launch)
+            if (ws != kWsNone) {
+                const unsigned long long key = P.bestKey[lane];
+                if (key != kEmptyKey) {  // first cell with any hit wins (:380); whatever the walker found beyond it is dropped
+                    w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
+                    ws = kWsNone;
+                } else if (ws == kWsFinished) {
+                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                    ws = kWsNone;
+                }
+                seqNext = 0;
             }
-            seqNext = 0;
+        } else {
+            // some walks of this warp are cut into parts: a part reports to its group, the group decides
+            const uint32_t grp = ws != kWsNone ? P.grp[lane] : 0u;
+            const uint32_t headLane = grp & 31u, order = (grp >> 8) & 15u;
+            const unsigned long long key = P.bestKey[lane];
+            if (ws != kWsNone) {
+                if (grp == 0u) {   // a whole ray: as above
+                    if (key != kEmptyKey) {
+                        w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
+                        ws = kWsNone;
+                    } else if (ws == kWsFinished) {
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                        ws = kWsNone;
+                    }
+                } else if (ws != kWsHeld) {
+                    if (key != kEmptyKey) {   // this part's first cell with a hit: held until every part before it has finished
+                        atomicOr(&P.gHit[headLane], 1u << order);
+                        ws = kWsHeld;
+                    } else if (ws == kWsFinished) {
+                        atomicOr(&P.gMiss[headLane], 1u << order);
+                        ws = kWsPartDone;
+                    }
+                }
+                seqNext = 0;
+            }
+            __syncwarp();
+            if (grp != 0u) {
+                const uint32_t hm = P.gHit[headLane], mm = P.gMiss[headLane];
+                const uint32_t firstHit = hm ? (uint32_t)(__ffs((int)hm) - 1) : 32u;
+                const uint32_t below = (1u << order) - 1u;
+                if (order > firstHit) {   // a part before this one has a hit: nothing found here can matter
+                    ws = kWsNone;
+                    P.grp[lane] = 0u;
+                } else if (ws == kWsHeld) {
+                    if ((mm & below) == below) {   // every part before it finished without a hit: this is the ray's result
+                        w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
+                        ws = kWsNone;
+                        P.grp[lane] = 0u;
+                        atomicSub(&P.groups, 1u);
+                    }
+                } else if (ws == kWsPartDone) {   // (its miss is on the group's record: the lane is free again)
+                    const uint32_t all = (1u << P.gParts[headLane]) - 1u;
+                    if (hm == 0u && (mm & all) == all && (atomicOr(&P.gMiss[headLane], 0x80000000u) >> 31) == 0u) {
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);   // the last parts to finish: one of them says so
+                        atomicSub(&P.groups, 1u);
+                    }
+                    ws = kWsNone;
+                    P.grp[lane] = 0u;
+                }
+            }
+            __syncwarp();
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);

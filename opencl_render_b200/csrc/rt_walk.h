@@ -282,21 +282,39 @@ OCLR_HD int pwalk_plan_parts(int c0x, int c0y, int c0z, int ex, int ey, int ez, 
 // (test infrastructure for the host; the kernel runs the same functions with the work of 32 rays interleaved).  Face masks skip
 // entries shared with the cell just left; a small direct-mapped mailbox skips triangles this ray already tested -- both exact
 // (rt_wavefront.cuh).
+// A walk interrupted between two cells (wf_pipe_kernel splits long walks at run time, see pwalk_split_plan): everything the walk
+// carries from cell to cell.  The current cell w.cpk has NOT been examined yet.
+enum : uint32_t { kWalkPaused = 0xFFFFFFFEu };
+struct WalkPause {
+    PackedWalk w;
+    int face;
+};
+
+// `pauseAfter` >= 0: the walk stops in front of the first level-0 cell it reaches after examining that many cells, stores its state in
+// *pause and returns kWalkPaused (test infrastructure for the run-time split).  `startFace`: entry face of the first cell (a resumed walk).
 template <bool COUNT>
 OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, PackedWalk w, float minD, float maxD, uint32_t excl, float& outT,
-                                  float& outAB, float& outAC, Counters* cnt) {
+                                  float& outAB, float& outAC, Counters* cnt, int pauseAfter = -1, WalkPause* pause = nullptr,
+                                  int startFace = kFaceNone, bool brickLoaded = false) {
     const int n = S.n;
     int nbShift = 0;
     while ((1 << nbShift) < S.nb) ++nbShift;
     const f3 o = w.o, r = w.r;
-    pwalk_load_brick(w, S.bricks);
-    if (COUNT) cnt->bricksLoaded++;
+    if (!brickLoaded) {
+        pwalk_load_brick(w, S.bricks);
+        if (COUNT) cnt->bricksLoaded++;
+    }
     uint32_t mailbox[16];
     for (int k = 0; k < 16; ++k) mailbox[k] = kNoTriangle;
-    int face = kFaceNone, lastAxis = 0;
+    int face = startFace, lastAxis = 0;
     float lastE = 0.f;
     outT = maxD;
     for (;;) {
+        if (w.level == 0 && pauseAfter >= 0 && pauseAfter-- == 0) {
+            pause->w = w;
+            pause->face = face;
+            return kWalkPaused;
+        }
         if (w.level == 0) {
             const int bit = pwalk_bit(w.cpk);
             if (COUNT) {
@@ -414,6 +432,88 @@ OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o,
             part.endBrick = first.endBrick;
         }
         const uint32_t hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt);
+        if (hit != kNoTriangle) return hit;
+    }
+    outT = maxD;
+    return kNoTriangle;
+}
+
+// ---- run-time split of a walk in progress (wf_pipe_kernel, tail of a launch) -------------------------------------------------------
+// A trace launch cannot end before its longest walk does, and a lone lane stepping through several hundred cells is ~0.3 ms of
+// latency that nothing else hides once the ray queue is dry.  Cutting walks by their ESTIMATED length before they start was tried
+// and backed out (most long-looking rays end at a nearby hit).  Here the cut is made at run time, for a ray that HAS walked into the
+// tail: the lane that owns it keeps the first part and idle lanes of the same warp take the others, every part starting from the
+// exact state pwalk_jump computes at its stop plane.  The first part (in walk order) with a hit gives the ray's result.
+//
+// Plan for the remaining walk of `w` (level 0, all direction components non-zero, current cell not yet examined): at most
+// `maxParts` parts of equal length along the dominant axis of the way to the end cell / the estimated exit cell.  Returns the number
+// of parts (1 = not worth cutting); cut[j] (j >= 1) = cell index along `axis` whose entry starts part j.
+OCLR_HD int pwalk_split_plan(const PackedWalk& w, int n, const float* px, const float* py, const float* pz, int maxParts, int minPartCells,
+                             int& axis, int cut[kMaxWalkParts]) {
+    const int c0x = pk_get(w.cpk, 0), c0y = pk_get(w.cpk, 1), c0z = pk_get(w.cpk, 2);
+    int ex, ey, ez;
+    if (w.epk != kPkNone && !pk_is_stop(w.epk)) {
+        ex = pk_get(w.epk, 0);
+        ey = pk_get(w.epk, 1);
+        ez = pk_get(w.epk, 2);
+    } else {
+        pwalk_exit_estimate(n, px, py, pz, w.o, w.r, ex, ey, ez);
+    }
+    const int dx = ex - c0x, dy = ey - c0y, dz = ez - c0z;
+    const int len = (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) + (dz < 0 ? -dz : dz);
+    int want = len / (minPartCells > 0 ? minPartCells : 1);
+    if (want > maxParts) want = maxParts;
+    if (want > kMaxWalkParts) want = kMaxWalkParts;
+    if (want < 2) return 1;
+    return pwalk_plan_parts(c0x, c0y, c0z, ex, ey, ez, (len + want - 1) / want, axis, cut);
+}
+
+// Part j >= 1 of that plan: the state right after the walk crosses into cut[j] (false: the walk leaves the grid first -- the part
+// does not exist), with the part's own end condition.  Part 0 is the interrupted walk itself with pwalk_split_head() applied.
+OCLR_HD bool pwalk_split_part(PackedWalk& part, const PackedWalk& w, int n, int nb, const float* px, const float* py, const float* pz, int axis,
+                              const int cut[kMaxWalkParts], int parts, int j) {
+    if (!pwalk_jump(part, n, nb, px, py, pz, w.o, w.r, pk_get(w.cpk, 0), pk_get(w.cpk, 1), pk_get(w.cpk, 2), axis, cut[j])) return false;
+    if (j + 1 < parts) {
+        part.epk = pk_stop(axis, cut[j + 1]);
+        part.endBrick = -1;
+    } else {
+        part.epk = w.epk;
+        part.endBrick = w.endBrick;
+    }
+    return true;
+}
+OCLR_HD void pwalk_split_head(PackedWalk& w, int axis, const int cut[kMaxWalkParts]) {
+    w.epk = pk_stop(axis, cut[1]);
+    w.endBrick = -1;
+}
+
+// Host form of the whole thing (tests/hostemu): walk `walkFirst` cells the ordinary way, then cut the rest into up to `maxParts` parts.
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_split_mid(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                      float& outAB, float& outAC, Counters* cnt, int walkFirst, int maxParts, int minPartCells) {
+    const int n = S.n;
+    const float* px = planes;
+    const float* py = planes + (n + 1);
+    const float* pz = planes + 2 * (n + 1);
+    PackedWalk first;
+    pwalk_setup(first, n, S.nb, px, py, pz, o, r, minD, maxD);
+    if (COUNT) cnt->gridRays++;
+    WalkPause pause;
+    uint32_t hit = grid_walk_packed<COUNT>(S, planes, first, minD, maxD, excl, outT, outAB, outAC, cnt, walkFirst, &pause);
+    if (hit != kWalkPaused) return hit;
+    PackedWalk head = pause.w;
+    int axis = 0, cut[kMaxWalkParts];
+    const int parts = head.coarseOk ? pwalk_split_plan(head, n, px, py, pz, maxParts, minPartCells, axis, cut) : 1;
+    if (parts < 2) return grid_walk_packed<COUNT>(S, planes, head, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, pause.face, true);
+    for (int j = 0; j < parts; ++j) {
+        PackedWalk part = head;
+        if (j == 0) {
+            pwalk_split_head(part, axis, cut);
+            hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, pause.face, true);
+        } else {
+            if (!pwalk_split_part(part, head, n, S.nb, px, py, pz, axis, cut, parts, j)) break;
+            hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt);
+        }
         if (hit != kNoTriangle) return hit;
     }
     outT = maxD;

@@ -1358,13 +1358,15 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // host thread per GPU)
     static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        TraceTuning t = {0, 1, 0, 0, 0, 0};
+        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
         t.walkMin3 = env("OCLR_WALK_MIN3", 8);
         t.switchMin = env("OCLR_SWITCH_MIN", 6);
         t.tailDrain = env("OCLR_TAIL_DRAIN", 8);
+        t.splitMin = getenv("OCLR_SPLIT_MIN") ? atoi(getenv("OCLR_SPLIT_MIN")) : 48;   // 0: never cut a walk
+        t.splitPart = env("OCLR_SPLIT_PART", 16);
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));

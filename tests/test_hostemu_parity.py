@@ -138,3 +138,21 @@ def test_counters_equal_instrumented_reference(name, hostemu, ref, monkeypatch):
     # of a bump-mapped hit (raytrace_opencl.c:244-247)
     extra = want["tests"] - want["primCandidates"] - want["gridCandidates"]
     assert 0 <= extra <= 2 * want["shadedHits"] and (extra == 0 or name == "terrain_textured")
+
+
+@pytest.mark.parametrize("mode", [2000 + 100 * 0 + 8, 2000 + 100 * 1 + 2, 2000 + 100 * 6 + 8, 2000 + 100 * 25 + 5])
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_run_time_split_is_exact(name, mode, hostemu, monkeypatch):
+    """The trace kernel's run-time split (rt_walk.h pwalk_split_plan / pwalk_split_part): every walk is interrupted in front of the
+    cell it reaches after examining (mode - 2000) // 100 cells, and what is left of it is cut into up to (mode % 100) parts that
+    start from states computed WITHOUT walking from the interrupted walk's current cell; first part with a hit wins.  Planes, ids
+    and flags identical to the uncut reference walk; the parts together visit exactly the non-empty cells the uncut walk visits."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", str(mode))
+    split = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], split[0][c])
+    assert np.array_equal(flat[1], split[1]) and np.array_equal(flat[2], split[2])
+    assert split[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
