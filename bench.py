@@ -390,39 +390,43 @@ def measure_config(run: Run, cfg_id: int, steps: int, warmup: int, primary: bool
                 pass
         res["roofline"] = roof
 
-    # ---- end to end through the drop-in call (host buffers) ---------------------------------------------------------------------------
+    # ---- end to end through the drop-in call (host buffers), made by ONE plain host process like the plugin -------------------------
     if want_e2e and lists is not None:
-        e2e_steps = max(3, min(steps, 10))
-        e2e = None
+        run.cpu_barrier()                                     # nothing but the probe process touches the GPUs from here to the next barrier
         if rank == 0:
-            e2e = odist.EndToEnd(sc, cam, lists, world, local, n_devices=torch.cuda.device_count())
-        run.cpu_barrier()                                     # nothing but rank 0 touches the GPUs from here to the next barrier
-        if rank == 0:
-            for _ in range(2):
-                e2e.step(S)
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e.step(S)
-            dt = time.perf_counter() - t0
-            res["e2e"] = {"value": rays_frame * e2e_steps / dt / 1e6, "unit": "Mrays/s", "ms_per_call": dt / e2e_steps * 1e3,
-                          "h2d_bytes_per_step": e2e.h2d_bytes, "h2d_bytes_per_step_per_gpu": e2e.h2d_bytes // world,
-                          "d2h_bytes_per_step": e2e.d2h_bytes, "steps": e2e_steps, "host_arrays": "pinned", "call": e2e.call}
-            if planes_1gpu is not None:
-                parity["raytrace_all_vs_1gpu"] = bool(all(np.array_equal(e2e.out[c], planes_1gpu[c]) for c in range(3)))
-            # The same call the way the plugin makes it: plain (pageable) arrays, as render.cpp:1086-1134 allocates them.  Measured
-            # after the pinned figure: the driver's pageable staging path was seen to slow the pinned calls that followed it.
-            if os.environ.get("OCLR_BENCH_NO_PAGEABLE") != "1":
-                pg = e2e.pageable_copy()
-                for _ in range(2):
-                    pg.step(S)
-                t0 = time.perf_counter()
-                for _ in range(5):
-                    pg.step(S)
-                res["e2e"]["value_pageable_host_arrays"] = rays_frame * 5 / (time.perf_counter() - t0) / 1e6
+            e2e_calls = max(5, min(steps, 10))
+            try:
+                import hashlib
+                r = subprocess.run([sys.executable, "-m", "opencl_render_b200.e2e_probe", str(cfg_id), str(world), str(e2e_calls)], cwd=ROOT,
+                                   capture_output=True, text=True, timeout=300)
+                lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                if r.returncode != 0 or not lines:
+                    raise RuntimeError(f"rc {r.returncode}: {r.stderr[-600:]}")
+                pr = json.loads(lines[-1])
+                call = (f"RaytraceAll(all devices) on {world} GPUs from one host process (C-ABI, host buffers; 1/{world} of the scene per GPU over PCIe, "
+                        "NVLink fan-out)") if world > 1 else "RaytraceAll (C-ABI, host buffers) from a plain host process"
+                res["e2e"] = {"value": pr["rays"] / pr["ms_per_call"] / 1e3, "unit": "Mrays/s", "ms_per_call": pr["ms_per_call"],
+                              "ms_median": pr["ms_median"], "spread": pr["spread"], "h2d_bytes_per_step": pr["h2d_bytes"],
+                              "h2d_bytes_per_step_per_gpu": pr["h2d_bytes"] // world, "d2h_bytes_per_step": pr["d2h_bytes"],
+                              "steps": pr["calls"], "host_arrays": pr["host_arrays"], "call": call}
+                want_sha = None
                 if planes_1gpu is not None:
-                    parity["raytrace_all_pageable_vs_1gpu"] = bool(all(np.array_equal(pg.out[c], planes_1gpu[c]) for c in range(3)))
-                del pg
-            del e2e
+                    hsh = hashlib.sha256()
+                    for pl in planes_1gpu:
+                        hsh.update(np.ascontiguousarray(pl).tobytes())
+                    want_sha = hsh.hexdigest()
+                    parity["raytrace_all_vs_1gpu"] = pr["sha256"] == want_sha
+                if "pageable" in pr:         # the same call the way the plugin makes it: plain new[] arrays (render.cpp:1086-1134)
+                    pg = pr["pageable"]
+                    res["e2e"]["value_pageable_host_arrays"] = pg["rays"] / pg["ms_per_call"] / 1e3
+                    res["e2e"]["pageable"] = {"ms_per_call": pg["ms_per_call"], "ms_median": pg["ms_median"], "spread": pg["spread"],
+                                              "steps": pg["calls"]}
+                    if want_sha is not None:
+                        parity["raytrace_all_pageable_vs_1gpu"] = pg["sha256"] == want_sha
+            except Exception as e:
+                res["e2e"] = {"value": None, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                              "error": f"{type(e).__name__}: {e}"}
+                print(f"[bench] e2e probe failed: {type(e).__name__}: {e}", file=sys.stderr)
         run.cpu_barrier()
     if rank == 0:
         res["parity"] = parity

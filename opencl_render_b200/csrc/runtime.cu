@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -48,119 +49,187 @@ static void prepare_pool(int device) {
     done[device] = true;
 }
 
-// Host -> device copies from PAGEABLE memory.  The plugin hands RaytraceAll plain new[] arrays (render.cpp:1086-1134) -- 133 MB for
-// config 2 -- and cudaMemcpyAsync moves pageable memory through the driver's own staging buffer at ~10 GB/s on one thread (the
-// call then spends 14 ms of its 20 ms uploading, scripts/e2e_trace.py).  StagePool does the staging itself with several host
-// threads: each copies its chunks into its own two pinned slots and enqueues the H2D copy of a chunk as soon as it is staged, so
-// the copies of all threads overlap with each other and with the PCIe transfers.  Pinned / registered sources skip it.
-// OPT-IN (OCLR_STAGING=1): measured on the B200 box (scripts/pageable_probe.py, config 2) the call drops from 19.8 ms to 14.2 ms
-// with 4 threads, but individual calls took 27 ms, and with 8-16 threads single phases stalled for 10-340 ms (driver lock
-// contention between the staging threads is the suspect) -- not dependable enough to be the default this round.
-class StagePool {
+// Host <-> device copies from / to PAGEABLE memory.  The plugin hands RaytraceAll plain new[] arrays (render.cpp:1086-1134) -- 133 MB
+// for config 2 -- and cudaMemcpyAsync moves pageable memory through the driver's own bounce buffer at ~10 GB/s on the calling thread
+// (the call then spends 14 of its 20 ms uploading).  Here the staging is done by a small pool of copier threads that do NOTHING but
+// memcpy (2 MB blocks, caller's array -> a pinned arena that lives as long as the process); every CUDA call stays on the calling
+// thread, which enqueues the H2D copy of a block as soon as that block is staged -- so block k crosses PCIe while blocks k+1.. are
+// still being staged.  (Round 1's first attempt let every copier thread issue its own cudaMemcpyAsync: 19.8 -> 14.2 ms on average but
+// single calls stalled for up to 340 ms on the driver's locks; that is why the CUDA calls are now made by one thread per device.)
+// The arena is per device (RaytraceAll on all devices: one uploading thread per GPU, each staging only its 1/N slice) and is reused
+// from the start by the next call; a copy that does not fit what is left waits for the stream to drain first.
+class CopyPool {
 public:
-    static StagePool* get(int device) {
-        static std::mutex m;
-        static StagePool* pools[64] = {nullptr};
-        std::lock_guard<std::mutex> lock(m);
-        if (device < 0 || device >= 64) return nullptr;
-        if (!pools[device]) pools[device] = new StagePool(device);   // lives until the process ends (its threads are detached)
-        return pools[device]->ok_ ? pools[device] : nullptr;
+    struct Job {
+        void* dst;
+        const void* src;
+        size_t n;
+        std::atomic<int>* done;
+    };
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool();   // lives until the process ends (its threads are detached)
+        return *p;
     }
-    // Enqueues dst[0, n) = src[0, n) on `st`; returns after the last chunk has been ENQUEUED (the caller may then enqueue consumers).
-    bool copy(void* dst, const void* src, size_t n, cudaStream_t st) {
-        std::unique_lock<std::mutex> lock(m_);
-        while (busy_) cvDone_.wait(lock);   // one job at a time per device
-        busy_ = true;
-        dst_ = (char*)dst;
-        src_ = (const char*)src;
-        n_ = n;
-        st_ = st;
-        failed_ = false;
-        remaining_ = kThreads;
-        ++generation_;
-        cvJob_.notify_all();
-        while (remaining_ != 0) cvDone_.wait(lock);
-        busy_ = false;
-        cvDone_.notify_all();
-        return !failed_;
+    void submit(const Job* jobs, size_t count) {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (size_t i = 0; i < count; ++i) q_.push_back(jobs[i]);
+        }
+        if (count == 1) cv_.notify_one(); else cv_.notify_all();
     }
+    // The calling thread lends a hand while it waits: runs one queued job, if there is one.
+    bool help() {
+        Job j;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            if (q_.empty()) return false;
+            j = q_.front();
+            q_.pop_front();
+        }
+        run(j);
+        return true;
+    }
+    int threads() const { return threads_; }
 
 private:
-    enum { kMaxThreads = 32 };
-    static constexpr size_t kChunk = 2u << 20;
-    int kThreads = 4;
-    explicit StagePool(int device) : device_(device) {
-        if (const char* v = getenv("OCLR_STAGING_THREADS")) kThreads = std::max(1, std::min(atoi(v), (int)kMaxThreads));
-        kThreads = std::min<int>(kThreads, std::max(1u, std::thread::hardware_concurrency()));
-        cudaSetDevice(device);
-        for (int t = 0; t < kThreads && ok_; ++t)
-            for (int k = 0; k < 2 && ok_; ++k)
-                ok_ = cudaHostAlloc(&slot_[t][k], kChunk, cudaHostAllocDefault) == cudaSuccess &&
-                      cudaEventCreateWithFlags(&event_[t][k], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok_) {
-            cudaGetLastError();
-            return;
-        }
-        for (int t = 0; t < kThreads; ++t) std::thread([this, t]() { worker(t); }).detach();
+    CopyPool() {
+        threads_ = 6;
+        if (const char* v = getenv("OCLR_STAGING_THREADS")) threads_ = std::max(1, std::min(atoi(v), 32));
+        threads_ = std::min<int>(threads_, std::max(1u, std::thread::hardware_concurrency()));
+        for (int t = 0; t < threads_; ++t) std::thread([this]() { worker(); }).detach();
     }
-    void worker(int t) {
-        cudaSetDevice(device_);
-        unsigned long long seen = 0;
-        bool used[2] = {false, false};
+    static void run(const Job& j) {
+        memcpy(j.dst, j.src, j.n);
+        j.done->store(1, std::memory_order_release);
+    }
+    void worker() {
         for (;;) {
+            Job j;
             {
                 std::unique_lock<std::mutex> lock(m_);
-                while (generation_ == seen) cvJob_.wait(lock);
-                seen = generation_;
+                cv_.wait(lock, [this] { return !q_.empty(); });
+                j = q_.front();
+                q_.pop_front();
             }
-            bool bad = false;
-            int k = 0;
-            for (size_t off = (size_t)t * kChunk; off < n_ && !bad; off += (size_t)kThreads * kChunk, k ^= 1) {
-                const size_t len = std::min(kChunk, n_ - off);
-                if (used[k]) bad = cudaEventSynchronize(event_[t][k]) != cudaSuccess;   // the slot's previous H2D copy has left it
-                memcpy(slot_[t][k], src_ + off, len);
-                bad = bad || cudaMemcpyAsync(dst_ + off, slot_[t][k], len, cudaMemcpyHostToDevice, st_) != cudaSuccess ||
-                      cudaEventRecord(event_[t][k], st_) != cudaSuccess;
-                used[k] = true;
-            }
-            std::lock_guard<std::mutex> lock(m_);
-            if (bad) failed_ = true;
-            if (--remaining_ == 0) cvDone_.notify_all();
+            run(j);
         }
     }
-    int device_;
-    bool ok_ = true;
-    void* slot_[kMaxThreads][2] = {};
-    cudaEvent_t event_[kMaxThreads][2] = {};
     std::mutex m_;
-    std::condition_variable cvJob_, cvDone_;
-    unsigned long long generation_ = 0;
-    int remaining_ = 0;
-    bool busy_ = false, failed_ = false;
-    char* dst_ = nullptr;
-    const char* src_ = nullptr;
-    size_t n_ = 0;
-    cudaStream_t st_ = nullptr;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    int threads_ = 0;
 };
 
-static bool host_to_device(void* dst, const void* src, size_t n, cudaStream_t st, std::string& err) {
-    static const bool staging = [] { const char* v = getenv("OCLR_STAGING"); return v && atoi(v) != 0; }();
-    if (staging && n >= (4u << 20)) {
-        cudaPointerAttributes attr;
-        const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
-        cudaGetLastError();
-        int device = 0;
-        if (pageable && cudaGetDevice(&device) == cudaSuccess) {
-            StagePool* pool = StagePool::get(device);
-            if (pool) {
-                if (pool->copy(dst, src, n, st)) return true;
-                err = "staged host-to-device copy failed";
+struct StageArena {   // pinned, per device, grow-only up to the cap
+    char* p = nullptr;
+    size_t bytes = 0, used = 0;
+    std::mutex m;   // one staged copy at a time per device (the copier threads are shared anyway)
+};
+static constexpr size_t kStageBlock = 2u << 20;
+static StageArena& stage_arena(int device) {
+    static StageArena arenas[64];
+    return arenas[device & 63];
+}
+// Space for n bytes in the device's arena, or nullptr (then the driver's own staging is used).  When the arena has to be recycled or
+// regrown the stream is drained first: copies enqueued earlier may still be reading from it.
+static char* stage_reserve(int device, size_t n, cudaStream_t st) {
+    static const size_t cap = [] { const char* v = getenv("OCLR_STAGING_MB"); return (size_t)(v ? std::max(16, atoi(v)) : 1024) << 20; }();
+    StageArena& a = stage_arena(device);
+    if (n > cap) return nullptr;
+    if (a.used + n > a.bytes) {
+        if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;   // (whatever stream earlier staged copies were enqueued on)
+        a.used = 0;
+        if (n > a.bytes) {
+            const size_t want = std::min(cap, std::max(n, std::max<size_t>(a.bytes * 2, 64u << 20)));
+            if (a.p) cudaFreeHost(a.p);
+            a.p = nullptr;
+            a.bytes = 0;
+            if (cudaHostAlloc((void**)&a.p, want, cudaHostAllocPortable) != cudaSuccess) {
                 cudaGetLastError();
-                return false;
+                return nullptr;
             }
+            a.bytes = want;
+        }
+    }
+    char* p = a.p + a.used;
+    a.used += (n + 255) & ~(size_t)255;
+    return p;
+}
+// A new top-level call (RaytraceAll, scene_create) starts from an empty arena: everything the previous one enqueued has completed
+// (those calls synchronise before they return).
+static void stage_reset(int device) {
+    StageArena& a = stage_arena(device);
+    std::lock_guard<std::mutex> lock(a.m);
+    a.used = 0;
+}
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    const bool pageable = cudaPointerGetAttributes(&attr, p) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    return pageable;
+}
+static bool staging_enabled() {
+    static const bool on = [] { const char* v = getenv("OCLR_STAGING"); return !v || atoi(v) != 0; }();
+    return on;
+}
+
+static bool host_to_device(void* dst, const void* src, size_t n, cudaStream_t st, std::string& err) {
+    int device = 0;
+    if (staging_enabled() && n >= (1u << 20) && is_pageable(src) && cudaGetDevice(&device) == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(stage_arena(device).m);
+        char* stage = stage_reserve(device, n, st);
+        if (stage) {
+            const size_t blocks = (n + kStageBlock - 1) / kStageBlock;
+            std::vector<std::atomic<int>> done(blocks);
+            std::vector<CopyPool::Job> jobs(blocks);
+            for (size_t b = 0; b < blocks; ++b) {
+                done[b].store(0);
+                const size_t off = b * kStageBlock;
+                jobs[b] = {stage + off, (const char*)src + off, std::min(kStageBlock, n - off), &done[b]};
+            }
+            CopyPool& pool = CopyPool::get();
+            pool.submit(jobs.data(), blocks);
+            for (size_t b = 0; b < blocks; ++b) {
+                while (done[b].load(std::memory_order_acquire) == 0)
+                    if (!pool.help()) std::this_thread::yield();
+                const size_t off = b * kStageBlock;
+                OCLR_CUDA(cudaMemcpyAsync((char*)dst + off, stage + off, jobs[b].n, cudaMemcpyHostToDevice, st));
+            }
+            return true;
         }
     }
     OCLR_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+// Device -> pageable host memory: one transfer into the arena, then the copier threads (and the caller) spread it out.  Synchronous.
+static bool device_to_host(void* dst, const void* src, size_t n, cudaStream_t st, std::string& err) {
+    int device = 0;
+    if (staging_enabled() && n >= (1u << 20) && is_pageable(dst) && cudaGetDevice(&device) == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(stage_arena(device).m);
+        char* stage = stage_reserve(device, n, st);
+        if (stage) {
+            OCLR_CUDA(cudaMemcpyAsync(stage, src, n, cudaMemcpyDeviceToHost, st));
+            OCLR_CUDA(cudaStreamSynchronize(st));
+            const size_t blocks = (n + kStageBlock - 1) / kStageBlock;
+            std::vector<std::atomic<int>> done(blocks);
+            std::vector<CopyPool::Job> jobs(blocks);
+            for (size_t b = 0; b < blocks; ++b) {
+                done[b].store(0);
+                const size_t off = b * kStageBlock;
+                jobs[b] = {(char*)dst + off, stage + off, std::min(kStageBlock, n - off), &done[b]};
+            }
+            CopyPool& pool = CopyPool::get();
+            pool.submit(jobs.data(), blocks);
+            for (size_t b = 0; b < blocks; ++b)
+                while (done[b].load(std::memory_order_acquire) == 0)
+                    if (!pool.help()) std::this_thread::yield();
+            return true;
+        }
+    }
+    OCLR_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st));
+    OCLR_CUDA(cudaStreamSynchronize(st));
     return true;
 }
 
@@ -364,6 +433,16 @@ bool run_on_devices(int world, bool shareUpload, const std::function<void(int ra
         err = "bad device count";
         return false;
     }
+    struct RestoreDevice {   // the caller's current device is its own business (set-up below visits every GPU)
+        int d = -1;
+        RestoreDevice() {
+            if (cudaGetDevice(&d) != cudaSuccess) d = -1;
+        }
+        ~RestoreDevice() {
+            if (d >= 0) cudaSetDevice(d);
+            cudaGetLastError();
+        }
+    } restore;
     DevicePool& pool = DevicePool::get();
     std::string peerErr;
     const bool share = shareUpload && world > 1 && ensure_peer_access(world, peerErr);
@@ -726,6 +805,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     }
     s->smCount = sms;
     prepare_pool(s->device);
+    stage_reset(s->device);   // (every earlier staged copy of this device has completed: the calls that made them synchronise)
     if (!validate_scene(h, err, true)) return false;
     const bool buildGrid = !h.gridStart;   // no grid given: SceneTriangleList::New runs on the device (grid_builder.cuh)
 
@@ -1739,6 +1819,10 @@ bool frame_read(Frame* f, uint32_t rowBegin, uint32_t rowEnd, uint16_t* outR, ui
     const size_t P = (size_t)f->cam.width * f->cam.height;
     const size_t off = (size_t)rowBegin * f->cam.width, cnt = (size_t)(rowEnd - rowBegin) * f->cam.width;
     const uint16_t* d = (const uint16_t*)f->planesRGB.p;
+    if (staging_enabled() && cnt * 2 >= (1u << 20) && is_pageable(outR + off)) {   // pageable planes: pinned arena + copier threads
+        return device_to_host(outR + off, d + off, cnt * 2, st, err) && device_to_host(outG + off, d + P + off, cnt * 2, st, err) &&
+               device_to_host(outB + off, d + 2 * P + off, cnt * 2, st, err);
+    }
     OCLR_CUDA(cudaMemcpyAsync(outR + off, d + off, cnt * 2, cudaMemcpyDeviceToHost, st));
     OCLR_CUDA(cudaMemcpyAsync(outG + off, d + P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
     OCLR_CUDA(cudaMemcpyAsync(outB + off, d + 2 * P + off, cnt * 2, cudaMemcpyDeviceToHost, st));
