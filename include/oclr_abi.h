@@ -219,7 +219,8 @@ typedef struct oclr_counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
         mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
-        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters;
+        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters,
+        splitAttempts, splitsDone, splitParts, splitCancelled;   /* run-time split of long walks (experimental kernel instantiation) */
 } oclr_counters;
 
 typedef struct oclr_render_stats {

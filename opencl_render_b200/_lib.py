@@ -40,7 +40,8 @@ class Counters(C.Structure):
     """oclr_counters"""
     _fields_ = [(n, C.c_ulonglong) for n in ("segments", "primCandidates", "gridRays", "cells", "cellsNonEmpty",
                                               "gridCandidates", "shadedHits", "occluderLookups", "bricksLoaded", "emptyBrickCells", "walkWarpIters", "walkLaneIters", "testWarpIters",
-                                              "testLaneIters", "mailboxSkips", "coarseSteps", "coarseEnters", "switchWarpIters", "switchLaneIters", "walkIdleLanes", "walkParkedLanes", "walkFinishedLanes", "walkLowIters", "walkExhaustedIters")]
+                                              "testLaneIters", "mailboxSkips", "coarseSteps", "coarseEnters", "switchWarpIters", "switchLaneIters", "walkIdleLanes", "walkParkedLanes", "walkFinishedLanes", "walkLowIters", "walkExhaustedIters",
+                                              "splitAttempts", "splitsDone", "splitParts", "splitCancelled")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

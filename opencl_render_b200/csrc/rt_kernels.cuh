@@ -40,6 +40,10 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     if (c.walkFinishedLanes) atomicAdd(&g->walkFinishedLanes, c.walkFinishedLanes);
     if (c.walkLowIters) atomicAdd(&g->walkLowIters, c.walkLowIters);
     if (c.walkExhaustedIters) atomicAdd(&g->walkExhaustedIters, c.walkExhaustedIters);
+    if (c.splitAttempts) atomicAdd(&g->splitAttempts, c.splitAttempts);
+    if (c.splitsDone) atomicAdd(&g->splitsDone, c.splitsDone);
+    if (c.splitParts) atomicAdd(&g->splitParts, c.splitParts);
+    if (c.splitCancelled) atomicAdd(&g->splitCancelled, c.splitCancelled);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

@@ -32,6 +32,7 @@ struct TraceTuning {
     int switchMin;     // run parked level switches once this many lanes wait for one
     int splitMin;      // queue dry: a walk with at least this many cells to go is cut into parts for the warp's idle lanes (0 = never)
     int splitPart;     // ... of at least this many cells each
+    int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
 };
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
@@ -168,6 +169,7 @@ struct WarpPipe {
     uint32_t gHit[32], gMiss[32];   // per group, indexed by head lane: bit j = part j holds a hit / finished without one (bit 31 of gMiss: result written)
     uint32_t gParts[32];            // parts of the group
     uint32_t groups;                // live groups of this warp
+    uint32_t birth[32];             // outer iteration in which the lane took its ray (early split: only rays that HAVE walked are cut)
     int sParts, sAxis, sCut[kMaxWalkParts];   // plan of the split in progress
 };
 
@@ -184,7 +186,7 @@ __device__ __forceinline__ uint32_t next_entry(uint32_t begin, uint32_t end, uin
     return k < end ? k : end;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(SceneView S, WfState w, WalkRecords rec, TraceTuning tune,
                                                                             Counters* gcnt) {
     extern __shared__ float shPlanes[];
@@ -208,9 +210,15 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     const unsigned long long kEmptyKey = ~0ull;
 
 
-    P.grp[lane] = 0u;
-    if (lane == 0) P.groups = 0u;
+    if (SPLIT) {
+        P.grp[lane] = 0u;
+        P.gParts[lane] = 0u;
+        P.birth[lane] = 0u;
+        if (lane == 0) P.groups = 0u;
+        __syncwarp();
+    }
     int splitWait = 0;   // warp-uniform: outer iterations until the next split attempt
+    uint32_t iter = 0;   // warp-uniform: outer iterations so far
     const float* px = shPlanes;
     const float* py = shPlanes + (n + 1);
     const float* pz = shPlanes + 2 * (n + 1);
@@ -228,69 +236,19 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     uint32_t cq = 0;        // warp-uniform: cells queued
 
     for (;;) {
-        // ---- refill idle lanes: one atomic per warp, records read in queue order ----
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, ws == kWsNone);
-        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
-            const int nIdle = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(w.queueCursor, (uint32_t)nIdle);
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (base + (uint32_t)nIdle >= count) exhausted = true;
-            if (ws == kWsNone) {
-                const uint32_t pos = base + (uint32_t)__popc(idle & ltMask);
-                if (pos < count) {
-                    uint32_t cls = 0;
-#pragma unroll
-                    for (int c = 1; c < kLengthClasses; ++c) cls += pos >= classOff[c];
-                    const uint32_t idx = rec.order[(size_t)cls * rec.Q + (pos - classOff[cls])];
-                    const float4 ro = rec.o[idx], rd = rec.d[idx], s0 = rec.s0[idx];
-                    const uint4 s1 = rec.s1[idx];
-                    g.o = mk3(ro.x, ro.y, ro.z);
-                    g.r = mk3(rd.x, rd.y, rd.z);
-                    maxD = rd.w;
-                    P.ray[0][lane] = ro.x;
-                    P.ray[1][lane] = ro.y;
-                    P.ray[2][lane] = ro.z;
-                    P.ray[3][lane] = rd.x;
-                    P.ray[4][lane] = rd.y;
-                    P.ray[5][lane] = rd.z;
-                    P.ray[6][lane] = ro.w;
-                    P.ray[7][lane] = rd.w;
-                    P.excl[lane] = s1.y;
-                    P.bestKey[lane] = kEmptyKey;
-                    g.tx = s0.x;
-                    g.ty = s0.y;
-                    g.tz = s0.z;
-                    g.cpk = __float_as_uint(s0.w);
-                    g.epk = s1.x;
-                    path = s1.z;
-                    g.coarseOk = s1.w != 0u;
-                    g.level = 0;
-                    g.brick = ((pk_get(g.cpk, 0) >> 2) + (((pk_get(g.cpk, 1) >> 2) + ((pk_get(g.cpk, 2) >> 2) << nbShift)) << nbShift));
-                    g.endBrick = g.epk == kPkNone
-                                     ? -1
-                                     : ((pk_get(g.epk, 0) >> 2) + (((pk_get(g.epk, 1) >> 2) + ((pk_get(g.epk, 2) >> 2) << nbShift)) << nbShift));
-                    pwalk_load_brick(g, S.bricks);
-                    ws = kWsRun;
-                    face = kFaceNone;
-                    seqNext = 0;
-                    if (COUNT) {
-                        cnt.gridRays++;
-                        cnt.bricksLoaded++;
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(0xFFFFFFFFu, ws != kWsNone) == 0u) break;
-        __syncwarp();
-
-        // ---- SPLIT: queue dry, idle lanes -> they take parts of the longest whole walk this warp still holds ---------------------------
-        if (tune.splitMin > 0 && exhausted && --splitWait < 0) {
+        // ---- SPLIT: idle lanes take parts of the longest whole walk this warp holds (queue dry; or, early mode, a ray that has been
+        //      walking for tune.splitEarly outer iterations already -- in FRONT of the refill, which takes what idle lanes are left) -----
+        ++iter;
+        if (SPLIT && tune.splitMin > 0 && (exhausted || tune.splitEarly > 0) && --splitWait < 0) {
             const unsigned idleNow = __ballot_sync(0xFFFFFFFFu, ws == kWsNone);
             int best = 0, who = lane;
             if (idleNow != 0u) {
-                if (ws == kWsRun && g.level == 0 && g.coarseOk && P.grp[lane] == 0u) best = walk_length_estimate(g, n, px, py, pz);
+                if (COUNT && lane == 0) cnt.splitAttempts++;
+                // a whole ray at cell level whose group record is free (a lane that headed a group before keeps that record until
+                // the group has its result), old enough when the queue still has rays
+                if (ws == kWsRun && g.level == 0 && g.coarseOk && P.grp[lane] == 0u && P.gParts[lane] == 0u &&
+                    (exhausted || iter - P.birth[lane] >= (uint32_t)tune.splitEarly))
+                    best = walk_length_estimate(g, n, px, py, pz);
 #pragma unroll
                 for (int off = 16; off; off >>= 1) {
                     const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off), ow = __shfl_xor_sync(0xFFFFFFFFu, who, off);
@@ -316,6 +274,10 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                         P.gMiss[cand] = 0u;
                         P.gParts[cand] = (uint32_t)parts;
                         P.groups += 1u;
+                        if (COUNT) {
+                            cnt.splitsDone++;
+                            cnt.splitParts += (unsigned long long)parts;
+                        }
                     }
                 }
                 __syncwarp();
@@ -371,6 +333,64 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             }
         }
 
+        // ---- refill idle lanes: one atomic per warp, records read in queue order ----
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, ws == kWsNone);
+        if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(w.queueCursor, (uint32_t)nIdle);
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + (uint32_t)nIdle >= count) exhausted = true;
+            if (ws == kWsNone) {
+                const uint32_t pos = base + (uint32_t)__popc(idle & ltMask);
+                if (pos < count) {
+                    uint32_t cls = 0;
+#pragma unroll
+                    for (int c = 1; c < kLengthClasses; ++c) cls += pos >= classOff[c];
+                    const uint32_t idx = rec.order[(size_t)cls * rec.Q + (pos - classOff[cls])];
+                    const float4 ro = rec.o[idx], rd = rec.d[idx], s0 = rec.s0[idx];
+                    const uint4 s1 = rec.s1[idx];
+                    g.o = mk3(ro.x, ro.y, ro.z);
+                    g.r = mk3(rd.x, rd.y, rd.z);
+                    maxD = rd.w;
+                    P.ray[0][lane] = ro.x;
+                    P.ray[1][lane] = ro.y;
+                    P.ray[2][lane] = ro.z;
+                    P.ray[3][lane] = rd.x;
+                    P.ray[4][lane] = rd.y;
+                    P.ray[5][lane] = rd.z;
+                    P.ray[6][lane] = ro.w;
+                    P.ray[7][lane] = rd.w;
+                    P.excl[lane] = s1.y;
+                    P.bestKey[lane] = kEmptyKey;
+                    g.tx = s0.x;
+                    g.ty = s0.y;
+                    g.tz = s0.z;
+                    g.cpk = __float_as_uint(s0.w);
+                    g.epk = s1.x;
+                    path = s1.z;
+                    g.coarseOk = s1.w != 0u;
+                    g.level = 0;
+                    g.brick = ((pk_get(g.cpk, 0) >> 2) + (((pk_get(g.cpk, 1) >> 2) + ((pk_get(g.cpk, 2) >> 2) << nbShift)) << nbShift));
+                    g.endBrick = g.epk == kPkNone
+                                     ? -1
+                                     : ((pk_get(g.epk, 0) >> 2) + (((pk_get(g.epk, 1) >> 2) + ((pk_get(g.epk, 2) >> 2) << nbShift)) << nbShift));
+                    pwalk_load_brick(g, S.bricks);
+                    ws = kWsRun;
+                    face = kFaceNone;
+                    seqNext = 0;
+                    if (SPLIT) P.birth[lane] = iter;
+                    if (COUNT) {
+                        cnt.gridRays++;
+                        cnt.bricksLoaded++;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, ws != kWsNone) == 0u) break;
+        __syncwarp();
+
         // ---- WALK burst: step every walking lane until the cell queue is worth draining or too few lanes still walk ----------------
         for (;;) {
             const bool walking = ws == kWsRun;
@@ -422,7 +442,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     if (COUNT && coarse) cnt.coarseSteps++;
                     if (!pwalk_step(g, n, nbShift, shPlanes, lastAxis, up, lastE, crossed)) {
                         ws = kWsFinished;
-                    } else if (pk_is_stop(g.epk) && pwalk_stopped(g, lastAxis, up)) {
+                    } else if (SPLIT && pk_is_stop(g.epk) && pwalk_stopped(g, lastAxis, up)) {
                         ws = kWsFinished;   // this part of a cut walk ends here; the cell just entered belongs to the next part
                     } else {
                         face = coarse ? (int)kFaceNone : lastAxis * 2 + up;
@@ -433,7 +453,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     }
                 }
                 if ((ws == kWsFinished) & (seqNext == 0u)) {  // walk over and nothing of this ray awaits a test: miss
-                    if (P.grp[lane] == 0u) {                  // (a part of a cut walk reports to its group in RESOLVE instead)
+                    if (!SPLIT || P.grp[lane] == 0u) {        // (a part of a cut walk reports to its group in RESOLVE instead)
                         w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
                         ws = kWsNone;
                     }
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
 
         // ---- RESOLVE ----------------------------------------------------------------------------------------------------------------
-        if (P.groups == 0u) {   // (warp-uniform; the only case outside the tail of a launch)
+        if (!SPLIT || P.groups == 0u) {   // (warp-uniform; the only case outside the tail of a launch)
             if (ws != kWsNone) {
                 const unsigned long long key = P.bestKey[lane];
                 if (key != kEmptyKey) {  // first cell with any hit wins (:380); whatever the walker found beyond it is dropped
@@ -582,6 +602,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 seqNext = 0;
             }
             __syncwarp();
+            bool closes = false;   // this lane wrote its group's result
             if (grp != 0u) {
                 const uint32_t hm = P.gHit[headLane], mm = P.gMiss[headLane];
                 const uint32_t firstHit = hm ? (uint32_t)(__ffs((int)hm) - 1) : 32u;
@@ -589,23 +610,28 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 if (order > firstHit) {   // a part before this one has a hit: nothing found here can matter
                     ws = kWsNone;
                     P.grp[lane] = 0u;
+                    if (COUNT) cnt.splitCancelled++;
                 } else if (ws == kWsHeld) {
                     if ((mm & below) == below) {   // every part before it finished without a hit: this is the ray's result
                         w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
                         ws = kWsNone;
                         P.grp[lane] = 0u;
                         atomicSub(&P.groups, 1u);
+                        closes = true;
                     }
                 } else if (ws == kWsPartDone) {   // (its miss is on the group's record: the lane is free again)
                     const uint32_t all = (1u << P.gParts[headLane]) - 1u;
                     if (hm == 0u && (mm & all) == all && (atomicOr(&P.gMiss[headLane], 0x80000000u) >> 31) == 0u) {
                         w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);   // the last parts to finish: one of them says so
                         atomicSub(&P.groups, 1u);
+                        closes = true;
                     }
                     ws = kWsNone;
                     P.grp[lane] = 0u;
                 }
             }
+            __syncwarp();
+            if (closes) P.gParts[headLane] = 0u;   // the head lane's group record is free again
             __syncwarp();
         }
     }

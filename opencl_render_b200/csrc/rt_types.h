@@ -124,7 +124,8 @@ struct Counters {
     unsigned long long segments, primCandidates, gridRays, cells, cellsNonEmpty, gridCandidates, shadedHits,
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
         mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
-        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters;   // lanes of a walk iteration that were not walking, by reason
+        walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters,
+        splitAttempts, splitsDone, splitParts, splitCancelled;   // lanes of a walk iteration that were not walking, by reason
 };
 
 }  // namespace oclr

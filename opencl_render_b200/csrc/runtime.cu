@@ -1430,23 +1430,24 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     const size_t shBytes = sizeof(float) * 3 * (S.n + 1);
     int perSm = 0;
     if (dcnt)
-        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<true>, 128, shBytes));
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<true, false>, 128, shBytes));
     else
-        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false>, 128, shBytes));
+        OCLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_pipe_kernel<false, false>, 128, shBytes));
     if (perSm < 1) perSm = 1;
     // (function-local static built by a lambda: initialised once, thread-safe -- RaytraceAll's all-devices mode launches from one
     // host thread per GPU)
     static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0};
+        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
         t.walkMin3 = env("OCLR_WALK_MIN3", 8);
         t.switchMin = env("OCLR_SWITCH_MIN", 6);
         t.tailDrain = env("OCLR_TAIL_DRAIN", 8);
-        t.splitMin = getenv("OCLR_SPLIT_MIN") ? atoi(getenv("OCLR_SPLIT_MIN")) : 48;   // 0: never cut a walk
+        t.splitMin = getenv("OCLR_SPLIT_MIN") ? atoi(getenv("OCLR_SPLIT_MIN")) : 0;   // 0: never cut a walk (default, see rt_trace.cuh)
         t.splitPart = env("OCLR_SPLIT_PART", 16);
+        t.splitEarly = getenv("OCLR_SPLIT_EARLY") ? atoi(getenv("OCLR_SPLIT_EARLY")) : 0;
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -1531,10 +1532,16 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     }
                     wf_setup_kernel<<<setupGrid[k], 256, shBytes, ks>>>(S, w[k], rec[k]);
                     ++launches;
-                    if (dcnt)
-                        wf_pipe_kernel<true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                    // (the run-time split of long walks is an instantiation of its own: compiled into the production kernel it cost
+                    // 10 % through register pressure even when switched off)
+                    if (dcnt && tune.splitMin > 0)
+                        wf_pipe_kernel<true, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                    else if (dcnt)
+                        wf_pipe_kernel<true, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                    else if (tune.splitMin > 0)
+                        wf_pipe_kernel<false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
                     else
-                        wf_pipe_kernel<false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                        wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
                     if (timeTrace) {
                         OCLR_CUDA(cudaEventRecord(sl.traceEvents[sl.traceEventsUsed + 1], ks));
                         sl.traceEventsUsed += 2;

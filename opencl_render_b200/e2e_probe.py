@@ -77,7 +77,7 @@ def measure(cfg_id: int, world: int, calls: int, pinned: bool, rt):
     h2d = int(sum(getattr(s2, n).nbytes for n in SCENE_ARRAYS) + l2.start.nbytes + l2.end.nbytes + l2.list.nbytes)
     med = float(np.median(ts))
     return {"ms_per_call": float(np.mean(ts)), "ms_median": med, "ms_min": float(min(ts)), "ms_max": float(max(ts)),
-            "spread": (max(ts) - min(ts)) / med, "calls": calls, "sha256": h.hexdigest(), "h2d_bytes": h2d,
+            "spread": (max(ts) - min(ts)) / med, "ms_all": [round(t, 3) for t in ts], "calls": calls, "sha256": h.hexdigest(), "h2d_bytes": h2d,
             "d2h_bytes": int(6 * cam.width * cam.height), "rays": int(cam.width * cam.height * S), "devices_visible": n_dev}
 
 

@@ -15,3 +15,7 @@ for _ in range(reps):
     print(f"cfg{cfg_id} rank 0 of {world}: {ms:.3f} ms, trace {fr.last_trace_ms:.3f} ms, {launches} launches")
     best = (ms, fr.last_trace_ms) if best is None or ms < best[0] else best
 print(f"cfg{cfg_id} rank 0 of {world}: BEST {best[0]:.3f} ms, trace {best[1]:.3f} ms")
+if os.environ.get("OCLR_SPLIT_MIN", "0") != "0":
+    _, _, c = fr.render_bands(cfg["samples"], 16, 0, world, count=True)
+    print("   split: attempts %d, splits %d, parts %d, cancelled %d; walk iterations after the queue ran dry %.3f" % (
+        c["splitAttempts"], c["splitsDone"], c["splitParts"], c["splitCancelled"], c["walkExhaustedIters"] / max(c["walkWarpIters"], 1)))
