@@ -125,7 +125,7 @@ struct StageArena {   // pinned, per device, grow-only up to the cap
     size_t bytes = 0, used = 0;
     std::mutex m;   // one staged copy at a time per device (the copier threads are shared anyway)
 };
-static constexpr size_t kStageBlock = 2u << 20;
+static const size_t kStageBlock = [] { const char* v = getenv("OCLR_STAGING_BLOCK_KB"); return (size_t)(v && atoi(v) >= 64 ? atoi(v) : 512) << 10; }();   // (measured: 512 KB 10.1 ms, 2 MB 12.0 ms, 8 MB 14.1 ms per config-2 call)
 static StageArena& stage_arena(int device) {
     static StageArena arenas[64];
     return arenas[device & 63];
@@ -262,8 +262,10 @@ static void pinned_release(void* p) {
 struct DeviceBuffer {
     void* p = nullptr;
     size_t bytes = 0;
+    bool borrowed = false;   // p points into memory somebody else owns (the shared-upload landing arena): never freed here
     bool alloc(size_t n, std::string& err, cudaStream_t st = 0) {
         bytes = n;
+        borrowed = false;
         OCLR_CUDA(cudaMallocAsync(&p, n ? n : 16, st));
         return true;
     }
@@ -273,15 +275,16 @@ struct DeviceBuffer {
         return true;
     }
     void release(cudaStream_t st = 0) {
-        if (p) cudaFreeAsync(p, st);
+        if (p && !borrowed) cudaFreeAsync(p, st);
         p = nullptr;
+        borrowed = false;
     }
 };
 
 // ---- one scene, N GPUs of one box: sharded upload + NVLink fan-out ---------------------------------------------------------------------
 // RaytraceAll(all devices) used to let every GPU pull the WHOLE scene (133 MB for config 2) over its own PCIe link.  Now GPU k
-// uploads the k-th 1/N of every large array into its own buffer and one kernel stores that slice into the same place of every
-// peer's buffer over NVLink peer memory (16-byte stores, like push_rows_kernel); events order the consumers behind all N slices.
+// uploads the k-th 1/N of every large array into its own landing arena and one kernel stores that slice into the same place of every
+// peer's arena over NVLink peer memory (16-byte stores, like push_rows_kernel); events order the consumers behind all N slices.
 // PCIe moves every byte once in total instead of once per GPU.  Arrays travel in two groups so that the triangle repack and the
 // primary-ray round start while the grid (the larger group) is still in flight.
 enum { kMaxPeers = 16, kShardArrays = 12, kShardGroups = 2 };
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(256) fanout_kernel(const __grid_constant__ Fan
 struct ShardCtx {
     int world = 0;
     int devices[kMaxPeers] = {0};
-    cudaEvent_t allocReady[kMaxPeers] = {}, pushed[kShardGroups][kMaxPeers] = {};
+    cudaEvent_t pushed[kShardGroups][kMaxPeers] = {};
     void* ptr[kShardArrays][kMaxPeers] = {};
     // spin barrier with a verdict: every thread arrives with its own status, all leave with the AND (a thread that failed keeps
     // arriving at the remaining barriers so that nobody waits for it forever)
@@ -329,6 +332,21 @@ struct ShardCtx {
     }
 };
 
+// Where the shared upload lands: one plain cudaMalloc block per GPU that lives as long as the process (grow-only), carved up anew by
+// every call.  Peers store into it over NVLink, so it is classic peer-mapped memory whose addresses never change under a running
+// kernel.  (The first version took these buffers from the stream-ordered pool with cudaMemPoolSetAccess: on config 3, where the
+// primary-ray round's 5 GB of path state is allocated from the same pool WHILE the peers' grid slices arrive, memory got stomped --
+// every array verified correct when checked (OCLR_SHARD_VERIFY) and the fault went away with CUDA_LAUNCH_BLOCKING=1, with the shared
+// upload off, or with the early frame off.  Pool memory is no longer written by peers at all.)
+struct LandingArena {
+    char* p = nullptr;
+    size_t bytes = 0;
+};
+static LandingArena& landing_arena(int device) {
+    static LandingArena arenas[64];
+    return arenas[device & 63];
+}
+
 // Slice k of n bytes cut N ways on 256-byte boundaries.
 static inline void shard_range(size_t n, int k, int world, size_t& begin, size_t& end) {
     const size_t per = ((n + (size_t)world - 1) / (size_t)world + 255) & ~(size_t)255;
@@ -336,7 +354,7 @@ static inline void shard_range(size_t n, int k, int world, size_t& begin, size_t
     end = std::min(n, begin + per);
 }
 
-// Peer access between the first `world` devices, for direct stores and for memory from the stream-ordered pools.  Once per process.
+// Peer access between the first `world` devices (direct stores into the peers' landing arenas).  Once per process.
 static bool ensure_peer_access(int world, std::string& err) {
     static std::mutex m;
     static int enabledFor = 0;
@@ -347,8 +365,6 @@ static bool ensure_peer_access(int world, std::string& err) {
     for (int i = 0; i < world && usable; ++i) {
         if (cudaSetDevice(i) != cudaSuccess) usable = false;
         prepare_pool(i);
-        cudaMemPool_t pool;
-        if (usable && cudaDeviceGetDefaultMemPool(&pool, i) != cudaSuccess) usable = false;
         for (int j = 0; j < world && usable; ++j) {
             if (i == j) continue;
             int can = 0;
@@ -359,12 +375,6 @@ static bool ensure_peer_access(int world, std::string& err) {
             const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) usable = false;
             cudaGetLastError();
-            // device j may read and write what device i's pool hands out
-            cudaMemAccessDesc desc = {};
-            desc.location.type = cudaMemLocationTypeDevice;
-            desc.location.id = j;
-            desc.flags = cudaMemAccessFlagsProtReadWrite;
-            if (usable && cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) usable = false;
         }
     }
     cudaGetLastError();
@@ -467,9 +477,9 @@ bool run_on_devices(int world, bool shareUpload, const std::function<void(int ra
     ctx->bad.store(0);
     for (int d = 0; d < world; ++d) {
         ctx->devices[d] = d;
-        if (!ctx->allocReady[d]) {
+        if (!ctx->pushed[0][d]) {
             cudaSetDevice(d);
-            bool ok = cudaEventCreateWithFlags(&ctx->allocReady[d], cudaEventDisableTiming) == cudaSuccess;
+            bool ok = true;
             for (int g = 0; g < kShardGroups; ++g) ok = ok && cudaEventCreateWithFlags(&ctx->pushed[g][d], cudaEventDisableTiming) == cudaSuccess;
             if (!ok) {
                 err = "cannot create the upload events";
@@ -736,21 +746,38 @@ struct ShardArray {
 static bool shard_upload(ShardCtx* ctx, ShardBarriers& barriers, int rank, ShardArray* arrays, int count, std::string& err) {
     const int world = ctx->world;
     bool ok = count <= kShardArrays;
-    // 1. allocate (16-byte padded: the fan-out moves whole vectors), publish the addresses
-    for (int a = 0; ok && a < count; ++a) {
-        ok = arrays[a].buf->alloc((arrays[a].bytes + 15) & ~(size_t)15, err);
-        arrays[a].buf->bytes = arrays[a].bytes;
-        ctx->ptr[a][rank] = arrays[a].buf->p;
+    // 1. carve the landing arena (256-byte aligned pieces: the fan-out moves whole 16-byte vectors), publish the addresses.  The arena
+    //    is free: the previous call synchronised every GPU before it returned, and this call's peers write only after the barrier.
+    size_t total = 0;
+    for (int a = 0; a < count; ++a) total += (arrays[a].bytes + 255) & ~(size_t)255;
+    LandingArena& arena = landing_arena(ctx->devices[rank]);
+    if (ok && total > arena.bytes) {
+        if (arena.p) {
+            cudaDeviceSynchronize();
+            cudaFree(arena.p);
+        }
+        arena.p = nullptr;
+        arena.bytes = 0;
+        const size_t want = total + total / 4;
+        if (cudaMalloc((void**)&arena.p, want) != cudaSuccess) {
+            cudaGetLastError();
+            err = "out of device memory (shared-upload landing arena)";
+            ok = false;
+        } else {
+            arena.bytes = want;
+        }
     }
-    if (ok && cudaEventRecord(ctx->allocReady[rank], 0) != cudaSuccess) {
-        err = "cudaEventRecord failed";
-        ok = false;
+    size_t off = 0;
+    for (int a = 0; ok && a < count; ++a) {
+        arrays[a].buf->release();
+        arrays[a].buf->p = arena.p + off;
+        arrays[a].buf->bytes = arrays[a].bytes;
+        arrays[a].buf->borrowed = true;
+        ctx->ptr[a][rank] = arrays[a].buf->p;
+        off += (arrays[a].bytes + 255) & ~(size_t)255;
     }
     ok = barriers.arrive(ok);
-    // 2. own slices up, then out to the peers -- peers' buffers are written only after their allocation point in THEIR stream
-    if (ok)
-        for (int d = 0; d < world && ok; ++d)
-            if (d != rank) ok = cudaStreamWaitEvent(0, ctx->allocReady[d], 0) == cudaSuccess;
+    // 2. own slices up, then out to the peers
     for (int g = 0; g < kShardGroups; ++g) {
         FanoutTable t = {};
         t.peers = world - 1;
@@ -790,6 +817,27 @@ static bool shard_wait_group(ShardCtx* ctx, int group, std::string& err) {
     for (int d = 0; d < ctx->world; ++d) OCLR_CUDA(cudaStreamWaitEvent(0, ctx->pushed[group][d], 0));
     return true;
 }
+// Self-test of the shared upload (OCLR_SHARD_VERIFY=1): after the waits every array on this GPU must equal the caller's.
+static bool shard_verify(int rank, const ShardArray* arrays, int count, int group, std::string& err) {
+    static const bool on = [] { const char* v = getenv("OCLR_SHARD_VERIFY"); return v && atoi(v) != 0; }();
+    if (!on) return true;
+    OCLR_CUDA(cudaStreamSynchronize(0));
+    for (int a = 0; a < count; ++a) {
+        if (arrays[a].group != group || arrays[a].bytes == 0) continue;
+        std::vector<unsigned char> back(arrays[a].bytes);
+        OCLR_CUDA(cudaMemcpy(back.data(), arrays[a].buf->p, arrays[a].bytes, cudaMemcpyDeviceToHost));
+        const unsigned char* want = (const unsigned char*)arrays[a].host;
+        size_t bad = 0, first = 0;
+        for (size_t i = 0; i < arrays[a].bytes; ++i)
+            if (back[i] != want[i]) {
+                if (!bad) first = i;
+                ++bad;
+            }
+        fprintf(stderr, "[opencl_render_b200] shard verify: rank %d group %d array %d (%zu bytes): %zu bytes differ%s\n", rank, group, a,
+                arrays[a].bytes, bad, bad ? (", first at " + std::to_string(first)).c_str() : "");
+    }
+    return true;
+}
 
 static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const std::function<void(Scene*)>* early, UploadShare* share) {
     ShardCtx* ctx = share ? share->ctx : nullptr;
@@ -823,6 +871,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     // 1a. everything the primary-ray round needs -- triangles, materials, lights -- goes first: raw reference arrays -> HBM straight
     //     from the caller's memory (async on the default stream), repacked by pack_triangles_kernel
     DeviceBuffer vertex, triIdx, triMat, triUv, triNormal, boxMin, gridStart, counts, rankBase, scanTmp, errFlag, cellIds;
+    std::vector<ShardArray> sharded;   // (kept for the self-test of the second group)
     bool ok;
     if (ctx) {
         // one of N GPUs uploading the same arrays: slice + fan-out for the large ones (group 0 = what the triangle repack and the
@@ -847,10 +896,13 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
         share->staged.end = camEnd.p;
         share->staged.list = camList.p;
         share->staged.listSize = share->camListSize;
+        share->staged.borrowed = camStart.borrowed;
         ok = ok && s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
              s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
              s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&
              (buildGrid || boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err)) && shard_wait_group(ctx, 0, err);
+        sharded.assign(arrays, arrays + sizeof(arrays) / sizeof(arrays[0]));
+        ok = ok && shard_verify(share->rank, sharded.data(), (int)sharded.size(), 0, err);
     } else {
         ok = vertex.upload(h.vertex, sizeof(float4) * h.vertexCount, err) && triIdx.upload(h.triIdx, sizeof(int4) * N, err) &&
              triMat.upload(h.triMat, sizeof(int32_t) * N, err) && triUv.upload(h.triUv, sizeof(float2) * 3 * N, err) &&
@@ -886,7 +938,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
         if (early && *early) (*early)(s);
     }
     // 1b. the grid
-    ok = ok && (buildGrid || (ctx ? shard_wait_group(ctx, 1, err)
+    ok = ok && (buildGrid || (ctx ? (shard_wait_group(ctx, 1, err) && shard_verify(share->rank, sharded.data(), (int)sharded.size(), 1, err))
                                   : (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
                                      gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
                                      s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err)))) &&
@@ -1059,6 +1111,7 @@ static bool frame_setup(Frame* f, const uint32_t* camStart, const uint32_t* camE
         f->camEnd.bytes = sizeof(uint32_t) * P;
         f->camList.p = staged->list;
         f->camList.bytes = sizeof(uint32_t) * staged->listSize;
+        f->camStart.borrowed = f->camEnd.borrowed = f->camList.borrowed = staged->borrowed;
         listSize = staged->listSize;
     } else {
         if (!camStart || !camEnd || (listSize && !camList)) {
@@ -1197,7 +1250,7 @@ static bool frame_build_camera_lists(Frame* f, std::string& err) {
 }
 
 void staged_release(StagedCamLists& st) {
-    if (st.adopted) return;
+    if (st.adopted || st.borrowed) return;
     if (st.start) cudaFreeAsync(st.start, 0);
     if (st.end) cudaFreeAsync(st.end, 0);
     if (st.list) cudaFreeAsync(st.list, 0);
@@ -1902,14 +1955,25 @@ bool frame_read_bands(Frame* f, uint32_t bandRows, uint32_t rank, uint32_t world
         err = std::string("frame_read_bands: ") + cudaGetErrorString(e);
         return false;
     }
+    // scatter: one job per band and plane, shared out among the copier threads (and this one)
     const uint16_t* src = (const uint16_t*)st.p;
     uint16_t* dst[3] = {outR, outG, outB};
+    const size_t bands = (owned + bandRows - 1) / bandRows;
+    std::vector<std::atomic<int>> done(3 * bands);
+    std::vector<CopyPool::Job> jobs;
+    jobs.reserve(3 * bands);
     for (int plane = 0; plane < 3; ++plane)
         for (uint32_t k = 0; k < owned; k += bandRows) {   // one band = consecutive frame rows
             const uint32_t y = (k / bandRows) * (bandRows * world) + rank * bandRows;
             const uint32_t rows = std::min(bandRows, owned - k);
-            memcpy(dst[plane] + (size_t)y * W, src + ((size_t)plane * owned + k) * W, sizeof(uint16_t) * (size_t)rows * W);
+            done[jobs.size()].store(0);
+            jobs.push_back({dst[plane] + (size_t)y * W, src + ((size_t)plane * owned + k) * W, sizeof(uint16_t) * (size_t)rows * W, &done[jobs.size()]});
         }
+    CopyPool& pool = CopyPool::get();
+    pool.submit(jobs.data(), jobs.size());
+    for (size_t b = 0; b < jobs.size(); ++b)
+        while (done[b].load(std::memory_order_acquire) == 0)
+            if (!pool.help()) std::this_thread::yield();
     return true;
 }
 

@@ -73,6 +73,7 @@ struct StagedCamLists {   // camera lists that went up with the scene; frame_cre
     void* list = nullptr;
     size_t listSize = 0;
     bool adopted = false;
+    bool borrowed = false;   // the lists live in the shared-upload landing arena: nobody frees them
 };
 struct UploadShare {
     ShardCtx* ctx = nullptr;
