@@ -476,6 +476,13 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
                                   ShardCtx* shareCtx, cl_ushort* r, cl_ushort* g, cl_ushort* b, std::string& err) {
     const bool trace = getenv("OCLR_TRACE") != nullptr;
     static const bool overlap = [] { const char* v = getenv("OCLR_OVERLAP_UPLOAD"); return !v || atoi(v) != 0; }();
+    static const bool cacheBlocks = [] { const char* v = getenv("OCLR_BLOCK_CACHE"); return !v || atoi(v) != 0; }();
+    struct Scope {   // device blocks of this call are recycled by the next one (runtime.cu, BlockCache)
+        void* s;
+        ~Scope() {
+            if (s) allocation_cache_leave(s);
+        }
+    } scope = {cacheBlocks ? allocation_cache_enter(device) : nullptr};
     const double t0 = now_ms();
     const uint32_t bandWorld = (uint32_t)(world > 1 ? world : 1);
     // The camera lists go up and the primary-ray round starts as soon as the triangles are on the device, under the upload of the

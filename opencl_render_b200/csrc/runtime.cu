@@ -281,14 +281,127 @@ static void pinned_release(void* p) {
     g_pinFree.push_back(p);
 }
 
+// ---- per-device caches of driver objects -------------------------------------------------------------------------------------------
+// One RaytraceAll call makes ~40 device allocations, as many frees, half a dozen events and a stream -- per GPU.  Each is a driver
+// call behind a process-wide lock: cheap alone (2-5 us), but with one host thread per GPU of an 8-GPU box they queue up behind each
+// other and were ~1 ms of a 4 ms call (phases "camera lists" 0.5 ms and "release" 0.3-0.5 ms at N = 8, 0.15 ms each at N = 1).  The
+// call repeats with the same sizes frame after frame, so: blocks freed inside RaytraceAll go to a free list of their device and the
+// next call's allocations of the same size come from there without a driver call; events and streams are recycled the same way.
+// Stream-ordered discipline is what cudaMallocAsync already asked for: a block is released only when its last use is complete or
+// enqueued on the device's default stream, and every use on another stream is ordered behind an event recorded on that stream.
+struct CachedBlock {
+    void* p;
+    size_t size;             // size it was allocated with
+    unsigned long long epoch;   // call during which it was put back
+};
+struct BlockCache {
+    std::mutex m;
+    std::vector<CachedBlock> free;
+    unsigned long long epoch = 0;                 // RaytraceAll calls on this device so far
+    std::vector<cudaEvent_t> events[2];           // [0] timing, [1] cudaEventDisableTiming
+    std::vector<cudaStream_t> streams;            // non-blocking
+};
+static BlockCache& block_cache(int device) {
+    static BlockCache caches[64];
+    return caches[device & 63];
+}
+static thread_local int g_cacheDevice = -1;   // >= 0: this thread is inside RaytraceAll on that device (DeviceBuffer uses the free list)
+struct CacheScope {
+    int saved, device;
+    explicit CacheScope(int d) : saved(g_cacheDevice), device(d) { g_cacheDevice = d; }
+    ~CacheScope() {
+        g_cacheDevice = saved;
+        // blocks nobody asked for during the last three calls go back to the driver (a camera sweep changes the list sizes every frame)
+        BlockCache& c = block_cache(device);
+        std::vector<void*> stale;
+        {
+            std::lock_guard<std::mutex> lock(c.m);
+            ++c.epoch;
+            for (size_t i = 0; i < c.free.size();)
+                if (c.free[i].epoch + 3 < c.epoch) {
+                    stale.push_back(c.free[i].p);
+                    c.free[i] = c.free.back();
+                    c.free.pop_back();
+                } else {
+                    ++i;
+                }
+        }
+        if (!stale.empty() && cudaSetDevice(device) == cudaSuccess)
+            for (void* p : stale) cudaFreeAsync(p, 0);
+    }
+};
+void* allocation_cache_enter(int device) { return new CacheScope(device); }
+void allocation_cache_leave(void* scope) { delete (CacheScope*)scope; }
+
+static cudaError_t make_event(int device, cudaEvent_t* e, bool timing) {
+    BlockCache& c = block_cache(device);
+    {
+        std::lock_guard<std::mutex> lock(c.m);
+        auto& v = c.events[timing ? 0 : 1];
+        if (!v.empty()) {
+            *e = v.back();
+            v.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaEventCreateWithFlags(e, timing ? cudaEventDefault : cudaEventDisableTiming);
+}
+static void drop_event(int device, cudaEvent_t e, bool timing) {
+    if (!e) return;
+    BlockCache& c = block_cache(device);
+    std::lock_guard<std::mutex> lock(c.m);
+    c.events[timing ? 0 : 1].push_back(e);
+}
+static cudaError_t make_stream(int device, cudaStream_t* st) {
+    BlockCache& c = block_cache(device);
+    {
+        std::lock_guard<std::mutex> lock(c.m);
+        if (!c.streams.empty()) {
+            *st = c.streams.back();
+            c.streams.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+}
+static void drop_stream(int device, cudaStream_t st) {   // (the stream is idle: its owner waited for its work)
+    if (!st) return;
+    BlockCache& c = block_cache(device);
+    std::lock_guard<std::mutex> lock(c.m);
+    c.streams.push_back(st);
+}
+
 struct DeviceBuffer {
     void* p = nullptr;
     size_t bytes = 0;
+    size_t cachedSize = 0;   // != 0: the block belongs to the device's free list (size it was allocated with)
+    int cachedDevice = -1;
     bool borrowed = false;   // p points into memory somebody else owns (the shared-upload landing arena): never freed here
     bool alloc(size_t n, std::string& err, cudaStream_t st = 0) {
         bytes = n;
         borrowed = false;
-        OCLR_CUDA(cudaMallocAsync(&p, n ? n : 16, st));
+        cachedSize = 0;
+        const size_t want = ((n ? n : 16) + 255) & ~(size_t)255;
+        if (g_cacheDevice >= 0) {
+            BlockCache& c = block_cache(g_cacheDevice);
+            {
+                std::lock_guard<std::mutex> lock(c.m);
+                for (size_t i = 0; i < c.free.size(); ++i)
+                    if (c.free[i].size == want) {   // the call repeats with the same sizes: exact fits
+                        p = c.free[i].p;
+                        c.free[i] = c.free.back();
+                        c.free.pop_back();
+                        cachedSize = want;
+                        cachedDevice = g_cacheDevice;
+                        return true;
+                    }
+            }
+            OCLR_CUDA(cudaMallocAsync(&p, want, st));
+            cachedSize = want;
+            cachedDevice = g_cacheDevice;
+            return true;
+        }
+        OCLR_CUDA(cudaMallocAsync(&p, want, st));
         return true;
     }
     bool upload(const void* src, size_t n, std::string& err, cudaStream_t st = 0) {
@@ -297,9 +410,21 @@ struct DeviceBuffer {
         return true;
     }
     void release(cudaStream_t st = 0) {
-        if (p && !borrowed) cudaFreeAsync(p, st);
+        if (p && !borrowed) {
+            if (cachedSize) {
+                BlockCache& c = block_cache(cachedDevice);
+                std::lock_guard<std::mutex> lock(c.m);
+                if (c.free.size() < 256)
+                    c.free.push_back({p, cachedSize, c.epoch});
+                else
+                    cudaFreeAsync(p, st);
+            } else {
+                cudaFreeAsync(p, st);
+            }
+        }
         p = nullptr;
         borrowed = false;
+        cachedSize = 0;
     }
 };
 
@@ -1114,9 +1239,9 @@ static bool frame_setup_common(Frame* f, std::string& err, bool sync = true) {
         return false;
     }
     OCLR_CUDA(cudaMemsetAsync(f->planesRGB.p, 0, f->planesRGB.bytes, 0));
-    OCLR_CUDA(cudaEventCreateWithFlags(&f->ev0, cudaEventDefault));
-    OCLR_CUDA(cudaEventCreateWithFlags(&f->ev1, cudaEventDefault));
-    OCLR_CUDA(cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
+    OCLR_CUDA(make_event(f->device, &f->ev0, true));
+    OCLR_CUDA(make_event(f->device, &f->ev1, true));
+    OCLR_CUDA(make_event(f->device, &f->evFork, false));
     if (sync) OCLR_CUDA(cudaStreamSynchronize(0));
     return true;
 }
@@ -1324,21 +1449,21 @@ void frame_destroy(Frame* f) {
     DeviceBuffer* all[] = {&f->camStart, &f->camEnd, &f->camList, &f->planesRGB, &f->ids, &f->flags, &f->counters, &f->accum, &f->doneCount,
                            &f->camCheck};
     for (DeviceBuffer* b : all) b->release();
-    if (f->progStream) cudaStreamDestroy(f->progStream);
+    drop_stream(f->device, f->progStream);
     pinned_release(f->hostDone);
-    if (f->preStream) cudaStreamDestroy(f->preStream);
-    if (f->preReady) cudaEventDestroy(f->preReady);
-    if (f->preDone) cudaEventDestroy(f->preDone);
+    drop_stream(f->device, f->preStream);
+    drop_event(f->device, f->preReady, false);
+    drop_event(f->device, f->preDone, false);
     for (WfSlice& sl : f->slices) {
         for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release();
-        if (sl.stream) cudaStreamDestroy(sl.stream);
-        if (sl.done) cudaEventDestroy(sl.done);
-        for (cudaEvent_t e : sl.traceEvents) cudaEventDestroy(e);
+        drop_stream(f->device, sl.stream);
+        drop_event(f->device, sl.done, false);
+        for (cudaEvent_t e : sl.traceEvents) drop_event(f->device, e, true);
     }
     pinned_release(f->hostCount);
-    if (f->ev0) cudaEventDestroy(f->ev0);
-    if (f->ev1) cudaEventDestroy(f->ev1);
-    if (f->evFork) cudaEventDestroy(f->evFork);
+    drop_event(f->device, f->ev0, true);
+    drop_event(f->device, f->ev1, true);
+    drop_event(f->device, f->evFork, false);
     delete f;
 }
 
@@ -1469,8 +1594,8 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                 return false;
             sl.capacity = Q;
         }
-        if (k > 0 && !sl.stream) OCLR_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        if (!sl.done) OCLR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        if (k > 0 && !sl.stream) OCLR_CUDA(make_stream(f->device, &sl.stream));
+        if (!sl.done) OCLR_CUDA(make_event(f->device, &sl.done, false));
         stream[k] = k == 0 ? st : sl.stream;
         sl.traceEventsUsed = 0;
         w[k].Q = Q;
@@ -1530,9 +1655,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     if (Fall.flagOut && !resumePre) OCLR_CUDA(cudaMemsetAsync(Fall.flagOut, 0, (size_t)Fall.cam.width * Fall.cam.height, st));
     if (prelaunchOnly) {
         if (!f->preStream) {
-            OCLR_CUDA(cudaStreamCreateWithFlags(&f->preStream, cudaStreamNonBlocking));
-            OCLR_CUDA(cudaEventCreateWithFlags(&f->preReady, cudaEventDisableTiming));
-            OCLR_CUDA(cudaEventCreateWithFlags(&f->preDone, cudaEventDisableTiming));
+            OCLR_CUDA(make_stream(f->device, &f->preStream));
+            OCLR_CUDA(make_event(f->device, &f->preReady, false));
+            OCLR_CUDA(make_event(f->device, &f->preDone, false));
         }
         WfSlice& sl = f->slices[0];
         uint32_t* counters = (uint32_t*)sl.workCounter.p;
@@ -1600,7 +1725,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     if (timeTrace) {
                         while (sl.traceEvents.size() < (size_t)sl.traceEventsUsed + 2) {
                             cudaEvent_t e;
-                            OCLR_CUDA(cudaEventCreate(&e));
+                            OCLR_CUDA(make_event(f->device, &e, true));
                             sl.traceEvents.push_back(e);
                         }
                         OCLR_CUDA(cudaEventRecord(sl.traceEvents[sl.traceEventsUsed], ks));
@@ -2080,7 +2205,7 @@ bool frame_progress(Frame* f, unsigned long long* done, unsigned long long* tota
     *done = 0;
     if (*total == 0) return true;
     if (cudaSetDevice(f->device) != cudaSuccess) return false;
-    if (!f->progStream && cudaStreamCreateWithFlags(&f->progStream, cudaStreamNonBlocking) != cudaSuccess) {   // first poll of this frame
+    if (!f->progStream && make_stream(f->device, &f->progStream) != cudaSuccess) {   // first poll of this frame
         cudaGetLastError();
         f->progStream = nullptr;
         return false;

@@ -84,6 +84,10 @@ struct UploadShare {
     size_t camListSize = 0, pixels = 0;
     StagedCamLists staged;
 };
+// Inside RaytraceAll device blocks come from / go back to a per-device free list instead of the driver (runtime.cu, BlockCache): the
+// calling thread brackets its work on `device` with these two.
+void* allocation_cache_enter(int device);
+void allocation_cache_leave(void* scope);
 bool run_on_devices(int world, bool shareUpload, const std::function<void(int rank, ShardCtx* share)>& fn, std::string& err);
 void staged_release(StagedCamLists& st);
 

@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "opencl_render_b200", "libopencl_render_b200.so")
-want = sys.argv[1] if len(sys.argv) > 1 else "wf_pipe_kernelILb0"
+want = sys.argv[1] if len(sys.argv) > 1 else "wf_pipe_kernelILb0ELb0"
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 blocks = re.split(r"\n\s*Function : ", out)
 for b in blocks[1:]:
