@@ -391,7 +391,7 @@ def measure_config(run: Run, cfg_id: int, steps: int, warmup: int, primary: bool
         res["roofline"] = roof
 
     # ---- end to end through the drop-in call (host buffers), made by ONE plain host process like the plugin -------------------------
-    if want_e2e and lists is not None:
+    if want_e2e and lists is not None and os.environ.get("OCLR_BENCH_NO_E2E") != "1":     # (profiling runs skip the probe process)
         run.cpu_barrier()                                     # nothing but the probe process touches the GPUs from here to the next barrier
         if rank == 0:
             e2e_calls = max(5, min(steps, 10))

@@ -551,6 +551,7 @@ public:
             world_ = world;
             pending_ = world;
             ++generation_;
+            posted_.store(generation_, std::memory_order_release);
         }
         cvJob_.notify_all();
         std::unique_lock<std::mutex> lock(m_);
@@ -566,6 +567,10 @@ private:
         for (;;) {
             const std::function<void(int)>* fn = nullptr;
             {
+                // a render loop calls back within a fraction of a millisecond: stay awake that long before sleeping on the condition
+                // variable (a wake-up is 50-100 us, paid by every GPU's thread at the start of every call)
+                const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+                while (posted_.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < until) std::this_thread::yield();
                 std::unique_lock<std::mutex> lock(m_);
                 cvJob_.wait(lock, [&] { return generation_ != seen; });
                 seen = generation_;
@@ -583,6 +588,7 @@ private:
     unsigned workers_ = 0;
     int world_ = 0, pending_ = 0;
     unsigned long long generation_ = 0;
+    std::atomic<unsigned long long> posted_{0};   // == generation_, readable without the lock by workers that are still awake
 };
 
 bool run_on_devices(int world, bool shareUpload, const std::function<void(int rank, ShardCtx* share)>& fn, std::string& err) {

@@ -1,9 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
 nvidia-smi -L | wc -l; nproc
-timeout 900 python -m pytest tests -m gpu -q --maxfail=5 --timeout 600 > gpurun_out/r02g_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02g_gpu_tests.log
-OCLR_TRACE=1 timeout 200 python scripts/e2e_trace.py 2 1 12 > gpurun_out/r02g_e2e_trace_1.log 2>&1; grep -E "x1:" gpurun_out/r02g_e2e_trace_1.log; grep "RaytraceAll dev" gpurun_out/r02g_e2e_trace_1.log | sed -n 10,12p; grep "RaytraceAll dev" gpurun_out/r02g_e2e_trace_1.log | tail -2
-OCLR_TRACE=1 timeout 200 python scripts/e2e_trace.py 2 2 12 > gpurun_out/r02g_e2e_trace_2.log 2>&1; grep -E "x2:" gpurun_out/r02g_e2e_trace_2.log; grep "RaytraceAll dev" gpurun_out/r02g_e2e_trace_2.log | sed -n 19,22p
-OCLR_BLOCK_CACHE=0 timeout 200 python scripts/e2e_trace.py 2 2 12 2>&1 | grep -E "x2:"
-timeout 200 python scripts/e2e_trace.py 3 2 8 2>&1 | grep -E "x2:"
-timeout 200 python scripts/e2e_trace.py 5 2 8 2>&1 | grep -E "x2:"
+python scripts/sweep_env.py 2 2 "OCLR_NONE=1" "OCLR_REFILL_MIN=2" "OCLR_REFILL_MIN=8" "OCLR_REFILL_MIN=12" "OCLR_DRAIN_MIN=32" "OCLR_DRAIN_MIN=64" "OCLR_WALK_MIN3=4" "OCLR_WALK_MIN3=12" "OCLR_WALK_MIN3=16" "OCLR_SWITCH_MIN=3" "OCLR_SWITCH_MIN=10" "OCLR_SWITCH_MIN=16" "OCLR_TAIL_DRAIN=4" "OCLR_TAIL_DRAIN=16" "OCLR_TRACE_CTAS=6" "OCLR_TRACE_CTAS=7" > gpurun_out/r02i_knobs.log 2>&1
+grep -E "^---|variant 2:" gpurun_out/r02i_knobs.log
+bash scripts/profile_round.sh r02 > gpurun_out/r02_profile_round.log 2>&1; tail -5 gpurun_out/r02_profile_round.log
