@@ -36,6 +36,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defs: str, verbose: bool = False) -> Path:
+    """A/B build of the same library with extra nvcc defines (e.g. -DOCLR_CELLQ_CAP=128): libopencl_render_b200_<name>.so next to the
+    production library, loaded through OCLR_LIB (developer knob of _lib.load)."""
+    out = PKG / f"libopencl_render_b200_{name}.so"
+    obj = OBJ / f"runtime_{name}.o"
+    OBJ.mkdir(parents=True, exist_ok=True)
+    build()
+    cmd = [str(CUDA / "bin" / "nvcc"), *NVCC_FLAGS, *defs.split(), "-c", str(CSRC / "runtime.cu"), "-o", str(obj)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    (OBJ / f"runtime_{name}.ptxas.txt").write_text(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stderr}")
+    objs = [str(obj)] + [str(OBJ / (n + ".o")) for n, _ in SOURCES if n != "runtime.cu"]
+    r = subprocess.run([str(CUDA / "bin" / "nvcc"), "-shared", "-o", str(out), *objs, "-cudart", "static", "-Xlinker", "-Bsymbolic", "-lpthread", "-lz"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     stamp = OBJ / "stamp.txt"
     dig = _digest() + os.environ.get("OCLR_NVCC_DEFS", "")
@@ -76,4 +96,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))
+    if "--variant" in sys.argv:      # python -m opencl_render_b200.build --variant q128 "-DOCLR_CELLQ_CAP=128"
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

@@ -1487,7 +1487,7 @@ uint32_t band_owned_rows(uint32_t height, uint32_t bandRows, uint32_t rank, uint
 // launch gives up.  Pixels are independent, so the cut is invisible in the output.
 // Measured (B200, gpurun_out/slices*.log): config 3 (8.3 M paths) 24.4 -> 23.7 ms with 2 slices, flat to 4, worse at 8; config 2
 // (2.1 M paths) 4.51 ms with 1 or 2 slices and slower beyond -- every slice's launches end in their own partly filled warps, which
-// costs what the overlap wins.  Default: one slice per 4 M paths, at most 4 (OCLR_SLICES=k forces k).
+// costs what the overlap wins.  Default: one slice per 3 M paths, at most 4 (OCLR_SLICES=k forces k; round 2: config 3, 8.3 M paths, 23.5 -> 22.8 ms with 2).
 // Tracing one round ahead (rt_wavefront.cuh): 0 never, 1 for every segment but the camera's, 2 for all.  -1 = automatic.
 static std::atomic<int> g_aheadMode(-2);
 void set_ahead_mode(int m) { g_aheadMode.store(m < -1 || m > 2 ? -1 : m); }
@@ -1515,7 +1515,7 @@ static int slice_count_for(uint32_t rows, uint32_t width) {
     const int forced = g_sliceCount.load();
     if (forced) return forced;
     const uint64_t paths = (uint64_t)rows * width;
-    return (int)std::min<uint64_t>(4, std::max<uint64_t>(1, paths / (4ull << 20)));
+    return (int)std::min<uint64_t>(4, std::max<uint64_t>(1, paths / (3ull << 20)));   // (config 3's 8.3 M paths: 2 slices, 23.5 -> 22.8 ms)
 }
 
 static bool same_request(const FrameView& a, const FrameView& b);
@@ -1647,7 +1647,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
-        t.drainMin = std::min(env("OCLR_DRAIN_MIN", 48), (int)kCellQCap - 31);
+        t.drainMin = std::min(env("OCLR_DRAIN_MIN", 64), (int)kCellQCap - 31);   // (round 2 sweep: 64 is ~1 % faster than 48 on configs 2 and 3)
         t.walkMin3 = env("OCLR_WALK_MIN3", 8);
         t.switchMin = env("OCLR_SWITCH_MIN", 6);
         t.tailDrain = env("OCLR_TAIL_DRAIN", 8);
