@@ -535,7 +535,9 @@ static bool render_rows_on_device(int device, const HostScene& h, const Camera& 
         RenderStats rs;
         const double a = now_ms();
         // all bands of this device in one launch sequence
-        ok = frame_render_bands(f, sampleCount, 0, sampleCount, bandRows, (uint32_t)rank, bandWorld, default_variant(), false, nullptr, &rs, err);
+        // (render statistics -- an event pair around every trace launch and a synchronisation of their own -- only when somebody reads them)
+        ok = frame_render_bands(f, sampleCount, 0, sampleCount, bandRows, (uint32_t)rank, bandWorld, default_variant(), false, nullptr,
+                                trace ? &rs : nullptr, err);
         const double c = now_ms();
         ok = ok && frame_read_bands(f, bandRows, (uint32_t)rank, bandWorld, r, g, b, err);
         tRender += c - a;
