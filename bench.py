@@ -232,8 +232,12 @@ def run_reference(args):
     rays = n_rows * w * cfg["samples"]
     value = rays * args.steps / dt / 1e6
     sample = f"every {ROW_STEP}th row of all {h} ({rays} pixel-samples) per step"
+    try:                                            # (evidence for the reader of the line: which shared libraries of this repo the process mapped)
+        mapped = sorted({l.split("/")[-1].strip() for l in open("/proc/self/maps") if "/oracle/" in l or "libopencl_render_b200" in l})
+    except OSError:
+        mapped = None
     print(json.dumps({
-        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "repo_libraries_mapped": mapped, "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config_keys(cfg, sc, cam), "sampling": sample, "acceleration_lists": lists_by,
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},

@@ -1045,11 +1045,13 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
             {&s->cellList, h.gridList, buildGrid ? 0 : sizeof(uint32_t) * total, 1},
         };
         ok = shard_upload(ctx, barriers, share->rank, arrays, (int)(sizeof(arrays) / sizeof(arrays[0])), err);
-        share->staged.start = camStart.p;   // handed to the frame (frame_create adopts them) or freed by staged_release()
-        share->staged.end = camEnd.p;
-        share->staged.list = camList.p;
-        share->staged.listSize = share->camListSize;
-        share->staged.borrowed = camStart.borrowed;
+        if (share->camStart) {   // handed to the frame (frame_create adopts them); no lists given: the frame builds its own on the device
+            share->staged.start = camStart.p;
+            share->staged.end = camEnd.p;
+            share->staged.list = camList.p;
+            share->staged.listSize = share->camListSize;
+            share->staged.borrowed = camStart.borrowed;
+        }
         ok = ok && s->matSize.upload(h.matSize, sizeof(uint2) * kMaterialChannels * h.materialCount, err) &&
              s->matStart.upload(h.matStart, sizeof(int32_t) * (kMaterialChannels * h.materialCount + (h.materialCount ? 1 : 0)), err) &&
              s->lights.upload(lights.data(), sizeof(Light) * lights.size(), err) &&

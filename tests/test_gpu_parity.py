@@ -421,3 +421,36 @@ def test_scene_upload_builds_grid_on_device():
     assert all(np.array_equal(x, y) for x, y in zip(fa.read(), fb.read()))
     for h in (fa, fb, a, b):
         h.close()
+
+
+def test_e2e_probe_process_prints_one_line_and_the_right_planes():
+    """bench.py's `e2e` comes from a plain host process (opencl_render_b200/e2e_probe.py) that calls the drop-in RaytraceAll with
+    page-locked and with pageable host arrays: one JSON line, and the planes' digest equals the digest of the same frame rendered
+    through the resident scene / frame API in this process."""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "opencl_render_b200.e2e_probe", "1", "1", "2"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    cfg = scenes.CONFIGS[1]
+    sc = cfg["make"]()
+    m = sc.meta["camera"]
+    cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], cfg["width"], cfg["height"])
+    lists = api.camera_triangle_list(cam, sc)
+    api.scene_triangle_list(sc, 256)
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    fr.render(cfg["samples"])
+    h = hashlib.sha256()
+    for p in fr.read():
+        h.update(np.ascontiguousarray(p).tobytes())
+    assert d["sha256"] == h.hexdigest() and d["pageable"]["sha256"] == h.hexdigest()
+    assert d["rays"] == cam.width * cam.height * cfg["samples"] and d["ms_per_call"] > 0 and d["h2d_bytes"] > 0
+    fr.close()
+    ds.close()
