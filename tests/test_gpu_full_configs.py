@@ -159,3 +159,18 @@ def test_raytrace_all_on_all_devices_of_the_box(port):
     want = port.render(cam, lists, sc, 2)
     for c in range(3):
         assert np.array_equal(one[c], want[c]) and np.array_equal(every[c], want[c])
+    # the shared upload (1/N of every array per GPU over PCIe, NVLink fan-out into the peers' landing arenas) at awkward sizes: a width
+    # that is no multiple of 8, fewer bands than GPUs (some GPUs own nothing), one pixel; the "devices" option; repeated calls with
+    # changing array sizes (the per-device block caches and arenas are reused and regrown)
+    for (w, h, samples) in [(333, 77, 1), (64, 8, 3), (1, 1, 1), (400, 600, 1)]:
+        cam = api.set_camera(m["eye"], m["look_at"], m["up"], m["fov"], w, h)
+        lists = api.camera_triangle_list(cam, sc)
+        want = port.render(cam, lists, sc, samples)
+        every = api.raytrace_all(n + 1, cam, lists, samples, sc)
+        assert all(np.array_equal(every[c], want[c]) for c in range(3)), (w, h, samples)
+    api.set_option("devices", 2)
+    try:
+        two = api.raytrace_all(n + 1, cam, lists, 1, sc)
+        assert all(np.array_equal(two[c], want[c]) for c in range(3))
+    finally:
+        api.set_option("devices", 0)
