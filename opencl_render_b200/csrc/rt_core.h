@@ -52,7 +52,7 @@ OCLR_HD uint64_t xorshift64star(uint64_t v) {
     v ^= v >> 27;
     return v * 2685821657736338717ull;
 }
-OCLR_HD float rand_f(uint64_t& s, float lo, float hi) {
+OCLR_HD_OUT(1) float rand_f(uint64_t& s, float lo, float hi) {
     s ^= xorshift64star((rotl64(s, 55) ^ rotl64(s, 3)) * 0xc23f3c0ad9da6357ull);
     s ^= xorshift64star((rotl64(s, 35) ^ rotl64(s, 3)) ^ 0xce84d6af03c16b89ull);
     s ^= xorshift64star((rotl64(s, 63) ^ rotl64(s, 35)) * 0xf097ef8bbe03ddccull);
@@ -66,7 +66,7 @@ OCLR_HD float rand_f(uint64_t& s, float lo, float hi) {
 }
 
 // raytrace_opencl.c:30-45.  The number of draws is state-visible (rejection loop).
-OCLR_HD f3 sphere_point(uint64_t& s, float radius) {
+OCLR_HD_OUT(2) f3 sphere_point(uint64_t& s, float radius) {
     f3 p;
     float len;
     do {
@@ -97,7 +97,7 @@ OCLR_HD float point_to_line_sq(f3 o, f3 d, f3 p) {
 }
 
 // raytrace_opencl.c:103-122.  `size.x - 1` is unsigned arithmetic in the reference.
-OCLR_HD f3 table_value(const uchar4* table, uint2 size, float u0, float v0, float u1, float v1, float u2, float v2,
+OCLR_HD_OUT(3) f3 table_value(const uchar4* table, uint2 size, float u0, float v0, float u1, float v1, float u2, float v2,
                        float abL, float acL) {
     float pu = positive_modf(u0 + (u1 - u0) * abL + (u2 - u0) * acL);
     float pv = positive_modf(v0 + (v1 - v0) * abL + (v2 - v0) * acL);
@@ -592,7 +592,7 @@ OCLR_HD void light_ray(const Light& L, f3 loc, uint64_t& rng, LightRay& lr) {
 }
 
 // :629-635
-OCLR_HD void light_accumulate(const Light& L, f3 nrm, const LightRay& lr, f3 att, f3 face[2]) {
+OCLR_HD_OUT(2) void light_accumulate(const Light& L, f3 nrm, const LightRay& lr, f3 att, f3 face[2]) {
     const float d = dot3(nrm, lr.dir);
     const float effect = fabsf(d);
     const int idx = (int)(0.f <= d);

@@ -36,6 +36,33 @@
 #else
 #define OCLR_HD inline
 #endif
+// Code size of the logic kernel: with everything forced inline it is 7 560 SASS instructions (121 KB), 40 % of them the 14 inlined
+// copies of the reference's 64-bit RNG, and "no instruction" (instruction-cache misses) is its first stall reason (3.7 warp-cycles per
+// issue; the 1 368-instruction trace kernel: 0.2).  OCLR_OUTLINE_LEVEL >= 1 makes rand_f one function, >= 2 also sphere_point and the
+// light accumulation (a double-precision pow), >= 3 also the texture lookup.  Same arithmetic either way.
+#ifndef OCLR_OUTLINE_LEVEL
+#define OCLR_OUTLINE_LEVEL 0
+#endif
+#if defined(__CUDACC__)
+#define OCLR_HD_OUT(level) __host__ __device__ OCLR_OUTLINE_##level
+#if OCLR_OUTLINE_LEVEL >= 1
+#define OCLR_OUTLINE_1 __noinline__
+#else
+#define OCLR_OUTLINE_1 __forceinline__
+#endif
+#if OCLR_OUTLINE_LEVEL >= 2
+#define OCLR_OUTLINE_2 __noinline__
+#else
+#define OCLR_OUTLINE_2 __forceinline__
+#endif
+#if OCLR_OUTLINE_LEVEL >= 3
+#define OCLR_OUTLINE_3 __noinline__
+#else
+#define OCLR_OUTLINE_3 __forceinline__
+#endif
+#else
+#define OCLR_HD_OUT(level) inline
+#endif
 
 namespace oclr {
 
