@@ -41,7 +41,9 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in ("segments", "primCandidates", "gridRays", "cells", "cellsNonEmpty",
                                               "gridCandidates", "shadedHits", "occluderLookups", "bricksLoaded", "emptyBrickCells", "walkWarpIters", "walkLaneIters", "testWarpIters",
                                               "testLaneIters", "mailboxSkips", "coarseSteps", "coarseEnters", "switchWarpIters", "switchLaneIters", "walkIdleLanes", "walkParkedLanes", "walkFinishedLanes", "walkLowIters", "walkExhaustedIters",
-                                              "splitAttempts", "splitsDone", "splitParts", "splitCancelled")]
+                                              "splitAttempts", "splitsDone", "splitParts", "splitCancelled") +
+                                             tuple("exitHist%02d" % i for i in range(16)) + tuple("exhaustHist%02d" % i for i in range(16)) +
+                                             ("warpOuterItersMax", "warpOuterItersSum", "warpsRun")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     const float* pz = shPlanes + 2 * (n + 1);
 
     Counters cnt = {};
+    unsigned long long tWarpStart = 0, outerIters = 0;
+    bool exhaustSeen = false;
+    if (COUNT) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tWarpStart));
     PackedWalk g;
     g.level = 0;
     float maxD = 0.f;
@@ -390,6 +393,16 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
         if (__ballot_sync(0xFFFFFFFFu, ws != kWsNone) == 0u) break;
         __syncwarp();
+        if (COUNT) {
+            ++outerIters;
+            if (exhausted && !exhaustSeen && lane == 0) {   // when this warp learnt that the queue is dry
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                const unsigned long long b = (t - tWarpStart) >> 15;
+                atomicAdd(&gcnt->exhaustHist00 + (b < 15 ? b : 15), 1ull);
+            }
+            exhaustSeen = exhausted;
+        }
 
         // ---- WALK burst: step every walking lane until the cell queue is worth draining or too few lanes still walk ----------------
         for (;;) {
@@ -635,7 +648,18 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             __syncwarp();
         }
     }
-    if (COUNT) flush_counters(cnt, gcnt);
+    if (COUNT) {
+        flush_counters(cnt, gcnt);
+        if (lane == 0) {   // when this warp left (32.768-us buckets since its start; all CTAs of the persistent grid start together)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            const unsigned long long b = (t - tWarpStart) >> 15;
+            atomicAdd(&gcnt->exitHist00 + (b < 15 ? b : 15), 1ull);
+            atomicMax(&gcnt->warpOuterItersMax, outerIters);
+            atomicAdd(&gcnt->warpOuterItersSum, outerIters);
+            atomicAdd(&gcnt->warpsRun, 1ull);
+        }
+    }
 }
 
 }  // namespace oclr

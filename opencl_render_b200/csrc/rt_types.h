@@ -152,7 +152,9 @@ struct Counters {
         occluderLookups, bricksLoaded, emptyBrickCells, walkWarpIters, walkLaneIters, testWarpIters, testLaneIters,
         mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
         walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters,
-        splitAttempts, splitsDone, splitParts, splitCancelled;   // lanes of a walk iteration that were not walking, by reason
+        splitAttempts, splitsDone, splitParts, splitCancelled,
+        /* per-warp timing of the trace kernel, counting build: when warps leave / see the queue dry, 32-us buckets since their start */
+        exitHist00, exitHist01, exitHist02, exitHist03, exitHist04, exitHist05, exitHist06, exitHist07, exitHist08, exitHist09, exitHist10, exitHist11, exitHist12, exitHist13, exitHist14, exitHist15, exhaustHist00, exhaustHist01, exhaustHist02, exhaustHist03, exhaustHist04, exhaustHist05, exhaustHist06, exhaustHist07, exhaustHist08, exhaustHist09, exhaustHist10, exhaustHist11, exhaustHist12, exhaustHist13, exhaustHist14, exhaustHist15, warpOuterItersMax, warpOuterItersSum, warpsRun;   // lanes of a walk iteration that were not walking, by reason
 };
 
 }  // namespace oclr
