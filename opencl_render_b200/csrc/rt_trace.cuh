@@ -68,7 +68,8 @@ __device__ __forceinline__ int walk_length_estimate(const PackedWalk& g, int n, 
         if (!(t < OCLR_INF) || t < 0.f) t = 0.f;
         box_address(n, px, py, pz, mk3(g.o.x + t * g.r.x, g.o.y + t * g.r.y, g.o.z + t * g.r.z), ex, ey, ez);
     }
-    return abs(ex - pk_get(g.cpk, 0)) + abs(ey - pk_get(g.cpk, 1)) + abs(ez - pk_get(g.cpk, 2));
+    const int sh = g.level ? 2 : 0;   // (level 1: brick coordinates)
+    return abs(ex - (pk_get(g.cpk, 0) << sh)) + abs(ey - (pk_get(g.cpk, 1) << sh)) + abs(ez - (pk_get(g.cpk, 2) << sh));
 }
 
 __global__ void __launch_bounds__(256) wf_setup_kernel(SceneView S, WfState w, WalkRecords rec) {
@@ -247,9 +248,9 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             int best = 0, who = lane;
             if (idleNow != 0u) {
                 if (COUNT && lane == 0) cnt.splitAttempts++;
-                // a whole ray at cell level whose group record is free (a lane that headed a group before keeps that record until
+                // a whole ray (at either level of the walk) whose group record is free (a lane that headed a group before keeps that record until
                 // the group has its result), old enough when the queue still has rays
-                if (ws == kWsRun && g.level == 0 && g.coarseOk && P.grp[lane] == 0u && P.gParts[lane] == 0u &&
+                if (ws == kWsRun && g.coarseOk && P.grp[lane] == 0u && P.gParts[lane] == 0u &&
                     (exhausted || iter - P.birth[lane] >= (uint32_t)tune.splitEarly))
                     best = walk_length_estimate(g, n, px, py, pz);
 #pragma unroll
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     head.o = mk3(P.ray[0][cand], P.ray[1][cand], P.ray[2][cand]);
                     head.r = mk3(P.ray[3][cand], P.ray[4][cand], P.ray[5][cand]);
                     head.cpk = __shfl_sync(0xFFFFFFFFu, g.cpk, cand);
+                    head.level = __shfl_sync(0xFFFFFFFFu, g.level, cand);
                     head.epk = __shfl_sync(0xFFFFFFFFu, g.epk, cand);
                     head.endBrick = __shfl_sync(0xFFFFFFFFu, g.endBrick, cand);
                     const uint32_t headPath = __shfl_sync(0xFFFFFFFFu, path, cand);

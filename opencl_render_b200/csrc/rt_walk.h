@@ -287,32 +287,35 @@ OCLR_HD int pwalk_plan_parts(int c0x, int c0y, int c0z, int ex, int ey, int ez, 
 enum : uint32_t { kWalkPaused = 0xFFFFFFFEu };
 struct WalkPause {
     PackedWalk w;
-    int face;
+    int face, lastAxis;
+    float lastE;
 };
 
-// `pauseAfter` >= 0: the walk stops in front of the first level-0 cell it reaches after examining that many cells, stores its state in
-// *pause and returns kWalkPaused (test infrastructure for the run-time split).  `startFace`: entry face of the first cell (a resumed walk).
+// `pauseAfter` >= 0: the walk stops at the top of its loop -- at either level -- after that many iterations, stores its state in *pause
+// and returns kWalkPaused (test infrastructure for the run-time split).  `resume`: the state a paused walk continues from.
 template <bool COUNT>
 OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, PackedWalk w, float minD, float maxD, uint32_t excl, float& outT,
                                   float& outAB, float& outAC, Counters* cnt, int pauseAfter = -1, WalkPause* pause = nullptr,
-                                  int startFace = kFaceNone, bool brickLoaded = false) {
+                                  const WalkPause* resume = nullptr) {
     const int n = S.n;
     int nbShift = 0;
     while ((1 << nbShift) < S.nb) ++nbShift;
     const f3 o = w.o, r = w.r;
-    if (!brickLoaded) {
+    if (!resume) {
         pwalk_load_brick(w, S.bricks);
         if (COUNT) cnt->bricksLoaded++;
     }
     uint32_t mailbox[16];
     for (int k = 0; k < 16; ++k) mailbox[k] = kNoTriangle;
-    int face = startFace, lastAxis = 0;
-    float lastE = 0.f;
+    int face = resume ? resume->face : (int)kFaceNone, lastAxis = resume ? resume->lastAxis : 0;
+    float lastE = resume ? resume->lastE : 0.f;
     outT = maxD;
     for (;;) {
-        if (w.level == 0 && pauseAfter >= 0 && pauseAfter-- == 0) {
+        if (pauseAfter >= 0 && pauseAfter-- == 0) {
             pause->w = w;
             pause->face = face;
+            pause->lastAxis = lastAxis;
+            pause->lastE = lastE;
             return kWalkPaused;
         }
         if (w.level == 0) {
@@ -445,12 +448,22 @@ OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o,
 // tail: the lane that owns it keeps the first part and idle lanes of the same warp take the others, every part starting from the
 // exact state pwalk_jump computes at its stop plane.  The first part (in walk order) with a hit gives the ray's result.
 //
-// Plan for the remaining walk of `w` (level 0, all direction components non-zero, current cell not yet examined): at most
+// Plan for the remaining walk of `w` (either level, all direction components non-zero, current cell not yet examined): at most
 // `maxParts` parts of equal length along the dominant axis of the way to the end cell / the estimated exit cell.  Returns the number
 // of parts (1 = not worth cutting); cut[j] (j >= 1) = cell index along `axis` whose entry starts part j.
+// Cell index along `axis` from which the crossings still ahead of the walk are counted: the current cell at level 0; at level 1 (the
+// walk is somewhere inside an empty brick) the brick's first cell in travel direction -- every plane before it has been crossed, and
+// pwalk_count_before is a search over a monotone predicate, so a lower bound is all it needs.
+OCLR_HD int pwalk_floor_cell(const PackedWalk& w, int axis) {
+    const int c = pk_get(w.cpk, axis);
+    if (w.level == 0) return c;
+    const float r = axis == 0 ? w.r.x : (axis == 1 ? w.r.y : w.r.z);
+    return (c << 2) + ((0 <= r) ? 0 : 3);
+}
+
 OCLR_HD int pwalk_split_plan(const PackedWalk& w, int n, const float* px, const float* py, const float* pz, int maxParts, int minPartCells,
                              int& axis, int cut[kMaxWalkParts]) {
-    const int c0x = pk_get(w.cpk, 0), c0y = pk_get(w.cpk, 1), c0z = pk_get(w.cpk, 2);
+    const int c0x = pwalk_floor_cell(w, 0), c0y = pwalk_floor_cell(w, 1), c0z = pwalk_floor_cell(w, 2);
     int ex, ey, ez;
     if (w.epk != kPkNone && !pk_is_stop(w.epk)) {
         ex = pk_get(w.epk, 0);
@@ -472,7 +485,7 @@ OCLR_HD int pwalk_split_plan(const PackedWalk& w, int n, const float* px, const 
 // does not exist), with the part's own end condition.  Part 0 is the interrupted walk itself with pwalk_split_head() applied.
 OCLR_HD bool pwalk_split_part(PackedWalk& part, const PackedWalk& w, int n, int nb, const float* px, const float* py, const float* pz, int axis,
                               const int cut[kMaxWalkParts], int parts, int j) {
-    if (!pwalk_jump(part, n, nb, px, py, pz, w.o, w.r, pk_get(w.cpk, 0), pk_get(w.cpk, 1), pk_get(w.cpk, 2), axis, cut[j])) return false;
+    if (!pwalk_jump(part, n, nb, px, py, pz, w.o, w.r, pwalk_floor_cell(w, 0), pwalk_floor_cell(w, 1), pwalk_floor_cell(w, 2), axis, cut[j])) return false;
     if (j + 1 < parts) {
         part.epk = pk_stop(axis, cut[j + 1]);
         part.endBrick = -1;
@@ -504,12 +517,12 @@ OCLR_HD uint32_t grid_trace_split_mid(const SceneView& S, const float* planes, f
     PackedWalk head = pause.w;
     int axis = 0, cut[kMaxWalkParts];
     const int parts = head.coarseOk ? pwalk_split_plan(head, n, px, py, pz, maxParts, minPartCells, axis, cut) : 1;
-    if (parts < 2) return grid_walk_packed<COUNT>(S, planes, head, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, pause.face, true);
+    if (parts < 2) return grid_walk_packed<COUNT>(S, planes, head, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, &pause);
     for (int j = 0; j < parts; ++j) {
         PackedWalk part = head;
         if (j == 0) {
             pwalk_split_head(part, axis, cut);
-            hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, pause.face, true);
+            hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt, -1, nullptr, &pause);
         } else {
             if (!pwalk_split_part(part, head, n, S.nb, px, py, pz, axis, cut, parts, j)) break;
             hit = grid_walk_packed<COUNT>(S, planes, part, minD, maxD, excl, outT, outAB, outAC, cnt);

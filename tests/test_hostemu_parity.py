@@ -140,12 +140,12 @@ def test_counters_equal_instrumented_reference(name, hostemu, ref, monkeypatch):
     assert 0 <= extra <= 2 * want["shadedHits"] and (extra == 0 or name == "terrain_textured")
 
 
-@pytest.mark.parametrize("mode", [2000 + 100 * 0 + 8, 2000 + 100 * 1 + 2, 2000 + 100 * 6 + 8, 2000 + 100 * 25 + 5])
+@pytest.mark.parametrize("mode", [2000 + 100 * 0 + 8, 2000 + 100 * 1 + 2, 2000 + 100 * 3 + 8, 2000 + 100 * 6 + 8, 2000 + 100 * 12 + 4, 2000 + 100 * 25 + 5])
 @pytest.mark.parametrize("name", helpers.CASE_NAMES)
 def test_run_time_split_is_exact(name, mode, hostemu, monkeypatch):
-    """The trace kernel's run-time split (rt_walk.h pwalk_split_plan / pwalk_split_part): every walk is interrupted in front of the
-    cell it reaches after examining (mode - 2000) // 100 cells, and what is left of it is cut into up to (mode % 100) parts that
-    start from states computed WITHOUT walking from the interrupted walk's current cell; first part with a hit wins.  Planes, ids
+    """The trace kernel's run-time split (rt_walk.h pwalk_split_plan / pwalk_split_part): every walk is interrupted after
+    (mode - 2000) // 100 iterations of its loop -- at whichever level it is then, cell by cell or crossing empty bricks -- and what is
+    left of it is cut into up to (mode % 100) parts that start from states computed WITHOUT walking; first part with a hit wins.  Planes, ids
     and flags identical to the uncut reference walk; the parts together visit exactly the non-empty cells the uncut walk visits."""
     sc, cam, lists, samples = helpers.make_case(name)
     monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
