@@ -221,6 +221,7 @@ typedef struct oclr_counters {
         mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
         walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters,
         splitAttempts, splitsDone, splitParts, splitCancelled,
+        superSteps, superEnters, superRefines,   /* three-level walk: steps / level switches at super-brick granularity */
         /* per-warp timing of the trace kernel, counting build: when warps leave / see the queue dry, 32-us buckets since their start */
         exitHist00, exitHist01, exitHist02, exitHist03, exitHist04, exitHist05, exitHist06, exitHist07, exitHist08, exitHist09, exitHist10, exitHist11, exitHist12, exitHist13, exitHist14, exitHist15, exhaustHist00, exhaustHist01, exhaustHist02, exhaustHist03, exhaustHist04, exhaustHist05, exhaustHist06, exhaustHist07, exhaustHist08, exhaustHist09, exhaustHist10, exhaustHist11, exhaustHist12, exhaustHist13, exhaustHist14, exhaustHist15, warpOuterItersMax, warpOuterItersSum, warpsRun;   /* run-time split of long walks (experimental kernel instantiation) */
 } oclr_counters;
@@ -258,6 +259,9 @@ oclr_frame* oclr_frame_create(oclr_scene* scene, const oclr_camera* camera, cons
                               const cl_uint* cameraPixelTriangleListEnd, const cl_uint* cameraPixelTriangleList,
                               size_t cameraPixelTriangleListSize);
 void oclr_frame_destroy(oclr_frame* frame);
+/* Bytes of wavefront path state the frame holds in HBM (0 before its first render): about 510 B per path of the largest launch domain
+ * so far for a scene without mirror / glass materials (ring of 2 slots), about 990 B otherwise (ring of 12, raytrace_opencl.c:461-468). */
+size_t oclr_frame_state_bytes(const oclr_frame* frame);
 /* Same frame, but CameraTriangleList::New (source/util/trianglelist.cpp:520-626) runs on the device from the resident scene:
  * no host lists are needed (they are per-frame inputs; the host builder costs 0.15-0.45 s per frame).  The lists are
  * entry-for-entry those of oclr_build_camera_lists(); oclr_frame_read_camera_lists() copies them back (`list` must hold

@@ -41,7 +41,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in ("segments", "primCandidates", "gridRays", "cells", "cellsNonEmpty",
                                               "gridCandidates", "shadedHits", "occluderLookups", "bricksLoaded", "emptyBrickCells", "walkWarpIters", "walkLaneIters", "testWarpIters",
                                               "testLaneIters", "mailboxSkips", "coarseSteps", "coarseEnters", "switchWarpIters", "switchLaneIters", "walkIdleLanes", "walkParkedLanes", "walkFinishedLanes", "walkLowIters", "walkExhaustedIters",
-                                              "splitAttempts", "splitsDone", "splitParts", "splitCancelled") +
+                                              "splitAttempts", "splitsDone", "splitParts", "splitCancelled", "superSteps", "superEnters", "superRefines") +
                                              tuple("exitHist%02d" % i for i in range(16)) + tuple("exhaustHist%02d" % i for i in range(16)) +
                                              ("warpOuterItersMax", "warpOuterItersSum", "warpsRun")]
 
@@ -73,7 +73,7 @@ EXPORTS = [
     # Part 2: extension
     "oclr_last_error", "oclr_device_count", "oclr_version", "oclr_scene_create", "oclr_scene_destroy", "oclr_scene_device_bytes", "oclr_scene_debug_read",
     "oclr_set_camera", "oclr_frame_create", "oclr_frame_create_device_lists", "oclr_frame_camera_list_size",
-    "oclr_frame_read_camera_lists", "oclr_frame_destroy", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
+    "oclr_frame_read_camera_lists", "oclr_frame_destroy", "oclr_frame_state_bytes", "oclr_frame_render", "oclr_frame_render_bands", "oclr_frame_read",
     "oclr_frame_read_primary_ids", "oclr_frame_read_flags", "oclr_frame_last_launches", "oclr_frame_device_planes", "oclr_band_partition", "oclr_raytrace_all_p",
     "oclr_build_camera_lists", "oclr_build_scene_grid", "oclr_build_scene_grid_device", "oclr_free_camera_lists", "oclr_free_scene_grid",
     # progressive rendering, progress, image output
@@ -123,6 +123,8 @@ def load() -> C.CDLL:
     lib.oclr_frame_read_camera_lists.restype = C.c_int
     lib.oclr_frame_read_camera_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oclr_frame_destroy.argtypes = [C.c_void_p]
+    lib.oclr_frame_state_bytes.argtypes = [C.c_void_p]
+    lib.oclr_frame_state_bytes.restype = C.c_size_t
     lib.oclr_frame_destroy.restype = None
     lib.oclr_frame_render.restype = C.c_int
     lib.oclr_frame_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p,

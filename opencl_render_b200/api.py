@@ -310,6 +310,11 @@ class DeviceFrame:
         if not self.handle:
             raise OclrError(_lib.last_error())
 
+    @property
+    def state_bytes(self) -> int:
+        """Wavefront path state held in HBM (0 before the first render)."""
+        return int(self._lib.oclr_frame_state_bytes(self.handle))
+
     def camera_lists(self) -> "CameraLists":
         """Copies the frame's camera lists (uploaded or device-built) back to the host."""
         P = self.camera.width * self.camera.height

@@ -283,6 +283,7 @@ int oclr_frame_read_camera_lists(oclr_frame* frame, cl_uint* start, cl_uint* end
     }
     return 1;
 }
+size_t oclr_frame_state_bytes(const oclr_frame* frame) { return frame ? frame_state_bytes(frame->impl) : 0; }
 void oclr_frame_destroy(oclr_frame* frame) {
     if (!frame) return;
     frame_destroy(frame->impl);

@@ -44,6 +44,9 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g) {
     if (c.splitsDone) atomicAdd(&g->splitsDone, c.splitsDone);
     if (c.splitParts) atomicAdd(&g->splitParts, c.splitParts);
     if (c.splitCancelled) atomicAdd(&g->splitCancelled, c.splitCancelled);
+    if (c.superSteps) atomicAdd(&g->superSteps, c.superSteps);
+    if (c.superEnters) atomicAdd(&g->superEnters, c.superEnters);
+    if (c.superRefines) atomicAdd(&g->superRefines, c.superRefines);
 }
 
 // ---- kernel A: one thread per pixel, serial control flow (the straightforward restatement) --------------------

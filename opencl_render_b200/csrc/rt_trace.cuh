@@ -25,7 +25,7 @@ namespace oclr {
 // OCLR_TAIL_DRAIN / OCLR_HIERARCHICAL; the defaults are the measured optimum on config 2, flat within a few per cent).
 struct TraceTuning {
     int refillMin;     // refill from the queue once this many lanes are idle
-    int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level walk)
+    int hierarchical;  // 1: cross empty 4x4x4 bricks at brick granularity (exact two-level walk); 2: and empty super-bricks in one step
     int tailDrain;     // queue dry: drain only once this many cells wait (latency of the last long rays)
     int drainMin;      // drain the warp's cell queue at this size
     int walkMin3;      // end a walk burst below this many walking lanes
@@ -68,7 +68,7 @@ __device__ __forceinline__ int walk_length_estimate(const PackedWalk& g, int n, 
         if (!(t < OCLR_INF) || t < 0.f) t = 0.f;
         box_address(n, px, py, pz, mk3(g.o.x + t * g.r.x, g.o.y + t * g.r.y, g.o.z + t * g.r.z), ex, ey, ez);
     }
-    const int sh = g.level ? 2 : 0;   // (level 1: brick coordinates)
+    const int sh = 2 * g.level;   // (level 1: brick coordinates, level 2: super-brick coordinates)
     return abs(ex - (pk_get(g.cpk, 0) << sh)) + abs(ey - (pk_get(g.cpk, 1) << sh)) + abs(ez - (pk_get(g.cpk, 2) << sh));
 }
 
@@ -152,6 +152,9 @@ enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4, kW
 //
 // No mailbox here: pairs of one ray are tested concurrently, and face masks already remove the repeats between adjacent cells
 // (a per-lane mailbox removed 6 % more in the lane-owned kernel).
+#ifndef OCLR_SUPER_LEVEL
+#define OCLR_SUPER_LEVEL 1   /* 0 compiles the super-brick level of the walk out (A/B builds) */
+#endif
 #ifndef OCLR_CELLQ_CAP
 #define OCLR_CELLQ_CAP 96
 #endif
@@ -439,14 +442,17 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             if (walking) {
                 const bool coarse = g.level != 0;
                 const bool brickEmpty = (g.maskLo | g.maskHi) == 0u;
-                const bool inEnd = g.brick == g.endBrick;
+                const bool inEnd = g.brick == g.endBrick;   // (level 2: both are super-brick records, rt_walk.h)
                 if (COUNT && !coarse) {
                     cnt.cells++;
                     if (brickEmpty) cnt.emptyBrickCells++;
                 }
                 const bool atEnd = (!coarse) & (g.cpk == g.epk);
                 const bool needRefine = coarse & ((!brickEmpty) | inEnd);
-                const bool needEnter = (!coarse) & brickEmpty & g.coarseOk & (!inEnd) & (tune.hierarchical != 0);
+                // one level up: from the cells of an empty brick; from brick level when the record of the empty brick says that its whole
+                // super-brick is empty (bit 0 of what is the rank base of other bricks; super-brick records never carry it)
+                const bool up2 = OCLR_SUPER_LEVEL && ((g.rankBase & 1u) != 0u) & (tune.hierarchical >= 2) & !(SPLIT && pk_is_stop(g.epk));
+                const bool needEnter = brickEmpty & g.coarseOk & (!inEnd) & (tune.hierarchical != 0) & ((!coarse) | up2);
                 if (atEnd) {
                     ws = kWsFinished;
                 } else if (needRefine | needEnter) {
@@ -455,6 +461,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     int up;
                     bool crossed;
                     if (COUNT && coarse) cnt.coarseSteps++;
+                    if (COUNT && g.level == 2) cnt.superSteps++;
                     if (!pwalk_step(g, n, nbShift, shPlanes, lastAxis, up, lastE, crossed)) {
                         ws = kWsFinished;
                     } else if (SPLIT && pk_is_stop(g.epk) && pwalk_stopped(g, lastAxis, up)) {
@@ -488,11 +495,28 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     if ((ws == kWsRefine) | (ws == kWsEnter)) cnt.switchLaneIters++;
                 }
                 if (ws == kWsEnter) {
-                    pwalk_enter_coarse(g, n, shPlanes);
+                    if (g.level == 0) {
+                        pwalk_enter_coarse(g, n, nbShift, shPlanes);
+                        if (COUNT) cnt.coarseEnters++;
+                    }
+                    if (OCLR_SUPER_LEVEL && tune.hierarchical >= 2 && (g.rankBase & 1u) != 0u) {   // (straight on to level 2 when the flag says so)
+                        if (pwalk_super_allowed(g)) {
+                            pwalk_enter_coarse(g, n, nbShift, shPlanes);
+                            if (COUNT) cnt.superEnters++;
+                        } else {
+                            g.rankBase = 0u;   // the end cell's super-brick: brick by brick (the next brick's record asks again)
+                        }
+                    }
                     ws = kWsRun;
-                    if (COUNT) cnt.coarseEnters++;
                 } else if (ws == kWsRefine) {
-                    pwalk_refine(g, n, shPlanes, lastAxis, lastE);
+                    pwalk_refine(g, n, nbShift, shPlanes, lastAxis, lastE);
+                    if (OCLR_SUPER_LEVEL && g.level == 1) {   // back from the super-brick level: the brick the walk stands in is new to it
+                        pwalk_load_brick(g, S.bricks);
+                        if (COUNT) {
+                            cnt.bricksLoaded++;
+                            cnt.superRefines++;
+                        }
+                    }
                     face = kFaceNone;
                     ws = kWsRun;
                 }

@@ -63,6 +63,16 @@
 #else
 #define OCLR_HD_OUT(level) inline
 #endif
+// Level switches of the walk (rt_walk.h: 3 + 6 IEEE divisions, ~20 % of the trace kernel's code, run by 10 lanes at a time):
+// OCLR_OUTLINE_SWITCH=1 makes them real functions (A/B builds).
+#ifndef OCLR_OUTLINE_SWITCH
+#define OCLR_OUTLINE_SWITCH 0
+#endif
+#if defined(__CUDACC__) && OCLR_OUTLINE_SWITCH
+#define OCLR_HD_SW __host__ __device__ __noinline__
+#else
+#define OCLR_HD_SW OCLR_HD
+#endif
 
 namespace oclr {
 
@@ -153,6 +163,7 @@ struct Counters {
         mailboxSkips, coarseSteps, coarseEnters, switchWarpIters, switchLaneIters,
         walkIdleLanes, walkParkedLanes, walkFinishedLanes, walkLowIters, walkExhaustedIters,
         splitAttempts, splitsDone, splitParts, splitCancelled,
+        superSteps, superEnters, superRefines,   /* three-level walk: steps / level switches at super-brick granularity */
         /* per-warp timing of the trace kernel, counting build: when warps leave / see the queue dry, 32-us buckets since their start */
         exitHist00, exitHist01, exitHist02, exitHist03, exitHist04, exitHist05, exitHist06, exitHist07, exitHist08, exitHist09, exitHist10, exitHist11, exitHist12, exitHist13, exitHist14, exitHist15, exhaustHist00, exhaustHist01, exhaustHist02, exhaustHist03, exhaustHist04, exhaustHist05, exhaustHist06, exhaustHist07, exhaustHist08, exhaustHist09, exhaustHist10, exhaustHist11, exhaustHist12, exhaustHist13, exhaustHist14, exhaustHist15, warpOuterItersMax, warpOuterItersSum, warpsRun;   // lanes of a walk iteration that were not walking, by reason
 };

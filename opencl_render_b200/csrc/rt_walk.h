@@ -6,8 +6,8 @@
 // (tests/test_hostemu_parity.py).  The exactness argument of the two-level walk is the one written above
 // walk_enter_coarse() in rt_core.h; this file only changes the bookkeeping:
 //
-//   cpk     cell coordinates (level 0) or 4x4x4-brick coordinates (level 1), 10 bits per axis: x | y << 10 | z << 20
-//           (axesDivCount <= 1024; the plugin passes 256, render.cpp:1334);
+//   cpk     cell coordinates (level 0), 4x4x4-brick coordinates (level 1) or super-brick coordinates (level 2: 4x4x4 bricks =
+//           16x16x16 cells), 10 bits per axis: x | y << 10 | z << 20 (axesDivCount <= 1024; the plugin passes 256, render.cpp:1334);
 //   brick   linear id of the brick the walk is in, updated by +-nb^axis only when a step crosses a brick face, so the
 //           16-byte brick record is fetched exactly once per brick;
 //   step    axis = argmin of the three next-crossing values with the reference's tie rule (x only if strictly smallest,
@@ -29,17 +29,42 @@ OCLR_HD int pk_get(uint32_t pk, int axis) { return (int)((pk >> (axis * kPkBits)
 OCLR_HD uint32_t pk_stop(int axis, int cellIndex) { return 0x80000000u | ((uint32_t)axis << kPkBits) | (uint32_t)cellIndex; }
 OCLR_HD bool pk_is_stop(uint32_t epk) { return (epk >> 30) == 2u; }
 
+// Three-level walk.  The argument that makes the brick-level walk exact (rt_core.h, walk_enter_coarse: the walk is a 3-way merge of
+// per-axis crossing sequences whose order depends on values and the tie rule alone, so the merge of every 4th plane visits the bricks
+// the cell walk visits, in its order, with the same crossing values) holds for any subsequence of the planes, hence also for every
+// 16th: an entirely empty SUPER-BRICK (4x4x4 bricks) is crossed in one step and the brick-level state is rebuilt on entering a
+// super-brick that holds triangles -- or the ray's end cell -- by the same refinement that rebuilds the cell state inside a brick.
+//
+// Kept out of the hot loop (a first version that told the levels apart there cost config 2, whose super-bricks are all occupied, 5 %):
+//   * super-brick records {non-empty, 0, 0, 0} live behind the nb^3 brick records of the same array at the BRICK strides -- record of
+//     super-brick (sx, sy, sz) = nb^3 + sx + nb * (sy + nb * sz) -- so the incremental id update of a step is the same at every level;
+//   * an EMPTY brick's record carries in .z (the rank base nobody reads: the brick has no cells to rank) bit 0 = "my whole super-brick
+//     is empty"; pack_grid / super_brick_kernel decide, the walk only obeys, and the flag is never set on a grid without this level;
+//   * while the walk is at level 2 `endBrick` holds the record index of the END CELL's super-brick (swapped on the level switch), so
+//     "never skip the end" is the same comparison at every level.
+// Config 3: 65 of 130 steps per path are brick-level steps, 41 with this level (config 2: 39 of 106, 35).
 struct PackedWalk {
     f3 o, r;
     float tx, ty, tz;    // next crossing per axis at the current level
-    uint32_t cpk;        // current cell (level 0) / brick (level 1)
+    uint32_t cpk;        // current cell (level 0) / brick (level 1) / super-brick (level 2)
     uint32_t epk;        // end cell, or kPkNone
-    int brick;           // linear id of the current brick
-    int endBrick;        // brick of the end cell (walked cell by cell, never skipped), or -1
-    uint32_t maskLo, maskHi, rankBase;   // record of `brick`
-    int level;           // 0: cells, 1: bricks
+    int brick;           // index of the current brick's record; level 2: of the current super-brick's record
+    int endBrick;        // brick (level 2: super-brick) of the end cell -- walked at the finer level, never skipped --, or -1
+    uint32_t maskLo, maskHi, rankBase;   // record of `brick`; empty brick: bit 0 of rankBase = the whole super-brick is empty
+    int level;           // 0: cells, 1: bricks, 2: super-bricks
     bool coarseOk;       // all direction components non-zero and n >= 4
 };
+
+// Super-brick coordinates (packed, 10-bit fields) of a packed cell / brick coordinate.
+OCLR_HD uint32_t pk_super_of_cell(uint32_t pk) { return (pk >> 4) & 0x03F0FC3Fu; }
+OCLR_HD uint32_t pk_super_of_brick(uint32_t pk) { return (pk >> 2) & 0x0FF3FCFFu; }
+// Index of a super-brick's record in the brick array (nb = 1 << nbShift bricks per axis; brick strides, see above).
+OCLR_HD int pk_super_record(uint32_t spk, int nbShift) {
+    return (1 << (3 * nbShift)) + (int)((spk & kPkMask) + ((((spk >> kPkBits) & kPkMask) + (((spk >> (2 * kPkBits)) & kPkMask) << nbShift)) << nbShift));
+}
+OCLR_HD int pk_brick_record(uint32_t cellPk, int nbShift) {
+    return (pk_get(cellPk, 0) >> 2) + (((pk_get(cellPk, 1) >> 2) + ((pk_get(cellPk, 2) >> 2) << nbShift)) << nbShift);
+}
 
 // Ray -> initial walk state: raytrace_opencl.c:350-362 (BindInCube on start and end, GetBoxAddress) + the first three crossing values.
 OCLR_HD void pwalk_setup(PackedWalk& w, int n, int nb, const float* px, const float* py, const float* pz, f3 o, f3 r, float minD,
@@ -77,6 +102,12 @@ OCLR_HD void pwalk_load_brick(PackedWalk& w, const uint4* bricks) {
     w.maskLo = br.x;
     w.maskHi = br.y;
     w.rankBase = br.z;
+}
+// At level 1 in an empty brick whose record says "the whole super-brick is empty": may the walk go on super-brick by super-brick?
+// Not through the super-brick that holds the end cell (it would be skipped), and not as a part of a cut walk (a part ends at a plane
+// only brick-level steps are sure to land on).  kPkNone gives a coordinate only a 1024^3 grid has: a refusal too many there.
+OCLR_HD bool pwalk_super_allowed(const PackedWalk& w) {
+    return (pk_super_of_brick(w.cpk) != pk_super_of_cell(w.epk)) & !pk_is_stop(w.epk);
 }
 
 // Bit of the current cell inside its brick's occupancy mask: (x & 3) | (y & 3) << 2 | (z & 3) << 4.
@@ -117,28 +148,35 @@ OCLR_HD bool pwalk_step(PackedWalk& w, int n, int nbShift, const float* planes, 
     w.ty = ymin ? t : w.ty;
     w.tz = (xmin | ymin) ? w.tz : t;
     crossed = (w.level != 0) | (((c ^ cn) & ~3) != 0);
-    if (crossed) w.brick += dir * (1 << (axis * nbShift));
+    if (crossed) w.brick += dir * (1 << (axis * nbShift));   // (the same at level 2: super-brick records sit at the brick strides)
     return true;
 }
 
 // After a successful step along `axis`: did the walk just cross into the cell index at which this part ends?
 OCLR_HD bool pwalk_stopped(const PackedWalk& w, int axis, int up) {
     if (!pk_is_stop(w.epk) || (int)((w.epk >> kPkBits) & 3u) != axis) return false;
-    const int c = pk_get(w.cpk, axis);
-    const int cell = w.level ? (up ? (c << 2) : (c << 2) + 3) : c;
+    const int c = pk_get(w.cpk, axis), lsh = 2 * w.level;
+    const int cell = up ? (c << lsh) : (c << lsh) + (1 << lsh) - 1;
     return cell == (int)(w.epk & kPkMask);
 }
 
-// Level 0 -> level 1 inside an empty brick: coordinates become brick coordinates, the heads become the brick-exit crossings.
-OCLR_HD void pwalk_enter_coarse(PackedWalk& w, int n, const float* planes) {
+// One level up inside an empty brick (0 -> 1) / an empty super-brick (1 -> 2): coordinates become those of the coarser level, the
+// heads become the crossings that leave the brick / super-brick.
+OCLR_HD_SW void pwalk_enter_coarse(PackedWalk& w, int n, int nbShift, const float* planes) {
     w.cpk = (w.cpk >> 2) & 0x0FF3FCFFu;
+    w.level += 1;
+    const int lsh = 2 * w.level;
     const float* px = planes;
     const float* py = planes + (n + 1);
     const float* pz = planes + 2 * (n + 1);
-    w.tx = (px[(pk_get(w.cpk, 0) + (0 <= w.r.x)) << 2] - w.o.x) / w.r.x;
-    w.ty = (py[(pk_get(w.cpk, 1) + (0 <= w.r.y)) << 2] - w.o.y) / w.r.y;
-    w.tz = (pz[(pk_get(w.cpk, 2) + (0 <= w.r.z)) << 2] - w.o.z) / w.r.z;
-    w.level = 1;
+    w.tx = (px[(pk_get(w.cpk, 0) + (0 <= w.r.x)) << lsh] - w.o.x) / w.r.x;
+    w.ty = (py[(pk_get(w.cpk, 1) + (0 <= w.r.y)) << lsh] - w.o.y) / w.r.y;
+    w.tz = (pz[(pk_get(w.cpk, 2) + (0 <= w.r.z)) << lsh] - w.o.z) / w.r.z;
+    if (w.level == 2) {   // (its record says "empty", like the masks the walk holds)
+        w.brick = pk_super_record(w.cpk, nbShift);
+        w.endBrick = w.epk == kPkNone ? -1 : pk_super_record(pk_super_of_cell(w.epk), nbShift);
+        w.rankBase = 0u;
+    }
 }
 
 // One axis of the refinement, select-only form of refine_axis() / the entry-axis case of walk_refine() (rt_core.h): every lane of a
@@ -146,35 +184,42 @@ OCLR_HD void pwalk_enter_coarse(PackedWalk& w, int n, const float* planes) {
 // profiles/r01d_wf_pipe_cfg2_phases.txt).  For the entry axis the answer is "first cell in travel direction, next crossing = the
 // plane that cell is left through" -- exactly what the probe sequence yields when both probes are forced to "not before E" (the
 // second probe then reads crossing 0, the very plane the entry case divides by), so forcing the predicates is all it takes.
-OCLR_HD void prefine_axis(bool entry, int b, float tExit, float o, float r, const float* p, float E, bool strict, int& cell, float& tNext) {
+// `psh`: the planes of the level being entered are every (1 << psh)-th cell plane (0: cells inside a brick, 2: bricks inside a super-brick).
+OCLR_HD void prefine_axis(bool entry, int b, float tExit, float o, float r, const float* p, float E, bool strict, int psh, int& cell, float& tNext) {
     const int up = (0 <= r) ? 1 : 0;
     const int base = b << 2;
-    const float t1 = (p[base + 2] - o) / r;
+    const float t1 = (p[(base + 2) << psh] - o) / r;
     const bool pre1 = (!entry) & (strict ? (t1 < E) : (t1 <= E));
     const int p2 = (pre1 == (up != 0)) ? base + 3 : base + 1;   // pre1: crossing 2 (up: base+3, down: base+1); else crossing 0 (up: base+1, down: base+3)
-    const float t2 = (p[p2] - o) / r;
+    const float t2 = (p[p2 << psh] - o) / r;
     const bool pre2 = (!entry) & (strict ? (t2 < E) : (t2 <= E));
     const int j = (pre1 ? 2 : 0) + (pre2 ? 1 : 0);
     tNext = pre1 ? (pre2 ? tExit : t2) : (pre2 ? t1 : t2);
     cell = up ? base + j : base + 3 - j;
 }
 
-// Level 1 -> level 0 after the brick-level step along `axis` (crossing value E) entered a brick that has to be walked cell
-// by cell: the exact cell state the cell-level walk would have on entering this brick (rt_core.h: walk_refine).
-OCLR_HD void pwalk_refine(PackedWalk& w, int n, const float* planes, int axis, float E) {
+// One level down after the step along `axis` (crossing value E) entered a brick that has to be walked cell by cell (1 -> 0) / a
+// super-brick that has to be walked brick by brick (2 -> 1): the exact state the finer walk would have on entering it (rt_core.h:
+// walk_refine).  Arriving at level 1 the brick id is recomputed; its record is the caller's to load.
+OCLR_HD_SW void pwalk_refine(PackedWalk& w, int n, int nbShift, const float* planes, int axis, float E) {
     const float* px = planes;
     const float* py = planes + (n + 1);
     const float* pz = planes + 2 * (n + 1);
+    const int psh = 2 * (w.level - 1);
     int cx, cy, cz;
     float tx, ty, tz;
-    prefine_axis(axis == 0, pk_get(w.cpk, 0), w.tx, w.o.x, w.r.x, px, E, true, cx, tx);       // x precedes y / z crossings only when strictly smaller
-    prefine_axis(axis == 1, pk_get(w.cpk, 1), w.ty, w.o.y, w.r.y, py, E, axis == 2, cy, ty);  // y: "<= E" against x, "< E" against z
-    prefine_axis(axis == 2, pk_get(w.cpk, 2), w.tz, w.o.z, w.r.z, pz, E, false, cz, tz);      // z wins ties against x and y
+    prefine_axis(axis == 0, pk_get(w.cpk, 0), w.tx, w.o.x, w.r.x, px, E, true, psh, cx, tx);       // x precedes y / z crossings only when strictly smaller
+    prefine_axis(axis == 1, pk_get(w.cpk, 1), w.ty, w.o.y, w.r.y, py, E, axis == 2, psh, cy, ty);  // y: "<= E" against x, "< E" against z
+    prefine_axis(axis == 2, pk_get(w.cpk, 2), w.tz, w.o.z, w.r.z, pz, E, false, psh, cz, tz);      // z wins ties against x and y
     w.cpk = pk_make(cx, cy, cz);
     w.tx = tx;
     w.ty = ty;
     w.tz = tz;
-    w.level = 0;
+    w.level -= 1;
+    if (w.level == 1) {
+        w.brick = cx + ((cy + (cz << nbShift)) << nbShift);
+        w.endBrick = w.epk == kPkNone ? -1 : pk_brick_record(w.epk, nbShift);
+    }
 }
 
 // Position of the k-th still-untested list entry at or after `k` (rt_wavefront.cuh next_candidate, serial form without a mailbox).
@@ -352,18 +397,33 @@ OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, Packe
             }
             if (w.cpk == w.epk) break;
             if (((w.maskLo | w.maskHi) == 0u) & w.coarseOk & (w.brick != w.endBrick)) {
-                pwalk_enter_coarse(w, n, planes);
+                pwalk_enter_coarse(w, n, nbShift, planes);
                 if (COUNT) cnt->coarseEnters++;
                 continue;
             }
         } else if (((w.maskLo | w.maskHi) != 0u) | (w.brick == w.endBrick)) {
-            pwalk_refine(w, n, planes, lastAxis, lastE);
+            pwalk_refine(w, n, nbShift, planes, lastAxis, lastE);
+            if (w.level == 1) {
+                pwalk_load_brick(w, S.bricks);
+                if (COUNT) {
+                    cnt->bricksLoaded++;
+                    cnt->superRefines++;
+                }
+            }
             face = kFaceNone;
             continue;
+        } else if ((w.rankBase & 1u) != 0u) {   // (level 1, empty brick: the flag of its record)
+            if (pwalk_super_allowed(w)) {
+                pwalk_enter_coarse(w, n, nbShift, planes);
+                if (COUNT) cnt->superEnters++;
+                continue;
+            }
+            w.rankBase = 0u;   // refused: through this brick at brick level (its neighbour's record raises the question again)
         }
         int up;
         bool crossed;
         if (COUNT && w.level) cnt->coarseSteps++;
+        if (COUNT && w.level == 2) cnt->superSteps++;
         if (!pwalk_step(w, n, nbShift, planes, lastAxis, up, lastE, crossed)) break;
         if (pwalk_stopped(w, lastAxis, up)) break;   // this part of the walk ends here; the cell belongs to the next part
         face = w.level ? (int)kFaceNone : lastAxis * 2 + up;
@@ -458,11 +518,13 @@ OCLR_HD int pwalk_floor_cell(const PackedWalk& w, int axis) {
     const int c = pk_get(w.cpk, axis);
     if (w.level == 0) return c;
     const float r = axis == 0 ? w.r.x : (axis == 1 ? w.r.y : w.r.z);
-    return (c << 2) + ((0 <= r) ? 0 : 3);
+    const int lsh = 2 * w.level;
+    return (c << lsh) + ((0 <= r) ? 0 : (1 << lsh) - 1);
 }
 
 OCLR_HD int pwalk_split_plan(const PackedWalk& w, int n, const float* px, const float* py, const float* pz, int maxParts, int minPartCells,
                              int& axis, int cut[kMaxWalkParts]) {
+    if (w.level == 2) return 1;   // (a part ends at a plane super-brick steps can jump: the walk is cut once it is back at brick level)
     const int c0x = pwalk_floor_cell(w, 0), c0y = pwalk_floor_cell(w, 1), c0z = pwalk_floor_cell(w, 2);
     int ex, ey, ez;
     if (w.epk != kPkNone && !pk_is_stop(w.epk)) {

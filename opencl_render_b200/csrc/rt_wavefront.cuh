@@ -45,7 +45,8 @@ struct WfState {
     uint32_t* ctl;       // stage | begin << 4 | end << 8 | light << 12
     uint64_t* rng;
     float4* colour;
-    float4* ring;        // [slot * 3 + part][Q]
+    float4* ring;        // [slot * 3 + part][Q], slot < ringSlots
+    uint32_t ringSlots;  // kRingSize, or 2 for a scene without mirror / glass materials (runtime.cu, Scene::ringSlots)
     float4* carry;       // [part][Q], part < 7
     // two ray slots per path, slot-major [slot * Q + path]: slot 0 = the query the path is suspended on, slot 1 = the closest-hit
     // query of the NEXT ring segment traced one round ahead.  Queue entries are these flat indices (the trace stage knows no paths).
@@ -69,6 +70,7 @@ struct Segment {
 };
 
 __device__ __forceinline__ void ring_store(const WfState& w, uint32_t q, int slot, const Segment& s) {
+    if ((uint32_t)slot >= w.ringSlots) __trap();   // (unreachable: the slot count follows from the material table the spawn rules read)
     float4* p = w.ring + (size_t)(slot * kRingParts) * w.Q + q;
     p[0] = make_float4(s.o.x, s.o.y, s.o.z, s.v.x);
     p[w.Q] = make_float4(s.v.y, s.v.z, s.mul.x, s.mul.y);

@@ -651,6 +651,11 @@ struct Scene {
     SceneView view = {};
     size_t bytes = 0;
     int smCount = 148;
+    // Ring slots a path of this scene can occupy (rt_wavefront.cuh): only mirror / glass segments (raytrace_opencl.c:682-722) push the
+    // ring beyond {current segment, its diffuse bounce} -- a scene in which no material has a reflection or a transparency channel
+    // (or only all-black ones, the plugin's 1x1 fallback) never touches slot 2, so its frames allocate 2 slots (96 B per path)
+    // instead of kRingSize (576 B)
+    int ringSlots = kRingSize;
 };
 
 // Wavefront path state of one slice of a launch domain (launch_wavefront): its own buffers, queue counters and stream, so
@@ -1013,6 +1018,23 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     const size_t N = h.triangleCount;
     const int n = h.axesDivCount, nb = n >= 4 ? n / 4 : 1;
     const size_t cells = (size_t)n * n * n, nBricks = (size_t)nb * nb * nb;
+    const int ns = super_bricks_per_axis(n);   // super-brick records of the three-level walk follow the brick records (rt_walk.h)
+    const size_t nSuper = super_brick_records(n);
+    // ring depth of this scene's paths (host data only, and decided before the early hook below starts a frame on the scene)
+    s->ringSlots = 2;
+    for (uint32_t m = 0; m < h.materialCount && s->ringSlots == 2; ++m)
+        for (int ch : {(int)kChReflection, (int)kChTransparency}) {
+            // a channel that is present but black everywhere (the plugin's 1x1 fallback for "no reflection") spawns nothing either: the
+            // segment multiplier is 0 < 3/256 (:684, :703).  Large maps are not scanned: taken as "may be non-zero"
+            const uint2 size = h.matSize[kMaterialChannels * m + ch];
+            const size_t texels = (size_t)size.x * size.y;
+            if (texels == 0) continue;
+            bool black = texels <= ((size_t)1 << 20);
+            const uchar4* t = h.textures + h.matStart[kMaterialChannels * m + ch];
+            for (size_t i = 0; black && i < texels; ++i) black = (t[i].x | t[i].y | t[i].z) == 0;
+            if (!black) s->ringSlots = kRingSize;
+        }
+    if (const char* v = getenv("OCLR_RING_SLOTS")) s->ringSlots = std::max(s->ringSlots, std::min(atoi(v), (int)kRingSize));   // (test knob: more, never fewer)
     uint32_t total = buildGrid ? 0u : h.gridStart[cells];
     if (total && !h.gridList) {
         err = "scenePixelTriangleList missing";
@@ -1097,7 +1119,7 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
                                   : (boxMin.upload(h.boxMin, sizeof(float4) * (n + 1), err) &&
                                      gridStart.upload(h.gridStart, sizeof(uint32_t) * (cells + 1), err) &&
                                      s->cellList.upload(h.gridList, sizeof(uint32_t) * total, err)))) &&
-         s->bricks.alloc(sizeof(uint4) * nBricks, err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
+         s->bricks.alloc(sizeof(uint4) * (nBricks + nSuper), err) && s->planes.alloc(sizeof(float) * 3 * (n + 1), err) &&
          counts.alloc(sizeof(uint32_t) * (nBricks + 1), err) && rankBase.alloc(sizeof(uint32_t) * (nBricks + 1), err);
     uint32_t nonEmpty = 0, flag = 0;
     if (ok && buildGrid) {
@@ -1147,6 +1169,8 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
             brick_write_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (const uint32_t*)rankBase.p,
                                                                           (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (uint32_t*)cellIds.p,
                                                                           (uint32_t*)errFlag.p);
+            if (nSuper) cudaMemsetAsync((uint4*)s->bricks.p + nBricks, 0, sizeof(uint4) * nSuper, 0);
+            super_brick_kernel<<<ns ? (unsigned)(ns * ns * ns) : (unsigned)((nBricks + 63) / 64), 64>>>((uint4*)s->bricks.p, nb, ns, super_policy());
             if (nonEmpty)
                 face_mask_kernel<<<(unsigned)(((size_t)nonEmpty * 6 + 255) / 256), 256>>>((const uint32_t*)gridStart.p, n, total, nonEmpty,
                                                                                          (const uint32_t*)cellIds.p, (const uint2*)s->cellRange.p,
@@ -1220,6 +1244,14 @@ void scene_destroy(Scene* s) {
 }
 
 size_t scene_device_bytes(const Scene* s) { return s->bytes; }
+// Wavefront path state a frame holds in HBM (all slices: ring, carry, ray / hit slots, walk records, queue) -- what a launch domain
+// of `capacity` paths costs; 0 before the first render.
+size_t frame_state_bytes(Frame* f) {
+    size_t n = 0;
+    for (WfSlice& sl : f->slices)
+        for (int i = 0; sl.buffers(i); ++i) n += sl.buffers(i)->bytes;
+    return n;
+}
 
 // Debug/test door: copies one packed device array back (0 triGeo, 1 triShade, 2 bricks, 3 cellRange, 4 planes, 5 cellList).
 size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap) {
@@ -1590,7 +1622,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
             for (int i = 0; sl.buffers(i); ++i) sl.buffers(i)->release(st);
             const size_t q = Q;
             if (!sl.ctl.alloc(sizeof(uint32_t) * q, err, st) || !sl.rng.alloc(sizeof(uint64_t) * q, err, st) ||
-                !sl.colour.alloc(sizeof(float4) * q, err, st) || !sl.ring.alloc(sizeof(float4) * q * kRingSize * kRingParts, err, st) ||
+                !sl.colour.alloc(sizeof(float4) * q, err, st) || !sl.ring.alloc(sizeof(float4) * q * (size_t)f->scene->ringSlots * kRingParts, err, st) ||
                 !sl.carry.alloc(sizeof(float4) * q * kCarryParts, err, st) ||
                 // two ray slots per path (rt_wavefront.cuh: the next segment's closest hit is traced one round ahead)
                 !sl.rayO.alloc(sizeof(float4) * 2 * q, err, st) || !sl.rayD.alloc(sizeof(float4) * 2 * q, err, st) ||
@@ -1611,6 +1643,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         w[k].rng = (uint64_t*)sl.rng.p;
         w[k].colour = (float4*)sl.colour.p;
         w[k].ring = (float4*)sl.ring.p;
+        w[k].ringSlots = (uint32_t)f->scene->ringSlots;
         w[k].carry = (float4*)sl.carry.p;
         w[k].rayO = (float4*)sl.rayO.p;
         w[k].rayD = (float4*)sl.rayD.p;
@@ -1648,7 +1681,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
         TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
-        t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 1;
+        t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 2;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 64), (int)kCellQCap - 31);   // (round 2 sweep: 64 is ~1 % faster than 48 on configs 2 and 3)
         t.walkMin3 = env("OCLR_WALK_MIN3", 8);
         t.switchMin = env("OCLR_SWITCH_MIN", 6);

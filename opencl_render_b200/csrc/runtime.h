@@ -52,6 +52,11 @@ struct PackedGrid {
 };
 void pack_triangles(const HostScene& h, float4* triGeo /*4N*/, float4* triShade /*8N*/, int threads);
 bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err);
+// super-brick level of the three-level walk (rt_walk.h): records appended to the brick array, flags in the empty bricks' .w
+int super_bricks_per_axis(int n);   // n / 16 for power-of-two grids of >= 32 cells per axis, else 0 (no super-brick level)
+size_t super_brick_records(int n);  // records behind the nb^3 brick records (super-brick records sit at the brick strides)
+int super_policy();                 // OCLR_SUPER: 0 = never enter the super-brick level, 1 (default) = in every empty super-brick
+void append_super_bricks(std::vector<uint4>& bricks, int n, int nb, int policy);
 void pack_lights(const HostScene& h, std::vector<Light>& out);
 // gridMayBeMissing: sceneBoxMin == scenePixelTriangleListStart == NULL is accepted (the device runtime then builds the grid itself)
 bool validate_scene(const HostScene& h, std::string& err, bool gridMayBeMissing = false);
@@ -97,6 +102,7 @@ Scene* scene_create(int device, const HostScene& h, std::string& err, const std:
                     UploadShare* share = nullptr);
 void scene_destroy(Scene* s);
 size_t scene_device_bytes(const Scene* s);
+size_t frame_state_bytes(Frame* f);
 int scene_device(const Scene* s);
 size_t scene_debug_read(Scene* s, int which, void* dst, size_t cap);
 

@@ -2,6 +2,7 @@
 // the GPU layout of rt_types.h.  Compiled with g++ -ffp-contract=off: the hoisted per-triangle terms must be the
 // exact fp32 values the reference's RayIntersectsTriangle would compute per ray (raytrace_opencl.c:131-149).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <thread>
@@ -174,7 +175,50 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
         out.cellRange.push_back(make_uint2(0, 0));
         out.faceMask.assign(6, 0xFFFFFFFFu);
     }
+    append_super_bricks(out.bricks, n, nb, super_policy());
     return true;
+}
+
+// Super-brick level of the three-level walk (rt_walk.h).  Behind the nb^3 brick records: the record {non-empty, 0, 0, 0} of super-brick
+// (sx, sy, sz) at nb^3 + sx + nb * (sy + nb * sz) -- the brick strides, so a step updates the record index the same way at every level;
+// the slots between them stay zero.  In the record of an EMPTY brick .z (a rank base nobody reads) becomes the flag "my whole
+// super-brick is empty: cross it in one step".  Only for power-of-two grids of at least 32 cells per axis.
+int super_bricks_per_axis(int n) { return (n >= 32 && (n & (n - 1)) == 0) ? n / 16 : 0; }
+size_t super_brick_records(int n) {   // records appended to the brick array
+    const size_t ns = (size_t)super_bricks_per_axis(n), nb = (size_t)n / 4;
+    return ns * nb * nb;
+}
+
+int super_policy() {   // (read per scene, not cached: tests switch it between two scenes of one process)
+    const char* e = getenv("OCLR_SUPER");
+    return e ? atoi(e) : 1;
+}
+
+void append_super_bricks(std::vector<uint4>& bricks, int n, int nb, int policy) {
+    const int ns = super_bricks_per_axis(n);
+    const size_t nBricks = (size_t)nb * nb * nb;
+    bricks.resize(nBricks + super_brick_records(n), make_uint4(0, 0, 0, 0));
+    for (int sz = 0; sz < ns; ++sz)
+        for (int sy = 0; sy < ns; ++sy)
+            for (int sx = 0; sx < ns; ++sx) {
+                uint32_t any = 0;
+                for (int z = 0; z < 4; ++z)
+                    for (int y = 0; y < 4; ++y)
+                        for (int x = 0; x < 4; ++x) {
+                            const uint4& b = bricks[(size_t)(sx * 4 + x) + (size_t)nb * ((sy * 4 + y) + (size_t)nb * (sz * 4 + z))];
+                            any |= b.x | b.y;
+                        }
+                bricks[nBricks + (size_t)sx + (size_t)nb * (sy + (size_t)nb * sz)] = make_uint4(any ? 1u : 0u, 0, 0, 0);
+                for (int z = 0; z < 4; ++z)
+                    for (int y = 0; y < 4; ++y)
+                        for (int x = 0; x < 4; ++x) {
+                            uint4& b = bricks[(size_t)(sx * 4 + x) + (size_t)nb * ((sy * 4 + y) + (size_t)nb * (sz * 4 + z))];
+                            if ((b.x | b.y) == 0u) b.z = (any == 0u && policy > 0) ? 1u : 0u;
+                        }
+            }
+    if (ns == 0)   // no super-brick level: the flag is never raised
+        for (size_t b = 0; b < nBricks; ++b)
+            if ((bricks[b].x | bricks[b].y) == 0u) bricks[b].z = 0u;
 }
 
 void pack_lights(const HostScene& h, std::vector<Light>& out) {

@@ -8,5 +8,6 @@ for setting in sys.argv[3:]:
     for kv in setting.split():
         k, v = kv.split("="); env[k] = v
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_target_band.py"), cfg, world, "6"], env=env, capture_output=True, text=True)
-    best = min((l for l in out.stdout.strip().splitlines()), key=lambda l: float(l.split(":")[1].split("ms")[0]), default=out.stderr[-300:])
+    best = min((l for l in out.stdout.strip().splitlines() if " ms" in l), key=lambda l: float(l.split(":")[1].replace("BEST", "").split("ms")[0]),
+               default=out.stderr[-300:])
     print(f"--- {setting}: {best}", flush=True)

@@ -155,6 +155,58 @@ def test_tracing_one_round_ahead_is_invisible(mode):
         api.set_option("ahead", -1)
 
 
+def test_super_brick_level_of_the_walk_is_invisible(monkeypatch):
+    """rt_walk.h, three-level walk: entirely empty super-bricks (4x4x4 bricks) are crossed in one step.  A scene packed with
+    OCLR_SUPER=0 (the flag the walk obeys is never raised: two-level walk) and the same scene packed by default give identical planes,
+    ids and flags; the default really takes super-brick steps and loads fewer brick records."""
+    for name in ("soup", "soup_mirror_glass", "terrain_textured", "soup_axis_light", "soup_s4", "coarse_grid"):
+        sc, cam, lists, samples = helpers.make_case(name)
+        out = {}
+        for policy in ("0", "1"):
+            monkeypatch.setenv("OCLR_SUPER", policy)
+            ds = api.DeviceScene(sc, 0)
+            fr = api.DeviceFrame(ds, cam, lists)
+            _, _, cnt = fr.render(samples, count=True)
+            out[policy] = (fr.read(), fr.primary_ids(), fr.undefined_flags(), cnt)
+            fr.close()
+            ds.close()
+        two, three = out["0"], out["1"]
+        assert _equal(two[0], three[0]) and np.array_equal(two[1], three[1]) and np.array_equal(two[2], three[2]), name
+        assert two[3]["superSteps"] == 0 and two[3]["superEnters"] == 0
+        if sc.axes_div >= 256:
+            assert three[3]["superSteps"] > 0 and three[3]["coarseSteps"] < two[3]["coarseSteps"], name
+            assert three[3]["bricksLoaded"] < two[3]["bricksLoaded"]
+        elif sc.axes_div < 32:
+            assert three[3]["superSteps"] == 0
+
+
+def test_ring_depth_follows_the_materials(monkeypatch):
+    """runtime.cu Scene::ringSlots: only mirror / glass segments push a path's ring beyond two slots (raytrace_opencl.c:682-722), so a
+    scene without reflection / transparency channels gets 2 ring slots per path instead of 12 -- same planes as with the full ring
+    (OCLR_RING_SLOTS=12), about half the path state."""
+    sc, cam, lists, samples = helpers.make_case("spheres")
+    gold = np.load(GOLDEN / "spheres.npz")
+    paths = ((cam.height + 7) // 8 * 8) * cam.width
+    per_path = {}
+    for slots in (None, "12"):
+        if slots:
+            monkeypatch.setenv("OCLR_RING_SLOTS", slots)
+        ds = api.DeviceScene(sc, 0)
+        fr = api.DeviceFrame(ds, cam, lists)
+        assert fr.state_bytes == 0
+        fr.render(samples)
+        assert helpers.compare_rgb(fr.read(), (gold["r"], gold["g"], gold["b"]))["diff_pixels"] == 0
+        per_path[slots] = fr.state_bytes / paths
+        fr.close()
+        ds.close()
+    assert per_path[None] < 520 < 980 < per_path["12"] < 1000, per_path
+    monkeypatch.delenv("OCLR_RING_SLOTS")
+    sc, cam, lists, samples = helpers.make_case("spheres_mirror")       # mirrors: the full ring, whatever the knob says
+    fr = api.DeviceFrame(api.DeviceScene(sc, 0), cam, lists)
+    fr.render(samples)
+    assert fr.state_bytes / (((cam.height + 7) // 8 * 8) * cam.width) > 980
+
+
 def test_progress_counter_counts_pixel_samples():
     sc, cam, lists, _ = helpers.make_case("spheres")
     samples = 24

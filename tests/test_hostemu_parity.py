@@ -75,10 +75,39 @@ def test_packed_walk_is_exact(name, hostemu, monkeypatch):
     for c in range(3):
         assert np.array_equal(flat[0][c], packed[0][c])
     assert np.array_equal(flat[1], packed[1]) and np.array_equal(flat[2], packed[2])
-    assert packed[3]["bricksLoaded"] == flat[3]["bricksLoaded"]
+    assert packed[3]["bricksLoaded"] <= flat[3]["bricksLoaded"]          # (super-brick steps pass bricks by without reading them)
     assert packed[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
     assert packed[3]["gridCandidates"] <= flat[3]["gridCandidates"]
     assert packed[3]["cells"] <= flat[3]["cells"]
+
+
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_three_level_walk_is_exact(name, hostemu, monkeypatch):
+    """The super-brick level of rt_walk.h (an entirely empty block of 4x4x4 bricks is crossed in one step, the brick-level state is
+    rebuilt on entering a super-brick that holds triangles or the ray's end cell): identical planes, ids and flags, the same non-empty
+    cells and the same triangle tests as the two-level walk (OCLR_SUPER=0: the packer never raises the flag the walk obeys), which
+    in turn reads exactly the reference's brick sequence."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "2")
+    monkeypatch.setenv("OCLR_SUPER", "0")
+    two = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL")
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "2")
+    monkeypatch.setenv("OCLR_SUPER", "1")
+    three = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(two[0][c], three[0][c])
+    assert np.array_equal(two[1], three[1]) and np.array_equal(two[2], three[2])
+    assert two[3]["superSteps"] == 0 and two[3]["bricksLoaded"] == flat[3]["bricksLoaded"]
+    for k in ("cells", "cellsNonEmpty", "gridCandidates", "coarseEnters", "gridRays"):
+        assert three[3][k] == two[3][k], k
+    assert three[3]["superEnters"] >= three[3]["superRefines"]
+    if sc.axes_div >= 256:
+        assert three[3]["superSteps"] > 0
+        assert three[3]["coarseSteps"] < two[3]["coarseSteps"] and three[3]["bricksLoaded"] < two[3]["bricksLoaded"]
+    elif sc.axes_div < 32:   # no super-brick level on a 16^3 grid
+        assert three[3]["superSteps"] == 0 and three[3]["coarseSteps"] == two[3]["coarseSteps"]
 
 
 @pytest.mark.parametrize("part_cells", [3, 7, 40])
