@@ -43,6 +43,14 @@ def build_variant(name: str, defs: str, verbose: bool = False) -> Path:
     obj = OBJ / f"runtime_{name}.o"
     OBJ.mkdir(parents=True, exist_ok=True)
     build()
+    stamp = OBJ / f"stamp_{name}.txt"
+    dig = _digest() + defs
+    if out.is_file() and stamp.is_file() and stamp.read_text() == dig:
+        return out
+    if not (CUDA / "bin" / "nvcc").is_file():
+        if out.is_file():
+            return out  # prebuilt variant travelled with the snapshot
+        raise RuntimeError(f"nvcc not found and no prebuilt {out.name}")
     cmd = [str(CUDA / "bin" / "nvcc"), *NVCC_FLAGS, *defs.split(), "-c", str(CSRC / "runtime.cu"), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (OBJ / f"runtime_{name}.ptxas.txt").write_text(r.stderr)
@@ -53,6 +61,7 @@ def build_variant(name: str, defs: str, verbose: bool = False) -> Path:
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed\n{r.stderr}")
+    stamp.write_text(dig)
     return out
 
 

@@ -97,26 +97,20 @@ __global__ void __launch_bounds__(128) brick_write_kernel(const uint32_t* __rest
     if (b >= nb * nb * nb) return;
     const uint32_t base = rankBase[b];
     const uint64_t mask = brick_mask(start, n, nb, total, b, error, cellRange + base, cellIds + base);
-    bricks[b] = make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), base, 0u);
+    bricks[b] = make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), mask ? base : 0u, 0u);   // (.z of an empty brick: flags of the three-level walk, rt_walk.h)
 }
 
 // Super-brick level of the three-level walk (rt_walk.h): one 64-thread CTA per super-brick (4x4x4 bricks) writes its record
 // {non-empty, 0, 0, 0} behind the nb^3 brick records (at the brick strides; the slots between are zeroed by the caller) and turns .z of
 // its EMPTY bricks into the flag "the whole super-brick is empty".  Same result as append_super_bricks (scene_pack.cpp), byte for byte.
-// ns == 0 (no such level on this grid): launched with one CTA per 64 bricks, it only clears .z of the empty bricks.
-__global__ void __launch_bounds__(64) super_brick_kernel(uint4* __restrict__ bricks, int nb, int ns, int policy) {
+__global__ void __launch_bounds__(64) super_brick_kernel(uint4* __restrict__ bricks, int nb, int ns) {
     const int s = blockIdx.x, t = threadIdx.x;
-    if (ns == 0) {
-        const size_t b = (size_t)s * 64 + t;
-        if (b < (size_t)nb * nb * nb && (bricks[b].x | bricks[b].y) == 0u) bricks[b].z = 0u;
-        return;
-    }
     const int sx = s % ns, sy = (s / ns) % ns, sz = s / (ns * ns);
     const size_t b = (size_t)(sx * 4 + (t & 3)) + (size_t)nb * ((size_t)(sy * 4 + ((t >> 2) & 3)) + (size_t)nb * (size_t)(sz * 4 + (t >> 4)));
     const uint4 br = bricks[b];
     const int any = __syncthreads_or((br.x | br.y) != 0u);
     if (t == 0) bricks[(size_t)nb * nb * nb + (size_t)sx + (size_t)nb * ((size_t)sy + (size_t)nb * (size_t)sz)] = make_uint4(any ? 1u : 0u, 0u, 0u, 0u);
-    if ((br.x | br.y) == 0u) bricks[b].z = (!any && policy > 0) ? 1u : 0u;
+    if (!any) bricks[b].z = 1u;
 }
 
 // Face masks (rt_types.h): bit e set = list entry e of the cell is absent from the list of the neighbour the walk comes from.

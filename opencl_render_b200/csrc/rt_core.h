@@ -96,11 +96,14 @@ OCLR_HD float point_to_line_sq(f3 o, f3 d, f3 p) {
     return dot3(dv, dv);
 }
 
-// raytrace_opencl.c:103-122.  `size.x - 1` is unsigned arithmetic in the reference.
-OCLR_HD_OUT(3) f3 table_value(const uchar4* table, uint2 size, float u0, float v0, float u1, float v1, float u2, float v2,
-                       float abL, float acL) {
-    float pu = positive_modf(u0 + (u1 - u0) * abL + (u2 - u0) * acL);
-    float pv = positive_modf(v0 + (v1 - v0) * abL + (v2 - v0) * acL);
+// raytrace_opencl.c:103-122.  `size.x - 1` is unsigned arithmetic in the reference.  In two halves: the wrapped texture coordinate
+// depends on the triangle's UVs and the hit's barycentrics only -- one value for all the channels fetched at a hit (the reference
+// recomputes it, two double-precision modf each, for every channel) --, the fetch on the channel's image.
+OCLR_HD void table_uv(float u0, float v0, float u1, float v1, float u2, float v2, float abL, float acL, float& pu, float& pv) {
+    pu = positive_modf(u0 + (u1 - u0) * abL + (u2 - u0) * acL);
+    pv = positive_modf(v0 + (v1 - v0) * abL + (v2 - v0) * acL);
+}
+OCLR_HD f3 table_fetch(const uchar4* table, uint2 size, float pu, float pv) {
     float lx = pu * (float)(size.x - 1u);
     float ly = pv * (float)(size.y - 1u);
     int ix = (int)floorf(lx);
@@ -108,6 +111,12 @@ OCLR_HD_OUT(3) f3 table_value(const uchar4* table, uint2 size, float u0, float v
     int idx = (int)((uint32_t)ix + (uint32_t)iy * size.x);
     uchar4 t = OCLR_LDG(table + idx);
     return mk3((float)t.x / 255.f, (float)t.y / 255.f, (float)t.z / 255.f);
+}
+OCLR_HD_OUT(3) f3 table_value(const uchar4* table, uint2 size, float u0, float v0, float u1, float v1, float u2, float v2,
+                       float abL, float acL) {
+    float pu, pv;
+    table_uv(u0, v0, u1, v1, u2, v2, abL, acL, pu, pv);
+    return table_fetch(table, size, pu, pv);
 }
 
 // ---- ray / triangle: raytrace_opencl.c:124-172 against the packed triGeo record --------------------------------
@@ -484,6 +493,21 @@ OCLR_HD f3 channel_value(const SceneView& S, int mat, int channel, uint2 size, c
     return table_value(S.textures + start, size, ts.u0, ts.v0, ts.u1, ts.v1, ts.u2, ts.v2, abL, acL);
 }
 
+// The four material channels read at every shaded hit (:541-561; absent channels leave their argument untouched), with the
+// texture coordinate computed once.
+OCLR_HD void shade_channels(const SceneView& S, const TriShade& ts, float abL, float acL, f3& tex, f3& transp, f3& refl, f3& lum) {
+    float pu, pv;
+    table_uv(ts.u0, ts.v0, ts.u1, ts.v1, ts.u2, ts.v2, abL, acL, pu, pv);
+    uint2 sz;
+    if (channel_present(S, ts.mat, kChColor, sz)) tex = table_fetch(S.textures + OCLR_LDG(S.matStart + kMaterialChannels * ts.mat + kChColor), sz, pu, pv);
+    if (channel_present(S, ts.mat, kChTransparency, sz))
+        transp = table_fetch(S.textures + OCLR_LDG(S.matStart + kMaterialChannels * ts.mat + kChTransparency), sz, pu, pv);
+    if (channel_present(S, ts.mat, kChReflection, sz))
+        refl = table_fetch(S.textures + OCLR_LDG(S.matStart + kMaterialChannels * ts.mat + kChReflection), sz, pu, pv);
+    if (channel_present(S, ts.mat, kChLuminance, sz))
+        lum = table_fetch(S.textures + OCLR_LDG(S.matStart + kMaterialChannels * ts.mat + kChLuminance), sz, pu, pv);
+}
+
 // raytrace_opencl.c:124-172 on raw vertices (bump-mapping helper rays only, :244, :249): result flag ignored there,
 // abL/acL keep their previous value when the plane distance is outside (0, inf).
 OCLR_HD bool tri_bary_raw(f3 o, f3 r, f3 a, f3 b, f3 c, float& abL, float& acL) {
@@ -709,13 +733,7 @@ OCLR_HD f3 trace_sample(const SceneView& S, const FrameView& F, const float* px,
         f3 face[2] = {mk3(0.1f, 0.1f, 0.1f), mk3(0.1f, 0.1f, 0.1f)};
         const f3 loc = mk3(ro.x + hitT * rv.x, ro.y + hitT * rv.y, ro.z + hitT * rv.z);
         const f3 nrm = triangle_normal(S, cam, ts, loc, ro, rv, hitAB, hitAC, undefinedRef);
-        {
-            uint2 sz;
-            if (channel_present(S, m, kChColor, sz)) tex = channel_value(S, m, kChColor, sz, ts, hitAB, hitAC);
-            if (channel_present(S, m, kChTransparency, sz)) transp = channel_value(S, m, kChTransparency, sz, ts, hitAB, hitAC);
-            if (channel_present(S, m, kChReflection, sz)) refl = channel_value(S, m, kChReflection, sz, ts, hitAB, hitAC);
-            if (channel_present(S, m, kChLuminance, sz)) lum = channel_value(S, m, kChLuminance, sz, ts, hitAB, hitAC);
-        }
+        shade_channels(S, ts, hitAB, hitAC, tex, transp, refl, lum);
         for (uint32_t j = 0; j < S.lightCount; ++j) {
             const Light& L = S.lights[j];
             LightRay lr;

@@ -152,8 +152,20 @@ enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4, kW
 //
 // No mailbox here: pairs of one ray are tested concurrently, and face masks already remove the repeats between adjacent cells
 // (a per-lane mailbox removed 6 % more in the lane-owned kernel).
+// Super-brick level of the walk (rt_walk.h, three-level walk): exact, and measured -- it removes 37 % of config 3's brick-level steps
+// and 10 % of config 2's, but the kernel sits exactly at its 64-register cap: compiled in, the level costs 5 % more executed
+// instructions and spills into the loops (long-scoreboard stalls 1.6 -> 2.6 per issue), config 2 -7 %, config 3 -3 % even when it is
+// used (profiles/r02_super_level.txt).  Off in the production build; `-DOCLR_SUPER_LEVEL=1` builds the variant the tests exercise.
 #ifndef OCLR_SUPER_LEVEL
-#define OCLR_SUPER_LEVEL 1   /* 0 compiles the super-brick level of the walk out (A/B builds) */
+#define OCLR_SUPER_LEVEL 0
+#endif
+#ifndef OCLR_END_KEY
+#define OCLR_END_KEY 1
+#endif
+// 1: the walk reads origin / direction of the stepped axis from the warp's shared ray table (the tests read it from there anyway)
+// instead of holding all six components in registers through every phase of the kernel; the signs of the direction stay in a register
+#ifndef OCLR_RAY_IN_SMEM
+#define OCLR_RAY_IN_SMEM 1
 #endif
 #ifndef OCLR_CELLQ_CAP
 #define OCLR_CELLQ_CAP 96
@@ -161,7 +173,7 @@ enum { kWsNone = 0, kWsRun = 1, kWsRefine = 2, kWsEnter = 3, kWsFinished = 4, kW
 enum { kCellQCap = OCLR_CELLQ_CAP, kPairQCap = 64 };
 
 struct WarpPipe {
-    float ray[8][32];               // [o.x o.y o.z r.x r.y r.z minD maxD][owner lane]
+    float ray[8][32];               // [o.x o.y o.z r.x r.y r.z minD maxD][owner lane] (a miss reports maxD from here: no register for it)
     uint32_t excl[32];
     unsigned long long bestKey[32];
     uint32_t bestTri[32];
@@ -233,11 +245,11 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     if (COUNT) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tWarpStart));
     PackedWalk g;
     g.level = 0;
-    float maxD = 0.f;
     uint32_t path = 0;
     int ws = kWsNone;
     bool exhausted = false;
     int face = kFaceNone, lastAxis = 0;
+    uint32_t sgn = 0;       // bit a: direction component a is >= 0 (the walk goes up along that axis)
     float lastE = 0.f;
     uint32_t seqNext = 0;   // cells this ray has in the current batch
     uint32_t cq = 0;        // warp-uniform: cells queued
@@ -255,7 +267,13 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 // the group has its result), old enough when the queue still has rays
                 if (ws == kWsRun && g.coarseOk && P.grp[lane] == 0u && P.gParts[lane] == 0u &&
                     (exhausted || iter - P.birth[lane] >= (uint32_t)tune.splitEarly))
+                {
+#if OCLR_RAY_IN_SMEM
+                    g.o = mk3(P.ray[0][lane], P.ray[1][lane], P.ray[2][lane]);   // (the estimate and the plan below read the ray from the walk state)
+                    g.r = mk3(P.ray[3][lane], P.ray[4][lane], P.ray[5][lane]);
+#endif
                     best = walk_length_estimate(g, n, px, py, pz);
+                }
 #pragma unroll
                 for (int off = 16; off; off >>= 1) {
                     const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off), ow = __shfl_xor_sync(0xFFFFFFFFu, who, off);
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                             g = part;
                             pwalk_load_brick(g, S.bricks);
                             const float minD = P.ray[6][cand];
-                            maxD = P.ray[7][cand];
+                            const float maxD = P.ray[7][cand];
                             P.ray[0][lane] = head.o.x;
                             P.ray[1][lane] = head.o.y;
                             P.ray[2][lane] = head.o.z;
@@ -321,6 +339,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                             P.excl[lane] = P.excl[cand];
                             P.bestKey[lane] = kEmptyKey;
                             P.grp[lane] = 0x80000000u | (uint32_t)cand | ((uint32_t)myPart << 8);
+                            sgn = (0 <= head.r.x ? 1u : 0u) | (0 <= head.r.y ? 2u : 0u) | (0 <= head.r.z ? 4u : 0u);
                             path = headPath;
                             ws = kWsRun;
                             face = kFaceNone;
@@ -359,9 +378,12 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     const uint32_t idx = rec.order[(size_t)cls * rec.Q + (pos - classOff[cls])];
                     const float4 ro = rec.o[idx], rd = rec.d[idx], s0 = rec.s0[idx];
                     const uint4 s1 = rec.s1[idx];
+#if OCLR_RAY_IN_SMEM
+                    sgn = (0 <= rd.x ? 1u : 0u) | (0 <= rd.y ? 2u : 0u) | (0 <= rd.z ? 4u : 0u);
+#else
                     g.o = mk3(ro.x, ro.y, ro.z);
                     g.r = mk3(rd.x, rd.y, rd.z);
-                    maxD = rd.w;
+#endif
                     P.ray[0][lane] = ro.x;
                     P.ray[1][lane] = ro.y;
                     P.ray[2][lane] = ro.z;
@@ -381,9 +403,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     g.coarseOk = s1.w != 0u;
                     g.level = 0;
                     g.brick = ((pk_get(g.cpk, 0) >> 2) + (((pk_get(g.cpk, 1) >> 2) + ((pk_get(g.cpk, 2) >> 2) << nbShift)) << nbShift));
-                    g.endBrick = g.epk == kPkNone
-                                     ? -1
-                                     : ((pk_get(g.epk, 0) >> 2) + (((pk_get(g.epk, 1) >> 2) + ((pk_get(g.epk, 2) >> 2) << nbShift)) << nbShift));
+                    g.endBrick = pwalk_end_key(g.epk, nbShift);   // (the hot loop below reads this word, never the end cell itself)
                     pwalk_load_brick(g, S.bricks);
                     ws = kWsRun;
                     face = kFaceNone;
@@ -442,12 +462,16 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             if (walking) {
                 const bool coarse = g.level != 0;
                 const bool brickEmpty = (g.maskLo | g.maskHi) == 0u;
-                const bool inEnd = g.brick == g.endBrick;   // (level 2: both are super-brick records, rt_walk.h)
+                const bool inEnd = pwalk_in_end(g);   // (level 2: both are super-brick records, rt_walk.h)
                 if (COUNT && !coarse) {
                     cnt.cells++;
                     if (brickEmpty) cnt.emptyBrickCells++;
                 }
-                const bool atEnd = (!coarse) & (g.cpk == g.epk);
+#if OCLR_END_KEY
+                const bool atEnd = (!coarse) & pwalk_at_end(g, bit);
+#else
+                const bool atEnd = (!coarse) & (g.cpk == g.epk);   // (A/B build: the end cell stays live through the loop -- and is spilled)
+#endif
                 const bool needRefine = coarse & ((!brickEmpty) | inEnd);
                 // one level up: from the cells of an empty brick; from brick level when the record of the empty brick says that its whole
                 // super-brick is empty (bit 0 of what is the rank base of other bricks; super-brick records never carry it)
@@ -462,7 +486,14 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     bool crossed;
                     if (COUNT && coarse) cnt.coarseSteps++;
                     if (COUNT && g.level == 2) cnt.superSteps++;
-                    if (!pwalk_step(g, n, nbShift, shPlanes, lastAxis, up, lastE, crossed)) {
+#if OCLR_RAY_IN_SMEM
+                    lastAxis = pwalk_step_axis(g, lastE);
+                    up = (int)((sgn >> lastAxis) & 1u);
+                    const bool inside = pwalk_step_along(g, n, nbShift, shPlanes, lastAxis, P.ray[lastAxis][lane], P.ray[3 + lastAxis][lane], up, crossed);
+#else
+                    const bool inside = pwalk_step(g, n, nbShift, shPlanes, lastAxis, up, lastE, crossed);
+#endif
+                    if (!inside) {
                         ws = kWsFinished;
                     } else if (SPLIT && pk_is_stop(g.epk) && pwalk_stopped(g, lastAxis, up)) {
                         ws = kWsFinished;   // this part of a cut walk ends here; the cell just entered belongs to the next part
@@ -476,7 +507,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 }
                 if ((ws == kWsFinished) & (seqNext == 0u)) {  // walk over and nothing of this ray awaits a test: miss
                     if (!SPLIT || P.grp[lane] == 0u) {        // (a part of a cut walk reports to its group in RESOLVE instead)
-                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), P.ray[7][lane], 0.f, 0.f);
                         ws = kWsNone;
                     }
                 }
@@ -494,6 +525,12 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     if (lane == 0) cnt.switchWarpIters++;
                     if ((ws == kWsRefine) | (ws == kWsEnter)) cnt.switchLaneIters++;
                 }
+#if OCLR_RAY_IN_SMEM
+                if ((ws == kWsEnter) | (ws == kWsRefine)) {   // the level switches divide along all three axes
+                    g.o = mk3(P.ray[0][lane], P.ray[1][lane], P.ray[2][lane]);
+                    g.r = mk3(P.ray[3][lane], P.ray[4][lane], P.ray[5][lane]);
+                }
+#endif
                 if (ws == kWsEnter) {
                     if (g.level == 0) {
                         pwalk_enter_coarse(g, n, nbShift, shPlanes);
@@ -610,7 +647,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
                     ws = kWsNone;
                 } else if (ws == kWsFinished) {
-                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                    w.hit[path] = make_float4(__uint_as_float(kNoTriangle), P.ray[7][lane], 0.f, 0.f);
                     ws = kWsNone;
                 }
                 seqNext = 0;
@@ -626,7 +663,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                         w.hit[path] = make_float4(__uint_as_float(P.bestTri[lane]), __uint_as_float((uint32_t)(key >> 24)), P.bestAB[lane], P.bestAC[lane]);
                         ws = kWsNone;
                     } else if (ws == kWsFinished) {
-                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), P.ray[7][lane], 0.f, 0.f);
                         ws = kWsNone;
                     }
                 } else if (ws != kWsHeld) {
@@ -661,7 +698,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 } else if (ws == kWsPartDone) {   // (its miss is on the group's record: the lane is free again)
                     const uint32_t all = (1u << P.gParts[headLane]) - 1u;
                     if (hm == 0u && (mm & all) == all && (atomicOr(&P.gMiss[headLane], 0x80000000u) >> 31) == 0u) {
-                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);   // the last parts to finish: one of them says so
+                        w.hit[path] = make_float4(__uint_as_float(kNoTriangle), P.ray[7][lane], 0.f, 0.f);   // the last parts to finish: one of them says so
                         atomicSub(&P.groups, 1u);
                         closes = true;
                     }

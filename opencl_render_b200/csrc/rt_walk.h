@@ -49,7 +49,8 @@ struct PackedWalk {
     uint32_t cpk;        // current cell (level 0) / brick (level 1) / super-brick (level 2)
     uint32_t epk;        // end cell, or kPkNone
     int brick;           // index of the current brick's record; level 2: of the current super-brick's record
-    int endBrick;        // brick (level 2: super-brick) of the end cell -- walked at the finer level, never skipped --, or -1
+    int endBrick;        // where the walk ends, as one word (pwalk_end_key): record index of the end cell's brick (level 2: super-brick)
+                         // -- walked at the finer level, never skipped -- | the cell's bit inside the brick << 25; or kEndNone
     uint32_t maskLo, maskHi, rankBase;   // record of `brick`; empty brick: bit 0 of rankBase = the whole super-brick is empty
     int level;           // 0: cells, 1: bricks, 2: super-bricks
     bool coarseOk;       // all direction components non-zero and n >= 4
@@ -65,6 +66,22 @@ OCLR_HD int pk_super_record(uint32_t spk, int nbShift) {
 OCLR_HD int pk_brick_record(uint32_t cellPk, int nbShift) {
     return (pk_get(cellPk, 0) >> 2) + (((pk_get(cellPk, 1) >> 2) + ((pk_get(cellPk, 2) >> 2) << nbShift)) << nbShift);
 }
+// Bit of a cell inside its brick's occupancy mask: (x & 3) | (y & 3) << 2 | (z & 3) << 4.
+OCLR_HD int pwalk_bit(uint32_t cpk) {
+    const uint32_t t = cpk & 0x00300C03u;
+    return (int)((t | (t >> 8) | (t >> 16)) & 63u);
+}
+// The end of a bounded walk as ONE word, so that the trace kernel's hot loop needs neither the end cell nor a second comparison (ncu:
+// at 64 registers the end cell was the value ptxas spilled, and every walk iteration began with its reload from local memory):
+//   record index of the end cell's brick (< 2^25: nb^3 brick + nb^3 / 4 super-brick records, nb <= 256) | bit of the end cell << 25
+// "in the end brick" = the low 25 bits (and bit 31) agree with `brick`; "on the end cell" = the whole word equals brick | bit << 25.
+// kEndNone (bit 31): no end cell -- an unbounded ray, or a part of a cut walk, which ends at a plane.
+enum : uint32_t { kEndNone = 0x80000000u, kEndBrickMask = 0x81FFFFFFu };
+enum { kEndBitShift = 25 };
+OCLR_HD int pwalk_end_key(uint32_t epk, int nbShift) {
+    if ((epk >> 31) != 0u) return (int)kEndNone;   // kPkNone / a stop plane
+    return pk_brick_record(epk, nbShift) | (pwalk_bit(epk) << kEndBitShift);
+}
 
 // Ray -> initial walk state: raytrace_opencl.c:350-362 (BindInCube on start and end, GetBoxAddress) + the first three crossing values.
 OCLR_HD void pwalk_setup(PackedWalk& w, int n, int nb, const float* px, const float* py, const float* pz, f3 o, f3 r, float minD,
@@ -79,14 +96,14 @@ OCLR_HD void pwalk_setup(PackedWalk& w, int n, int nb, const float* px, const fl
     box_address(n, px, py, pz, start, cx, cy, cz);
     w.cpk = pk_make(cx, cy, cz);
     w.epk = kPkNone;
-    w.endBrick = -1;
+    w.endBrick = (int)kEndNone;
     if (maxD < OCLR_INF) {
         f3 end = mk3(o.x + maxD * r.x, o.y + maxD * r.y, o.z + maxD * r.z);
         bind_in_cube(end, r, lo, hi);
         int ex, ey, ez;
         box_address(n, px, py, pz, end, ex, ey, ez);
         w.epk = pk_make(ex, ey, ez);
-        w.endBrick = (ex >> 2) + nb * ((ey >> 2) + nb * (ez >> 2));
+        w.endBrick = ((ex >> 2) + nb * ((ey >> 2) + nb * (ez >> 2))) | (pwalk_bit(w.epk) << kEndBitShift);
     }
     w.tx = (px[cx + (0 <= r.x)] - o.x) / r.x;
     w.ty = (py[cy + (0 <= r.y)] - o.y) / r.y;
@@ -110,11 +127,8 @@ OCLR_HD bool pwalk_super_allowed(const PackedWalk& w) {
     return (pk_super_of_brick(w.cpk) != pk_super_of_cell(w.epk)) & !pk_is_stop(w.epk);
 }
 
-// Bit of the current cell inside its brick's occupancy mask: (x & 3) | (y & 3) << 2 | (z & 3) << 4.
-OCLR_HD int pwalk_bit(uint32_t cpk) {
-    const uint32_t t = cpk & 0x00300C03u;
-    return (int)((t | (t >> 8) | (t >> 16)) & 63u);
-}
+OCLR_HD bool pwalk_in_end(const PackedWalk& w) { return ((uint32_t)(w.endBrick ^ w.brick) & kEndBrickMask) == 0u; }
+OCLR_HD bool pwalk_at_end(const PackedWalk& w, int bit) { return (uint32_t)w.endBrick == ((uint32_t)w.brick | ((uint32_t)bit << kEndBitShift)); }
 OCLR_HD bool pwalk_occupied(const PackedWalk& w, int bit) {
     const uint32_t half = (bit & 32) ? w.maskHi : w.maskLo;
     return ((half >> (bit & 31)) & 1u) != 0u;
@@ -125,16 +139,19 @@ OCLR_HD uint32_t pwalk_rank(const PackedWalk& w, int bit) {
     return w.rankBase + (uint32_t)OCLR_POPCLL(m & ((1ull << bit) - 1ull));
 }
 
-// One step at the current level (:383-398).  Returns false when the walk left the grid.  `axis`, `up` and `tEvent`
-// describe the crossing taken; `crossed` is set when the step entered another brick (always at level 1).
-OCLR_HD bool pwalk_step(PackedWalk& w, int n, int nbShift, const float* planes, int& axis, int& up, float& tEvent, bool& crossed) {
+// One step at the current level (:383-398), in two halves so that a caller that keeps the ray somewhere else than in registers (the
+// trace kernel: its shared-memory ray table -- six registers less in a loop that sits at the register cap) fetches the origin and
+// direction component of the stepped axis only.
+// First half: the axis whose crossing comes next and its value.  (x only if strictly smallest, else y if strictly smaller than z, else z)
+OCLR_HD int pwalk_step_axis(const PackedWalk& w, float& tEvent) {
     const bool xmin = (w.tx < w.ty) & (w.tx < w.tz);
     const bool ymin = (!xmin) & (w.ty < w.tz);
-    axis = xmin ? 0 : (ymin ? 1 : 2);
     tEvent = xmin ? w.tx : (ymin ? w.ty : w.tz);
-    const float rr = xmin ? w.r.x : (ymin ? w.r.y : w.r.z);
-    const float oo = xmin ? w.o.x : (ymin ? w.o.y : w.o.z);
-    up = (0 <= rr) ? 1 : 0;
+    return xmin ? 0 : (ymin ? 1 : 2);
+}
+// Second half: the step along `axis` (oo, rr = origin / direction component of that axis, up = (0 <= rr)).  Returns false when the walk
+// left the grid; `crossed` is set when the step entered another brick (always above level 0).
+OCLR_HD bool pwalk_step_along(PackedWalk& w, int n, int nbShift, const float* planes, int axis, float oo, float rr, int up, bool& crossed) {
     const int sh = axis * kPkBits;
     const int c = (int)((w.cpk >> sh) & kPkMask);
     const int dir = up ? 1 : -1;
@@ -144,12 +161,20 @@ OCLR_HD bool pwalk_step(PackedWalk& w, int n, int nbShift, const float* planes, 
     if ((uint32_t)cn >= (uint32_t)(n >> lsh)) return false;
     const float t = (planes[axis * (n + 1) + ((cn + up) << lsh)] - oo) / rr;
     w.cpk += (uint32_t)dir << sh;   // two's complement: -1 << sh subtracts one from the axis' field
-    w.tx = xmin ? t : w.tx;
-    w.ty = ymin ? t : w.ty;
-    w.tz = (xmin | ymin) ? w.tz : t;
+    w.tx = axis == 0 ? t : w.tx;
+    w.ty = axis == 1 ? t : w.ty;
+    w.tz = axis == 2 ? t : w.tz;
     crossed = (w.level != 0) | (((c ^ cn) & ~3) != 0);
     if (crossed) w.brick += dir * (1 << (axis * nbShift));   // (the same at level 2: super-brick records sit at the brick strides)
     return true;
+}
+// Both halves, the ray taken from the walk state.  `axis`, `up` and `tEvent` describe the crossing taken.
+OCLR_HD bool pwalk_step(PackedWalk& w, int n, int nbShift, const float* planes, int& axis, int& up, float& tEvent, bool& crossed) {
+    axis = pwalk_step_axis(w, tEvent);
+    const float rr = axis == 0 ? w.r.x : (axis == 1 ? w.r.y : w.r.z);
+    const float oo = axis == 0 ? w.o.x : (axis == 1 ? w.o.y : w.o.z);
+    up = (0 <= rr) ? 1 : 0;
+    return pwalk_step_along(w, n, nbShift, planes, axis, oo, rr, up, crossed);
 }
 
 // After a successful step along `axis`: did the walk just cross into the cell index at which this part ends?
@@ -174,7 +199,7 @@ OCLR_HD_SW void pwalk_enter_coarse(PackedWalk& w, int n, int nbShift, const floa
     w.tz = (pz[(pk_get(w.cpk, 2) + (0 <= w.r.z)) << lsh] - w.o.z) / w.r.z;
     if (w.level == 2) {   // (its record says "empty", like the masks the walk holds)
         w.brick = pk_super_record(w.cpk, nbShift);
-        w.endBrick = w.epk == kPkNone ? -1 : pk_super_record(pk_super_of_cell(w.epk), nbShift);
+        w.endBrick = (w.epk >> 31) != 0u ? (int)kEndNone : pk_super_record(pk_super_of_cell(w.epk), nbShift);
         w.rankBase = 0u;
     }
 }
@@ -218,7 +243,7 @@ OCLR_HD_SW void pwalk_refine(PackedWalk& w, int n, int nbShift, const float* pla
     w.level -= 1;
     if (w.level == 1) {
         w.brick = cx + ((cy + (cz << nbShift)) << nbShift);
-        w.endBrick = w.epk == kPkNone ? -1 : pk_brick_record(w.epk, nbShift);
+        w.endBrick = pwalk_end_key(w.epk, nbShift);
     }
 }
 
@@ -395,13 +420,13 @@ OCLR_HD uint32_t grid_walk_packed(const SceneView& S, const float* planes, Packe
                 }
                 if (closest != kNoTriangle) return closest;
             }
-            if (w.cpk == w.epk) break;
-            if (((w.maskLo | w.maskHi) == 0u) & w.coarseOk & (w.brick != w.endBrick)) {
+            if (pwalk_at_end(w, bit)) break;
+            if (((w.maskLo | w.maskHi) == 0u) & w.coarseOk & !pwalk_in_end(w)) {
                 pwalk_enter_coarse(w, n, nbShift, planes);
                 if (COUNT) cnt->coarseEnters++;
                 continue;
             }
-        } else if (((w.maskLo | w.maskHi) != 0u) | (w.brick == w.endBrick)) {
+        } else if (((w.maskLo | w.maskHi) != 0u) | pwalk_in_end(w)) {
             pwalk_refine(w, n, nbShift, planes, lastAxis, lastE);
             if (w.level == 1) {
                 pwalk_load_brick(w, S.bricks);
@@ -489,7 +514,7 @@ OCLR_HD uint32_t grid_trace_split(const SceneView& S, const float* planes, f3 o,
         if (j > 0 && !pwalk_jump(part, n, S.nb, px, py, pz, o, r, c0x, c0y, c0z, axis, cut[j])) break;
         if (j + 1 < parts) {  // ends at the next cut
             part.epk = pk_stop(axis, cut[j + 1]);
-            part.endBrick = -1;
+            part.endBrick = (int)kEndNone;
         } else {  // last part: the ray's own end condition
             part.epk = first.epk;
             part.endBrick = first.endBrick;
@@ -550,7 +575,7 @@ OCLR_HD bool pwalk_split_part(PackedWalk& part, const PackedWalk& w, int n, int 
     if (!pwalk_jump(part, n, nb, px, py, pz, w.o, w.r, pwalk_floor_cell(w, 0), pwalk_floor_cell(w, 1), pwalk_floor_cell(w, 2), axis, cut[j])) return false;
     if (j + 1 < parts) {
         part.epk = pk_stop(axis, cut[j + 1]);
-        part.endBrick = -1;
+        part.endBrick = (int)kEndNone;
     } else {
         part.epk = w.epk;
         part.endBrick = w.endBrick;
@@ -559,7 +584,7 @@ OCLR_HD bool pwalk_split_part(PackedWalk& part, const PackedWalk& w, int n, int 
 }
 OCLR_HD void pwalk_split_head(PackedWalk& w, int axis, const int cut[kMaxWalkParts]) {
     w.epk = pk_stop(axis, cut[1]);
-    w.endBrick = -1;
+    w.endBrick = (int)kEndNone;
 }
 
 // Host form of the whole thing (tests/hostemu): walk `walkFirst` cells the ordinary way, then cut the rest into up to `maxParts` parts.

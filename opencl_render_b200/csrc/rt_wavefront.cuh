@@ -302,11 +302,7 @@ __global__ void __launch_bounds__(128, OCLR_LOGIC_MIN_CTAS) wf_logic_kernel(Scen
                 face[0] = face[1] = mk3(0.1f, 0.1f, 0.1f);
                 loc = mk3(seg.o.x + hitT * seg.v.x, seg.o.y + hitT * seg.v.y, seg.o.z + hitT * seg.v.z);
                 nrm = triangle_normal(S, cam, ts, loc, seg.o, seg.v, hitAB, hitAC, undef);
-                uint2 sz;
-                if (channel_present(S, ts.mat, kChColor, sz)) tex = channel_value(S, ts.mat, kChColor, sz, ts, hitAB, hitAC);
-                if (channel_present(S, ts.mat, kChTransparency, sz)) transp = channel_value(S, ts.mat, kChTransparency, sz, ts, hitAB, hitAC);
-                if (channel_present(S, ts.mat, kChReflection, sz)) refl = channel_value(S, ts.mat, kChReflection, sz, ts, hitAB, hitAC);
-                if (channel_present(S, ts.mat, kChLuminance, sz)) lum = channel_value(S, ts.mat, kChLuminance, sz, ts, hitAB, hitAC);
+                shade_channels(S, ts, hitAB, hitAC, tex, transp, refl, lum);
                 j = 0;
                 go = GO_LIGHTS;
             } else if (go == GO_LIGHTS) {  // :563-637, suspended at :611

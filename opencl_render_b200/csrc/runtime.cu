@@ -1018,8 +1018,10 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
     const size_t N = h.triangleCount;
     const int n = h.axesDivCount, nb = n >= 4 ? n / 4 : 1;
     const size_t cells = (size_t)n * n * n, nBricks = (size_t)nb * nb * nb;
-    const int ns = super_bricks_per_axis(n);   // super-brick records of the three-level walk follow the brick records (rt_walk.h)
-    const size_t nSuper = super_brick_records(n);
+    // super-brick records of the three-level walk follow the brick records (rt_walk.h) -- in builds whose trace kernel has that level
+    const int superPolicy = OCLR_SUPER_LEVEL ? super_policy(1) : 0;
+    const int ns = superPolicy > 0 ? super_bricks_per_axis(n) : 0;
+    const size_t nSuper = superPolicy > 0 ? super_brick_records(n) : 0;
     // ring depth of this scene's paths (host data only, and decided before the early hook below starts a frame on the scene)
     s->ringSlots = 2;
     for (uint32_t m = 0; m < h.materialCount && s->ringSlots == 2; ++m)
@@ -1169,8 +1171,10 @@ static bool scene_upload(Scene* s, const HostScene& h, std::string& err, const s
             brick_write_kernel<<<(unsigned)((nBricks + 127) / 128), 128>>>((const uint32_t*)gridStart.p, n, nb, total, (const uint32_t*)rankBase.p,
                                                                           (uint4*)s->bricks.p, (uint2*)s->cellRange.p, (uint32_t*)cellIds.p,
                                                                           (uint32_t*)errFlag.p);
-            if (nSuper) cudaMemsetAsync((uint4*)s->bricks.p + nBricks, 0, sizeof(uint4) * nSuper, 0);
-            super_brick_kernel<<<ns ? (unsigned)(ns * ns * ns) : (unsigned)((nBricks + 63) / 64), 64>>>((uint4*)s->bricks.p, nb, ns, super_policy());
+            if (nSuper) {
+                cudaMemsetAsync((uint4*)s->bricks.p + nBricks, 0, sizeof(uint4) * nSuper, 0);
+                super_brick_kernel<<<(unsigned)(ns * ns * ns), 64>>>((uint4*)s->bricks.p, nb, ns);
+            }
             if (nonEmpty)
                 face_mask_kernel<<<(unsigned)(((size_t)nonEmpty * 6 + 255) / 256), 256>>>((const uint32_t*)gridStart.p, n, total, nonEmpty,
                                                                                          (const uint32_t*)cellIds.p, (const uint2*)s->cellRange.p,

@@ -55,7 +55,7 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err);
 // super-brick level of the three-level walk (rt_walk.h): records appended to the brick array, flags in the empty bricks' .w
 int super_bricks_per_axis(int n);   // n / 16 for power-of-two grids of >= 32 cells per axis, else 0 (no super-brick level)
 size_t super_brick_records(int n);  // records behind the nb^3 brick records (super-brick records sit at the brick strides)
-int super_policy();                 // OCLR_SUPER: 0 = never enter the super-brick level, 1 (default) = in every empty super-brick
+int super_policy(int dflt);         // OCLR_SUPER (else dflt): 0 = no super-brick records / flags at all, 1 = flag every empty super-brick
 void append_super_bricks(std::vector<uint4>& bricks, int n, int nb, int policy);
 void pack_lights(const HostScene& h, std::vector<Light>& out);
 // gridMayBeMissing: sceneBoxMin == scenePixelTriangleListStart == NULL is accepted (the device runtime then builds the grid itself)

@@ -169,13 +169,13 @@ bool pack_grid(const HostScene& h, PackedGrid& out, std::string& err) {
                             }
                         }
                 out.bricks[(size_t)bx + (size_t)nb * (by + (size_t)nb * bz)] =
-                    make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), rankBase, 0);
+                    make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), mask ? rankBase : 0u, 0);   // (.z of an empty brick: flags, rt_walk.h)
             }
     if (out.cellRange.empty()) {
         out.cellRange.push_back(make_uint2(0, 0));
         out.faceMask.assign(6, 0xFFFFFFFFu);
     }
-    append_super_bricks(out.bricks, n, nb, super_policy());
+    append_super_bricks(out.bricks, n, nb, super_policy(0));   // (the production kernel has no super-brick level: nothing is appended unless asked)
     return true;
 }
 
@@ -189,13 +189,14 @@ size_t super_brick_records(int n) {   // records appended to the brick array
     return ns * nb * nb;
 }
 
-int super_policy() {   // (read per scene, not cached: tests switch it between two scenes of one process)
+int super_policy(int dflt) {   // (read per scene, not cached: tests switch it between two scenes of one process)
     const char* e = getenv("OCLR_SUPER");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : dflt;
 }
 
 void append_super_bricks(std::vector<uint4>& bricks, int n, int nb, int policy) {
-    const int ns = super_bricks_per_axis(n);
+    const int ns = policy > 0 ? super_bricks_per_axis(n) : 0;
+    if (ns == 0) return;
     const size_t nBricks = (size_t)nb * nb * nb;
     bricks.resize(nBricks + super_brick_records(n), make_uint4(0, 0, 0, 0));
     for (int sz = 0; sz < ns; ++sz)
@@ -209,16 +210,11 @@ void append_super_bricks(std::vector<uint4>& bricks, int n, int nb, int policy) 
                             any |= b.x | b.y;
                         }
                 bricks[nBricks + (size_t)sx + (size_t)nb * (sy + (size_t)nb * sz)] = make_uint4(any ? 1u : 0u, 0, 0, 0);
+                if (any) continue;
                 for (int z = 0; z < 4; ++z)
                     for (int y = 0; y < 4; ++y)
-                        for (int x = 0; x < 4; ++x) {
-                            uint4& b = bricks[(size_t)(sx * 4 + x) + (size_t)nb * ((sy * 4 + y) + (size_t)nb * (sz * 4 + z))];
-                            if ((b.x | b.y) == 0u) b.z = (any == 0u && policy > 0) ? 1u : 0u;
-                        }
+                        for (int x = 0; x < 4; ++x) bricks[(size_t)(sx * 4 + x) + (size_t)nb * ((sy * 4 + y) + (size_t)nb * (sz * 4 + z))].z = 1u;
             }
-    if (ns == 0)   // no super-brick level: the flag is never raised
-        for (size_t b = 0; b < nBricks; ++b)
-            if ((bricks[b].x | bricks[b].y) == 0u) bricks[b].z = 0u;
 }
 
 void pack_lights(const HostScene& h, std::vector<Light>& out) {

@@ -1,15 +1,9 @@
-# round 2, session e: why does code the trace kernel never runs cost it 5-8 %?  A/B of the production kernel with and without the
-# super-brick level compiled in, with the level switches as real functions; warp-state / scheduler / instruction sections of ncu for both
+# round 2, session g: stepped-axis ray components from the shared ray table instead of six registers; 9 / 10 trace CTAs per SM on top
 set -x
 cd $GRAFT_REPO_ROOT
 P=$GRAFT_REPO_ROOT/opencl_render_b200/libopencl_render_b200
-timeout 300 python -m pytest tests -m gpu -x -q --timeout 300 -k "ring or super or packers" > gpurun_out/r02s_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02s_tests.log
-( timeout 400 python scripts/sweep_env.py 2 2 "OCLR_LIB=${P}_nosuper.so" "OCLR_LIB=${P}_outsw.so" "OCLR_LIB=${P}_outsw_super.so" "OCLR_HIERARCHICAL=2" "OCLR_LIB=${P}_nosuper.so" "OCLR_LIB=${P}_outsw.so"
-  timeout 400 python scripts/sweep_env.py 3 2 "OCLR_LIB=${P}_nosuper.so" "OCLR_LIB=${P}_outsw.so" "OCLR_LIB=${P}_outsw_super.so" "OCLR_HIERARCHICAL=2" ) > gpurun_out/r02s_ab.log 2>&1
-grep -E "^---|frame" gpurun_out/r02s_ab.log
-SEC="--section WarpStateStats --section SchedulerStats --section InstructionStats --section LaunchStats --section SpeedOfLight"
-OCLR_LIB=${P}_nosuper.so ncu $SEC --clock-control none -k regex:wf_pipe -c 2 python scripts/ncu_target.py 2 2 1 > gpurun_out/r02s_ncu_nosuper.log 2>&1
-OCLR_HIERARCHICAL=1 ncu $SEC --clock-control none -k regex:wf_pipe -c 2 python scripts/ncu_target.py 2 2 1 > gpurun_out/r02s_ncu_super_h1.log 2>&1
-OCLR_LIB=${P}_nosuper.so ncu --metrics smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum --clock-control none -k regex:wf_pipe -c 2 python scripts/ncu_target.py 2 2 1 > gpurun_out/r02s_ncu_stall_nosuper.log 2>&1
-OCLR_HIERARCHICAL=1 ncu --metrics smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum --clock-control none -k regex:wf_pipe -c 2 python scripts/ncu_target.py 2 2 1 > gpurun_out/r02s_ncu_stall_super_h1.log 2>&1
-grep -E "no_instruction|long_scoreboard|wait_per|branch_res|short_score|math_pipe|not_selected|inst_executed|time_duration" gpurun_out/r02s_ncu_stall_nosuper.log gpurun_out/r02s_ncu_stall_super_h1.log
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "golden or ring or super or packers or whole_frame or split" > gpurun_out/r02u_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02u_tests.log
+( timeout 400 python scripts/sweep_env.py 2 2 "OCLR_LIB=${P}_rayreg.so" "OCLR_X=default" "OCLR_LIB=${P}_ctas9.so" "OCLR_LIB=${P}_ctas10.so" "OCLR_LIB=${P}_rayreg.so" "OCLR_X=default"
+  timeout 400 python scripts/sweep_env.py 3 2 "OCLR_LIB=${P}_rayreg.so" "OCLR_X=default" "OCLR_LIB=${P}_ctas9.so" "OCLR_LIB=${P}_ctas10.so" ) > gpurun_out/r02u_ab.log 2>&1
+grep -E "^---|frame|walk util" gpurun_out/r02u_ab.log
+( timeout 200 python scripts/share_sweep.py 2 8 "OCLR_LIB=${P}_rayreg.so" "OCLR_X=default" "OCLR_LIB=${P}_ctas9.so" ) 2>&1 | tee gpurun_out/r02u_share.log

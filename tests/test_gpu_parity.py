@@ -121,8 +121,7 @@ def test_device_packers_equal_host_packers(hostemu):
         n, N = sc.axes_div, sc.triangle_count
         nb = max(n // 4, 1)
         geo, shade = np.zeros(64 * N, np.uint8), np.zeros(128 * N, np.uint8)
-        ns = n // 16 if n >= 32 else 0   # super-brick records of the three-level walk follow the brick records, at the brick strides
-        bricks, planes = np.zeros(16 * (nb ** 3 + ns * nb * nb), np.uint8), np.zeros(12 * (n + 1), np.uint8)
+        bricks, planes = np.zeros(16 * nb ** 3, np.uint8), np.zeros(12 * (n + 1), np.uint8)
         ranges = np.zeros(8 * max(int((np.diff(sc.grid_start) > 0).sum()), 1), np.uint8)
         d = sc.desc()
         p = lambda a: a.ctypes.data_as(C.c_void_p)

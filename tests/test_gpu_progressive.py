@@ -3,6 +3,7 @@
 counter (raytrace.c:156-173, 566-587) and the slice cut of a launch domain.  Everything goes through the C-ABI; expected
 values are the golden vectors generated from the reference build."""
 import threading
+import os
 from pathlib import Path
 
 import numpy as np
@@ -155,29 +156,60 @@ def test_tracing_one_round_ahead_is_invisible(mode):
         api.set_option("ahead", -1)
 
 
-def test_super_brick_level_of_the_walk_is_invisible(monkeypatch):
-    """rt_walk.h, three-level walk: entirely empty super-bricks (4x4x4 bricks) are crossed in one step.  A scene packed with
-    OCLR_SUPER=0 (the flag the walk obeys is never raised: two-level walk) and the same scene packed by default give identical planes,
-    ids and flags; the default really takes super-brick steps and loads fewer brick records."""
-    for name in ("soup", "soup_mirror_glass", "terrain_textured", "soup_axis_light", "soup_s4", "coarse_grid"):
-        sc, cam, lists, samples = helpers.make_case(name)
-        out = {}
-        for policy in ("0", "1"):
-            monkeypatch.setenv("OCLR_SUPER", policy)
-            ds = api.DeviceScene(sc, 0)
-            fr = api.DeviceFrame(ds, cam, lists)
-            _, _, cnt = fr.render(samples, count=True)
-            out[policy] = (fr.read(), fr.primary_ids(), fr.undefined_flags(), cnt)
-            fr.close()
-            ds.close()
-        two, three = out["0"], out["1"]
-        assert _equal(two[0], three[0]) and np.array_equal(two[1], three[1]) and np.array_equal(two[2], three[2]), name
-        assert two[3]["superSteps"] == 0 and two[3]["superEnters"] == 0
-        if sc.axes_div >= 256:
-            assert three[3]["superSteps"] > 0 and three[3]["coarseSteps"] < two[3]["coarseSteps"], name
-            assert three[3]["bricksLoaded"] < two[3]["bricksLoaded"]
-        elif sc.axes_div < 32:
-            assert three[3]["superSteps"] == 0
+_SUPER_PROBE = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd())
+from opencl_render_b200 import api
+from tests import helpers
+out = {}
+for name in ("soup", "soup_mirror_glass", "terrain_textured", "soup_axis_light", "soup_s4", "coarse_grid"):
+    sc, cam, lists, samples = helpers.make_case(name)
+    res = {}
+    for policy in ("0", "1"):
+        os.environ["OCLR_SUPER"] = policy
+        ds = api.DeviceScene(sc, 0)
+        fr = api.DeviceFrame(ds, cam, lists)
+        _, _, cnt = fr.render(samples, count=True)
+        res[policy] = (fr.read(), fr.primary_ids(), fr.undefined_flags(), cnt, len(ds.debug_read(2)))
+        fr.close(); ds.close()
+    two, three = res["0"], res["1"]
+    gold = np.load(os.path.join("tests", "golden", name + ".npz"))
+    out[name] = dict(equal=bool(all(np.array_equal(a, b) for a, b in zip(two[0], three[0])) and np.array_equal(two[1], three[1])
+                                and np.array_equal(two[2], three[2])),
+                     golden=int(helpers.compare_rgb(three[0], (gold["r"], gold["g"], gold["b"]), mask=(three[2] == 0))["diff_pixels"]),
+                     axes=int(sc.axes_div), brick_bytes=[two[4], three[4]],
+                     two={k: two[3][k] for k in ("superSteps", "superEnters", "coarseSteps", "bricksLoaded")},
+                     three={k: three[3][k] for k in ("superSteps", "superEnters", "superRefines", "coarseSteps", "bricksLoaded")})
+print("SUPER_PROBE " + json.dumps(out))
+"""
+
+
+def test_super_brick_level_of_the_walk_is_invisible():
+    """rt_walk.h, three-level walk: entirely empty super-bricks (4x4x4 bricks) are crossed in one step.  The level is compiled out of
+    the production kernel (it costs more than it saves at the kernel's register cap, rt_trace.cuh); build() also makes the variant
+    library that has it, and this test drives that library in a process of its own: a scene packed with OCLR_SUPER=0 (no flags: the
+    two-level walk) and the same scene packed with the flags give identical planes, ids and flags, equal to the golden vectors; with
+    the flags the walk really takes super-brick steps and reads fewer brick records."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "opencl_render_b200" / "libopencl_render_b200_super.so"
+    if not lib.is_file():
+        pytest.skip("variant library with the super-brick level not built (python -m opencl_render_b200.build --variant super -DOCLR_SUPER_LEVEL=1)")
+    env = dict(os.environ, OCLR_LIB=str(lib), OCLR_HIERARCHICAL="2")
+    r = subprocess.run([sys.executable, "-c", _SUPER_PROBE], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("SUPER_PROBE ")][-1][len("SUPER_PROBE "):])
+    for name, o in out.items():
+        assert o["equal"] and o["golden"] == 0, (name, o)
+        assert o["two"]["superSteps"] == 0 and o["two"]["superEnters"] == 0, (name, o)
+        if o["axes"] >= 256:
+            assert o["three"]["superSteps"] > 0 and o["three"]["coarseSteps"] < o["two"]["coarseSteps"], (name, o)
+            assert o["three"]["bricksLoaded"] < o["two"]["bricksLoaded"] and o["brick_bytes"][1] > o["brick_bytes"][0], (name, o)
+        elif o["axes"] < 32:
+            assert o["three"]["superSteps"] == 0 and o["brick_bytes"][1] == o["brick_bytes"][0], (name, o)
 
 
 def test_ring_depth_follows_the_materials(monkeypatch):
