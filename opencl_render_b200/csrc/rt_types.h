@@ -36,12 +36,14 @@
 #else
 #define OCLR_HD inline
 #endif
-// Code size of the logic kernel: with everything forced inline it is 7 560 SASS instructions (121 KB), 40 % of them the 14 inlined
-// copies of the reference's 64-bit RNG, and "no instruction" (instruction-cache misses) is its first stall reason (3.7 warp-cycles per
-// issue; the 1 368-instruction trace kernel: 0.2).  OCLR_OUTLINE_LEVEL >= 1 makes rand_f one function, >= 2 also sphere_point and the
-// light accumulation (a double-precision pow), >= 3 also the texture lookup.  Same arithmetic either way.
+// Code size of the logic kernel: with everything forced inline it is 7 430 SASS instructions (119 KB against a 32 KB L1.5 instruction
+// cache), 40 % of them the 14 inlined copies of the reference's 64-bit RNG, and "no instruction" (instruction-cache misses) is its first
+// stall reason (3.7 warp-cycles per issue; the 1 424-instruction trace kernel: 0.2).  OCLR_OUTLINE_LEVEL >= 1 makes rand_f one function,
+// >= 2 also sphere_point and the light accumulation (a double-precision pow), >= 3 also the texture lookup (4 020 instructions).  Same
+// arithmetic either way.  Default 3 since the end of round 2: config 2 4.31 -> 4.21 ms, config 3 22.53 -> 22.38, config 5 10.88 -> 10.79,
+// 1/8 shares unchanged / +1.8 % (profiles/r02_outline_experiment.txt; the first measurement, on the round's earlier code, had been a wash).
 #ifndef OCLR_OUTLINE_LEVEL
-#define OCLR_OUTLINE_LEVEL 0
+#define OCLR_OUTLINE_LEVEL 3
 #endif
 #if defined(__CUDACC__)
 #define OCLR_HD_OUT(level) __host__ __device__ OCLR_OUTLINE_##level

@@ -9,6 +9,19 @@ for i in range(start, len(src)):
     m = re.match(r"\s*// ---- ([A-Za-z]+)", src[i])
     if m: marks.append((i + 1, m.group(1).lower()))
     if src[i].startswith("}"): end = i + 1; break
+# function a source line belongs to: the last `OCLR_HD... name(` / `__device__ ... name(` definition at or above it
+_defs = {}
+def fn_of(fname, line):
+    if fname not in _defs:
+        d = []
+        for i, l in enumerate(open("opencl_render_b200/csrc/" + fname).read().split("\n")):
+            m = re.match(r"(?:template <[^>]*>\s*)?(?:OCLR_HD\w*(?:\(\d\))?|__device__ __forceinline__|__global__)\s+[\w:<> ]*?\b(\w+)\(", l)
+            if m: d.append((i + 1, m.group(1)))
+        _defs[fname] = d
+    name = None
+    for l0, n in _defs[fname]:
+        if l0 <= line: name = n
+    return name
 def phase(line):
     if line < start or line > end: return None
     p = "prologue"
@@ -27,11 +40,12 @@ for r in csv.reader(io.StringIO(txt)):
     except Exception: continue
     l = int(d["Line No"])
     if cur == "rt_trace.cuh":
-        g = phase(l) or ("next_entry" if 295 <= l <= 312 else "rt_trace other")
+        g = phase(l) or ("next_entry" if fn_of("rt_trace.cuh", l) == "next_entry" else "rt_trace other")
     elif cur == "rt_walk.h":
-        g = "walk (rt_walk.h step/bit/rank)" if l <= 116 else "switch (rt_walk.h)"
+        f = fn_of("rt_walk.h", l)
+        g = "switch (rt_walk.h)" if f in ("pwalk_enter_coarse", "prefine_axis", "pwalk_refine", "pwalk_super_allowed") else "walk (rt_walk.h step/bit/rank)"
     elif cur == "rt_core.h":
-        g = "tri_test (rt_core.h)" if (115 <= l <= 137 or l == 41) else ("switch (refine_axis)" if 322 <= l <= 345 else "rt_core other")
+        g = "tri_test (rt_core.h)" if fn_of("rt_core.h", l) in ("tri_test", "dot3") else "rt_core other"
     else:
         g = cur
     a = agg.setdefault(g, [0, 0, 0]); a[0] += inst; a[1] += thr; a[2] += samp
