@@ -331,7 +331,9 @@ def measure_config(run: Run, cfg_id: int, steps: int, warmup: int, primary: bool
            "value": rays_frame / ms_step / 1e3, "unit": "Mrays/s", "ms_per_step": ms_step, "steps": steps,
            "acceleration_lists": "built on the device (cam_builder.cuh / grid_builder.cuh)" if device_built else "host builders",
            "gather": {"kind": gather_kind, "ms_per_step": (ms_total - ms_render) / steps,
-                      "value_without_gather": rays_frame / (ms_render / steps) / 1e3}}
+                      "value_without_gather": rays_frame / (ms_render / steps) / 1e3},
+           # HBM held by the wavefront path state of this rank's launch domain (ring depth follows the scene's materials)
+           "path_state": {"bytes": fr.state_bytes, "bytes_per_path": fr.state_bytes / max(((part.owned_rows + 7) // 8 * 8) * w, 1)}}
 
     # ---- parity inside the run: 1-GPU render of the same frame on rank 0 (N > 1) / the independent per-pixel kernel (N = 1) ----------
     planes_1gpu = None
@@ -532,7 +534,8 @@ def run_b200(args):
             "metric": "Mrays/s", "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_keys(cfg, sc, cam),
-            "run": {"band_rows": args.band_rows, "kernel_variant": args.variant, "frame_assembly": main["gather"]["kind"]},
+            "run": {"band_rows": args.band_rows, "kernel_variant": args.variant, "frame_assembly": main["gather"]["kind"],
+                    "path_state": main.get("path_state")},
             "e2e": e2e, "gpu_launches": ex["launches"], "clocks": ex["clocks"], "roofline": main.get("roofline"),
             "gather": dict(main["gather"], included_in_value=world > 1),
             "parity_ok": main.get("parity_ok"), "parity": main.get("parity"),
