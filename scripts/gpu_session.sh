@@ -1,9 +1,8 @@
-# round 2, session l: refill inside a walk burst once enough lanes sit idle (OCLR_REFILL_BURST; 0 = between bursts only)
+# round 2, final session on one GPU: the whole GPU suite, the default bench line, the reference arm, and the round's ncu evidence (r02c)
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "golden or whole_frame or config3 or sliced" > gpurun_out/r02z_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02z_tests.log
-( timeout 400 python scripts/sweep_env.py 2 2 "OCLR_REFILL_BURST=0" "OCLR_REFILL_BURST=4" "OCLR_REFILL_BURST=6" "OCLR_REFILL_BURST=8" "OCLR_REFILL_BURST=12" "OCLR_REFILL_BURST=16" "OCLR_REFILL_BURST=0" "OCLR_REFILL_BURST=8"
-  timeout 400 python scripts/sweep_env.py 3 2 "OCLR_REFILL_BURST=0" "OCLR_REFILL_BURST=4" "OCLR_REFILL_BURST=8" "OCLR_REFILL_BURST=12"
-  timeout 400 python scripts/sweep_env.py 5 2 "OCLR_REFILL_BURST=0" "OCLR_REFILL_BURST=8" ) > gpurun_out/r02z_ab.log 2>&1
-grep -E "^---|frame|walk util|walk-iteration" gpurun_out/r02z_ab.log
-( timeout 300 python scripts/share_sweep.py 2 8 "OCLR_REFILL_BURST=0" "OCLR_REFILL_BURST=4" "OCLR_REFILL_BURST=8" "OCLR_REFILL_BURST=16" ) 2>&1 | tee gpurun_out/r02z_share.log
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/r02c_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02c_tests.log
+timeout 900 python bench.py > gpurun_out/r02c_bench_n1.json 2> gpurun_out/r02c_bench_n1.err; echo "bench rc=$?"; cut -c1-900 gpurun_out/r02c_bench_n1.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02c_bench_ref.json 2> gpurun_out/r02c_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/r02c_bench_ref.json
+timeout 900 bash scripts/profile_round.sh r02c
+python -c "import __graft_entry__ as g; g.smoke()"
