@@ -1,8 +1,6 @@
-# round 2, final session on one GPU: the whole GPU suite, the default bench line, the reference arm, and the round's ncu evidence (r02c)
+# round 2, two-GPU sanity session on the final code: the tests that need two GPUs, and the bench line at N = 2
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/r02c_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02c_tests.log
-timeout 900 python bench.py > gpurun_out/r02c_bench_n1.json 2> gpurun_out/r02c_bench_n1.err; echo "bench rc=$?"; cut -c1-900 gpurun_out/r02c_bench_n1.json
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02c_bench_ref.json 2> gpurun_out/r02c_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/r02c_bench_ref.json
-timeout 900 bash scripts/profile_round.sh r02c
-python -c "import __graft_entry__ as g; g.smoke()"
+nvidia-smi -L | wc -l
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "all_devices or two_gpus or raytrace_all" > gpurun_out/r02c_tests_n2.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02c_tests_n2.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r02c_bench_n2.json 2> gpurun_out/r02c_bench_n2.err; echo "bench rc=$?"; cut -c1-1200 gpurun_out/r02c_bench_n2.json; tail -3 gpurun_out/r02c_bench_n2.err
