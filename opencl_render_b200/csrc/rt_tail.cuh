@@ -1,0 +1,231 @@
+// rt_tail.cuh -- the tail of a small trace launch: ONE ray per warp, walked by cooperative bursts.
+//
+// A trace launch cannot end before its longest walk does.  On a whole 1080p frame that tail is 6 % of the walk iterations; on the 1/8
+// share an 8-GPU run gives each GPU it is 38 %, and the launch takes 0.38 ms where its throughput bound is 0.11 ms -- the floor that
+// holds strong scaling of small frames at 0.5.  The rays in that tail are few and long (a ray skimming the floor
+// quad crosses several hundred occupied cells), and a lane walks them one dependent step at a time, ~1 000 cycles per cell.
+//
+// wf_pipe_kernel<., ., HANDOFF = true> (chosen by the host for SMALL launch domains only: the whole-frame kernel stays as it is) gives
+// such rays up: a warp that has spent a few outer iterations with the queue dry writes {ray, current cell, entry face} of every lane
+// that is walking at cell level with nothing pending into a hand-off list and is done with them.  This kernel picks them up, a warp
+// per ray.  One burst = 32 lanes take the next 11 / 11 / 10 plane crossings of the x / y / z axis (one division each); the merge
+// order of the reference's walk (:387-398) gives every crossing its position directly (rt_walk.h, coop_burst_serial: the host form the
+// tests compare with the reference's cell walk), so ~25 cells are classified per burst with no serial dependency; their bricks are
+// looked up side by side, the occupied ones are opened and their (ray, triangle) pairs tested 32 at a time exactly as in the pipe
+// kernel's drain -- key = position of the cell in the walk | t | pair index, smallest key wins = the reference's first-cell-wins rule.
+// A 600-cell walk is ~25 bursts of a few hundred instructions instead of 600 dependent steps.
+//
+// Result (round 2, sessions n / o): bit-exact on every golden case with the hand-off forced as early as possible -- and not faster.  ncu
+// on a 1/8 share of config 2: the two ray-carrying pipe launches take 0.49 + 0.26 ms for 305 M + 102 M warp instructions (68 % / 43 %
+// of the whole-frame issue rate); handing rays off 4 outer iterations after the queue runs dry shortens them to 0.43-0.47 + 0.22 ms
+// and adds 0.05 + 0.075 ms of tail kernel (5 M + 21 M warp instructions): what a small launch loses is the decaying lane fill of
+// EVERY warp's last batch, thousands of medium rays, not a handful of very long ones.  Off by default (OCLR_HANDOFF_MAX_PATHS = 0);
+// tests/test_gpu_progressive.py::test_tail_handoff_is_invisible keeps it exact.
+#pragma once
+#include "rt_trace.cuh"
+
+namespace oclr {
+
+struct TailWarp {
+    float t[3][11];                  // crossing values of the burst's candidates
+    uint32_t slotCell[32];           // cells of the burst in walk order
+    uint32_t slotFace[32];
+    uint32_t pairTri[kPairQCap], pairSeq[kPairQCap];
+    unsigned long long bestKey;
+    uint32_t bestTri;
+    float bestAB, bestAC;
+};
+
+__global__ void __launch_bounds__(128) wf_tail_kernel(SceneView S, WfState w, TailQueue tq) {
+    extern __shared__ float shPlanes[];
+    __shared__ TailWarp warps[4];
+    const uint32_t total = min(*tq.count, tq.capacity);
+    if (total == 0u) return;   // (the usual case on a whole frame: nothing was handed off)
+    load_planes(shPlanes, S);
+    const int lane = threadIdx.x & 31;
+    TailWarp& T = warps[threadIdx.x >> 5];
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int n = S.n, nb = S.nb;
+    const float* px = shPlanes;
+    const float* py = shPlanes + (n + 1);
+    const float* pz = shPlanes + 2 * (n + 1);
+    const unsigned long long kEmptyKey = ~0ull;
+
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(tq.cursor, 1u);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= total) break;
+        const uint4 e = tq.entries[idx];
+        const uint32_t path = e.x;
+        const float4 ro = w.rayO[path], rd = w.rayD[path];
+        const uint32_t excl = w.rayExcl[path];
+        const f3 o = mk3(ro.x, ro.y, ro.z), r = mk3(rd.x, rd.y, rd.z);
+        const float minD = ro.w, maxD = rd.w;
+        CoopRay ray;
+        ray.o = o;
+        ray.r = r;
+        {   // the end cell, as wf_setup_kernel computed it (raytrace_opencl.c:357-361)
+            PackedWalk s;
+            pwalk_setup(s, n, nb, px, py, pz, o, r, minD, maxD);
+            ray.epk = s.epk;
+        }
+        ray.c0[0] = pk_get(e.y, 0);
+        ray.c0[1] = pk_get(e.y, 1);
+        ray.c0[2] = pk_get(e.y, 2);
+        if (lane == 0) {
+            T.bestKey = kEmptyKey;
+            T.slotCell[0] = e.y;
+            T.slotFace[0] = e.z;
+        }
+        __syncwarp();
+
+        // opens the cells in slots [0, count) -- walk order -- and tests their untested list entries against the ray
+        auto process_cells = [&](uint32_t count) {
+            uint32_t k = 0, kEnd = 0, kBegin = 0, fm = 0;
+            if ((uint32_t)lane < count) {
+                const uint32_t cell = T.slotCell[lane], face = T.slotFace[lane];
+                const int cx = pk_get(cell, 0), cy = pk_get(cell, 1), cz = pk_get(cell, 2);
+                const uint4 br = __ldg(S.bricks + ((cx >> 2) + nb * ((cy >> 2) + nb * (cz >> 2))));
+                const int bit = pwalk_bit(cell);
+                const uint64_t mask = (uint64_t)br.x | ((uint64_t)br.y << 32);
+                if ((mask >> bit) & 1ull) {
+                    const uint32_t rank = br.z + (uint32_t)__popcll(mask & ((1ull << bit) - 1ull));
+                    const uint2 range = __ldg(S.cellRange + rank);
+                    fm = face != (uint32_t)kFaceNone ? __ldg(S.faceMask + 6 * (size_t)rank + face) : 0xFFFFFFFFu;
+                    kBegin = range.x;
+                    kEnd = range.y;
+                    k = next_entry(kBegin, kEnd, fm, kBegin);
+                }
+            }
+            uint32_t pqHead = 0, pqTail = 0;
+            auto test_round = [&](uint32_t take) {
+                __syncwarp();
+                bool hit = false;
+                unsigned long long key = kEmptyKey;
+                uint32_t tri = 0;
+                float ab = 0.f, ac = 0.f;
+                if ((uint32_t)lane < take) {
+                    const uint32_t pidx = pqHead + (uint32_t)lane;
+                    tri = T.pairTri[pidx & (kPairQCap - 1)];
+                    const uint32_t seq = T.pairSeq[pidx & (kPairQCap - 1)];
+                    float t;
+                    hit = tri_test(S.triGeo + 4 * (size_t)tri, o, r, minD, maxD, t, ab, ac);
+                    if (hit) {
+                        key = ((unsigned long long)seq << 56) | ((unsigned long long)__float_as_uint(t) << 24) | (unsigned long long)(pidx & 0xFFFFFFu);
+                        atomicMin(&T.bestKey, key);
+                    }
+                }
+                __syncwarp();
+                if (hit && T.bestKey == key) {
+                    T.bestTri = tri;
+                    T.bestAB = ab;
+                    T.bestAC = ac;
+                }
+                pqHead += take;
+            };
+            while (__any_sync(0xFFFFFFFFu, k < kEnd)) {
+                const bool more = k < kEnd;
+                uint32_t tri = 0;
+                if (more) tri = __ldg(S.cellList + k);
+                const bool valid = more & (tri != excl);
+                const unsigned vb = __ballot_sync(0xFFFFFFFFu, valid);
+                if (valid) {
+                    const uint32_t pos = (pqTail + (uint32_t)__popc(vb & ltMask)) & (kPairQCap - 1);
+                    T.pairTri[pos] = tri;
+                    T.pairSeq[pos] = (uint32_t)lane;   // position of the cell in the walk: the first cell with a hit wins (:380)
+                }
+                pqTail += (uint32_t)__popc(vb);
+                if (more) k = next_entry(kBegin, kEnd, fm, k + 1u);
+                if (pqTail - pqHead >= 32u) test_round(32u);
+            }
+            while (pqTail != pqHead) test_round(pqTail - pqHead < 32u ? pqTail - pqHead : 32u);
+            __syncwarp();
+        };
+        auto finish = [&](bool hit) {
+            if (lane == 0) {
+                const unsigned long long key = T.bestKey;
+                w.hit[path] = hit ? make_float4(__uint_as_float(T.bestTri), __uint_as_float((uint32_t)(key >> 24)), T.bestAB, T.bestAC)
+                                  : make_float4(__uint_as_float(kNoTriangle), maxD, 0.f, 0.f);
+            }
+            __syncwarp();
+        };
+
+        // the cell the lane stood in when it gave the ray up has not been examined yet
+        process_cells(1u);
+        if (T.bestKey != kEmptyKey) {
+            finish(true);
+            continue;
+        }
+        if (e.y == ray.epk) {
+            finish(false);
+            continue;
+        }
+        for (;;) {
+            // ---- one burst (rt_walk.h coop_burst_serial, one virtual lane per real lane) ------------------------------------------
+            const int a = lane % 3, kc = lane / 3;
+            int kmaxA;
+            const float tv = coop_crossing(ray, n, shPlanes, a, kc, kmaxA);
+            __syncwarp();
+            T.t[a][kc] = tv;
+            __syncwarp();
+            int cnt[3];
+            int rank = kc;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                if (b == a) {
+                    cnt[b] = kc + 1;
+                    continue;
+                }
+                int c = 0;
+                for (int kk = 0; kk < coop_candidates(b); ++kk) c += coop_precedes(b, T.t[b][kk], a, tv) ? 1 : 0;
+                cnt[b] = c;
+                rank += c;
+            }
+            const bool present = kc <= kmaxA;
+            const int kBig = 1 << 20;
+            // crossings with rank < R are certain: no crossing beyond the candidates can precede them
+            const int R = __reduce_min_sync(0xFFFFFFFFu, (kc == coop_candidates(a) - 1 && kmaxA >= coop_candidates(a)) ? rank + 1 : kCoopLanes);
+            const int exitRank = __reduce_min_sync(0xFFFFFFFFu, (present && kc == kmaxA) ? rank : kBig);
+            const float rx = ray.r.x, ry = ray.r.y, rz = ray.r.z;
+            const int cx = ray.c0[0] + ((0 <= rx) ? cnt[0] : -cnt[0]);
+            const int cy = ray.c0[1] + ((0 <= ry) ? cnt[1] : -cnt[1]);
+            const int cz = ray.c0[2] + ((0 <= rz) ? cnt[2] : -cnt[2]);
+            const uint32_t cellV = (present && kc < kmaxA) ? pk_make(cx & kPkMask, cy & kPkMask, cz & kPkMask) : (uint32_t)kPkNone;
+            const int endRank = __reduce_min_sync(0xFFFFFFFFu, (cellV != (uint32_t)kPkNone && cellV == ray.epk) ? rank : kBig);
+            int limit = R;
+            bool finished = false;
+            if (exitRank < limit) {   // the crossing that leaves the grid enters no cell
+                limit = exitRank;
+                finished = true;
+            }
+            if (endRank < limit) {   // the end cell is visited, then the walk stops (:381)
+                limit = endRank + 1;
+                finished = true;
+            }
+            if (rank < limit) {
+                const float ra = a == 0 ? rx : (a == 1 ? ry : rz);
+                T.slotCell[rank] = cellV;
+                T.slotFace[rank] = (uint32_t)(a * 2 + ((0 <= ra) ? 1 : 0));
+            }
+            __syncwarp();
+            if (limit > 0) {
+                process_cells((uint32_t)limit);
+                const uint32_t last = T.slotCell[limit - 1];
+                ray.c0[0] = pk_get(last, 0);
+                ray.c0[1] = pk_get(last, 1);
+                ray.c0[2] = pk_get(last, 2);
+            }
+            if (T.bestKey != kEmptyKey) {
+                finish(true);
+                break;
+            }
+            if (finished) {
+                finish(false);
+                break;
+            }
+        }
+    }
+}
+
+}  // namespace oclr

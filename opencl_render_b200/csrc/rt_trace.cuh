@@ -33,6 +33,15 @@ struct TraceTuning {
     int splitMin;      // queue dry: a walk with at least this many cells to go is cut into parts for the warp's idle lanes (0 = never)
     int splitPart;     // ... of at least this many cells each
     int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
+    int handoffAfter;  // HANDOFF instantiation: outer iterations a warp spends with the queue dry before it gives its long rays up (rt_tail.cuh)
+};
+
+// Rays a small launch's pipe kernel gives up in its tail, for wf_tail_kernel (rt_tail.cuh) to walk one per warp.
+struct TailQueue {
+    uint4* entries;     // {ray index (slot * Q + path), current cell (packed, not yet examined), entry face, 0}
+    uint32_t* count;    // entries written by the pipe kernel of this round
+    uint32_t* cursor;   // next entry to take
+    uint32_t capacity;
 };
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
@@ -202,9 +211,9 @@ __device__ __forceinline__ uint32_t next_entry(uint32_t begin, uint32_t end, uin
     return k < end ? k : end;
 }
 
-template <bool COUNT, bool SPLIT>
+template <bool COUNT, bool SPLIT, bool HANDOFF = false>
 __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(SceneView S, WfState w, WalkRecords rec, TraceTuning tune,
-                                                                            Counters* gcnt) {
+                                                                            Counters* gcnt, TailQueue tq) {
     extern __shared__ float shPlanes[];
     __shared__ WarpPipe pipes[4];
     __shared__ uint32_t classOff[kLengthClasses];   // first queue position of each length class (longest class first)
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     float lastE = 0.f;
     uint32_t seqNext = 0;   // cells this ray has in the current batch
     uint32_t cq = 0;        // warp-uniform: cells queued
+    int tailAge = 0;        // warp-uniform (HANDOFF): outer iterations since this warp saw the queue dry
 
     for (;;) {
         // ---- SPLIT: idle lanes take parts of the longest whole walk this warp holds (queue dry; or, early mode, a ray that has been
@@ -709,6 +719,27 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             __syncwarp();
             if (closes) P.gParts[headLane] = 0u;   // the head lane's group record is free again
             __syncwarp();
+        }
+
+        // ---- HANDOFF (small launches only): the queue has been dry for a while and what this warp still walks is the launch's tail ---
+        if (HANDOFF && exhausted && ++tailAge > tune.handoffAfter) {
+            // a lane walking at cell level with nothing pending (cells drained, keys resolved just above): its ray goes on in
+            // wf_tail_kernel from the cell it stands in, one warp to the ray (rt_tail.cuh)
+            const bool give = (ws == kWsRun) & (g.level == 0) & g.coarseOk & (!SPLIT || P.grp[lane] == 0u);
+            const unsigned gm = __ballot_sync(0xFFFFFFFFu, give);
+            if (gm != 0u) {
+                const int leader = __ffs(gm) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(tq.count, (uint32_t)__popc(gm));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (give) {
+                    const uint32_t pos = base + (uint32_t)__popc(gm & ltMask);
+                    if (pos < tq.capacity) {   // (a full list: the lane keeps its ray)
+                        tq.entries[pos] = make_uint4(path, g.cpk, (uint32_t)face, 0u);
+                        ws = kWsNone;
+                    }
+                }
+            }
         }
     }
     if (COUNT) {

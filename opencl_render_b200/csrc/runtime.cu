@@ -22,6 +22,7 @@
 #include "grid_builder.cuh"
 #include "pack_kernels.cuh"
 #include "rt_kernels.cuh"
+#include "rt_tail.cuh"
 #include "rt_trace.cuh"
 #include "rt_wavefront.cuh"
 #include "runtime.h"
@@ -661,10 +662,14 @@ struct Scene {
 // Wavefront path state of one slice of a launch domain (launch_wavefront): its own buffers, queue counters and stream, so
 // the rounds of different slices overlap on the GPU.
 enum { kMaxSlices = 8 };
+// per-round counters of a slice: {ray count, cursor, class counts, hand-off count, hand-off cursor}, two sets alternating between rounds
+enum { kCounterStride = 2 + kLengthClasses + 2 };
 struct WfSlice {
     DeviceBuffer ctl, rng, colour, ring, carry, rayO, rayD, rayExcl, hit, queue;
     DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
-    DeviceBuffer workCounter;                          // {count, cursor, class counts} x 2, alternating between rounds; then the round log
+    DeviceBuffer workCounter;                          // kCounterStride counters x 2, alternating between rounds; then the round log
+    DeviceBuffer tailEntries;                          // hand-off list of a small launch's trace tail (rt_tail.cuh); unallocated for large domains
+    uint32_t tailCapacity = 0;
     uint32_t capacity = 0;
     uint32_t lastRounds = 4;          // rounds the previous sample needed (first chunk of the next one)
     cudaStream_t stream = nullptr;    // internal stream (slice 0 runs on the caller's stream)
@@ -673,8 +678,8 @@ struct WfSlice {
     uint32_t traceEventsUsed = 0;
     DeviceBuffer* buffers(int i) {
         DeviceBuffer* all[] = {&ctl, &rng, &colour, &ring, &carry, &rayO, &rayD, &rayExcl, &hit, &queue, &recO, &recD, &recS0, &recS1,
-                               &recOrder, &workCounter};
-        return i < 16 ? all[i] : nullptr;
+                               &recOrder, &workCounter, &tailEntries};
+        return i < 17 ? all[i] : nullptr;
     }
 };
 
@@ -1567,6 +1572,13 @@ static bool resumes_prelaunch(const Frame* f, const FrameView& F);
 // `prelaunchOnly`: allocate the path state and enqueue nothing but the first logic round of the first sample, on the frame's own
 // stream behind everything already enqueued on `st` (frame_prelaunch).  A later normal call with the same view finds
 // f->prelaunched set, skips that round's logic launch and orders its first setup kernel behind it.
+// Launch domains of at most OCLR_HANDOFF_MAX_PATHS paths hand the tail of their trace launches to wf_tail_kernel (rt_tail.cuh).  Off by
+// default (0): exact, but a 1/8 share of config 2 gets slower (0.93 -> 0.97-1.08 ms) -- what a small launch loses is not a few very long
+// rays but the decaying lane fill of every warp's last batch, and one warp per ray is the wrong cure for that (profiles/r02_super_level.txt).
+static bool handoff_domain(uint32_t Q) {
+    static const uint32_t maxPaths = [] { const char* v = getenv("OCLR_HANDOFF_MAX_PATHS"); return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u; }();
+    return Q <= maxPaths;
+}
 static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall, int smCount, Counters* dcnt, cudaStream_t st,
                              uint32_t& launches, bool timeTrace, std::string& err, bool prelaunchOnly = false) {
     const uint32_t W = Fall.cam.width;
@@ -1634,8 +1646,13 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                 !sl.queue.alloc(sizeof(uint32_t) * 2 * q, err, st) || !sl.recO.alloc(sizeof(float4) * 2 * q, err, st) ||
                 !sl.recD.alloc(sizeof(float4) * 2 * q, err, st) || !sl.recS0.alloc(sizeof(float4) * 2 * q, err, st) ||
                 !sl.recS1.alloc(sizeof(uint4) * 2 * q, err, st) || !sl.recOrder.alloc(sizeof(uint32_t) * 2 * q * kLengthClasses, err, st) ||
-                !sl.workCounter.alloc(sizeof(uint32_t) * (2 * (2 + kLengthClasses) + kRoundLogSize), err, st))
+                !sl.workCounter.alloc(sizeof(uint32_t) * (2 * kCounterStride + kRoundLogSize), err, st))
                 return false;
+            sl.tailCapacity = 0;
+            if (handoff_domain(Q)) {   // small launch domain: its trace tail is handed to wf_tail_kernel (rt_tail.cuh)
+                sl.tailCapacity = (uint32_t)std::min<size_t>(2 * q, (size_t)1 << 20);
+                if (!sl.tailEntries.alloc(sizeof(uint4) * sl.tailCapacity, err, st)) return false;
+            }
             sl.capacity = Q;
         }
         if (k > 0 && !sl.stream) OCLR_CUDA(make_stream(f->device, &sl.stream));
@@ -1683,7 +1700,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // host thread per GPU)
     static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0};
+        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 2;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 64), (int)kCellQCap - 31);   // (round 2 sweep: 64 is ~1 % faster than 48 on configs 2 and 3)
@@ -1693,6 +1710,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         t.splitMin = getenv("OCLR_SPLIT_MIN") ? atoi(getenv("OCLR_SPLIT_MIN")) : 0;   // 0: never cut a walk (default, see rt_trace.cuh)
         t.splitPart = env("OCLR_SPLIT_PART", 16);
         t.splitEarly = getenv("OCLR_SPLIT_EARLY") ? atoi(getenv("OCLR_SPLIT_EARLY")) : 0;
+        t.handoffAfter = getenv("OCLR_HANDOFF_AFTER") ? atoi(getenv("OCLR_HANDOFF_AFTER")) : 2;
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -1708,11 +1726,11 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         uint32_t* counters = (uint32_t*)sl.workCounter.p;
         w[0].queueCount = counters;
         w[0].queueCursor = counters + 1;
-        w[0].roundLog = counters + 2 * (2 + kLengthClasses);
+        w[0].roundLog = counters + 2 * kCounterStride;
         w[0].roundIndex = 0;
         OCLR_CUDA(cudaEventRecord(f->preReady, st));
         OCLR_CUDA(cudaStreamWaitEvent(f->preStream, f->preReady, 0));
-        OCLR_CUDA(cudaMemsetAsync(w[0].queueCount, 0, sizeof(uint32_t) * (2 + kLengthClasses), f->preStream));
+        OCLR_CUDA(cudaMemsetAsync(w[0].queueCount, 0, sizeof(uint32_t) * kCounterStride, f->preStream));
         wf_logic_kernel<false><<<logicGrid[0], 128, 0, f->preStream>>>(S, FV[0], w[0], Fall.sampleBegin, 1u, nullptr, nullptr, aheadMode[0]);
         OCLR_CUDA(cudaGetLastError());
         OCLR_CUDA(cudaEventRecord(f->preDone, f->preStream));
@@ -1730,7 +1748,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // of its round from device memory and returns at once when there is nothing to do.  The host looks at the count of the last
     // enqueued round once per chunk; the first chunk is as long as the previous sample / frame needed.  Slices are enqueued round
     // by round, alternating, so that their launches interleave on the device.
-    const uint32_t cstride = 2 + kLengthClasses;
+    const uint32_t cstride = kCounterStride;
     for (uint32_t s = Fall.sampleBegin; s < Fall.sampleEnd; ++s) {
         uint32_t round[kMaxSlices] = {0};
         bool live[kMaxSlices];
@@ -1779,14 +1797,26 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     ++launches;
                     // (the run-time split of long walks is an instantiation of its own: compiled into the production kernel it cost
                     // 10 % through register pressure even when switched off)
+                    // (so is the hand-off of the tail to wf_tail_kernel: only the launches of small domains run that instantiation)
+                    TailQueue tq = {(uint4*)sl.tailEntries.p, w[k].queueCount + 2 + kLengthClasses, w[k].queueCount + 3 + kLengthClasses,
+                                    sl.tailCapacity};
+                    const bool handoff = sl.tailCapacity != 0 && tune.splitMin <= 0;
                     if (dcnt && tune.splitMin > 0)
-                        wf_pipe_kernel<true, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                        wf_pipe_kernel<true, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
+                    else if (dcnt && handoff)
+                        wf_pipe_kernel<true, false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
                     else if (dcnt)
-                        wf_pipe_kernel<true, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                        wf_pipe_kernel<true, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
                     else if (tune.splitMin > 0)
-                        wf_pipe_kernel<false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                        wf_pipe_kernel<false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
+                    else if (handoff)
+                        wf_pipe_kernel<false, false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
                     else
-                        wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt);
+                        wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
+                    if (handoff) {
+                        wf_tail_kernel<<<(unsigned)(smCount * 4), 128, shBytes, ks>>>(S, w[k], tq);
+                        ++launches;
+                    }
                     if (timeTrace) {
                         OCLR_CUDA(cudaEventRecord(sl.traceEvents[sl.traceEventsUsed + 1], ks));
                         sl.traceEventsUsed += 2;

@@ -212,6 +212,56 @@ def test_super_brick_level_of_the_walk_is_invisible():
             assert o["three"]["superSteps"] == 0 and o["brick_bytes"][1] == o["brick_bytes"][0], (name, o)
 
 
+_TAIL_PROBE = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd())
+from opencl_render_b200 import api
+from tests import helpers
+out = {}
+for name in helpers.CASE_NAMES:
+    sc, cam, lists, samples = helpers.make_case(name)
+    gold = np.load(os.path.join("tests", "golden", name + ".npz"))
+    ds = api.DeviceScene(sc, 0)
+    fr = api.DeviceFrame(ds, cam, lists)
+    _, launches, _ = fr.render(samples)
+    img, flags = fr.read(), fr.undefined_flags()
+    ids = fr.primary_ids()
+    if samples != 1:
+        fr.render(1)
+        ids = fr.primary_ids()
+    out[name] = dict(diff=int(helpers.compare_rgb(img, (gold["r"], gold["g"], gold["b"]), mask=(flags == 0))["diff_pixels"]),
+                     ids=int((ids != gold["ids"]).sum()), launches=int(launches))
+    fr.close(); ds.close()
+print("TAIL_PROBE " + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("after", ["0", "2", "off"])
+def test_tail_handoff_is_invisible(after):
+    """rt_tail.cuh: a launch domain may hand the rays still walking in the tail of a trace launch to wf_tail_kernel (one ray per warp,
+    cooperative bursts; an experiment that is exact but not faster, hence off by default).  With the hand-off forced as early as
+    possible (OCLR_HANDOFF_AFTER=0: every ray still walking at cell level when its warp sees the queue dry goes through the burst
+    walker), two outer iterations later, and switched off, every golden case gives the golden planes and ids.  (Environment knobs
+    are read once per process: each setting runs in a process of its own.)"""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ)
+    if after == "off":
+        env["OCLR_HANDOFF_MAX_PATHS"] = "0"
+    else:
+        env["OCLR_HANDOFF_MAX_PATHS"] = "4000000000"    # (off by default: not faster, rt_tail.cuh)
+        env["OCLR_HANDOFF_AFTER"] = after
+    r = subprocess.run([sys.executable, "-c", _TAIL_PROBE], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("TAIL_PROBE ")][-1][len("TAIL_PROBE "):])
+    assert set(out) == set(helpers.CASE_NAMES)
+    for name, o in out.items():
+        assert o["diff"] == 0 and o["ids"] == 0, (after, name, o)
+
+
 def test_ring_depth_follows_the_materials(monkeypatch):
     """runtime.cu Scene::ringSlots: only mirror / glass segments push a path's ring beyond two slots (raytrace_opencl.c:682-722), so a
     scene without reflection / transparency channels gets 2 ring slots per path instead of 12 -- same planes as with the full ring
