@@ -33,15 +33,23 @@ struct TraceTuning {
     int splitMin;      // queue dry: a walk with at least this many cells to go is cut into parts for the warp's idle lanes (0 = never)
     int splitPart;     // ... of at least this many cells each
     int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
-    int handoffAfter;  // HANDOFF instantiation: outer iterations a warp spends with the queue dry before it gives its long rays up (rt_tail.cuh)
+    int handoffAfter;  // HANDOFF instantiation: outer iterations a warp spends with the queue dry before it gives rays up (rt_tail.cuh)
+    int handoffMode;   // 1: to wf_tail_kernel, one ray per warp; 2: back into a queue of walk records for a second, densely packed pass
+    int handoffLanes;  // mode 2: a warp gives its rays up once at most this many of its lanes still walk
 };
 
-// Rays a small launch's pipe kernel gives up in its tail, for wf_tail_kernel (rt_tail.cuh) to walk one per warp.
+// Rays a launch's pipe kernel gives up in its tail (HANDOFF instantiation, small launch domains; rt_tail.cuh).
 struct TailQueue {
-    uint4* entries;     // {ray index (slot * Q + path), current cell (packed, not yet examined), entry face, 0}
-    uint32_t* count;    // entries written by the pipe kernel of this round
+    uint4* entries;     // mode 1: {ray index (slot * Q + path), current cell (packed, not yet examined), entry face, 0}
+    uint32_t* count;    // rays given up by the pipe kernel of this round; {count, 0, 0, 0} doubles as the class counts of the second pass
     uint32_t* cursor;   // next entry to take
     uint32_t capacity;
+    // mode 2: the rays as walk records (the setup kernel's format, resumed from the cell the lane stood in) + identity order
+    float4* o;
+    float4* d;
+    float4* s0;
+    uint4* s1;
+    uint32_t* order;
 };
 
 // Walk records written by wf_setup_kernel, indexed by queue slot, and the order in which the trace kernel takes them.
@@ -722,10 +730,12 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
 
         // ---- HANDOFF (small launches only): the queue has been dry for a while and what this warp still walks is the launch's tail ---
-        if (HANDOFF && exhausted && ++tailAge > tune.handoffAfter) {
-            // a lane walking at cell level with nothing pending (cells drained, keys resolved just above): its ray goes on in
-            // wf_tail_kernel from the cell it stands in, one warp to the ray (rt_tail.cuh)
-            const bool give = (ws == kWsRun) & (g.level == 0) & g.coarseOk & (!SPLIT || P.grp[lane] == 0u);
+        if (HANDOFF && exhausted && ++tailAge > tune.handoffAfter &&
+            (tune.handoffMode != 2 || __popc(__ballot_sync(0xFFFFFFFFu, ws != kWsNone)) <= tune.handoffLanes)) {
+            // a lane walking at cell level with nothing pending (cells drained, keys resolved just above) gives its ray up, to go on
+            // from the cell it stands in: mode 1 in wf_tail_kernel, one warp to the ray; mode 2 in a second pass of this kernel over
+            // the rays given up, which fills its warps densely again (rt_tail.cuh)
+            const bool give = (ws == kWsRun) & (g.level == 0) & (tune.handoffMode == 2 || g.coarseOk) & (!SPLIT || P.grp[lane] == 0u);
             const unsigned gm = __ballot_sync(0xFFFFFFFFu, give);
             if (gm != 0u) {
                 const int leader = __ffs(gm) - 1;
@@ -735,7 +745,15 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                 if (give) {
                     const uint32_t pos = base + (uint32_t)__popc(gm & ltMask);
                     if (pos < tq.capacity) {   // (a full list: the lane keeps its ray)
-                        tq.entries[pos] = make_uint4(path, g.cpk, (uint32_t)face, 0u);
+                        if (tune.handoffMode == 2) {   // a walk record like the setup kernel's: the state of a walk at cell level IS (cell, crossings)
+                            tq.o[pos] = make_float4(P.ray[0][lane], P.ray[1][lane], P.ray[2][lane], P.ray[6][lane]);
+                            tq.d[pos] = make_float4(P.ray[3][lane], P.ray[4][lane], P.ray[5][lane], P.ray[7][lane]);
+                            tq.s0[pos] = make_float4(g.tx, g.ty, g.tz, __uint_as_float(g.cpk));
+                            tq.s1[pos] = make_uint4(g.epk, P.excl[lane], path, g.coarseOk ? 1u : 0u);
+                            tq.order[pos] = pos;
+                        } else {
+                            tq.entries[pos] = make_uint4(path, g.cpk, (uint32_t)face, 0u);
+                        }
                         ws = kWsNone;
                     }
                 }

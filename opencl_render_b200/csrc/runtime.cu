@@ -662,13 +662,15 @@ struct Scene {
 // Wavefront path state of one slice of a launch domain (launch_wavefront): its own buffers, queue counters and stream, so
 // the rounds of different slices overlap on the GPU.
 enum { kMaxSlices = 8 };
-// per-round counters of a slice: {ray count, cursor, class counts, hand-off count, hand-off cursor}, two sets alternating between rounds
-enum { kCounterStride = 2 + kLengthClasses + 2 };
+// per-round counters of a slice: {ray count, cursor, class counts[4], hand-off count, 0, 0, 0, hand-off cursor}, two sets alternating
+// between rounds ({hand-off count, 0, 0, 0} doubles as the class counts of the second pass over the rays given up, rt_tail.cuh)
+enum { kCounterStride = 2 + kLengthClasses + 5 };
 struct WfSlice {
     DeviceBuffer ctl, rng, colour, ring, carry, rayO, rayD, rayExcl, hit, queue;
     DeviceBuffer recO, recD, recS0, recS1, recOrder;   // walk records in queue order + class order (rt_trace.cuh)
     DeviceBuffer workCounter;                          // kCounterStride counters x 2, alternating between rounds; then the round log
     DeviceBuffer tailEntries;                          // hand-off list of a small launch's trace tail (rt_tail.cuh); unallocated for large domains
+    DeviceBuffer tailO, tailD, tailS0, tailS1, tailOrder;   // ... as walk records, for the second pass (hand-off mode 2)
     uint32_t tailCapacity = 0;
     uint32_t capacity = 0;
     uint32_t lastRounds = 4;          // rounds the previous sample needed (first chunk of the next one)
@@ -678,8 +680,8 @@ struct WfSlice {
     uint32_t traceEventsUsed = 0;
     DeviceBuffer* buffers(int i) {
         DeviceBuffer* all[] = {&ctl, &rng, &colour, &ring, &carry, &rayO, &rayD, &rayExcl, &hit, &queue, &recO, &recD, &recS0, &recS1,
-                               &recOrder, &workCounter, &tailEntries};
-        return i < 17 ? all[i] : nullptr;
+                               &recOrder, &workCounter, &tailEntries, &tailO, &tailD, &tailS0, &tailS1, &tailOrder};
+        return i < 22 ? all[i] : nullptr;
     }
 };
 
@@ -1650,8 +1652,12 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                 return false;
             sl.tailCapacity = 0;
             if (handoff_domain(Q)) {   // small launch domain: its trace tail is handed to wf_tail_kernel (rt_tail.cuh)
-                sl.tailCapacity = (uint32_t)std::min<size_t>(2 * q, (size_t)1 << 20);
-                if (!sl.tailEntries.alloc(sizeof(uint4) * sl.tailCapacity, err, st)) return false;
+                sl.tailCapacity = (uint32_t)(2 * q);   // (every ray of a round could be given up: the list cannot overflow)
+                const size_t c = sl.tailCapacity;
+                if (!sl.tailEntries.alloc(sizeof(uint4) * c, err, st) || !sl.tailO.alloc(sizeof(float4) * c, err, st) ||
+                    !sl.tailD.alloc(sizeof(float4) * c, err, st) || !sl.tailS0.alloc(sizeof(float4) * c, err, st) ||
+                    !sl.tailS1.alloc(sizeof(uint4) * c, err, st) || !sl.tailOrder.alloc(sizeof(uint32_t) * c, err, st))
+                    return false;
             }
             sl.capacity = Q;
         }
@@ -1700,7 +1706,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // host thread per GPU)
     static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
+        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 16};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 2;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 64), (int)kCellQCap - 31);   // (round 2 sweep: 64 is ~1 % faster than 48 on configs 2 and 3)
@@ -1711,6 +1717,8 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         t.splitPart = env("OCLR_SPLIT_PART", 16);
         t.splitEarly = getenv("OCLR_SPLIT_EARLY") ? atoi(getenv("OCLR_SPLIT_EARLY")) : 0;
         t.handoffAfter = getenv("OCLR_HANDOFF_AFTER") ? atoi(getenv("OCLR_HANDOFF_AFTER")) : 2;
+        t.handoffMode = getenv("OCLR_HANDOFF_MODE") ? atoi(getenv("OCLR_HANDOFF_MODE")) : 1;
+        t.handoffLanes = getenv("OCLR_HANDOFF_LANES") ? atoi(getenv("OCLR_HANDOFF_LANES")) : 16;
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -1798,8 +1806,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                     // (the run-time split of long walks is an instantiation of its own: compiled into the production kernel it cost
                     // 10 % through register pressure even when switched off)
                     // (so is the hand-off of the tail to wf_tail_kernel: only the launches of small domains run that instantiation)
-                    TailQueue tq = {(uint4*)sl.tailEntries.p, w[k].queueCount + 2 + kLengthClasses, w[k].queueCount + 3 + kLengthClasses,
-                                    sl.tailCapacity};
+                    TailQueue tq = {(uint4*)sl.tailEntries.p, w[k].queueCount + 2 + kLengthClasses, w[k].queueCount + 6 + kLengthClasses,
+                                    sl.tailCapacity, (float4*)sl.tailO.p, (float4*)sl.tailD.p, (float4*)sl.tailS0.p, (uint4*)sl.tailS1.p,
+                                    (uint32_t*)sl.tailOrder.p};
                     const bool handoff = sl.tailCapacity != 0 && tune.splitMin <= 0;
                     if (dcnt && tune.splitMin > 0)
                         wf_pipe_kernel<true, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
@@ -1813,7 +1822,17 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                         wf_pipe_kernel<false, false, true><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
                     else
                         wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w[k], rec[k], tune, dcnt, tq);
-                    if (handoff) {
+                    if (handoff && tune.handoffMode == 2) {   // second pass: the same kernel over the rays given up, as their own little queue
+                        WfState w2 = w[k];
+                        w2.queueCount = tq.count;
+                        w2.queueCursor = tq.cursor;
+                        WalkRecords rec2 = {tq.o, tq.d, tq.s0, tq.s1, tq.order, tq.count, tq.capacity};
+                        if (dcnt)
+                            wf_pipe_kernel<true, false><<<traceGrid, 128, shBytes, ks>>>(S, w2, rec2, tune, dcnt, tq);
+                        else
+                            wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w2, rec2, tune, dcnt, tq);
+                        ++launches;
+                    } else if (handoff) {
                         wf_tail_kernel<<<(unsigned)(smCount * 4), 128, shBytes, ks>>>(S, w[k], tq);
                         ++launches;
                     }

@@ -1,18 +1,9 @@
-# round 2, session o: where does the time of a 1/8-share frame go with the tail hand-off on?  per-kernel durations and instruction counts
+# round 2, session p: hand-off mode 2 -- rays given up by thinly filled warps go back into a queue and a second pass packs them densely
 set -x
 cd $GRAFT_REPO_ROOT
-for a in 0 4 16; do
-OCLR_HANDOFF_AFTER=$a ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k "regex:wf_pipe|wf_tail" -c 12 --csv --log-file gpurun_out/r02o_after$a.csv python scripts/ncu_target_band.py 2 8 2 > gpurun_out/r02o_after$a.log 2>&1
-done
-OCLR_HANDOFF_MAX_PATHS=0 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k "regex:wf_pipe|wf_tail" -c 12 --csv --log-file gpurun_out/r02o_off.csv python scripts/ncu_target_band.py 2 8 2 > gpurun_out/r02o_off.log 2>&1
-python - <<'PY'
-import csv, glob
-for f in sorted(glob.glob("gpurun_out/r02o_*.csv")):
-    rows = list(csv.reader(open(f)))
-    h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-    ix = {k: i for i, k in enumerate(rows[h])}
-    print(f)
-    for r in rows[h + 1:]:
-        if len(r) > ix["Metric Value"]:
-            print("  ", r[ix["ID"]], r[ix["Kernel Name"]][:40], r[ix["Metric Name"]], r[ix["Metric Value"]], r[ix["Metric Unit"]])
-PY
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "tail_handoff" > gpurun_out/r02p_tests.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r02p_tests.log
+M="OCLR_HANDOFF_MAX_PATHS=4000000 OCLR_HANDOFF_MODE=2"
+( timeout 400 python scripts/share_sweep.py 2 8 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=8" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=16" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=24" "$M OCLR_HANDOFF_AFTER=1 OCLR_HANDOFF_LANES=16" "$M OCLR_HANDOFF_AFTER=2 OCLR_HANDOFF_LANES=16" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=32" "OCLR_X=off"
+  timeout 300 python scripts/share_sweep.py 2 4 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=16" "$M OCLR_HANDOFF_AFTER=1 OCLR_HANDOFF_LANES=12"
+  timeout 300 python scripts/share_sweep.py 3 8 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=16" "$M OCLR_HANDOFF_AFTER=1 OCLR_HANDOFF_LANES=12"
+  timeout 300 python scripts/share_sweep.py 2 1 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=0 OCLR_HANDOFF_LANES=16" ) 2>&1 | tee gpurun_out/r02p_share.log

@@ -237,7 +237,7 @@ print("TAIL_PROBE " + json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("after", ["0", "2", "off"])
+@pytest.mark.parametrize("after", ["0", "2", "off", "requeue-all", "requeue-16"])
 def test_tail_handoff_is_invisible(after):
     """rt_tail.cuh: a launch domain may hand the rays still walking in the tail of a trace launch to wf_tail_kernel (one ray per warp,
     cooperative bursts; an experiment that is exact but not faster, hence off by default).  With the hand-off forced as early as
@@ -251,6 +251,9 @@ def test_tail_handoff_is_invisible(after):
     env = dict(os.environ)
     if after == "off":
         env["OCLR_HANDOFF_MAX_PATHS"] = "0"
+    elif after.startswith("requeue"):   # mode 2: the rays given up go back into a queue of walk records, a second pass of the pipe kernel takes them
+        env.update(OCLR_HANDOFF_MAX_PATHS="4000000000", OCLR_HANDOFF_MODE="2", OCLR_HANDOFF_AFTER="0",
+                   OCLR_HANDOFF_LANES="32" if after.endswith("all") else "16")
     else:
         env["OCLR_HANDOFF_MAX_PATHS"] = "4000000000"    # (off by default: not faster, rt_tail.cuh)
         env["OCLR_HANDOFF_AFTER"] = after
