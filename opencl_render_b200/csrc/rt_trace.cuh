@@ -35,7 +35,7 @@ struct TraceTuning {
     int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
     int handoffAfter;  // HANDOFF instantiation: outer iterations a warp spends with the queue dry before it gives rays up (rt_tail.cuh)
     int handoffMode;   // 1: to wf_tail_kernel, one ray per warp; 2: back into a queue of walk records for a second, densely packed pass
-    int handoffLanes;  // mode 2: a warp gives its rays up once at most this many of its lanes still walk
+    int handoffLanes;  // a warp gives its rays up once at most this many of its lanes still hold one (32: whatever it holds)
 };
 
 // Rays a launch's pipe kernel gives up in its tail (HANDOFF instantiation, small launch domains; rt_tail.cuh).
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
 
         // ---- HANDOFF (small launches only): the queue has been dry for a while and what this warp still walks is the launch's tail ---
         if (HANDOFF && exhausted && ++tailAge > tune.handoffAfter &&
-            (tune.handoffMode != 2 || __popc(__ballot_sync(0xFFFFFFFFu, ws != kWsNone)) <= tune.handoffLanes)) {
+            __popc(__ballot_sync(0xFFFFFFFFu, ws != kWsNone)) <= tune.handoffLanes) {
             // a lane walking at cell level with nothing pending (cells drained, keys resolved just above) gives its ray up, to go on
             // from the cell it stands in: mode 1 in wf_tail_kernel, one warp to the ray; mode 2 in a second pass of this kernel over
             // the rays given up, which fills its warps densely again (rt_tail.cuh)

@@ -1718,7 +1718,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         t.splitEarly = getenv("OCLR_SPLIT_EARLY") ? atoi(getenv("OCLR_SPLIT_EARLY")) : 0;
         t.handoffAfter = getenv("OCLR_HANDOFF_AFTER") ? atoi(getenv("OCLR_HANDOFF_AFTER")) : 2;
         t.handoffMode = getenv("OCLR_HANDOFF_MODE") ? atoi(getenv("OCLR_HANDOFF_MODE")) : 1;
-        t.handoffLanes = getenv("OCLR_HANDOFF_LANES") ? atoi(getenv("OCLR_HANDOFF_LANES")) : 16;
+        t.handoffLanes = getenv("OCLR_HANDOFF_LANES") ? atoi(getenv("OCLR_HANDOFF_LANES")) : (t.handoffMode == 2 ? 16 : 32);
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
