@@ -19,7 +19,10 @@
 // on a 1/8 share of config 2: the two ray-carrying pipe launches take 0.49 + 0.26 ms for 305 M + 102 M warp instructions (68 % / 43 %
 // of the whole-frame issue rate); handing rays off 4 outer iterations after the queue runs dry shortens them to 0.43-0.47 + 0.22 ms
 // and adds 0.05 + 0.075 ms of tail kernel (5 M + 21 M warp instructions): what a small launch loses is the decaying lane fill of
-// EVERY warp's last batch, thousands of medium rays, not a handful of very long ones.  Off by default (OCLR_HANDOFF_MAX_PATHS = 0);
+// EVERY warp's last batch, thousands of medium rays, not a handful of very long ones.  And where only the longest walks are left -- a
+// 17-row share still needs 0.31 + 0.23 ms for its two trace launches -- giving up rays by their AGE is no faster either (0.556 -> 0.59 ms):
+// those rays cross mostly empty space, which the lane's two-level walk takes four cells at a step, while a burst works at cell
+// granularity.  The next step would be the burst over BRICK planes.  Off by default (OCLR_HANDOFF_MAX_PATHS = 0);
 // tests/test_gpu_progressive.py::test_tail_handoff_is_invisible keeps it exact.
 #pragma once
 #include "rt_trace.cuh"

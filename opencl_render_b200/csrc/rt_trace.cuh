@@ -33,7 +33,7 @@ struct TraceTuning {
     int splitMin;      // queue dry: a walk with at least this many cells to go is cut into parts for the warp's idle lanes (0 = never)
     int splitPart;     // ... of at least this many cells each
     int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
-    int handoffAfter;  // HANDOFF instantiation: outer iterations a warp spends with the queue dry before it gives rays up (rt_tail.cuh)
+    int handoffAfter;  // HANDOFF instantiation: outer iterations a ray has been with its warp before the warp gives it up (queue dry; rt_tail.cuh)
     int handoffMode;   // 1: to wf_tail_kernel, one ray per warp; 2: back into a queue of walk records for a second, densely packed pass
     int handoffLanes;  // a warp gives its rays up once at most this many of its lanes still hold one (32: whatever it holds)
 };
@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
     float lastE = 0.f;
     uint32_t seqNext = 0;   // cells this ray has in the current batch
     uint32_t cq = 0;        // warp-uniform: cells queued
-    int tailAge = 0;        // warp-uniform (HANDOFF): outer iterations since this warp saw the queue dry
 
     for (;;) {
         // ---- SPLIT: idle lanes take parts of the longest whole walk this warp holds (queue dry; or, early mode, a ray that has been
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                     ws = kWsRun;
                     face = kFaceNone;
                     seqNext = 0;
-                    if (SPLIT) P.birth[lane] = iter;
+                    if (SPLIT || HANDOFF) P.birth[lane] = iter;
                     if (COUNT) {
                         cnt.gridRays++;
                         cnt.bricksLoaded++;
@@ -730,12 +729,14 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
 
         // ---- HANDOFF (small launches only): the queue has been dry for a while and what this warp still walks is the launch's tail ---
-        if (HANDOFF && exhausted && ++tailAge > tune.handoffAfter &&
-            __popc(__ballot_sync(0xFFFFFFFFu, ws != kWsNone)) <= tune.handoffLanes) {
+        if (HANDOFF && exhausted && __popc(__ballot_sync(0xFFFFFFFFu, ws != kWsNone)) <= tune.handoffLanes) {
             // a lane walking at cell level with nothing pending (cells drained, keys resolved just above) gives its ray up, to go on
             // from the cell it stands in: mode 1 in wf_tail_kernel, one warp to the ray; mode 2 in a second pass of this kernel over
             // the rays given up, which fills its warps densely again (rt_tail.cuh)
-            const bool give = (ws == kWsRun) & (g.level == 0) & (tune.handoffMode == 2 || g.coarseOk) & (!SPLIT || P.grp[lane] == 0u);
+            // ... and that has been with this warp for handoffAfter outer iterations (~12 cells each) already: a LONG walk, which is what
+            // a launch with the queue dry is waiting for -- the many medium ones finish where they are
+            const bool give = (ws == kWsRun) & (g.level == 0) & (tune.handoffMode == 2 || g.coarseOk) & (!SPLIT || P.grp[lane] == 0u) &
+                              (iter - P.birth[lane] >= (uint32_t)tune.handoffAfter);
             const unsigned gm = __ballot_sync(0xFFFFFFFFu, give);
             if (gm != 0u) {
                 const int leader = __ffs(gm) - 1;
