@@ -34,13 +34,15 @@ struct TraceTuning {
     int splitPart;     // ... of at least this many cells each
     int splitEarly;    // > 0: also before the queue is dry, for a ray that has been with the warp for that many outer iterations
     int handoffAfter;  // HANDOFF instantiation: outer iterations a ray has been with its warp before the warp gives it up (queue dry; rt_tail.cuh)
-    int handoffMode;   // 1: to wf_tail_kernel, one ray per warp; 2: back into a queue of walk records for a second, densely packed pass
+    int handoffMode;   // 1 / 3: to a burst walker, one ray per warp (brick planes / cell planes); 2: back into a queue of walk records for a second pass
     int handoffLanes;  // a warp gives its rays up once at most this many of its lanes still hold one (32: whatever it holds)
+    int handoffBurst;  // HANDOFF: with the queue dry a walk burst ends after this many iterations at the latest (tail mode would let a lone
+                       // ray that crosses empty space -- no cell to drain -- walk to its end inside ONE burst, out of the hand-off's reach)
 };
 
 // Rays a launch's pipe kernel gives up in its tail (HANDOFF instantiation, small launch domains; rt_tail.cuh).
 struct TailQueue {
-    uint4* entries;     // mode 1: {ray index (slot * Q + path), current cell (packed, not yet examined), entry face, 0}
+    uint4* entries;     // modes 1, 3: {ray index (slot * Q + path), current cell (not yet examined) / empty brick, entry face, level}
     uint32_t* count;    // rays given up by the pipe kernel of this round; {count, 0, 0, 0} doubles as the class counts of the second pass
     uint32_t* cursor;   // next entry to take
     uint32_t capacity;
@@ -377,6 +379,13 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             }
         }
 
+        if (HANDOFF && !exhausted) {
+            // a warp learns that the queue is dry when it asks for more -- and a warp whose 32 rays are all long (the queue is sorted
+            // longest first) does not ask for a long time.  Small launches look: one read of the cursor per outer iteration
+            uint32_t cur = 0;
+            if (lane == 0) cur = *(volatile uint32_t*)w.queueCursor;
+            exhausted = __shfl_sync(0xFFFFFFFFu, cur, 0) >= count;
+        }
         // ---- refill idle lanes: one atomic per warp, records read in queue order ----
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, ws == kWsNone);
         if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refillMin)) {
@@ -447,6 +456,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
         }
 
         // ---- WALK burst: step every walking lane until the cell queue is worth draining or too few lanes still walk ----------------
+        int burstIters = 0;   // (HANDOFF only)
         for (;;) {
             const bool walking = ws == kWsRun;
             if (COUNT) {
@@ -532,6 +542,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             const int nSwitch = __popc(__ballot_sync(0xFFFFFFFFu, (ws == kWsRefine) | (ws == kWsEnter)));
             const int nWalk = __popc(__ballot_sync(0xFFFFFFFFu, ws == kWsRun));
             if (cq >= (uint32_t)tune.drainMin) break;   // (checked before anything that loops back: the queue holds drainMin + 31 cells)
+            if (HANDOFF && exhausted && ++burstIters >= tune.handoffBurst) break;
             // Tail of the launch (queue dry, a few long rays left): the launch cannot end before its longest walk does, so what
             // counts now is that ray's latency.  Draining after every step would put a full open + test round trip between two
             // steps; let a few cells accumulate instead (they are opened and tested side by side in one drain).
@@ -735,7 +746,11 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
             // the rays given up, which fills its warps densely again (rt_tail.cuh)
             // ... and that has been with this warp for handoffAfter outer iterations (~12 cells each) already: a LONG walk, which is what
             // a launch with the queue dry is waiting for -- the many medium ones finish where they are
-            const bool give = (ws == kWsRun) & (g.level == 0) & (tune.handoffMode == 2 || g.coarseOk) & (!SPLIT || P.grp[lane] == 0u) &
+            // (mode 1, the brick-plane burst walker, also takes a ray that is crossing an empty brick at brick level -- the long walks
+            // through empty space spend most of their time there; mode 3 = the cell-plane burst walker)
+            const bool atCells = g.level == 0;
+            const bool inEmptyBrick = (tune.handoffMode == 1) & (g.level == 1) & ((g.maskLo | g.maskHi) == 0u) & !pwalk_in_end(g);
+            const bool give = (ws == kWsRun) & (atCells | inEmptyBrick) & (tune.handoffMode == 2 || g.coarseOk) & (!SPLIT || P.grp[lane] == 0u) &
                               (iter - P.birth[lane] >= (uint32_t)tune.handoffAfter);
             const unsigned gm = __ballot_sync(0xFFFFFFFFu, give);
             if (gm != 0u) {
@@ -753,7 +768,7 @@ __global__ void __launch_bounds__(128, OCLR_TRACE_MIN_CTAS) wf_pipe_kernel(Scene
                             tq.s1[pos] = make_uint4(g.epk, P.excl[lane], path, g.coarseOk ? 1u : 0u);
                             tq.order[pos] = pos;
                         } else {
-                            tq.entries[pos] = make_uint4(path, g.cpk, (uint32_t)face, 0u);
+                            tq.entries[pos] = make_uint4(path, g.cpk, (uint32_t)face, (uint32_t)g.level);
                         }
                         ws = kWsNone;
                     }

@@ -1706,7 +1706,7 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
     // host thread per GPU)
     static const TraceTuning tune = [] {
         auto env = [](const char* k, int d) { const char* v = getenv(k); return v && atoi(v) > 0 ? atoi(v) : d; };
-        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 16};
+        TraceTuning t = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 16, 12};
         t.refillMin = env("OCLR_REFILL_MIN", 4);
         t.hierarchical = getenv("OCLR_HIERARCHICAL") ? atoi(getenv("OCLR_HIERARCHICAL")) : 2;
         t.drainMin = std::min(env("OCLR_DRAIN_MIN", 64), (int)kCellQCap - 31);   // (round 2 sweep: 64 is ~1 % faster than 48 on configs 2 and 3)
@@ -1718,7 +1718,9 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
         t.splitEarly = getenv("OCLR_SPLIT_EARLY") ? atoi(getenv("OCLR_SPLIT_EARLY")) : 0;
         t.handoffAfter = getenv("OCLR_HANDOFF_AFTER") ? atoi(getenv("OCLR_HANDOFF_AFTER")) : 2;
         t.handoffMode = getenv("OCLR_HANDOFF_MODE") ? atoi(getenv("OCLR_HANDOFF_MODE")) : 1;
+        if (t.handoffMode == 1 && getenv("OCLR_TAIL_BRICKS") && atoi(getenv("OCLR_TAIL_BRICKS")) == 0) t.handoffMode = 3;   // cell-plane bursts
         t.handoffLanes = getenv("OCLR_HANDOFF_LANES") ? atoi(getenv("OCLR_HANDOFF_LANES")) : (t.handoffMode == 2 ? 16 : 32);
+        t.handoffBurst = env("OCLR_HANDOFF_BURST", 12);
         return t;
     }();
     if (getenv("OCLR_TRACE_CTAS") && atoi(getenv("OCLR_TRACE_CTAS")) > 0) perSm = std::min(perSm, atoi(getenv("OCLR_TRACE_CTAS")));
@@ -1832,8 +1834,11 @@ static bool launch_wavefront(Frame* f, const SceneView& S, const FrameView& Fall
                         else
                             wf_pipe_kernel<false, false><<<traceGrid, 128, shBytes, ks>>>(S, w2, rec2, tune, dcnt, tq);
                         ++launches;
-                    } else if (handoff) {
-                        wf_tail_kernel<<<(unsigned)(smCount * 4), 128, shBytes, ks>>>(S, w[k], tq);
+                    } else if (handoff) {   // one ray per warp: bursts over brick planes (default) or over cell planes (OCLR_TAIL_BRICKS=0)
+                        if (tune.handoffMode == 1)
+                            wf_tail_brick_kernel<<<(unsigned)(smCount * 4), 128, shBytes, ks>>>(S, w[k], tq);
+                        else
+                            wf_tail_kernel<<<(unsigned)(smCount * 4), 128, shBytes, ks>>>(S, w[k], tq);
                         ++launches;
                     }
                     if (timeTrace) {

@@ -237,7 +237,7 @@ print("TAIL_PROBE " + json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("after", ["0", "2", "off", "requeue-all", "requeue-16"])
+@pytest.mark.parametrize("after", ["0", "2", "off", "requeue-all", "requeue-16", "cells-0"])
 def test_tail_handoff_is_invisible(after):
     """rt_tail.cuh: a launch domain may hand the rays still walking in the tail of a trace launch to wf_tail_kernel (one ray per warp,
     cooperative bursts; an experiment that is exact but not faster, hence off by default).  With the hand-off forced as early as
@@ -254,9 +254,10 @@ def test_tail_handoff_is_invisible(after):
     elif after.startswith("requeue"):   # mode 2: the rays given up go back into a queue of walk records, a second pass of the pipe kernel takes them
         env.update(OCLR_HANDOFF_MAX_PATHS="4000000000", OCLR_HANDOFF_MODE="2", OCLR_HANDOFF_AFTER="0",
                    OCLR_HANDOFF_LANES="32" if after.endswith("all") else "16")
-    else:
+    else:   # mode 1: one ray per warp, bursts over brick planes ("0", "2") or over cell planes ("cells-0")
         env["OCLR_HANDOFF_MAX_PATHS"] = "4000000000"    # (off by default: not faster, rt_tail.cuh)
-        env["OCLR_HANDOFF_AFTER"] = after
+        env["OCLR_HANDOFF_AFTER"] = after.split("-")[-1]
+        env["OCLR_TAIL_BRICKS"] = "0" if after.startswith("cells") else "1"
     r = subprocess.run([sys.executable, "-c", _TAIL_PROBE], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("TAIL_PROBE ")][-1][len("TAIL_PROBE "):])
