@@ -1,8 +1,6 @@
-# round 2, session z2: brick-plane burst walker that reads a brick's record before it does anything else for it
+# round 2, closing session: the whole GPU suite, smoke() and a short bench line on the final tree
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "tail_handoff" > gpurun_out/r02z3_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02z3_tests.log | cut -c1-300
-M="OCLR_HANDOFF_MAX_PATHS=4000000 OCLR_HANDOFF_MODE=1"
-( timeout 400 python scripts/share_sweep.py 2 64 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=2" "$M OCLR_HANDOFF_AFTER=4" "$M OCLR_HANDOFF_AFTER=6" "$M OCLR_HANDOFF_AFTER=8" "$M OCLR_HANDOFF_AFTER=12"
-  timeout 400 python scripts/share_sweep.py 2 8 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=8" "$M OCLR_HANDOFF_AFTER=12" "$M OCLR_HANDOFF_AFTER=16" "$M OCLR_HANDOFF_AFTER=24" "OCLR_X=off"
-  timeout 400 python scripts/share_sweep.py 2 16 "OCLR_X=off" "$M OCLR_HANDOFF_AFTER=8" "$M OCLR_HANDOFF_AFTER=12" ) 2>&1 | tee gpurun_out/r02z3_share.log
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/r02end_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02end_tests.log
+python -c "import __graft_entry__ as g; g.smoke()"
+OCLR_BENCH_NO_E2E=1 timeout 600 python bench.py --steps 10 --warmup 3 --extra none > gpurun_out/r02end_bench.json 2> gpurun_out/r02end_bench.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/r02end_bench.json
