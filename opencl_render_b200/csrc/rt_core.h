@@ -645,12 +645,19 @@ OCLR_HD uint32_t grid_trace_coop(const SceneView& S, const float* planes, f3 o, 
                                  float& outAB, float& outAC, Counters* cnt);
 
 template <bool COUNT>
+OCLR_HD uint32_t grid_trace_coop_bricks(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                        float& outAB, float& outAC, Counters* cnt);
+
+template <bool COUNT>
 OCLR_HD uint32_t grid_trace_mode(int walkMode, const SceneView& S, const float* px, const float* py, const float* pz, f3 o, f3 r,
                                  float minD, float maxD, uint32_t excl, float& outT, float& outAB, float& outAC, Counters* cnt) {
     if (walkMode == 2) return grid_trace_packed<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);  // px = base of all planes
     if (walkMode >= 2000)   // walkMode = 2000 + 100 * (cells walked before the cut) + parts: the trace kernel's run-time split (rt_walk.h)
         return grid_trace_split_mid<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, (walkMode - 2000) / 100, (walkMode - 2000) % 100, 3);
     if (walkMode == 1000) return grid_trace_coop<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);   // walked by cooperative bursts
+#if !defined(__CUDA_ARCH__)   // (host form of rt_tail.cuh's kernel: test infrastructure, kept out of the per-pixel kernel's stack frame)
+    if (walkMode == 1001) return grid_trace_coop_bricks<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);   // ... over brick planes
+#endif
     if (walkMode >= 3) return grid_trace_split<COUNT>(S, px, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode);  // parts of `walkMode` cells
     return grid_trace<COUNT>(S, px, py, pz, o, r, minD, maxD, excl, outT, outAB, outAC, cnt, walkMode == 1);
 }

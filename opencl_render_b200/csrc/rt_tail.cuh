@@ -236,6 +236,8 @@ __global__ void __launch_bounds__(128) wf_tail_kernel(SceneView S, WfState w, Ta
 // cell granularity is no faster than that (measured above).  Result of THIS kernel (profiles/r02_super_level.txt, sessions u - z2): exact
 // on every golden case; with bursts of the HANDOFF instantiation that end and warps that look at the queue cursor (two reasons why long
 // walks never reached the hand-off before) a 17-row share of config 2 goes 0.56 -> 0.52 ms, a 1/8 share stays at 0.94.  Off by default.
+// (Host form: rt_walk.h grid_trace_coop_bricks, compared with the reference's cell walk by tests/test_hostemu_parity.py::
+// test_brick_plane_bursts_are_exact; the counting build does not count what the tail kernels do.)
 // Here the 32 lanes take the next 11 / 11 / 10 crossings of every 4th plane:
 // each certain crossing enters one 4x4x4 brick, its lane rebuilds the exact cell state at that entry (pwalk_refine, the very function
 // the lanes' two-level walk uses) and walks the brick's cells on its own -- up to 10 dependent steps, 32 bricks side by side, nothing at

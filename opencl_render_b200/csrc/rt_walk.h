@@ -788,4 +788,159 @@ OCLR_HD uint32_t grid_trace_coop(const SceneView& S, const float* planes, f3 o, 
     return kNoTriangle;
 }
 
+// ---- the cooperative walk one level up: bursts over BRICK planes (host form of rt_tail.cuh's wf_tail_brick_kernel) --------------------
+// The 32 virtual lanes take the next 11 / 11 / 10 crossings of every 4th plane; each certain crossing enters one 4x4x4 brick.  An empty
+// brick that does not hold the ray's end cell has nothing to visit; for any other the exact cell state at the entry is rebuilt with
+// pwalk_refine -- the function the two-level walk uses -- and the brick's cells are walked one by one until the walk leaves the brick.
+// Cells are tested in (brick, step) order, the first cell with a hit wins, the end cell stops the walk.  The walk starts in the middle
+// of a brick: its rest is walked first.  Requires all direction components non-zero and n >= 4.
+template <bool COUNT>
+OCLR_HD uint32_t grid_trace_coop_bricks(const SceneView& S, const float* planes, f3 o, f3 r, float minD, float maxD, uint32_t excl, float& outT,
+                                        float& outAB, float& outAC, Counters* cnt) {
+    const int n = S.n, nb = S.nb;
+    const float* px = planes;
+    const float* py = planes + (n + 1);
+    const float* pz = planes + 2 * (n + 1);
+    PackedWalk start;
+    pwalk_setup(start, n, nb, px, py, pz, o, r, minD, maxD);
+    if (!start.coarseOk) return grid_trace_packed<COUNT>(S, planes, o, r, minD, maxD, excl, outT, outAB, outAC, cnt);
+    if (COUNT) cnt->gridRays++;
+    int nbShift = 0;
+    while ((1 << nbShift) < nb) ++nbShift;
+    const uint32_t epk = start.epk;
+    const uint32_t endBrickPk = epk == kPkNone ? (uint32_t)kPkNone : pk_super_of_brick(epk);   // (>> 2 per field: the end cell's brick)
+    const int up[3] = {(0 <= r.x) ? 1 : 0, (0 <= r.y) ? 1 : 0, (0 <= r.z) ? 1 : 0};
+    const float oc[3] = {o.x, o.y, o.z}, rc[3] = {r.x, r.y, r.z};
+    uint32_t closest = kNoTriangle;
+    bool stop = false;   // the end cell has been visited
+    // the cells of one brick from the state `g` (level 0) on, until the walk leaves the brick / the grid, finds a hit or reaches the end cell
+    auto walk_brick = [&](PackedWalk& g, int face) {
+        const uint4 br = OCLR_LDG(S.bricks + g.brick);
+        g.maskLo = br.x;
+        g.maskHi = br.y;
+        g.rankBase = br.z;
+        for (;;) {
+            const int bit = pwalk_bit(g.cpk);
+            if (COUNT) cnt->cells++;
+            if (pwalk_occupied(g, bit)) {
+                const uint32_t rank = pwalk_rank(g, bit);
+                const uint2 range = OCLR_LDG(S.cellRange + rank);
+                const uint32_t fm = face != kFaceNone ? OCLR_LDG(S.faceMask + 6 * (size_t)rank + face) : 0xFFFFFFFFu;
+                if (COUNT) cnt->cellsNonEmpty++;
+                outT = maxD;
+                for (uint32_t k = pwalk_next_entry(range.x, range.y, fm, range.x); k < range.y; k = pwalk_next_entry(range.x, range.y, fm, k + 1)) {
+                    const uint32_t tri = OCLR_LDG(S.cellList + k);
+                    if (tri == excl) continue;
+                    float t, ab, ac;
+                    if (COUNT) cnt->gridCandidates++;
+                    if (tri_test(S.triGeo + 4 * (size_t)tri, o, r, minD, outT, t, ab, ac)) {
+                        closest = tri;
+                        outT = t;
+                        outAB = ab;
+                        outAC = ac;
+                    }
+                }
+                if (closest != kNoTriangle) return;
+            }
+            if (g.cpk == epk) {
+                stop = true;
+                return;
+            }
+            int axis, upA;
+            float tE;
+            bool crossed;
+            if (!pwalk_step(g, n, nbShift, planes, axis, upA, tE, crossed)) return;
+            if (crossed) return;
+            face = axis * 2 + upA;
+        }
+    };
+    int bc0[3] = {pk_get(start.cpk, 0) >> 2, pk_get(start.cpk, 1) >> 2, pk_get(start.cpk, 2) >> 2};
+    {   // the rest of the brick the walk starts in
+        PackedWalk g = start;
+        walk_brick(g, kFaceNone);
+        if (closest != kNoTriangle) return closest;
+        if (stop) {
+            outT = maxD;
+            return kNoTriangle;
+        }
+    }
+    for (;;) {
+        float t[3][11];
+        int kmax[3];
+        for (int a = 0; a < 3; ++a) {
+            kmax[a] = up[a] ? (nb - 1 - bc0[a]) : bc0[a];
+            for (int k = 0; k < 11; ++k)
+                t[a][k] = (k < coop_candidates(a) && k <= kmax[a]) ? (planes[a * (n + 1) + ((bc0[a] + up[a] + (up[a] ? k : -k)) << 2)] - oc[a]) / rc[a]
+                                                                  : OCLR_INF;
+        }
+        int rank[kCoopLanes], cntv[kCoopLanes][3];
+        int R = kCoopLanes, exitRank = 1 << 20, endRank = 1 << 20;
+        for (int v = 0; v < kCoopLanes; ++v) {
+            const int a = v % 3, k = v / 3;
+            rank[v] = k;
+            for (int b = 0; b < 3; ++b) {
+                cntv[v][b] = b == a ? k + 1 : 0;
+                if (b == a) continue;
+                for (int kk = 0; kk < coop_candidates(b); ++kk) cntv[v][b] += coop_precedes(b, t[b][kk], a, t[a][k]) ? 1 : 0;
+                rank[v] += cntv[v][b];
+            }
+            const bool present = k <= kmax[a];
+            if (k == coop_candidates(a) - 1 && kmax[a] >= coop_candidates(a) && rank[v] + 1 < R) R = rank[v] + 1;
+            if (present && k == kmax[a] && rank[v] < exitRank) exitRank = rank[v];
+            if (present && k < kmax[a]) {
+                const uint32_t bpk = pk_make((bc0[0] + (up[0] ? cntv[v][0] : -cntv[v][0])) & kPkMask, (bc0[1] + (up[1] ? cntv[v][1] : -cntv[v][1])) & kPkMask,
+                                             (bc0[2] + (up[2] ? cntv[v][2] : -cntv[v][2])) & kPkMask);
+                if (bpk == endBrickPk && rank[v] < endRank) endRank = rank[v];
+            }
+        }
+        int limit = R;
+        bool finished = false;
+        if (exitRank < limit) {
+            limit = exitRank;
+            finished = true;
+        }
+        if (endRank < limit) limit = endRank + 1;   // nothing behind the end cell's brick belongs to this burst
+        for (int q = 0; q < limit; ++q)
+            for (int v = 0; v < kCoopLanes; ++v) {
+                if (rank[v] != q) continue;
+                const int a = v % 3;
+                const int bx = bc0[0] + (up[0] ? cntv[v][0] : -cntv[v][0]), by = bc0[1] + (up[1] ? cntv[v][1] : -cntv[v][1]),
+                          bz = bc0[2] + (up[2] ? cntv[v][2] : -cntv[v][2]);
+                const int brick = bx + ((by + (bz << nbShift)) << nbShift);
+                const uint4 br = OCLR_LDG(S.bricks + brick);
+                if (COUNT) cnt->bricksLoaded++;
+                if ((br.x | br.y) != 0u || pk_make(bx, by, bz) == endBrickPk) {
+                    PackedWalk g;
+                    g.o = o;
+                    g.r = r;
+                    g.epk = epk;
+                    g.endBrick = (int)kEndNone;
+                    g.coarseOk = true;
+                    g.level = 1;
+                    g.cpk = pk_make(bx, by, bz);
+                    g.tx = (px[(bx + up[0]) << 2] - o.x) / r.x;
+                    g.ty = (py[(by + up[1]) << 2] - o.y) / r.y;
+                    g.tz = (pz[(bz + up[2]) << 2] - o.z) / r.z;
+                    g.brick = brick;
+                    pwalk_refine(g, n, nbShift, planes, a, t[a][v / 3]);
+                    g.brick = brick;
+                    walk_brick(g, kFaceNone);
+                    if (closest != kNoTriangle) return closest;
+                    if (stop) {
+                        outT = maxD;
+                        return kNoTriangle;
+                    }
+                }
+                if (q == limit - 1) {
+                    bc0[0] = bx;
+                    bc0[1] = by;
+                    bc0[2] = bz;
+                }
+            }
+        if (finished) break;
+    }
+    outT = maxD;
+    return kNoTriangle;
+}
+
 }  // namespace oclr

@@ -146,6 +146,28 @@ def test_cooperative_walk_is_exact(name, hostemu, monkeypatch):
         assert coop[3]["cells"] <= flat[3]["cells"]
 
 
+@pytest.mark.parametrize("name", helpers.CASE_NAMES)
+def test_brick_plane_bursts_are_exact(name, hostemu, monkeypatch):
+    """rt_walk.h grid_trace_coop_bricks, the host form of rt_tail.cuh's wf_tail_brick_kernel: the walk taken 32 BRICK-plane crossings at
+    a time, the cell state rebuilt by pwalk_refine inside every brick that holds triangles or the ray's end cell -- identical planes,
+    ids and flags, exactly the non-empty cells and the triangle tests of the two-level walk, and fewer brick records read than the
+    reference's walk touches bricks (empty ones are looked at, never walked)."""
+    sc, cam, lists, samples = helpers.make_case(name)
+    monkeypatch.delenv("HOSTEMU_HIERARCHICAL", raising=False)
+    flat = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "2")
+    packed = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    monkeypatch.setenv("HOSTEMU_HIERARCHICAL", "1001")
+    bricks = helpers.hostemu_render(hostemu, cam, lists, sc, samples)
+    for c in range(3):
+        assert np.array_equal(flat[0][c], bricks[0][c])
+    assert np.array_equal(flat[1], bricks[1]) and np.array_equal(flat[2], bricks[2])
+    assert bricks[3]["cellsNonEmpty"] == flat[3]["cellsNonEmpty"]
+    assert bricks[3]["gridRays"] == packed[3]["gridRays"]
+    if name != "coarse_grid":      # (rays with a zero direction component fall back to the packed walk)
+        assert bricks[3]["cells"] <= flat[3]["cells"]
+
+
 @pytest.mark.parametrize("name", ["spheres", "soup_mirror_glass", "terrain_textured", "soup_lights_sun_last", "coarse_grid"])
 def test_counters_equal_instrumented_reference(name, hostemu, ref, monkeypatch):
     """the event counts behind `roofline.achieved` (the counting build of the product's own
