@@ -1,5 +1,5 @@
-# round 2, closing two-GPU check of the final tree: the tests that need two GPUs
+# round 2, last look at the final binaries: smoke() and the golden / hand-off tests
 set -x
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L | wc -l
-timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "all_devices or two_gpus or raytrace_all" 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()"
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "golden or tail_handoff or super or ring or packers" 2>&1 | tail -3
